@@ -1,0 +1,209 @@
+/* tqb200 -- C-ABI of the B200-native sampling-and-reduction hot path of torchquad.
+ *
+ * The reference (esa/torchquad v0.5.0) has NO native/FFI interface: every step below is Python over
+ * ATen reached through `autoray`.  Each entry point therefore cites the reference Python function
+ * (file:line under /root/reference) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain C: pointers are DEVICE pointers unless the name ends in _host; sizes are int64_t.
+ *   - `dtype` is TQ_F32 or TQ_F64 (the working dtype of the reference tensors); integer state is int64
+ *     exactly as in the reference (`counts`, `nh`).
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream and never
+ *     synchronises the device.  No call allocates device memory: temporaries come from the caller's
+ *     workspace `ws` (`ws_bytes` >= tq_workspace_bytes(), zero-initialised once by the caller).
+ *   - return value: TQ_OK (0) or a negative TQ_ERR_* / positive cudaError_t; tq_last_error() gives text.
+ *   - tensors are dense row-major; `[rows, dim]` means element (r, d) at r*dim + d.
+ */
+#ifndef TQB200_H
+#define TQB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TQ_API __attribute__((visibility("default")))
+#else
+#define TQ_API
+#endif
+
+#define TQ_OK 0
+#define TQ_ERR_INVALID_ARGUMENT (-1)
+#define TQ_ERR_WORKSPACE (-2)
+#define TQ_ERR_UNSUPPORTED (-3)
+
+#define TQ_F32 0
+#define TQ_F64 1
+
+#define TQ_MAX_DIM 32 /* integration dimensions supported by the fused kernels */
+
+/* Newton-Cotes rules (trapezoid.py, simpson.py, boole.py) */
+#define TQ_RULE_TRAPEZOID 0
+#define TQ_RULE_SIMPSON 1
+#define TQ_RULE_BOOLE 2
+
+/* Built-in integrand families for the fused kernels.  Genz families: SURVEY 8(d); the last four are
+ * the reference's test integrands (tests/integration_test_functions.py:146-325). */
+#define TQ_F_GENZ_OSCILLATORY 0
+#define TQ_F_GENZ_PRODUCT_PEAK 1
+#define TQ_F_GENZ_CORNER_PEAK 2
+#define TQ_F_GENZ_GAUSSIAN 3
+#define TQ_F_GENZ_C0 4
+#define TQ_F_GENZ_DISCONTINUOUS 5
+#define TQ_F_SUM_SIN 6
+#define TQ_F_SUM_EXP 7
+#define TQ_F_PROD_COS 8
+#define TQ_F_POLYNOMIAL 9
+#define TQ_F_COUNT 10
+
+/* Parameters of a built-in integrand, passed by value from the host.  `a`/`u` are the Genz difficulty
+ * and shift vectors; `coeff[0..ncoeff)` the polynomial coefficients (same for each dimension).
+ * The integrand is evaluated at x*size + start and multiplied by `scale` (VEGAS passes the domain
+ * volume, vegas.py:104-112). */
+typedef struct tq_integrand {
+    int32_t family;
+    int32_t dim;
+    int32_t ncoeff;
+    int32_t _pad;
+    double a[TQ_MAX_DIM];
+    double u[TQ_MAX_DIM];
+    double coeff[8];
+    double start[TQ_MAX_DIM];
+    double size[TQ_MAX_DIM];
+    double scale;
+} tq_integrand;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+TQ_API const char* tq_last_error(void);
+TQ_API int tq_version(void);
+TQ_API size_t tq_workspace_bytes(void);
+/* sm count / compute capability of the current device */
+TQ_API int tq_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- RNG: replaces RNG.uniform (torchquad/integration/rng.py:119-125) ----------------------------
+ * out[r - row_begin, d] = U[0,1)(seed, call_idx, r, d), r in [row_begin, row_end): counter-based
+ * Philox4x32-10, a pure function of its arguments, so ranks drawing disjoint row ranges of one call
+ * reproduce the single-process stream exactly. */
+TQ_API int tq_philox_uniform(void* out, int64_t row_begin, int64_t row_end, int32_t dim, int32_t dtype,
+                      uint64_t seed, uint32_t call_idx, void* stream);
+
+/* ---- Monte Carlo: replaces MonteCarlo.calculate_sample_points (monte_carlo.py:84-106) ------------
+ * out[r, d] = u*(domain[d,1]-domain[d,0]) + domain[d,0] with u as above (mul then add, not fused). */
+TQ_API int tq_mc_sample(void* out, const void* domain, int64_t row_begin, int64_t row_end, int32_t dim,
+                 int32_t dtype, uint64_t seed, uint32_t call_idx, void* stream);
+/* d(loss)/d(domain) for the op above: grad_domain[d,0] = sum_r g*(1-u), grad_domain[d,1] = sum_r g*u,
+ * uniforms regenerated from the counter.  grad_domain_f64 is double[dim*2] (device). */
+TQ_API int tq_mc_sample_backward(const void* grad_out, int64_t row_begin, int64_t row_end, int32_t dim,
+                          int32_t dtype, uint64_t seed, uint32_t call_idx, double* grad_domain_f64,
+                          void* ws, size_t ws_bytes, void* stream);
+/* Column sums of f[rows, cols] accumulated in fp64: sum_f64[c] = sum_r f[r,c], and if sumsq_f64 is not
+ * NULL sumsq_f64[c] = sum_r f[r,c]^2.  Replaces the `anp.sum(function_values, axis=0)` of
+ * MonteCarlo.calculate_result (monte_carlo.py:72-77); the variance moment is an extension. */
+TQ_API int tq_sum_columns(const void* f, int64_t rows, int64_t cols, int32_t dtype, double* sum_f64,
+                   double* sumsq_f64, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- VEGAS map (torchquad/integration/vegas_map.py) ---------------------------------------------
+ * forward: get_X (:44-58) + get_Jac (:60-74) + _get_interval_ID (:76-85) in one pass.
+ *   k = floor(y*Ni); o = y*Ni - k; x = xe[d,k] + dxe[d,k]*o; jac = prod_d Ni*dxe[d,k] (left to right).
+ *   x, jac, ids, offset may each be NULL.  ids is int32[rows, dim]; offset[rows, dim] is `o`
+ *   (_get_interval_offset :87-97). */
+TQ_API int tq_vegas_map_forward(const void* y, const void* x_edges, const void* dx_edges, void* x, void* jac,
+                         int32_t* ids, void* offset, int64_t rows, int32_t dim, int64_t n_intervals,
+                         int32_t dtype, void* stream);
+/* accumulate_weight (:99-111): weights[d,k] += jf2[r], counts[d,k] += 1 (int64, bit-exact). */
+TQ_API int tq_vegas_map_accumulate(const void* y, const void* jf2, void* weights, int64_t* counts, int64_t rows,
+                            int32_t dim, int64_t n_intervals, int32_t dtype, void* stream);
+/* Scratch bytes tq_vegas_map_smooth / tq_vegas_map_update need for a [dim, Ni] map (pass as ws). */
+TQ_API size_t tq_vegas_map_workspace_bytes(int32_t dim, int64_t n_intervals, int32_t dtype);
+/* _smooth_map (:113-172) written to `smoothed[dim, Ni]`; status[0] = 1 when a dimension sums to zero
+ * (the reference returns None).  weights/counts are not modified. */
+TQ_API int tq_vegas_map_smooth(const void* weights, const int64_t* counts, void* smoothed, int32_t dim,
+                        int64_t n_intervals, double alpha, int32_t dtype, int32_t* status, void* ws,
+                        size_t ws_bytes, void* stream);
+/* update_map (:185-261): smooth, equal-mass rebin (fp64 prefix sums), inf repair, dx = diff(x), reset
+ * of weights/counts.  status (device int32[4]): [0]=1 update skipped (zero dimension), [1]=number of
+ * non-finite edges that were repaired, [2]=1 unrepairable (reference raises RuntimeError), [3]=unused. */
+TQ_API int tq_vegas_map_update(void* x_edges, void* dx_edges, void* weights, int64_t* counts, int32_t dim,
+                        int64_t n_intervals, double alpha, int32_t dtype, int32_t* status, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* ---- VEGAS stratification (torchquad/integration/vegas_stratification.py) -----------------------
+ * get_NH (:92-103): nh[c] = max(2, floor(dh[c]*nevals_exp)) as int64, plus offsets[c] = sum_{c'<c} nh
+ * (offsets has n_cubes+1 entries; offsets[n_cubes] = M, the number of samples of the iteration). */
+TQ_API int tq_vegas_strat_nh(const void* dh, int64_t n_cubes, double nevals_exp, int32_t dtype, int64_t* nh,
+                      int64_t* offsets, void* ws, size_t ws_bytes, void* stream);
+/* offsets[c] = sum_{c'<c} nh[c'] (n_cubes+1 entries) for a caller-provided nh; the `anp.repeat(arange, nevals)`
+ * of get_Y / accumulate_weight (:58-59,:154-155) is never materialised, rows find their cube by search. */
+TQ_API int tq_vegas_strat_offsets(const int64_t* nh, int64_t n_cubes, int64_t* offsets, void* ws, size_t ws_bytes,
+                           void* stream);
+/* get_Y (:140-165) for sample rows [row_begin,row_end) of the cube-sorted order:
+ *   y = (digit_d(cube) + u)/N_strat, digit_d(c) = (c / N_strat^d) % N_strat, y >= 1 -> 0.999999.
+ * u_in != NULL: uniforms are read from u_in[row - row_begin, d] (injected RNG, tests/vegas_test.py:143-156);
+ * u_in == NULL: cube-keyed Philox stream (seed, call_idx, cube, index within cube, d). */
+TQ_API int tq_vegas_strat_sample(const int64_t* offsets, int64_t n_cubes, int32_t n_strat, int32_t dim,
+                          int32_t dtype, const void* u_in, uint64_t seed, uint32_t call_idx,
+                          int64_t row_begin, int64_t row_end, void* y, void* stream);
+/* accumulate_weight (:46-70) for cubes [cube_begin,cube_end): JF[c] = sum jf, JF2[c] = sum jf^2 over the
+ * cube's rows in row order (bit-identical to the CPU scatter_add_).  jf points at row `row_base`. */
+TQ_API int tq_vegas_strat_accumulate(const void* jf, int64_t row_base, const int64_t* offsets,
+                              int64_t cube_begin, int64_t cube_end, void* JF, void* JF2, int32_t dtype,
+                              void* stream);
+/* Backward of JF wrt jf: grad_jf[r] = grad_JF[cube(r)] for rows [row_begin,row_end). */
+TQ_API int tq_vegas_strat_accumulate_backward(const void* grad_JF, const int64_t* offsets, int64_t n_cubes,
+                                       int64_t row_begin, int64_t row_end, void* grad_jf, int32_t dtype,
+                                       void* stream);
+/* Iteration estimator (vegas.py:293-303) + update_DH (vegas_stratification.py:72-90) in one pass:
+ *   scalars_f64[0] = I_it = sum JF*V/n, [1] = sigma2_it = sum |JF2*V^2/n - ih^2|/n, [2] = sum d^beta;
+ *   dh[c] = d^beta / sum (left unnormalised when the sum is 0). */
+TQ_API int tq_vegas_strat_update(const void* JF, const void* JF2, const int64_t* nh, int64_t n_cubes,
+                          double v_cubes, double beta, int32_t dtype, void* dh, double* scalars_f64,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Newton-Cotes grids (integration_grid.py:64-99, grid_integrator.py:57-91, rule files) -------
+ * points[p - p_begin, d] = nodes[d, i_d(p)], i_d(p) = (p / n^(dim-1-d)) % n  (dim 0 slowest). */
+TQ_API int tq_nc_grid_points(const void* nodes, int32_t n, int32_t dim, int64_t p_begin, int64_t p_end,
+                      void* points, int32_t dtype, void* stream);
+/* Backward: grad_nodes_f64[d, j] = sum over rows with i_d(p) = j of grad_points[p, d]. */
+TQ_API int tq_nc_grid_points_backward(const void* grad_points, int32_t n, int32_t dim, int64_t p_begin,
+                               int64_t p_end, double* grad_nodes_f64, int32_t dtype, void* stream);
+/* out_f64[k] = sum_{p in [p_begin,p_end)} f[p - p_begin, k] * prod_d w[d, i_d(p)]: the tensor-product
+ * weight contraction that `_apply_composite_rule` evaluates axis by axis. */
+TQ_API int tq_nc_contract(const void* f, const void* w, int32_t n, int32_t dim, int64_t p_begin, int64_t p_end,
+                   int64_t cols, int32_t dtype, double* out_f64, void* ws, size_t ws_bytes, void* stream);
+/* W[p - p_begin] = prod_d w[d, i_d(p)] (used by the backward of tq_nc_contract). */
+TQ_API int tq_nc_point_weights(const void* w, int32_t n, int32_t dim, int64_t p_begin, int64_t p_end,
+                        void* out, int32_t dtype, void* stream);
+
+/* ---- fused paths for built-in integrands (no sample traffic to HBM) ------------------------------
+ * Monte Carlo over rows [row_begin,row_end) of the row-keyed stream: out_f64 = {sum f, sum f^2}. */
+TQ_API int tq_fused_mc(const tq_integrand* fn_host, int32_t dtype, int64_t row_begin, int64_t row_end,
+                uint64_t seed, uint32_t call_idx, double* out_f64, void* ws, size_t ws_bytes,
+                void* stream);
+/* Newton-Cotes: out_f64[0] = sum_p f(nodes[., i(p)]) * prod_d w[d, i_d(p)]. */
+TQ_API int tq_fused_nc(const tq_integrand* fn_host, const void* nodes, const void* w, int32_t n, int32_t dtype,
+                int64_t p_begin, int64_t p_end, double* out_f64, void* ws, size_t ws_bytes, void* stream);
+/* One VEGAS pass without writing samples: generate -> map -> evaluate -> accumulate.
+ *   stratified (offsets != NULL): rows [row_begin,row_end) of the cube-sorted order (vegas.py:268-291);
+ *     JF/JF2 (pre-zeroed by the caller) receive the per-cube sums.
+ *   warm-up (offsets == NULL): rows are plain samples y = u*0.999999 (vegas.py:236); out_f64 receives
+ *     {sum jf, sum jf^2}.
+ *   weights/counts (map histogram, vegas_map.py:99-111) are accumulated unless weights == NULL. */
+TQ_API int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
+                   int32_t n_strat, int64_t row_begin, int64_t row_end, const void* x_edges,
+                   const void* dx_edges, int64_t n_intervals, void* weights, int64_t* counts, void* JF,
+                   void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
+                   size_t ws_bytes, void* stream);
+
+/* Peak-rate microbenchmarks used by bench.py for the fused-path roofline denominators:
+ * kind 0 = dependent-free FP32 FMA chains, 1 = FP64 FMA chains, 2 = Philox4x32-10 blocks.
+ * Performs iters*threads*ops_per_iter operations; returns ops per launch through ops_out_host. */
+TQ_API int tq_peak_microbench(int32_t kind, int64_t iters, double* sink, double* ops_out_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TQB200_H */

@@ -1,0 +1,352 @@
+"""End-to-end parity of the integrator classes (the drop-in surface) against the oracle / golden fixtures,
+plus the behavioural pins of the reference test-suite (/root/reference/tests, cited per test)."""
+import math
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import torchquad_b200 as tq
+from oracle import ref_oracle as O
+from torchquad_b200 import integrands as F
+
+pytestmark = pytest.mark.gpu
+DT = {"f32": torch.float32, "f64": torch.float64}
+
+
+class Injected:
+    """rng whose uniform() replays the oracle's Philox stream (the reference's injection seam,
+    /root/reference/tests/vegas_test.py:143-156)."""
+
+    def __init__(self, seed):
+        self.seed, self.call = seed, 0
+
+    def uniform(self, size, dtype):
+        u = O.philox_uniform(self.seed, self.call, 0, size[0], size[1], dtype)
+        self.call += 1
+        return u
+
+
+def peak(x):
+    return torch.exp(-torch.sum(25.0 * (x - 0.3) ** 2, dim=1)) + 0.01
+
+
+@pytest.fixture(autouse=True)
+def _quiet():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        yield
+
+
+# ---------------------------------------------------------------- VEGAS on identical injected samples
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+@pytest.mark.parametrize("name,dim,N,fn", [
+    ("peak3", 3, 20000, peak),
+    ("sin2", 2, 10000, lambda x: torch.sum(torch.sin(x), dim=1)),
+])
+def test_vegas_identical_samples_match_reference(cuda, golden, tag, name, dim, N, fn):
+    g = golden(f"vegas_run_{tag}")
+    domain = torch.from_numpy(g[f"{name}_domain"]).to(cuda)
+    v = tq.VEGAS()
+    res = v.integrate(fn, dim, N=N, integration_domain=domain, rng=Injected(3))
+    want = float(g[f"{name}_result"])
+    assert res.dtype == DT[tag] and res.device.type == "cuda" and res.dim() == 0
+    assert v.it == int(g[f"{name}_it"])
+    if tag == "f64":
+        # schedule, sample counts and per-iteration estimates follow the reference run exactly
+        assert v._nr_of_fevals == int(g[f"{name}_fevals"])
+        assert abs(float(res) - want) <= 1e-10 * abs(want)
+        assert np.allclose([float(r) for r in v.results], g[f"{name}_results"], rtol=1e-10)
+        assert np.allclose([float(s) for s in v.sigma2], g[f"{name}_sigma2"], rtol=1e-8)
+        assert float((v.map.x_edges.cpu() - torch.from_numpy(g[f"{name}_x_edges"])).abs().max()) < 1e-11
+        assert torch.allclose(v.strat.dh.cpu(), torch.from_numpy(g[f"{name}_dh"]), rtol=1e-9, atol=1e-18)
+    else:
+        # fp32: a floor() in get_NH may flip on a last-ulp difference of pow(); compare statistically
+        sig = math.sqrt(float(sum(g[f"{name}_sigma2"])) / len(g[f"{name}_sigma2"]))
+        assert abs(float(res) - want) <= max(1e-4 * abs(want), 3 * sig)
+        assert abs(v._nr_of_fevals - int(g[f"{name}_fevals"])) <= 0.001 * int(g[f"{name}_fevals"])
+
+
+def test_vegas_c1_gaussian_matches_reference_record(cuda, golden):
+    """BASELINE configs[0]: 4-D Genz Gaussian, N=1e6, fp64.  Fresh RNG => agree within 3 sigma of the
+    reference's reported error; same schedule (10 iterations, ~645k evaluations)."""
+    rec = golden("reference_records")
+    fn = F.GenzGaussian(4, a=5.0, u=0.5)
+    exact = fn.exact()
+    assert abs(exact - float(rec["c1_exact"])) < 1e-15
+    for fused in (True, False):
+        v = tq.VEGAS()
+        f = fn if fused else (lambda x: fn(x))
+        res = v.integrate(f, 4, N=10**6, integration_domain=torch.tensor([[0.0, 1.0]] * 4, dtype=torch.float64, device=cuda), seed=0)
+        err = float(v._get_error())
+        assert v.it == int(rec["c1_it"])
+        assert abs(v._nr_of_fevals - int(rec["c1_fevals"])) < 0.02 * int(rec["c1_fevals"])
+        assert abs(float(res) - float(rec["c1_result"])) <= 3 * math.hypot(err, float(rec["c1_error"]))
+        assert abs(float(res) - exact) <= 4 * err
+        assert err < 3 * float(rec["c1_error"])
+
+
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_vegas_fused_equals_unfused(cuda, tag):
+    """Fused and unfused paths draw the same cube-keyed Philox samples => same estimate up to summation order."""
+    dt = DT[tag]
+    dom = torch.tensor([[0.0, 1.0], [0.0, 2.0], [-1.0, 1.0]], dtype=dt, device=cuda)
+    for fn in (F.GenzGaussian(3, a=[3.0, 2.0, 4.0], u=[0.3, 0.6, 0.5]), F.GenzProductPeak(3, a=2.0, u=0.4), F.SumOfSines(3)):
+        a = tq.VEGAS()
+        ra = a.integrate(fn, 3, N=60000, integration_domain=dom, seed=11)
+        b = tq.VEGAS()
+        rb = b.integrate(lambda x: fn(x), 3, N=60000, integration_domain=dom, seed=11)
+        tol = 1e-9 if tag == "f64" else 2e-3
+        assert a._nr_of_fevals == b._nr_of_fevals or tag == "f32"
+        assert abs(float(ra) - float(rb)) <= tol * abs(float(rb))
+
+
+def test_vegas_special_cases(cuda):
+    """/root/reference/tests/vegas_test.py:159-199."""
+    torch.set_default_dtype(torch.float64)
+    try:
+        integ = tq.VEGAS()
+        dom = torch.tensor([[0.0, 3.0]] * 2, device=cuda)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            zero = integ.integrate(lambda x: x[:, 0] * 0.0, 2, N=10000, integration_domain=dom, seed=0)
+        assert float(zero.abs()) == 0.0
+        const = integ.integrate(lambda x: x[:, 0] * 0.0 + 10.0, 2, N=10000, integration_domain=dom, seed=0)
+        assert abs(float(const) - 90.0) < 1e-13
+
+        class ModifiedRNG(tq.RNG):
+            """Half of the uniforms replaced by exact 0.0 / 1.0 (vegas_test.py:143-156)."""
+
+            def __init__(self, *a, **k):
+                super().__init__(*a, **k)
+                base = self.uniform
+                self.uniform = lambda *a, **k: self.modify(base(*a, **k))
+
+            @staticmethod
+            def modify(n):
+                return torch.where(n < 0.5, n * 2.0, torch.where(n < 0.75, torch.zeros_like(n), torch.ones_like(n)))
+
+        r = integ.integrate(lambda x: torch.sum(x, dim=1), 2, N=10000,
+                            integration_domain=torch.tensor([[0.0, 1.0]] * 2, device=cuda), rng=ModifiedRNG(seed=0))
+        assert isinstance(integ.rng, ModifiedRNG)
+        assert abs(float(r) - 1.0) < 0.1
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
+def test_vegas_peak_accuracy(cuda):
+    """/root/reference/tests/vegas_test.py:71-140 (hypercube peak and diagonal peaks, 5 seeds)."""
+    dt = torch.float64
+    dom = torch.tensor([[1.0, 5.0], [-4.0, 4.0], [2.0, 6.0]], dtype=dt, device=cuda)
+
+    def cube_peak(x):
+        return torch.prod((x >= 3.0) * (x < 4.0), dim=1).to(dt) + 0.001
+
+    ref = float(torch.prod(dom[:, 1] - dom[:, 0])) * 0.001 + 1.0
+    for seed in [0, 1, 2, 3, 41317]:
+        r = tq.VEGAS().integrate(cube_peak, 3, N=30000, integration_domain=dom, seed=seed)
+        assert abs(float(r) - ref) < 0.03
+    c = 100.0
+    dom2 = torch.tensor([[1.0, 1.0 + c], [-4.0, -4.0 + c]], dtype=dt, device=cuda)
+
+    def diag(x):
+        return torch.exp(torch.sum(dom2[:, 0] - x, dim=1)) + torch.exp(torch.sum(x - dom2[:, 1], dim=1))
+
+    ref2 = 2.0 - 4.0 * math.exp(-c) + 2.0 * math.exp(-2 * c)
+    for seed in [0, 1, 2, 3, 41317]:
+        r = tq.VEGAS().integrate(diag, 2, N=30000, integration_domain=dom2, seed=seed)
+        assert abs(float(r) - ref2) < 0.03
+
+
+# ---------------------------------------------------------------- Monte Carlo
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_monte_carlo_matches_oracle_on_same_samples(cuda, tag):
+    dt = DT[tag]
+    dom = torch.tensor([[0.0, 2.0], [-1.0, 1.5], [3.0, 3.5]], dtype=dt, device=cuda)
+    mc = tq.MonteCarlo()
+    fn = lambda x: torch.sum(torch.sin(x), dim=1)  # noqa: E731
+    res = mc.integrate(fn, 3, N=200_000, integration_domain=dom, seed=42)
+    u = O.philox_uniform(42, 0, 0, 200_000, 3, dt)
+    pts = O.mc_sample_points(u, dom.cpu())
+    want = O.mc_result(fn(pts), dom.cpu())
+    assert res.dtype == dt and res.dim() == 0 and mc._nr_of_fevals == 200_000
+    assert abs(float(res) - float(want)) <= (1e-12 if tag == "f64" else 1e-5) * abs(float(want))
+    # fused functor on the same stream
+    fres = mc.integrate(F.SumOfSines(3), 3, N=200_000, integration_domain=dom, seed=42)
+    assert abs(float(fres) - float(want)) <= (1e-12 if tag == "f64" else 1e-5) * abs(float(want))
+    assert mc.get_error_estimate() > 0
+    # vector-valued integrand
+    vres = mc.integrate(lambda x: torch.stack([fn(x), 2 * fn(x)], dim=1), 3, N=200_000, integration_domain=dom, seed=42)
+    assert vres.shape == (2,) and abs(float(vres[1]) - 2 * float(want)) <= 1e-5 * abs(float(want))
+
+
+def test_monte_carlo_constant_is_exact_and_chunking_is_invisible(cuda):
+    """Order-0 polynomials integrate with zero error (/root/reference/tests/monte_carlo_test.py:29-30)."""
+    dom = torch.tensor([[0.0, 2.0]], dtype=torch.float32, device=cuda)
+    mc = tq.MonteCarlo()
+    r = mc.integrate(lambda x: x[:, 0] * 0 + 2.0, 1, N=100_000, integration_domain=dom, seed=0)
+    assert float(r) == 4.0
+    fn = lambda x: torch.sum(torch.exp(x), dim=1)  # noqa: E731
+    dom3 = torch.tensor([[0.0, 1.0]] * 3, dtype=torch.float64, device=cuda)
+    whole = tq.MonteCarlo().integrate(fn, 3, N=300_001, integration_domain=dom3, seed=5)
+    chunked = tq.MonteCarlo()
+    chunked.max_points_bytes = 100_000 * 3 * 8
+    part = chunked.integrate(fn, 3, N=300_001, integration_domain=dom3, seed=5)
+    assert abs(float(whole) - float(part)) <= 1e-13 * abs(float(whole))
+    assert chunked._nr_of_fevals == 300_001
+
+
+def test_monte_carlo_list_domain_and_types(cuda):
+    """Result dtype/device follow the domain (/root/reference/tests/integrator_types_test.py:19-113)."""
+    tq.set_up_backend("torch", "float64")
+    try:
+        for integ, kw in [(tq.MonteCarlo(), dict(N=1000, seed=0)), (tq.VEGAS(), dict(N=2000, seed=0)),
+                          (tq.Trapezoid(), dict(N=100)), (tq.Simpson(), dict(N=121)), (tq.Boole(), dict(N=169))]:
+            seen = {}
+
+            def fn(x):
+                seen["dtype"], seen["shape"] = x.dtype, x.shape
+                return x[:, 0] * 0.0 - 1.0
+
+            r = integ.integrate(fn, 2, integration_domain=[[0, 2], [0, 2]], backend="torch", **kw)
+            assert r.dtype == torch.float64 and r.is_cuda and seen["dtype"] == torch.float64 and seen["shape"][1] == 2
+            assert abs(float(r) + 4.0) < (0.03 if isinstance(integ, tq.VEGAS) else 1e-5)
+            r32 = integ.integrate(fn, 2, integration_domain=torch.tensor([[0, 2], [0, 2]], dtype=torch.float32, device=cuda), **kw)
+            assert r32.dtype == torch.float32 and seen["dtype"] == torch.float32
+    finally:
+        torch.set_default_dtype(torch.float32)
+        torch.set_default_device("cpu")
+
+
+# ---------------------------------------------------------------- Newton-Cotes exactness pins
+def test_newton_cotes_polynomial_exactness(cuda):
+    """/root/reference/tests/{trapezoid,simpson,boole}_test.py: rules are exact up to degree 1/3/5."""
+    dt = torch.float64
+    dom1 = torch.tensor([[0.0, 2.0]], dtype=dt, device=cuda)
+    lin = lambda x: 3.0 * x[:, 0] + 1.0  # noqa: E731
+    assert abs(float(tq.Trapezoid().integrate(lin, 1, N=2, integration_domain=dom1)) - 8.0) < 1e-15
+    cub = lambda x: x[:, 0] ** 3 - x[:, 0] + 2.0  # noqa: E731
+    assert abs(float(tq.Simpson().integrate(cub, 1, N=3, integration_domain=dom1)) - 6.0) < 1e-14
+    quint = lambda x: x[:, 0] ** 5 + x[:, 0] ** 2  # noqa: E731
+    assert abs(float(tq.Boole().integrate(quint, 1, N=401, integration_domain=dom1)) - (64 / 6 + 8 / 3)) < 6.33e-11
+    dom3 = torch.tensor([[0.0, 1.0], [-1.0, 1.0], [0.0, 2.0]], dtype=dt, device=cuda)
+    f3 = lambda x: torch.sum(x**5, dim=1) + torch.prod(x, dim=1)  # noqa: E731
+    exact = (1 / 6) * 4 + 0 + (64 / 6) * 2 + 0.0
+    r = tq.Boole().integrate(f3, 3, N=1_076_890, integration_domain=dom3)  # adjusts 102 -> 101 per dim
+    assert abs(float(r) - exact) < 2e-11
+    with pytest.warns(UserWarning):
+        tq.Simpson().integrate(cub, 1, N=4, integration_domain=dom1)
+    # 10-D Simpson on 3^10 points (simpson_test.py:78-88)
+    dom10 = torch.tensor([[0.0, 1.0]] * 10, dtype=dt, device=cuda)
+    r10 = tq.Simpson().integrate(lambda x: torch.sum(x**2, dim=1), 10, N=3**10, integration_domain=dom10)
+    assert abs(float(r10) - 10 / 3) < 5e-9
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_newton_cotes_fused_and_chunked_equal_plain(cuda, tag):
+    dt = DT[tag]
+    dom = torch.tensor([[0.0, 1.0], [0.5, 2.0], [-1.0, 0.0], [0.0, 1.0]], dtype=dt, device=cuda)
+    fn = F.ProductOfCosines(4)
+    for cls, N in [(tq.Trapezoid, 20**4), (tq.Simpson, 21**4), (tq.Boole, 21**4)]:
+        plain = cls().integrate(lambda x: fn(x), 4, N=N, integration_domain=dom)
+        fused = cls().integrate(fn, 4, N=N, integration_domain=dom)
+        ch = cls()
+        ch.max_points_bytes = 50_000 * 4 * dom.element_size()
+        chunked = ch.integrate(lambda x: fn(x), 4, N=N, integration_domain=dom)
+        tol = 1e-12 if tag == "f64" else 2e-5
+        assert abs(float(fused) - float(plain)) <= tol * abs(float(plain))
+        assert abs(float(chunked) - float(plain)) <= tol * abs(float(plain))
+        exact = math.sin(1.0) * (math.sin(2.0) - math.sin(0.5)) * math.sin(1.0) * math.sin(1.0)
+        assert abs(float(plain) - exact) < 2e-3
+
+
+# ---------------------------------------------------------------- fused integrand families
+@pytest.mark.parametrize("cls,kw", [
+    (F.GenzOscillatory, dict(a=[0.5, 0.7, 0.2, 0.9, 0.4], u=[0.3] * 5)),
+    (F.GenzProductPeak, dict(a=[2.0, 1.5, 3.0, 1.0, 2.5], u=[0.5, 0.4, 0.6, 0.3, 0.7])),
+    (F.GenzCornerPeak, dict(a=[0.5, 0.3, 0.2, 0.6, 0.1])),
+    (F.GenzGaussian, dict(a=[2.0, 3.0, 1.0, 2.5, 1.5], u=[0.5, 0.4, 0.6, 0.3, 0.7])),
+    (F.GenzC0, dict(a=[2.0, 1.0, 3.0, 1.5, 0.5], u=[0.5, 0.4, 0.6, 0.3, 0.7])),
+    (F.GenzDiscontinuous, dict(a=[0.5, 0.3, 0.2, 0.6, 0.1], u=[0.6, 0.7, 0.5, 0.5, 0.5])),
+    (F.SumOfSines, {}), (F.SumOfExp, {}), (F.ProductOfCosines, {}),
+])
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_fused_integrands_match_torch_formulation_and_exact(cuda, cls, kw, tag):
+    dt = DT[tag]
+    fn = cls(5, **kw)
+    dom = torch.tensor([[0.0, 1.0]] * 5, dtype=dt, device=cuda)
+    N = 400_000
+    fused = tq.MonteCarlo()
+    rf = fused.integrate(fn, 5, N=N, integration_domain=dom, seed=9)
+    ru = tq.MonteCarlo().integrate(lambda x: fn(x), 5, N=N, integration_domain=dom, seed=9)
+    tol = 1e-11 if tag == "f64" else 2e-5
+    assert abs(float(rf) - float(ru)) <= tol * abs(float(ru)), "fused functor != torch formulation on identical samples"
+    err = fused.get_error_estimate()
+    assert abs(float(rf) - fn.exact()) <= 5 * err + 1e-6 * abs(fn.exact())
+    # oracle formulation agrees with the package's torch formulation
+    x = torch.rand(100, 5, dtype=torch.float64)
+    if cls.family.startswith("genz"):
+        assert torch.allclose(fn(x), O.genz(cls.family[5:], x, fn.a, fn.u), rtol=1e-13)
+        assert abs(fn.exact() - O.genz_exact(cls.family[5:], fn.a, fn.u)) <= 1e-13 * abs(fn.exact())
+
+
+def test_fused_polynomial(cuda):
+    fn = F.Polynomial(3, [1.0, -2.0, 0.5, 3.0])
+    dom = torch.tensor([[0.0, 1.0]] * 3, dtype=torch.float64, device=cuda)
+    r = tq.Boole().integrate(fn, 3, N=9**3, integration_domain=dom)
+    assert abs(float(r) - fn.exact()) < 1e-13
+    x = torch.rand(50, 3, dtype=torch.float64)
+    assert torch.allclose(fn(x), O.test_integrand("polynomial", x, fn.coeffs), rtol=1e-13)
+
+
+# ---------------------------------------------------------------- autograd (reference tests/gradient_test.py)
+@pytest.mark.parametrize("make,kw,tol", [
+    (tq.Trapezoid, dict(N=100001), 2e-2), (tq.Simpson, dict(N=100001), 2e-2), (tq.Boole, dict(N=100001), 2e-2),
+    (tq.MonteCarlo, dict(N=1_000_000, seed=0), 2e-2), (tq.VEGAS, dict(N=200_000, seed=0), 2e-2),
+])
+def test_gradient_wrt_domain(cuda, make, kw, tol):
+    """d/d(domain) of int 2|x| over [-1,1] is [-2, 2] (gradient_test.py:187-215)."""
+    dom = torch.tensor([[-1.0, 1.0]], dtype=torch.float64, device=cuda, requires_grad=True)
+    res = make().integrate(lambda x: 2.0 * torch.abs(x[:, 0]), 1, integration_domain=dom, **kw)
+    assert res.grad_fn is not None and res.dtype == torch.float64
+    res.backward()
+    g = dom.grad.cpu().numpy().ravel()
+    assert abs(g[0] + 2.0) < tol and abs(g[1] - 2.0) < tol
+    assert abs(float(res) - 2.0) < 1e-2
+
+
+@pytest.mark.parametrize("make,kw,tol", [
+    (tq.Trapezoid, dict(N=10201), 0.1), (tq.Simpson, dict(N=10201), 0.1), (tq.Boole, dict(N=10201), 0.1),
+    (tq.MonteCarlo, dict(N=200_000, seed=0), 0.1), (tq.VEGAS, dict(N=100_000, seed=0), 0.1),
+])
+def test_gradient_wrt_integrand_parameters(cuda, make, kw, tol):
+    """2-D polynomial with learnable coefficients (gradient_test.py:217-259): dI/dc_k = 2*int x^k over [0,1]^2... """
+    c = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64, device=cuda, requires_grad=True)
+    dom = torch.tensor([[0.0, 1.0], [0.0, 1.0]], dtype=torch.float64, device=cuda)
+
+    def fn(x):
+        return torch.sum(c[0] + c[1] * x + c[2] * x**2, dim=1)
+
+    res = make().integrate(fn, 2, integration_domain=dom, **kw)
+    res.backward()
+    want = np.array([2.0, 1.0, 2.0 / 3.0])
+    assert np.all(np.abs(c.grad.cpu().numpy() - want) < tol)
+    assert abs(float(res) - float((c.detach().cpu().numpy() * want).sum())) < 5e-2
+
+
+# ---------------------------------------------------------------- RNG surface (reference tests/rng_test.py)
+def test_rng_surface(cuda):
+    a = tq.RNG(backend="torch", seed=547).uniform(size=[3, 9], dtype=torch.float32, device=cuda)
+    b = tq.RNG(backend="torch", seed=547).uniform(size=[3, 9], dtype=torch.float32, device=cuda)
+    c = tq.RNG(backend="torch", seed=548).uniform(size=[3, 9], dtype=torch.float32, device=cuda)
+    d = tq.RNG(backend="torch").uniform(size=[3, 9], dtype=torch.float32, device=cuda)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
+    r = tq.RNG(backend="torch", seed=1)
+    x1, x2 = r.uniform([5], torch.float64, device=cuda), r.uniform([5], torch.float64, device=cuda)
+    assert x1.shape == (5,) and not torch.equal(x1, x2)
+    assert r.uniform([0], torch.float64, device=cuda).shape == (0,)
+    big = r.uniform([100000], torch.float32, device=cuda)
+    assert 0.0 <= float(big.min()) and float(big.max()) < 1.0 and abs(float(big.mean()) - 0.5) < 0.01
+    with pytest.raises(ValueError):
+        tq.RNG(backend="numpy")

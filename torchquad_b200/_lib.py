@@ -1,0 +1,151 @@
+"""ctypes binding of libtqb200.so (the C ABI declared in include/tqb200.h).
+
+PyTorch is used for device memory, streams and autograd plumbing only; every arithmetic step of the hot
+path is a kernel behind this boundary.  There is no CPU fallback: loading fails loudly when the shared
+library is missing, and every op raises when handed a non-CUDA tensor.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libtqb200.so")
+
+TQ_F32, TQ_F64 = 0, 1
+TQ_MAX_DIM = 32
+
+c_i32, c_i64, c_u32, c_u64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64
+c_f64, c_sz, c_p = ctypes.c_double, ctypes.c_size_t, ctypes.c_void_p
+
+
+class tq_integrand(ctypes.Structure):
+    """Mirror of `struct tq_integrand` (include/tqb200.h)."""
+
+    _fields_ = [
+        ("family", c_i32), ("dim", c_i32), ("ncoeff", c_i32), ("_pad", c_i32),
+        ("a", c_f64 * TQ_MAX_DIM), ("u", c_f64 * TQ_MAX_DIM), ("coeff", c_f64 * 8),
+        ("start", c_f64 * TQ_MAX_DIM), ("size", c_f64 * TQ_MAX_DIM), ("scale", c_f64),
+    ]
+
+
+_P_INTEGRAND = ctypes.POINTER(tq_integrand)
+
+# name -> (restype, argtypes); must list every symbol of include/tqb200.h (checked by tests/test_abi.py)
+PROTOTYPES = {
+    "tq_last_error": (ctypes.c_char_p, []),
+    "tq_version": (ctypes.c_int, []),
+    "tq_workspace_bytes": (c_sz, []),
+    "tq_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
+    "tq_philox_uniform": (ctypes.c_int, [c_p, c_i64, c_i64, c_i32, c_i32, c_u64, c_u32, c_p]),
+    "tq_mc_sample": (ctypes.c_int, [c_p, c_p, c_i64, c_i64, c_i32, c_i32, c_u64, c_u32, c_p]),
+    "tq_mc_sample_backward": (ctypes.c_int, [c_p, c_i64, c_i64, c_i32, c_i32, c_u64, c_u32, c_p, c_p, c_sz, c_p]),
+    "tq_sum_columns": (ctypes.c_int, [c_p, c_i64, c_i64, c_i32, c_p, c_p, c_p, c_sz, c_p]),
+    "tq_vegas_map_forward": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
+    "tq_vegas_map_accumulate": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
+    "tq_vegas_map_workspace_bytes": (c_sz, [c_i32, c_i64, c_i32]),
+    "tq_vegas_map_smooth": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_f64, c_i32, c_p, c_p, c_sz, c_p]),
+    "tq_vegas_map_update": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i32, c_i64, c_f64, c_i32, c_p, c_p, c_sz, c_p]),
+    "tq_vegas_strat_nh": (ctypes.c_int, [c_p, c_i64, c_f64, c_i32, c_p, c_p, c_p, c_sz, c_p]),
+    "tq_vegas_strat_offsets": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_sz, c_p]),
+    "tq_vegas_strat_sample": (ctypes.c_int, [c_p, c_i64, c_i32, c_i32, c_i32, c_p, c_u64, c_u32, c_i64, c_i64, c_p, c_p]),
+    "tq_vegas_strat_accumulate": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_i64, c_p, c_p, c_i32, c_p]),
+    "tq_vegas_strat_accumulate_backward": (ctypes.c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_i32, c_p]),
+    "tq_vegas_strat_update": (ctypes.c_int, [c_p, c_p, c_p, c_i64, c_f64, c_f64, c_i32, c_p, c_p, c_p, c_sz, c_p]),
+    "tq_nc_grid_points": (ctypes.c_int, [c_p, c_i32, c_i32, c_i64, c_i64, c_p, c_i32, c_p]),
+    "tq_nc_grid_points_backward": (ctypes.c_int, [c_p, c_i32, c_i32, c_i64, c_i64, c_p, c_i32, c_p]),
+    "tq_nc_contract": (ctypes.c_int, [c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_i64, c_i32, c_p, c_p, c_sz, c_p]),
+    "tq_nc_point_weights": (ctypes.c_int, [c_p, c_i32, c_i32, c_i64, c_i64, c_p, c_i32, c_p]),
+    "tq_fused_mc": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_i64, c_i64, c_u64, c_u32, c_p, c_p, c_sz, c_p]),
+    "tq_fused_nc": (ctypes.c_int, [_P_INTEGRAND, c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_p, c_p, c_sz, c_p]),
+    "tq_fused_vegas": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_p, c_i64, c_i32, c_i64, c_i64, c_p, c_p, c_i64, c_p, c_p,
+                                      c_p, c_p, c_u64, c_u32, c_p, c_p, c_sz, c_p]),
+    "tq_peak_microbench": (ctypes.c_int, [c_i32, c_i64, c_p, ctypes.POINTER(c_f64), c_p]),
+}
+
+_cdll = None
+_lock = threading.Lock()
+_workspaces = {}
+launch_count = 0  # kernels-launching C-ABI calls issued by this process (bench.py reports it)
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError with build instructions when it is missing."""
+    global _cdll
+    if _cdll is not None:
+        return _cdll
+    with _lock:
+        if _cdll is not None:
+            return _cdll
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"torchquad_b200: CUDA library {LIB_PATH} not found. Build it with "
+                "`python -m torchquad_b200.build` (needs nvcc); there is no CPU fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _cdll = lib
+    return _cdll
+
+
+def dtype_code(dtype):
+    if dtype == torch.float32:
+        return TQ_F32
+    if dtype == torch.float64:
+        return TQ_F64
+    raise ValueError(f"torchquad_b200 supports float32 and float64 only, got {dtype}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "torchquad_b200 runs on CUDA only (no CPU fallback): got a tensor on "
+                f"{t.device}. Create the integration domain on a CUDA device or call "
+                "torchquad_b200.set_up_backend('torch') on a GPU machine."
+            )
+
+
+def ptr(t):
+    """Device pointer of a contiguous tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise RuntimeError("torchquad_b200: internal error, non-contiguous tensor passed to the C ABI")
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def workspace(device):
+    """Per-device zero-initialised scratch buffer handed to every call that needs temporaries."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = load().tq_workspace_bytes()
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point and turn a non-zero status into RuntimeError."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.tq_last_error().decode()}")
+    launch_count += 1
+    return rc
+
+
+def device_info():
+    sm, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    call("tq_device_info", ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor))
+    return sm.value, major.value, minor.value

@@ -1,0 +1,481 @@
+// Fused generate -> map -> evaluate -> accumulate kernels for built-in integrands: no sample ever
+// reaches HBM.  The integrands are the Genz families (not in the reference) and the
+// reference's test integrands (tests/integration_test_functions.py:146-325), all of which factor as
+// finish(combine_d step(x_d)), so a thread streams over the dimensions without holding the point.
+#include "common.cuh"
+
+namespace tq {
+
+constexpr double TWO_PI = 6.283185307179586476925286766559;
+
+// Per-dimension parameters staged in shared memory in the working type.
+template <typename T>
+struct FnShared {
+    T a[TQ_MAX_DIM];      // difficulty
+    T u[TQ_MAX_DIM];      // shift
+    T c[TQ_MAX_DIM];      // family-specific precomputation (a^-2, a^2)
+    T start[TQ_MAX_DIM];  // domain start
+    T size[TQ_MAX_DIM];   // domain size
+    T coeff[8];
+    T scale;
+    T phase;
+    T expo;
+    int dim, ncoeff;
+};
+
+template <typename T>
+__device__ __forceinline__ void stage_integrand(const tq_integrand& P, FnShared<T>& S) {
+    for (int d = threadIdx.x; d < P.dim; d += blockDim.x) {
+        S.a[d] = (T)P.a[d];
+        S.u[d] = (T)P.u[d];
+        S.start[d] = (T)P.start[d];
+        S.size[d] = (T)P.size[d];
+        T c = (T)0;
+        if (P.family == TQ_F_GENZ_PRODUCT_PEAK) c = (T)(1.0 / (P.a[d] * P.a[d]));
+        if (P.family == TQ_F_GENZ_GAUSSIAN) c = (T)(P.a[d] * P.a[d]);
+        S.c[d] = c;
+    }
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 8; ++k) S.coeff[k] = (T)P.coeff[k];
+        S.scale = (T)P.scale;
+        S.phase = (T)(TWO_PI * P.u[0]);
+        S.expo = (T)(-(double)(P.dim + 1));
+        S.dim = P.dim;
+        S.ncoeff = P.ncoeff;
+    }
+    __syncthreads();
+}
+
+template <int FAM, typename T>
+struct Integrand {
+    T acc;
+    bool inside;
+    __device__ __forceinline__ void init() {
+        acc = (FAM == TQ_F_GENZ_PRODUCT_PEAK || FAM == TQ_F_PROD_COS) ? (T)1 : (T)0;
+        inside = true;
+    }
+    __device__ __forceinline__ void step(T x, int d, const FnShared<T>& S) {
+        if constexpr (FAM == TQ_F_GENZ_OSCILLATORY || FAM == TQ_F_GENZ_CORNER_PEAK) {
+            acc += S.a[d] * x;
+        } else if constexpr (FAM == TQ_F_GENZ_PRODUCT_PEAK) {
+            const T t = x - S.u[d];
+            acc *= (T)1 / (S.c[d] + t * t);
+        } else if constexpr (FAM == TQ_F_GENZ_GAUSSIAN) {
+            const T t = x - S.u[d];
+            acc += S.c[d] * t * t;
+        } else if constexpr (FAM == TQ_F_GENZ_C0) {
+            acc += S.a[d] * fabs(x - S.u[d]);
+        } else if constexpr (FAM == TQ_F_GENZ_DISCONTINUOUS) {
+            acc += S.a[d] * x;
+            if (d < 2 && x > S.u[d]) inside = false;
+        } else if constexpr (FAM == TQ_F_SUM_SIN) {
+            acc += sin(x);
+        } else if constexpr (FAM == TQ_F_SUM_EXP) {
+            acc += exp(x);
+        } else if constexpr (FAM == TQ_F_PROD_COS) {
+            acc *= cos(x);
+        } else if constexpr (FAM == TQ_F_POLYNOMIAL) {
+            T h = S.coeff[S.ncoeff - 1];
+            for (int k = S.ncoeff - 2; k >= 0; --k) h = h * x + S.coeff[k];
+            acc += h;
+        }
+    }
+    __device__ __forceinline__ T finish(const FnShared<T>& S) const {
+        if constexpr (FAM == TQ_F_GENZ_OSCILLATORY) return cos(S.phase + acc);
+        else if constexpr (FAM == TQ_F_GENZ_CORNER_PEAK) return pow((T)1 + acc, S.expo);
+        else if constexpr (FAM == TQ_F_GENZ_GAUSSIAN || FAM == TQ_F_GENZ_C0) return exp(-acc);
+        else if constexpr (FAM == TQ_F_GENZ_DISCONTINUOUS) return inside ? exp(acc) : (T)0;
+        else return acc;
+    }
+};
+
+// ------------------------------------------------------------------ fused Monte Carlo
+template <int FAM, typename T>
+__global__ void __launch_bounds__(256)
+fused_mc_kernel(const tq_integrand P, int64_t row_begin, int64_t nrows, uint64_t seed, uint32_t call,
+                double* partials, unsigned int* ticket, double* out) {
+    constexpr int LANES = U01<T>::LANES;
+    __shared__ FnShared<T> S;
+    __shared__ double sh[32 * 2];
+    stage_integrand<T>(P, S);
+    const int dim = S.dim;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t grow = (uint64_t)(row_begin + r);
+        Integrand<FAM, T> fn;
+        fn.init();
+        for (int d0 = 0; d0 < dim; d0 += LANES) {
+            T u[LANES];
+            philox_block<T>(seed, call, (uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)(d0 / LANES), u);
+#pragma unroll
+            for (int j = 0; j < LANES; ++j)
+                if (d0 + j < dim) fn.step(add_rn(mul_rn(u[j], S.size[d0 + j]), S.start[d0 + j]), d0 + j, S);
+        }
+        const double f = (double)(fn.finish(S) * S.scale);
+        acc[0] += f;
+        acc[1] += f * f;
+    }
+    grid_sum_finish<2>(acc, sh, partials, ticket, out);
+}
+
+// ------------------------------------------------------------------ fused Newton-Cotes
+template <int FAM, typename T>
+__global__ void __launch_bounds__(256)
+fused_nc_kernel(const tq_integrand P, const T* __restrict__ nodes, const T* __restrict__ w, uint32_t n,
+                int64_t p_begin, int64_t p_end, double* partials, unsigned int* ticket, double* out, bool use_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ FnShared<T> S;
+    __shared__ double sh[32];
+    stage_integrand<T>(P, S);
+    const int dim = S.dim;
+    const T* sn = nodes;
+    const T* sw = w;
+    if (use_smem) {
+        T* a = reinterpret_cast<T*>(smem_raw);
+        T* b = a + dim * n;
+        for (int i = threadIdx.x; i < dim * (int)n; i += blockDim.x) { a[i] = nodes[i]; b[i] = w[i]; }
+        __syncthreads();
+        sn = a;
+        sw = b;
+    }
+    double acc[1] = {0.0};
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < p_end - p_begin;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t p = (uint64_t)(p_begin + r);
+        Integrand<FAM, T> fn;
+        fn.init();
+        T wt = (T)1;
+        if (p <= 0xffffffffull) {
+            uint32_t q = (uint32_t)p;
+            for (int d = dim - 1; d >= 0; --d) {
+                const uint32_t t = q / n;
+                const uint32_t i = q - t * n;
+                q = t;
+                wt *= sw[d * n + i];
+                fn.step(sn[d * n + i], d, S);
+            }
+        } else {
+            for (int d = dim - 1; d >= 0; --d) {
+                const uint64_t t = p / n;
+                const uint32_t i = (uint32_t)(p - t * n);
+                p = t;
+                wt *= sw[d * n + i];
+                fn.step(sn[d * n + i], d, S);
+            }
+        }
+        acc[0] += (double)(fn.finish(S) * S.scale) * (double)wt;
+    }
+    grid_sum_finish<1>(acc, sh, partials, ticket, out);
+}
+
+// ------------------------------------------------------------------ fused VEGAS pass
+// One thread per sample row.  Each CTA owns a contiguous chunk of the (cube-sorted) rows and walks it in
+// tiles of FV_BLOCK rows: the slice of `offsets` a tile needs (<= FV_BLOCK/2+2 entries because nh >= 2) is
+// staged in shared memory, so the row -> cube lookup is a short shared-memory binary search; only the first
+// tile of a chunk pays a global binary search.  Bin ids of the row are parked in shared memory until jf is
+// known, then the f^2 histogram is updated (shared-memory privatised when the whole map fits, L2
+// reductions otherwise); per-cube sums go through shared accumulators and one global add per cube and tile.
+constexpr int FV_BLOCK = 256;
+constexpr int FV_SLICE = FV_BLOCK / 2 + 4;  // +1 cube of slack: the walk may start one cube early
+
+template <int FAM, typename T, bool STRAT>
+__global__ void __launch_bounds__(FV_BLOCK)
+fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, int64_t n_cubes, int n_strat,
+                   int64_t row_begin, int64_t row_end, int64_t rows_per_cta, const T* __restrict__ xe,
+                   const T* __restrict__ dxe, long long ni, T* __restrict__ weights,
+                   unsigned long long* __restrict__ counts, T* __restrict__ JF, T* __restrict__ JF2, uint64_t seed,
+                   uint32_t call, bool hist_smem, double* partials, unsigned int* ticket, double* out) {
+    constexpr int LANES = U01<T>::LANES;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ FnShared<T> S;
+    __shared__ double sh[32 * 2];
+    __shared__ long long s_off[FV_SLICE];
+    __shared__ T s_jf[FV_SLICE], s_jf2[FV_SLICE];
+    __shared__ long long s_cube_cur;
+    stage_integrand<T>(P, S);
+    const int dim = S.dim;
+    int* s_ids = reinterpret_cast<int*>(smem_raw);                        // [dim][FV_BLOCK]
+    T* s_w = reinterpret_cast<T*>(s_ids + dim * FV_BLOCK);                 // [dim*ni] when hist_smem
+    unsigned int* s_c = reinterpret_cast<unsigned int*>(s_w + (hist_smem ? dim * ni : 0));
+    const bool do_hist = weights != nullptr;
+    if (do_hist && hist_smem) {
+        for (int i = threadIdx.x; i < dim * (int)ni; i += blockDim.x) { s_w[i] = (T)0; s_c[i] = 0u; }
+    }
+    const int64_t r_lo = row_begin + (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r_hi = r_lo + rows_per_cta < row_end ? r_lo + rows_per_cta : row_end;
+    if (STRAT) {
+        if (threadIdx.x == 0 && r_lo < r_hi) {
+            long long lo = 0, hi = n_cubes - 1;  // largest c with offsets[c] <= r_lo
+            while (lo < hi) {
+                const long long mid = (lo + hi + 1) >> 1;
+                if (__ldg(&offsets[mid]) <= r_lo) lo = mid; else hi = mid - 1;
+            }
+            s_cube_cur = lo;
+        }
+    }
+    __syncthreads();
+    const T nif = (T)ni;
+    const T nsf = (T)n_strat;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t rb = r_lo; rb < r_hi; rb += FV_BLOCK) {
+        const int64_t row = rb + threadIdx.x;
+        const bool active = row < r_hi;
+        long long c_lo = 0;
+        int ci = 0;
+        if (STRAT) {
+            c_lo = s_cube_cur;
+            for (int i = threadIdx.x; i < FV_SLICE; i += blockDim.x) {
+                const long long c = c_lo + i;
+                s_off[i] = __ldg(&offsets[c <= n_cubes ? c : n_cubes]);
+                s_jf[i] = (T)0;
+                s_jf2[i] = (T)0;
+            }
+            __syncthreads();
+            if (active) {
+                int lo = 0, hi = FV_SLICE - 2;  // largest i with s_off[i] <= row (entries past the end repeat M)
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_off[mid] <= row) lo = mid; else hi = mid - 1;
+                }
+                ci = lo;
+            }
+        }
+        if (active) {
+            uint32_t i0, i1, c = 0;
+            if (STRAT) {
+                i0 = (uint32_t)(c_lo + ci);
+                i1 = (uint32_t)(row - s_off[ci]);
+                c = i0;
+            } else {
+                i0 = (uint32_t)(uint64_t)row;
+                i1 = (uint32_t)((uint64_t)row >> 32);
+            }
+            Integrand<FAM, T> fn;
+            fn.init();
+            T jac = (T)1;
+            for (int d0 = 0; d0 < dim; d0 += LANES) {
+                T u[LANES];
+                philox_block<T>(seed, call, i0, i1, (uint32_t)(d0 / LANES), u);
+#pragma unroll
+                for (int j = 0; j < LANES; ++j) {
+                    const int d = d0 + j;
+                    if (d < dim) {
+                        T y;
+                        if (STRAT) {
+                            const uint32_t q = c / (uint32_t)n_strat;
+                            const uint32_t p = c - q * (uint32_t)n_strat;
+                            c = q;
+                            y = div_rn(add_rn((T)p, u[j]), nsf);
+                            if (y >= (T)1) y = (T)0.999999;
+                        } else {
+                            y = mul_rn(u[j], (T)0.999999);
+                        }
+                        const T t = mul_rn(y, nif);
+                        const T fl = floor(t);
+                        long long k = (long long)fl;
+                        k = k < 0 ? 0 : (k >= ni ? ni - 1 : k);
+                        const T o = sub_rn(t, fl);
+                        const T dxv = __ldg(&dxe[(int64_t)d * ni + k]);
+                        const T xv = __ldg(&xe[(int64_t)d * (ni + 1) + k]);
+                        const T x = add_rn(xv, mul_rn(dxv, o));
+                        jac = mul_rn(jac, mul_rn(nif, dxv));
+                        s_ids[d * FV_BLOCK + threadIdx.x] = (int)k;
+                        fn.step(add_rn(mul_rn(x, S.size[d]), S.start[d]), d, S);
+                    }
+                }
+            }
+            const T f = mul_rn(fn.finish(S), S.scale);
+            const T jf = mul_rn(f, jac);
+            const T jf2 = mul_rn(jf, jf);
+            if (STRAT) {
+                atomicAdd(&s_jf[ci], jf);
+                atomicAdd(&s_jf2[ci], jf2);
+            } else {
+                acc[0] += (double)jf;
+                acc[1] += (double)jf2;
+            }
+            if (do_hist) {
+                if (hist_smem) {
+                    for (int d = 0; d < dim; ++d) {
+                        const int b = d * (int)ni + s_ids[d * FV_BLOCK + threadIdx.x];
+                        atomicAdd(&s_w[b], jf2);
+                        atomicAdd(&s_c[b], 1u);
+                    }
+                } else {
+                    for (int d = 0; d < dim; ++d) {
+                        const int64_t b = (int64_t)d * ni + s_ids[d * FV_BLOCK + threadIdx.x];
+                        atomicAdd(&weights[b], jf2);
+                        atomicAdd(&counts[b], 1ull);
+                    }
+                }
+            }
+        }
+        if (STRAT) {
+            __syncthreads();
+            // flush per-cube sums of this tile; cubes straddling tiles/CTAs accumulate through the atomics
+            const int64_t last_row = (rb + FV_BLOCK < r_hi ? rb + FV_BLOCK : r_hi) - 1;
+            for (int i = threadIdx.x; i < FV_SLICE - 1; i += blockDim.x) {
+                const long long c = c_lo + i;
+                if (c < n_cubes && s_off[i] <= last_row && s_off[i + 1] > rb) {
+                    atomicAdd(&JF[c], s_jf[i]);
+                    atomicAdd(&JF2[c], s_jf2[i]);
+                }
+            }
+            if (row == last_row) s_cube_cur = c_lo + ci;
+            __syncthreads();
+        }
+    }
+    if (do_hist && hist_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < dim * (int)ni; i += blockDim.x) {
+            const unsigned int cc = s_c[i];
+            if (cc) {
+                atomicAdd(&weights[i], s_w[i]);
+                atomicAdd(&counts[i], (unsigned long long)cc);
+            }
+        }
+    }
+    if (!STRAT) grid_sum_finish<2>(acc, sh, partials, ticket, out);
+}
+
+#define TQ_DISPATCH_FAMILY(fam, ...)                                                                  \
+    switch (fam) {                                                                                    \
+        case TQ_F_GENZ_OSCILLATORY: { constexpr int FAM = TQ_F_GENZ_OSCILLATORY; __VA_ARGS__; break; }      \
+        case TQ_F_GENZ_PRODUCT_PEAK: { constexpr int FAM = TQ_F_GENZ_PRODUCT_PEAK; __VA_ARGS__; break; }    \
+        case TQ_F_GENZ_CORNER_PEAK: { constexpr int FAM = TQ_F_GENZ_CORNER_PEAK; __VA_ARGS__; break; }      \
+        case TQ_F_GENZ_GAUSSIAN: { constexpr int FAM = TQ_F_GENZ_GAUSSIAN; __VA_ARGS__; break; }            \
+        case TQ_F_GENZ_C0: { constexpr int FAM = TQ_F_GENZ_C0; __VA_ARGS__; break; }                        \
+        case TQ_F_GENZ_DISCONTINUOUS: { constexpr int FAM = TQ_F_GENZ_DISCONTINUOUS; __VA_ARGS__; break; }  \
+        case TQ_F_SUM_SIN: { constexpr int FAM = TQ_F_SUM_SIN; __VA_ARGS__; break; }                        \
+        case TQ_F_SUM_EXP: { constexpr int FAM = TQ_F_SUM_EXP; __VA_ARGS__; break; }                        \
+        case TQ_F_PROD_COS: { constexpr int FAM = TQ_F_PROD_COS; __VA_ARGS__; break; }                      \
+        case TQ_F_POLYNOMIAL: { constexpr int FAM = TQ_F_POLYNOMIAL; __VA_ARGS__; break; }                  \
+        default: tq::set_error("unknown integrand family %d", (int)(fam)); return TQ_ERR_INVALID_ARGUMENT;  \
+    }
+
+static int check_integrand(const char* who, const tq_integrand* fn) {
+    TQ_REQUIRE(fn != nullptr, "%s: integrand is NULL", who);
+    TQ_REQUIRE(fn->dim >= 1 && fn->dim <= TQ_MAX_DIM, "%s: integrand dim %d out of range (max %d)", who, fn->dim, TQ_MAX_DIM);
+    TQ_REQUIRE(fn->family >= 0 && fn->family < TQ_F_COUNT, "%s: unknown integrand family %d", who, fn->family);
+    TQ_REQUIRE(fn->family != TQ_F_POLYNOMIAL || (fn->ncoeff >= 1 && fn->ncoeff <= 8), "%s: polynomial needs 1..8 coefficients", who);
+    return TQ_OK;
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" {
+
+int tq_fused_mc(const tq_integrand* fn_host, int32_t dtype, int64_t row_begin, int64_t row_end,
+                uint64_t seed, uint32_t call_idx, double* out_f64, void* ws, size_t ws_bytes,
+                void* stream) {
+    int rc = check_integrand("tq_fused_mc", fn_host);
+    if (rc) return rc;
+    TQ_REQUIRE(row_end >= row_begin && row_begin >= 0, "tq_fused_mc: bad row range");
+    Workspace w(ws, ws_bytes);
+    unsigned int* ticket = w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
+    const int64_t nrows = row_end - row_begin;
+    const int grid = grid_for(nrows, 256, 8);
+    double* partials = w.take<double>((size_t)grid * 2);
+    if (!ticket || !partials) { set_error("tq_fused_mc: workspace too small"); return TQ_ERR_WORKSPACE; }
+    cudaStream_t st = as_stream(stream);
+    TQ_DISPATCH_DTYPE(dtype, {
+        TQ_DISPATCH_FAMILY(fn_host->family, {
+            fused_mc_kernel<FAM, T><<<grid, 256, 0, st>>>(*fn_host, row_begin, nrows, seed, call_idx, partials, ticket, out_f64);
+        });
+    });
+    return check_launch("fused_mc_kernel");
+}
+
+int tq_fused_nc(const tq_integrand* fn_host, const void* nodes, const void* w, int32_t n, int32_t dtype,
+                int64_t p_begin, int64_t p_end, double* out_f64, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_integrand("tq_fused_nc", fn_host);
+    if (rc) return rc;
+    TQ_REQUIRE(n >= 1 && p_begin >= 0 && p_end >= p_begin, "tq_fused_nc: bad grid arguments");
+    Workspace wk(ws, ws_bytes);
+    unsigned int* ticket = wk.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
+    const int grid = grid_for(p_end - p_begin, 256, 8);
+    double* partials = wk.take<double>((size_t)grid);
+    if (!ticket || !partials) { set_error("tq_fused_nc: workspace too small"); return TQ_ERR_WORKSPACE; }
+    cudaStream_t st = as_stream(stream);
+    const int dim = fn_host->dim;
+    TQ_DISPATCH_DTYPE(dtype, {
+        const size_t table = (size_t)2 * dim * n * sizeof(T);
+        const bool use_smem = table <= 96 * 1024;
+        TQ_DISPATCH_FAMILY(fn_host->family, {
+            cudaFuncSetAttribute(fused_nc_kernel<FAM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            fused_nc_kernel<FAM, T><<<grid, 256, use_smem ? table : 0, st>>>(*fn_host, (const T*)nodes, (const T*)w, (uint32_t)n,
+                                                                           p_begin, p_end, partials, ticket, out_f64, use_smem);
+        });
+    });
+    return check_launch("fused_nc_kernel");
+}
+
+int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
+                   int32_t n_strat, int64_t row_begin, int64_t row_end, const void* x_edges,
+                   const void* dx_edges, int64_t n_intervals, void* weights, int64_t* counts, void* JF,
+                   void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
+                   size_t ws_bytes, void* stream) {
+    int rc = check_integrand("tq_fused_vegas", fn_host);
+    if (rc) return rc;
+    TQ_REQUIRE(row_end >= row_begin && row_begin >= 0, "tq_fused_vegas: bad row range");
+    TQ_REQUIRE(n_intervals >= 1 && n_intervals < (1LL << 31), "tq_fused_vegas: n_intervals out of range");
+    const bool strat = offsets != nullptr;
+    TQ_REQUIRE(!strat || (n_cubes >= 1 && n_cubes < (1LL << 31) && n_strat >= 1 && JF && JF2),
+               "tq_fused_vegas: stratified pass needs n_cubes, n_strat, JF, JF2");
+    TQ_REQUIRE(strat || out_f64 != nullptr, "tq_fused_vegas: warm-up pass needs out_f64");
+    const int64_t nrows = row_end - row_begin;
+    if (nrows == 0 && strat) return TQ_OK;
+    Workspace w(ws, ws_bytes);
+    unsigned int* ticket = w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
+    const int dim = fn_host->dim;
+    const size_t elt = dtype == TQ_F64 ? 8 : 4;
+    const size_t ids_bytes = (size_t)dim * FV_BLOCK * sizeof(int);
+    const size_t hist_bytes = (size_t)dim * n_intervals * (elt + 4);
+    // CTAs: persistent, each with a contiguous chunk of rows; fewer CTAs when the problem is small.
+    const int sms = num_sms();
+    int64_t tiles = (nrows + FV_BLOCK - 1) / FV_BLOCK;
+    if (tiles < 1) tiles = 1;
+    // shared-memory histogram only when it fits beside the id staging and each CTA sees enough rows to
+    // amortise zeroing + flushing the whole map
+    bool hist_smem = weights != nullptr && ids_bytes + hist_bytes <= 180 * 1024 &&
+                     nrows * dim >= (int64_t)4 * dim * n_intervals;
+    int64_t ctas;
+    if (hist_smem) {
+        ctas = (nrows * dim) / ((int64_t)4 * dim * n_intervals);
+        if (ctas > sms) ctas = sms;
+        if (ctas < 1) ctas = 1;
+    } else {
+        ctas = tiles < (int64_t)sms * 6 ? tiles : (int64_t)sms * 6;
+    }
+    int64_t rows_per_cta = (nrows + ctas - 1) / ctas;
+    rows_per_cta = ((rows_per_cta + FV_BLOCK - 1) / FV_BLOCK) * FV_BLOCK;
+    if (rows_per_cta < FV_BLOCK) rows_per_cta = FV_BLOCK;
+    ctas = nrows > 0 ? (nrows + rows_per_cta - 1) / rows_per_cta : 1;
+    double* partials = w.take<double>((size_t)ctas * 2);
+    if (!ticket || !partials) { set_error("tq_fused_vegas: workspace too small"); return TQ_ERR_WORKSPACE; }
+    const size_t smem = ids_bytes + (hist_smem ? hist_bytes : 0);
+    cudaStream_t st = as_stream(stream);
+    TQ_DISPATCH_DTYPE(dtype, {
+        TQ_DISPATCH_FAMILY(fn_host->family, {
+            if (strat) {
+                cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
+                fused_vegas_kernel<FAM, T, true><<<(unsigned)ctas, FV_BLOCK, smem, st>>>(
+                    *fn_host, (const long long*)offsets, n_cubes, n_strat, row_begin, row_end, rows_per_cta, (const T*)x_edges,
+                    (const T*)dx_edges, n_intervals, (T*)weights, (unsigned long long*)counts, (T*)JF, (T*)JF2, seed, call_idx,
+                    hist_smem, partials, ticket, out_f64);
+            } else {
+                cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
+                fused_vegas_kernel<FAM, T, false><<<(unsigned)ctas, FV_BLOCK, smem, st>>>(
+                    *fn_host, nullptr, 0, 1, row_begin, row_end, rows_per_cta, (const T*)x_edges, (const T*)dx_edges,
+                    n_intervals, (T*)weights, (unsigned long long*)counts, nullptr, nullptr, seed, call_idx, hist_smem,
+                    partials, ticket, out_f64);
+            }
+        });
+    });
+    return check_launch("fused_vegas_kernel");
+}
+
+}  // extern "C"

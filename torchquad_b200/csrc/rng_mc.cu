@@ -1,0 +1,296 @@
+// Philox uniform streams, Monte Carlo sample generation and the fp64 column reduction.
+// Replaces rng.py:119-125, monte_carlo.py:84-106 and the sum of monte_carlo.py:72-77.
+#include "common.cuh"
+
+namespace tq {
+
+// One thread per (row, Philox block): thread i of the flat index space writes the LANES consecutive
+// elements out[row*dim + blk*LANES ...], so a warp always covers one contiguous span of the row-major
+// output (128-bit stores when dim % LANES == 0, narrower ones otherwise).
+// The (row, blk) split of the flat index uses one 64-bit division per CTA tile and a 24-bit
+// multiply-shift per item (exact for item offsets < 2^16 and nblk <= 32).
+template <typename T, bool AFFINE>
+__global__ void __launch_bounds__(256)
+uniform_kernel(T* __restrict__ out, const T* __restrict__ domain, int64_t row_begin, int64_t nrows,
+               int dim, int nblk, uint32_t magic, uint64_t seed, uint32_t call) {
+    constexpr int LANES = U01<T>::LANES;
+    constexpr int ITEMS = 4;
+    constexpr int TILE = 256 * ITEMS;
+    __shared__ T s_start[TQ_MAX_DIM], s_size[TQ_MAX_DIM];
+    if (AFFINE) {
+        if (threadIdx.x < dim) {
+            T a = domain[2 * threadIdx.x], b = domain[2 * threadIdx.x + 1];
+            s_start[threadIdx.x] = a;
+            s_size[threadIdx.x] = sub_rn(b, a);
+        }
+        __syncthreads();
+    }
+    const int64_t total = nrows * nblk;
+    const bool vec_ok = (dim % LANES == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    for (int64_t base = (int64_t)blockIdx.x * TILE; base < total; base += (int64_t)gridDim.x * TILE) {
+        const int64_t row0 = base / nblk;
+        const uint32_t rem0 = (uint32_t)(base - row0 * nblk);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const uint32_t l = threadIdx.x + k * 256;
+            if (base + l >= total) break;
+            const uint32_t ll = rem0 + l;
+            const uint32_t q = (uint32_t)(((uint64_t)ll * magic) >> 24);
+            const uint32_t blk = ll - q * nblk;
+            const int64_t r = row0 + q;  // local row
+            const uint64_t grow = (uint64_t)(row_begin + r);
+            T u[LANES];
+            philox_block<T>(seed, call, (uint32_t)grow, (uint32_t)(grow >> 32), blk, u);
+            const int d0 = blk * LANES;
+            if (AFFINE) {
+#pragma unroll
+                for (int j = 0; j < LANES; ++j) {
+                    int d = d0 + j;
+                    if (d < dim) u[j] = add_rn(mul_rn(u[j], s_size[d]), s_start[d]);
+                }
+            }
+            T* p = out + r * dim + d0;
+            if (vec_ok) {
+                if constexpr (LANES == 4) {
+                    *reinterpret_cast<float4*>(p) = make_float4(u[0], u[1], u[2], u[3]);
+                } else {
+                    *reinterpret_cast<double2*>(p) = make_double2(u[0], u[1]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < LANES; ++j)
+                    if (d0 + j < dim) p[j] = u[j];
+            }
+        }
+    }
+}
+
+template <typename T>
+static int launch_uniform(T* out, const T* domain, int64_t row_begin, int64_t row_end, int dim,
+                          uint64_t seed, uint32_t call, cudaStream_t st) {
+    const int64_t nrows = row_end - row_begin;
+    if (nrows <= 0) return TQ_OK;
+    const int nblk = (dim + U01<T>::LANES - 1) / U01<T>::LANES;
+    const uint32_t magic = (uint32_t)((1u << 24) / (uint32_t)nblk) + 1u;
+    const int64_t items = nrows * nblk;
+    const int grid = grid_for((items + 3) / 4, 256, 8);
+    if (domain)
+        uniform_kernel<T, true><<<grid, 256, 0, st>>>(out, domain, row_begin, nrows, dim, nblk, magic, seed, call);
+    else
+        uniform_kernel<T, false><<<grid, 256, 0, st>>>(out, nullptr, row_begin, nrows, dim, nblk, magic, seed, call);
+    return check_launch("uniform_kernel");
+}
+
+// grad wrt domain of x = u*(b-a) + a:  d/da = 1-u, d/db = u.  One partial per CTA and dimension, then a
+// deterministic last-CTA sum.  Thread t walks rows t, t+stride, ... of a fixed block of dimensions.
+template <typename T>
+__global__ void __launch_bounds__(256)
+mc_sample_backward_kernel(const T* __restrict__ g, int64_t row_begin, int64_t nrows, int dim, uint64_t seed,
+                          uint32_t call, double* __restrict__ partials, unsigned int* ticket,
+                          double* __restrict__ out) {
+    constexpr int LANES = U01<T>::LANES;
+    __shared__ double sh[32 * 2];
+    __shared__ bool is_last;
+    const int nblk = (dim + LANES - 1) / LANES;
+    // partials layout: [gridDim.x][dim][2]
+    for (int blk = 0; blk < nblk; ++blk) {
+        double ga[LANES], gb[LANES];
+#pragma unroll
+        for (int j = 0; j < LANES; ++j) ga[j] = gb[j] = 0.0;
+        for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+            const uint64_t grow = (uint64_t)(row_begin + r);
+            T u[LANES];
+            philox_block<T>(seed, call, (uint32_t)grow, (uint32_t)(grow >> 32), blk, u);
+#pragma unroll
+            for (int j = 0; j < LANES; ++j) {
+                int d = blk * LANES + j;
+                if (d < dim) {
+                    double gv = (double)g[r * dim + d];
+                    gb[j] += gv * (double)u[j];
+                    ga[j] += gv * (1.0 - (double)u[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < LANES; ++j) {
+            int d = blk * LANES + j;
+            double v[2] = {ga[j], gb[j]};
+            block_sum<2>(v, sh);
+            if (threadIdx.x == 0 && d < dim) {
+                partials[((size_t)blockIdx.x * dim + d) * 2 + 0] = v[0];
+                partials[((size_t)blockIdx.x * dim + d) * 2 + 1] = v[1];
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int e = threadIdx.x; e < dim * 2; e += blockDim.x) {
+            double acc = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) acc += __ldcg(&partials[(size_t)b * dim * 2 + e]);
+            out[e] = acc;
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
+// Column sums of f[rows, cols] in fp64.  cols == 1: vectorised grid-stride loads, deterministic tree.
+template <typename T, bool SQ>
+__global__ void __launch_bounds__(256)
+sum1_kernel(const T* __restrict__ f, int64_t n, double* partials, unsigned int* ticket, double* out) {
+    constexpr int V = 16 / sizeof(T);
+    __shared__ double sh[32 * 2];
+    double s = 0.0, q = 0.0;
+    const int64_t nvec = ((reinterpret_cast<uintptr_t>(f) & 15) == 0) ? n / V : 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        uint4 raw = __ldcs(reinterpret_cast<const uint4*>(f) + i);
+        const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            double x = (double)e[j];
+            s += x;
+            if (SQ) q += x * x;
+        }
+    }
+    for (int64_t i = nvec * V + tid; i < n; i += stride) {
+        double x = (double)f[i];
+        s += x;
+        if (SQ) q += x * x;
+    }
+    double v[2] = {s, q};
+    grid_sum_finish<2>(v, sh, partials, ticket, out);
+}
+
+// cols > 1: thread t of the grid owns flat elements t, t+S, ... with S a multiple of cols, so its
+// column is fixed; per-CTA shared accumulators per column, then last-CTA finish.
+template <typename T, bool SQ>
+__global__ void __launch_bounds__(256)
+sumk_kernel(const T* __restrict__ f, int64_t rows, int64_t cols, int64_t S, double* partials,
+            unsigned int* ticket, double* out_s, double* out_q) {
+    extern __shared__ double sacc[];  // [cols*2]
+    __shared__ bool is_last;
+    for (int64_t c = threadIdx.x; c < cols * 2; c += blockDim.x) sacc[c] = 0.0;
+    __syncthreads();
+    const int64_t n = rows * cols;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < S) {
+        double s = 0.0, q = 0.0;
+        for (int64_t i = tid; i < n; i += S) {
+            double x = (double)f[i];
+            s += x;
+            if (SQ) q += x * x;
+        }
+        const int64_t c = tid % cols;
+        atomicAdd(&sacc[c], s);
+        if (SQ) atomicAdd(&sacc[cols + c], q);
+    }
+    __syncthreads();
+    for (int64_t c = threadIdx.x; c < cols * 2; c += blockDim.x) partials[(size_t)blockIdx.x * cols * 2 + c] = sacc[c];
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int64_t c = threadIdx.x; c < cols * 2; c += blockDim.x) {
+            double acc = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) acc += __ldcg(&partials[(size_t)b * cols * 2 + c]);
+            if (c < cols) out_s[c] = acc;
+            else if (SQ) out_q[c - cols] = acc;
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" {
+
+int tq_philox_uniform(void* out, int64_t row_begin, int64_t row_end, int32_t dim, int32_t dtype,
+                      uint64_t seed, uint32_t call_idx, void* stream) {
+    TQ_REQUIRE(dim >= 1 && dim <= TQ_MAX_DIM * 4, "tq_philox_uniform: dim %d out of range", dim);
+    TQ_REQUIRE(row_end >= row_begin && row_begin >= 0, "tq_philox_uniform: bad row range");
+    TQ_DISPATCH_DTYPE(dtype, {
+        const int nblk = (dim + U01<T>::LANES - 1) / U01<T>::LANES;
+        TQ_REQUIRE(nblk <= 32, "tq_philox_uniform: dim %d too large", dim);
+        return launch_uniform<T>((T*)out, nullptr, row_begin, row_end, dim, seed, call_idx, as_stream(stream));
+    });
+    return TQ_OK;
+}
+
+int tq_mc_sample(void* out, const void* domain, int64_t row_begin, int64_t row_end, int32_t dim,
+                 int32_t dtype, uint64_t seed, uint32_t call_idx, void* stream) {
+    TQ_REQUIRE(dim >= 1 && dim <= TQ_MAX_DIM, "tq_mc_sample: dim %d out of range (max %d)", dim, TQ_MAX_DIM);
+    TQ_REQUIRE(row_end >= row_begin && row_begin >= 0, "tq_mc_sample: bad row range");
+    TQ_REQUIRE(domain != nullptr, "tq_mc_sample: domain is NULL");
+    TQ_DISPATCH_DTYPE(dtype, {
+        return launch_uniform<T>((T*)out, (const T*)domain, row_begin, row_end, dim, seed, call_idx, as_stream(stream));
+    });
+    return TQ_OK;
+}
+
+int tq_mc_sample_backward(const void* grad_out, int64_t row_begin, int64_t row_end, int32_t dim,
+                          int32_t dtype, uint64_t seed, uint32_t call_idx, double* grad_domain_f64,
+                          void* ws, size_t ws_bytes, void* stream) {
+    TQ_REQUIRE(dim >= 1 && dim <= TQ_MAX_DIM, "tq_mc_sample_backward: dim %d out of range", dim);
+    const int64_t nrows = row_end - row_begin;
+    TQ_REQUIRE(nrows >= 0, "tq_mc_sample_backward: bad row range");
+    Workspace w(ws, ws_bytes);
+    unsigned int* ticket = w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
+    const int grid = grid_for(nrows, 256, 4);
+    double* partials = w.take<double>((size_t)grid * dim * 2);
+    if (!ticket || !partials) { set_error("tq_mc_sample_backward: workspace too small"); return TQ_ERR_WORKSPACE; }
+    TQ_DISPATCH_DTYPE(dtype, {
+        mc_sample_backward_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)grad_out, row_begin, nrows, dim, seed,
+                                                                         call_idx, partials, ticket, grad_domain_f64);
+    });
+    return check_launch("mc_sample_backward_kernel");
+}
+
+int tq_sum_columns(const void* f, int64_t rows, int64_t cols, int32_t dtype, double* sum_f64,
+                   double* sumsq_f64, void* ws, size_t ws_bytes, void* stream) {
+    TQ_REQUIRE(rows >= 0 && cols >= 1, "tq_sum_columns: bad shape [%lld, %lld]", (long long)rows, (long long)cols);
+    Workspace w(ws, ws_bytes);
+    unsigned int* ticket = w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
+    cudaStream_t st = as_stream(stream);
+    if (cols == 1) {
+        const int grid = grid_for((rows + 3) / 4, 256, 4);
+        double* partials = w.take<double>((size_t)grid * 2);
+        double* out = w.take<double>(2);
+        if (!ticket || !partials || !out) { set_error("tq_sum_columns: workspace too small"); return TQ_ERR_WORKSPACE; }
+        TQ_DISPATCH_DTYPE(dtype, {
+            if (sumsq_f64) sum1_kernel<T, true><<<grid, 256, 0, st>>>((const T*)f, rows, partials, ticket, out);
+            else sum1_kernel<T, false><<<grid, 256, 0, st>>>((const T*)f, rows, partials, ticket, out);
+        });
+        int rc = check_launch("sum1_kernel");
+        if (rc) return rc;
+        cudaMemcpyAsync(sum_f64, out, sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if (sumsq_f64) cudaMemcpyAsync(sumsq_f64, out + 1, sizeof(double), cudaMemcpyDeviceToDevice, st);
+        return check_launch("tq_sum_columns copy");
+    }
+    TQ_REQUIRE(cols <= 2048, "tq_sum_columns: at most 2048 integrand components (got %lld)", (long long)cols);
+    int grid = grid_for(rows * cols, 256, 2);
+    // stride S: largest multiple of cols not exceeding the thread count (at least cols)
+    int64_t threads = (int64_t)grid * 256;
+    if (threads < cols) { grid = (int)((cols + 255) / 256); threads = (int64_t)grid * 256; }
+    const int64_t S = (threads / cols) * cols;
+    double* partials = w.take<double>((size_t)grid * cols * 2);
+    if (!ticket || !partials) { set_error("tq_sum_columns: workspace too small"); return TQ_ERR_WORKSPACE; }
+    const size_t smem = (size_t)cols * 2 * sizeof(double);
+    TQ_DISPATCH_DTYPE(dtype, {
+        if (sumsq_f64) sumk_kernel<T, true><<<grid, 256, smem, st>>>((const T*)f, rows, cols, S, partials, ticket, sum_f64, sumsq_f64);
+        else sumk_kernel<T, false><<<grid, 256, smem, st>>>((const T*)f, rows, cols, S, partials, ticket, sum_f64, nullptr);
+    });
+    return check_launch("sumk_kernel");
+}
+
+}  // extern "C"

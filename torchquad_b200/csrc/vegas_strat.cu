@@ -1,0 +1,367 @@
+// VEGAS+ adaptive stratification: per-cube sample counts, stratified sampling, per-cube sums, damped
+// variance update and the per-iteration estimator.
+// Replaces torchquad/integration/vegas_stratification.py (get_NH :92-103, _get_indices/get_Y :105-165,
+// accumulate_weight :46-70, update_DH :72-90) and the estimator of vegas.py:293-303.
+#include "common.cuh"
+
+namespace tq {
+
+constexpr int ST_TILE = 1024;  // cubes (or rows) per CTA tile: 256 threads x 4
+
+template <typename T>
+__device__ __forceinline__ long long nh_of(T dh, T nev) {
+    T v = floor(mul_rn(dh, nev));
+    v = v < (T)2 ? (T)2 : v;  // clamp(min=2)
+    return (long long)v;
+}
+
+// ---- get_NH + exclusive scan (3 phases: tile sums, scan of tile sums, tile scans)
+template <typename T>
+__global__ void __launch_bounds__(256)
+nh_tile_sum_kernel(const T* __restrict__ dh, int64_t n_cubes, T nev, long long* __restrict__ tile_sums) {
+    __shared__ long long sh[33];
+    const int64_t c0 = (int64_t)blockIdx.x * ST_TILE + threadIdx.x * 4;
+    long long s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (c0 + i < n_cubes) s += nh_of<T>(dh[c0 + i], nev);
+    long long total;
+    block_excl_scan<long long>(s, sh, total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256)
+i64_tile_scan_kernel(long long* __restrict__ tile_sums, int64_t ntiles, long long* __restrict__ total_out) {
+    __shared__ long long sh[33];
+    long long carry = 0;
+    for (int64_t base = 0; base < ntiles; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const long long v = i < ntiles ? tile_sums[i] : 0;
+        long long total;
+        const long long ex = block_excl_scan<long long>(v, sh, total);
+        if (i < ntiles) tile_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+nh_scan_kernel(const T* __restrict__ dh, int64_t n_cubes, T nev, const long long* __restrict__ tile_offsets,
+               long long* __restrict__ nh, long long* __restrict__ offsets) {
+    __shared__ long long sh[33];
+    const int64_t c0 = (int64_t)blockIdx.x * ST_TILE + threadIdx.x * 4;
+    long long v[4], run = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[i] = (c0 + i < n_cubes) ? nh_of<T>(dh[c0 + i], nev) : 0;
+        run += v[i];
+    }
+    long long total;
+    long long ex = block_excl_scan<long long>(run, sh, total) + tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (c0 + i < n_cubes) {
+            nh[c0 + i] = v[i];
+            offsets[c0 + i] = ex;
+        }
+        ex += v[i];
+    }
+}
+
+// ---- exclusive scan of a caller-provided nh
+__global__ void __launch_bounds__(256)
+i64_tile_sum_kernel(const long long* __restrict__ v, int64_t n, long long* __restrict__ tile_sums) {
+    __shared__ long long sh[33];
+    const int64_t c0 = (int64_t)blockIdx.x * ST_TILE + threadIdx.x * 4;
+    long long s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (c0 + i < n) s += v[c0 + i];
+    long long total;
+    block_excl_scan<long long>(s, sh, total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256)
+i64_scan_kernel(const long long* __restrict__ in, int64_t n, const long long* __restrict__ tile_offsets,
+                long long* __restrict__ offsets) {
+    __shared__ long long sh[33];
+    const int64_t c0 = (int64_t)blockIdx.x * ST_TILE + threadIdx.x * 4;
+    long long v[4], run = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[i] = (c0 + i < n) ? in[c0 + i] : 0;
+        run += v[i];
+    }
+    long long total;
+    long long ex = block_excl_scan<long long>(run, sh, total) + tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (c0 + i < n) offsets[c0 + i] = ex;
+        ex += v[i];
+    }
+}
+
+// ---- row -> cube lookup shared by the sampling and backward kernels.
+// A CTA tile of ST_TILE consecutive rows overlaps at most ST_TILE/2 + 1 cubes (nh >= 2), so the slice of
+// `offsets` it needs fits in shared memory: two global binary searches per tile, then per-row searches
+// in shared memory.
+struct CubeSlice {
+    long long c_lo;
+    int count;  // cubes in the slice; s_off holds count+1 entries
+};
+
+__device__ __forceinline__ long long upper_cube(const long long* __restrict__ offsets, int64_t n_cubes, long long row) {
+    // largest c in [0, n_cubes) with offsets[c] <= row
+    long long lo = 0, hi = n_cubes - 1;
+    while (lo < hi) {
+        const long long mid = (lo + hi + 1) >> 1;
+        if (__ldg(&offsets[mid]) <= row) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ CubeSlice load_cube_slice(const long long* __restrict__ offsets, int64_t n_cubes,
+                                                     long long row_lo, long long row_hi /*inclusive*/,
+                                                     long long* s_off, long long* s_bounds) {
+    if (threadIdx.x == 0) s_bounds[0] = upper_cube(offsets, n_cubes, row_lo);
+    if (threadIdx.x == 32) s_bounds[1] = upper_cube(offsets, n_cubes, row_hi);
+    __syncthreads();
+    CubeSlice s;
+    s.c_lo = s_bounds[0];
+    s.count = (int)(s_bounds[1] - s_bounds[0] + 1);
+    for (int i = threadIdx.x; i <= s.count; i += blockDim.x) s_off[i] = __ldg(&offsets[s.c_lo + i]);
+    __syncthreads();
+    return s;
+}
+
+__device__ __forceinline__ int cube_in_slice(const long long* s_off, int count, long long row) {
+    int lo = 0, hi = count - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_off[mid] <= row) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ---- get_Y
+template <typename T>
+__global__ void __launch_bounds__(256)
+strat_sample_kernel(const long long* __restrict__ offsets, int64_t n_cubes, int n_strat, int dim,
+                    const T* __restrict__ u_in, uint64_t seed, uint32_t call, int64_t row_begin, int64_t row_end,
+                    T* __restrict__ y) {
+    constexpr int LANES = U01<T>::LANES;
+    __shared__ long long s_off[ST_TILE / 2 + 4];
+    __shared__ long long s_bounds[2];
+    const T nsf = (T)n_strat;
+    for (int64_t rb = row_begin + (int64_t)blockIdx.x * ST_TILE; rb < row_end; rb += (int64_t)gridDim.x * ST_TILE) {
+        const int64_t re = rb + ST_TILE < row_end ? rb + ST_TILE : row_end;
+        const CubeSlice sl = load_cube_slice(offsets, n_cubes, rb, re - 1, s_off, s_bounds);
+        for (int64_t row = rb + threadIdx.x; row < re; row += blockDim.x) {
+            const int ci = cube_in_slice(s_off, sl.count, row);
+            const uint32_t cube = (uint32_t)(sl.c_lo + ci);
+            const uint32_t k = (uint32_t)(row - s_off[ci]);
+            T* out = y + (row - row_begin) * dim;
+            const T* uin = u_in ? u_in + (row - row_begin) * dim : nullptr;
+            uint32_t c = cube;
+            for (int d0 = 0; d0 < dim; d0 += LANES) {
+                T u[LANES];
+                if (uin) {
+#pragma unroll
+                    for (int j = 0; j < LANES; ++j) u[j] = (d0 + j < dim) ? uin[d0 + j] : (T)0;
+                } else {
+                    philox_block<T>(seed, call, cube, k, (uint32_t)(d0 / LANES), u);
+                }
+#pragma unroll
+                for (int j = 0; j < LANES; ++j) {
+                    if (d0 + j < dim) {
+                        const uint32_t q = c / (uint32_t)n_strat;
+                        const uint32_t p = c - q * (uint32_t)n_strat;
+                        c = q;
+                        T v = div_rn(add_rn((T)p, u[j]), nsf);
+                        if (v >= (T)1) v = (T)0.999999;
+                        out[d0 + j] = v;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- accumulate_weight: one thread per cube, rows summed in order (bit-identical to the CPU scatter_add_).
+template <typename T>
+__global__ void __launch_bounds__(256)
+strat_accumulate_kernel(const T* __restrict__ jf, int64_t row_base, const long long* __restrict__ offsets,
+                        int64_t cube_begin, int64_t cube_end, T* __restrict__ JF, T* __restrict__ JF2) {
+    for (int64_t c = cube_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cube_end;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        const long long r0 = offsets[c] - row_base, r1 = offsets[c + 1] - row_base;
+        T s = (T)0, q = (T)0;
+        for (long long r = r0; r < r1; ++r) {
+            const T v = jf[r];
+            s = add_rn(s, v);
+            q = add_rn(q, mul_rn(v, v));
+        }
+        JF[c] = s;
+        JF2[c] = q;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+strat_accumulate_backward_kernel(const T* __restrict__ gJF, const long long* __restrict__ offsets, int64_t n_cubes,
+                                 int64_t row_begin, int64_t row_end, T* __restrict__ gjf) {
+    __shared__ long long s_off[ST_TILE / 2 + 4];
+    __shared__ long long s_bounds[2];
+    for (int64_t rb = row_begin + (int64_t)blockIdx.x * ST_TILE; rb < row_end; rb += (int64_t)gridDim.x * ST_TILE) {
+        const int64_t re = rb + ST_TILE < row_end ? rb + ST_TILE : row_end;
+        const CubeSlice sl = load_cube_slice(offsets, n_cubes, rb, re - 1, s_off, s_bounds);
+        for (int64_t row = rb + threadIdx.x; row < re; row += blockDim.x) {
+            const int ci = cube_in_slice(s_off, sl.count, row);
+            gjf[row - row_begin] = gJF[sl.c_lo + ci];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- estimator + update_DH
+template <typename T>
+__global__ void __launch_bounds__(256)
+strat_update_kernel(const T* __restrict__ JF, const T* __restrict__ JF2, const long long* __restrict__ nh,
+                    int64_t n_cubes, T V, T V2, T beta, T* __restrict__ dh, double* partials, unsigned int* ticket,
+                    double* scalars) {
+    __shared__ double sh[32 * 3];
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cubes;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        const T n = (T)nh[c];
+        const T inv = div_rn((T)1, n);
+        const T jf = JF[c], jf2 = JF2[c];
+        // vegas.py:293-303
+        const T ih = mul_rn(jf, mul_rn(inv, V));
+        const T sig2 = fabs(sub_rn(mul_rn(mul_rn(jf2, inv), V2), mul_rn(ih, ih)));
+        acc[0] += (double)ih;
+        acc[1] += (double)mul_rn(sig2, inv);
+        // vegas_stratification.py:78-85
+        const T m = div_rn(mul_rn(V, jf), n);
+        T dv = sub_rn(div_rn(mul_rn(V2, jf2), n), mul_rn(m, m));
+        if (dv < (T)0) dv = (T)0;
+        const T p = pow(dv, beta);
+        dh[c] = p;
+        acc[2] += (double)p;
+    }
+    grid_sum_finish<3>(acc, sh, partials, ticket, scalars);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+strat_normalise_kernel(T* __restrict__ dh, int64_t n_cubes, const double* __restrict__ scalars) {
+    const T s = (T)scalars[2];
+    if (s == (T)0) return;  // vegas_stratification.py:89-90
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cubes;
+         c += (int64_t)gridDim.x * blockDim.x)
+        dh[c] = div_rn(dh[c], s);
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" {
+
+int tq_vegas_strat_nh(const void* dh, int64_t n_cubes, double nevals_exp, int32_t dtype, int64_t* nh,
+                      int64_t* offsets, void* ws, size_t ws_bytes, void* stream) {
+    TQ_REQUIRE(n_cubes >= 1, "tq_vegas_strat_nh: n_cubes must be positive");
+    Workspace w(ws, ws_bytes);
+    w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
+    const int64_t ntiles = (n_cubes + ST_TILE - 1) / ST_TILE;
+    long long* tile_sums = w.take<long long>((size_t)ntiles);
+    if (!tile_sums) { set_error("tq_vegas_strat_nh: workspace too small for %lld cubes", (long long)n_cubes); return TQ_ERR_WORKSPACE; }
+    cudaStream_t st = as_stream(stream);
+    TQ_DISPATCH_DTYPE(dtype, {
+        nh_tile_sum_kernel<T><<<(unsigned)ntiles, 256, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, tile_sums);
+        i64_tile_scan_kernel<<<1, 256, 0, st>>>(tile_sums, ntiles, (long long*)offsets + n_cubes);
+        nh_scan_kernel<T><<<(unsigned)ntiles, 256, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, tile_sums,
+                                                           (long long*)nh, (long long*)offsets);
+    });
+    return check_launch("tq_vegas_strat_nh");
+}
+
+int tq_vegas_strat_offsets(const int64_t* nh, int64_t n_cubes, int64_t* offsets, void* ws, size_t ws_bytes,
+                           void* stream) {
+    TQ_REQUIRE(n_cubes >= 1, "tq_vegas_strat_offsets: n_cubes must be positive");
+    Workspace w(ws, ws_bytes);
+    w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
+    const int64_t ntiles = (n_cubes + ST_TILE - 1) / ST_TILE;
+    long long* tile_sums = w.take<long long>((size_t)ntiles);
+    if (!tile_sums) { set_error("tq_vegas_strat_offsets: workspace too small for %lld cubes", (long long)n_cubes); return TQ_ERR_WORKSPACE; }
+    cudaStream_t st = as_stream(stream);
+    i64_tile_sum_kernel<<<(unsigned)ntiles, 256, 0, st>>>((const long long*)nh, n_cubes, tile_sums);
+    i64_tile_scan_kernel<<<1, 256, 0, st>>>(tile_sums, ntiles, (long long*)offsets + n_cubes);
+    i64_scan_kernel<<<(unsigned)ntiles, 256, 0, st>>>((const long long*)nh, n_cubes, tile_sums, (long long*)offsets);
+    return check_launch("tq_vegas_strat_offsets");
+}
+
+int tq_vegas_strat_sample(const int64_t* offsets, int64_t n_cubes, int32_t n_strat, int32_t dim,
+                          int32_t dtype, const void* u_in, uint64_t seed, uint32_t call_idx,
+                          int64_t row_begin, int64_t row_end, void* y, void* stream) {
+    TQ_REQUIRE(n_cubes >= 1 && n_cubes < (1LL << 31), "tq_vegas_strat_sample: n_cubes out of range");
+    TQ_REQUIRE(n_strat >= 1 && dim >= 1, "tq_vegas_strat_sample: bad n_strat/dim");
+    TQ_REQUIRE(row_end >= row_begin && row_begin >= 0, "tq_vegas_strat_sample: bad row range");
+    if (row_end == row_begin) return TQ_OK;
+    const int grid = grid_for(row_end - row_begin, ST_TILE, 8);
+    TQ_DISPATCH_DTYPE(dtype, {
+        strat_sample_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const long long*)offsets, n_cubes, n_strat, dim,
+                                                                   (const T*)u_in, seed, call_idx, row_begin, row_end, (T*)y);
+    });
+    return check_launch("strat_sample_kernel");
+}
+
+int tq_vegas_strat_accumulate(const void* jf, int64_t row_base, const int64_t* offsets,
+                              int64_t cube_begin, int64_t cube_end, void* JF, void* JF2, int32_t dtype,
+                              void* stream) {
+    TQ_REQUIRE(cube_end >= cube_begin && cube_begin >= 0, "tq_vegas_strat_accumulate: bad cube range");
+    if (cube_end == cube_begin) return TQ_OK;
+    const int grid = grid_for(cube_end - cube_begin, 256, 8);
+    TQ_DISPATCH_DTYPE(dtype, {
+        strat_accumulate_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)jf, row_base, (const long long*)offsets,
+                                                                       cube_begin, cube_end, (T*)JF, (T*)JF2);
+    });
+    return check_launch("strat_accumulate_kernel");
+}
+
+int tq_vegas_strat_accumulate_backward(const void* grad_JF, const int64_t* offsets, int64_t n_cubes,
+                                       int64_t row_begin, int64_t row_end, void* grad_jf, int32_t dtype,
+                                       void* stream) {
+    TQ_REQUIRE(row_end >= row_begin && row_begin >= 0, "tq_vegas_strat_accumulate_backward: bad row range");
+    if (row_end == row_begin) return TQ_OK;
+    const int grid = grid_for(row_end - row_begin, ST_TILE, 8);
+    TQ_DISPATCH_DTYPE(dtype, {
+        strat_accumulate_backward_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(
+            (const T*)grad_JF, (const long long*)offsets, n_cubes, row_begin, row_end, (T*)grad_jf);
+    });
+    return check_launch("strat_accumulate_backward_kernel");
+}
+
+int tq_vegas_strat_update(const void* JF, const void* JF2, const int64_t* nh, int64_t n_cubes,
+                          double v_cubes, double beta, int32_t dtype, void* dh, double* scalars_f64,
+                          void* ws, size_t ws_bytes, void* stream) {
+    TQ_REQUIRE(n_cubes >= 1, "tq_vegas_strat_update: n_cubes must be positive");
+    Workspace w(ws, ws_bytes);
+    unsigned int* ticket = w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
+    const int grid = grid_for(n_cubes, 256, 4);
+    double* partials = w.take<double>((size_t)grid * 3);
+    if (!ticket || !partials) { set_error("tq_vegas_strat_update: workspace too small"); return TQ_ERR_WORKSPACE; }
+    cudaStream_t st = as_stream(stream);
+    TQ_DISPATCH_DTYPE(dtype, {
+        strat_update_kernel<T><<<grid, 256, 0, st>>>((const T*)JF, (const T*)JF2, (const long long*)nh, n_cubes,
+                                                    (T)v_cubes, (T)(v_cubes * v_cubes), (T)beta, (T*)dh, partials, ticket,
+                                                    scalars_f64);
+        strat_normalise_kernel<T><<<grid, 256, 0, st>>>((T*)dh, n_cubes, scalars_f64);
+    });
+    return check_launch("tq_vegas_strat_update");
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+"""Multi-GPU layer: one process per GPU, `torch.distributed` (NCCL over NVLink 5 / NVSwitch on the GPU box,
+gloo in the CPU tests).  The reference has nothing here ("spawn one process per GPU").
+
+Design (DESIGN.md "Multi-GPU"):
+  * every sample is a pure function of (seed, call, row / cube+index), so ranks take disjoint contiguous
+    row (MC, VEGAS) or leading-axis slab (Newton-Cotes) ranges of the *same* sample set;
+  * Monte Carlo / Newton-Cotes: no data-path collective, one all-reduce of the fp64 partial sums;
+  * VEGAS: per iteration one all-reduce over the statistics [weights | counts | JF | JF2]; map and
+    stratification state is then updated redundantly and stays bit-identical on all ranks.
+"""
+import torch
+
+_state = {"enabled": False, "group": None}
+
+
+def enable(group=None):
+    """Shard subsequent integrations over the ranks of `group` (default process group)."""
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised; call init_process_group first")
+    _state["enabled"] = True
+    _state["group"] = group
+
+
+def disable():
+    _state["enabled"] = False
+    _state["group"] = None
+
+
+def is_enabled():
+    return _state["enabled"]
+
+
+def rank_and_world():
+    if not _state["enabled"]:
+        return 0, 1
+    import torch.distributed as dist
+
+    return dist.get_rank(_state["group"]), dist.get_world_size(_state["group"])
+
+
+def shard_range(total, rank=None, world=None):
+    """Contiguous balanced split of range(total): rank r gets [total*r//R, total*(r+1)//R)."""
+    if rank is None or world is None:
+        rank, world = rank_and_world()
+    return (total * rank) // world, (total * (rank + 1)) // world
+
+
+def all_reduce_sum_(*tensors):
+    """In-place sum over ranks of every tensor (no-op when not enabled)."""
+    if not _state["enabled"]:
+        return
+    import torch.distributed as dist
+
+    for t in tensors:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_state["group"])
+
+
+def pack_all_reduce_sum_(tensors):
+    """Sum several same-dtype tensors over ranks with ONE collective (flatten -> all-reduce -> scatter back)."""
+    if not _state["enabled"] or not tensors:
+        return
+    import torch.distributed as dist
+
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=_state["group"])
+    off = 0
+    for t in tensors:
+        n = t.numel()
+        t.copy_(flat[off:off + n].reshape(t.shape))
+        off += n

@@ -1,0 +1,122 @@
+"""Grid-based integrators on the GPU (replaces torchquad/integration/grid_integrator.py).
+
+The reference reshapes the function values to [..., n, ..., n] and applies the composite rule as `dim`
+successive stencil-and-sum passes over the last axis (grid_integrator.py:57-91 and the rule files).  The
+same number is  sum_p f(p) * prod_d w[i_d(p)] * prod_d (h_d * c)  with the rule's 1-D weight pattern w, and
+that is what `tq_nc_contract` / `tq_fused_nc` evaluate in a single fp64-accumulated pass."""
+import torch
+
+from .. import distributed as tqdist
+from .. import ops
+from ..integrands import BuiltinIntegrand
+from .base_integrator import BaseIntegrator
+from .integration_grid import IntegrationGrid, grid_nodes
+from .utils import _linspace_with_grads, _setup_integration_domain, expand_func_values_and_squeeze_integral
+
+
+class GridIntegrator(BaseIntegrator):
+    """Base of the composite Newton-Cotes integrators."""
+
+    max_points_bytes = 8 << 30  # evaluation chunk of the unfused path
+
+    # 1-D weight pattern of the rule and the divisor of h: subclasses override.
+    _rule_denominator = 1.0
+
+    def __init__(self):
+        super().__init__()
+
+    @property
+    def _grid_func(self):
+        def f(integration_domain, N, requires_grad=False, backend=None):
+            return _linspace_with_grads(integration_domain[0], integration_domain[1], N, requires_grad=requires_grad)
+
+        return f
+
+    def _weights(self, N, dim, backend, requires_grad=False):
+        return None
+
+    @staticmethod
+    def _rule_weights_1d(n, dtype, device):
+        raise NotImplementedError
+
+    @staticmethod
+    def _adjust_N(dim, N):
+        return N
+
+    def _weight_table(self, n, dim, dtype, device):
+        w = self._rule_weights_1d(n, dtype, device)
+        return w.reshape(1, n).repeat(dim, 1).contiguous()
+
+    def _scale(self, hs):
+        """prod_d h_d / c, multiplied in the order the reference applies its passes."""
+        s = hs[0] / self._rule_denominator
+        for d in range(1, hs.shape[0]):
+            s = s * (hs[d] / self._rule_denominator)
+        return s
+
+    def integrate(self, fn, dim, N, integration_domain, backend):
+        """Composite Newton-Cotes integration (grid_integrator.py:32-55)."""
+        if N is None:
+            N = self._get_minimal_N(dim)
+        domain = _setup_integration_domain(dim, integration_domain, backend)
+        self._check_inputs(dim=dim, N=N, integration_domain=domain)
+        N = self._adjust_N(dim=dim, N=N)
+        rank, world = tqdist.rank_and_world()
+        fused = isinstance(fn, BuiltinIntegrand) and fn.dim == dim and not domain.requires_grad
+        n = int(N ** (1.0 / dim) + 1e-8)
+        total_points = n**dim
+        chunk_rows = max(1, self.max_points_bytes // (dim * domain.element_size()))
+        if not fused and world == 1 and total_points <= chunk_rows:
+            grid_points, hs, n_per_dim = self.calculate_grid(N, domain)
+            function_values, num_points = self.evaluate_integrand(
+                fn, grid_points, weights=self._weights(n_per_dim, dim, "torch"))
+            self._nr_of_fevals = num_points
+            return self.calculate_result(function_values, dim, n_per_dim, hs, domain)
+
+        # sharded / chunked / fused: contiguous point ranges of the same grid
+        IntegrationGrid._check_inputs(None, N, domain, False)
+        nodes, hs, n = grid_nodes(N, domain, self._grid_func)
+        table = self._weight_table(n, dim, domain.dtype, domain.device)
+        begin, end = tqdist.shard_range(total_points, rank, world)
+        if fused:
+            unit = fn.to_struct([0.0] * dim, [1.0] * dim, 1.0)  # nodes are already in domain coordinates
+            total = ops.fused_nc(unit, nodes.detach().contiguous(), table, begin, end)[0]
+        else:
+            total = None
+            for p0 in range(begin, end, chunk_rows):
+                p1 = min(end, p0 + chunk_rows)
+                pts = ops.nc_grid_points(nodes, p0, p1)
+                vals, _ = self.evaluate_integrand(fn, pts)
+                part = ops.nc_contract_f64(vals, table, p0, p1)
+                total = part if total is None else total + part
+                del pts, vals
+            if total is None:
+                probe = fn(nodes[:, 0].detach().reshape(1, -1).clone())
+                total = torch.zeros(probe.shape[1:], dtype=torch.float64, device=domain.device)
+        if world > 1:
+            total = ops.all_reduce_sum_autograd(total)
+        self._nr_of_fevals = total_points
+        return total.to(domain.dtype) * self._scale(hs)
+
+    @expand_func_values_and_squeeze_integral
+    def calculate_result(self, function_values, dim, n_per_dim, hs, integration_domain):
+        """Apply the composite rule to values on the full grid (grid_integrator.py:57-91)."""
+        table = self._weight_table(n_per_dim, dim, function_values.dtype, function_values.device)
+        return ops.nc_contract(function_values, table) * self._scale(hs)
+
+    def calculate_grid(self, N, integration_domain, disable_integration_domain_check=False):
+        """(points [n^dim, dim], h [dim], n) (grid_integrator.py:93-127)."""
+        N = self._adjust_N(dim=integration_domain.shape[0], N=N)
+        grid = IntegrationGrid(N, integration_domain, self._grid_func, disable_integration_domain_check)
+        return grid.points, grid.h, grid._N
+
+    def get_jit_compiled_integrate(self, dim, N=None, integration_domain=None, backend=None):
+        """API parity with grid_integrator.py:134-255; nothing to trace, returns a closure."""
+        if N is None:
+            N = self._get_minimal_N(dim)
+        domain0 = _setup_integration_domain(dim, integration_domain, backend)
+
+        def compiled_integrate(fn, integration_domain=None):
+            return self.integrate(fn, dim, N, domain0 if integration_domain is None else integration_domain, backend)
+
+        return compiled_integrate

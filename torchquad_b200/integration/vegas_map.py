@@ -1,0 +1,102 @@
+"""VEGAS+ adaptive map on the GPU (replaces torchquad/integration/vegas_map.py).
+
+State and method names follow the reference so its unit tests read the same (tests/vegas_map_test.py):
+`x_edges [dim, Ni+1]`, `dx_edges [dim, Ni]`, `weights [dim, Ni]` (float), `counts [dim, Ni]` (int64).
+All arithmetic is in libtqb200 (csrc/vegas_map.cu); the Python loops over `dim` of the reference are gone.
+"""
+import warnings
+
+import torch
+
+from .. import ops
+from ..utils.set_log_level import logger
+from .utils import _default_device, _require_torch_backend
+
+
+class VEGASMap:
+    """The piecewise-linear importance-sampling map of VEGAS Enhanced (arXiv:2009.05112, section II)."""
+
+    def __init__(self, N_intervals, dim, backend="torch", dtype=torch.float32, alpha=0.5, device=None):
+        _require_torch_backend(backend)
+        self.dim = dim
+        self.N_intervals = N_intervals
+        self.alpha = alpha
+        self.backend = "torch"
+        self.dtype = dtype
+        self.device = torch.device(device) if device is not None else _default_device()
+        # Uniform start (vegas_map.py:32-39): dx = 1/Ni, edges from linspace (not a cumsum of dx).
+        self.dx_edges = torch.ones((dim, N_intervals), dtype=dtype, device=self.device) / N_intervals
+        edges = torch.linspace(0.0, 1.0, N_intervals + 1, dtype=dtype, device=self.device)
+        self.x_edges = edges.reshape(1, -1).repeat(dim, 1).contiguous()
+        self._status = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._reset_weight()
+
+    # -- bin lookup ---------------------------------------------------------------------------
+    def get_X(self, y):
+        """Mapped points x(y), EQ 9 (vegas_map.py:44-58)."""
+        return ops.map_forward(y, self.x_edges, self.dx_edges, want_jac=False)[0]
+
+    def get_Jac(self, y):
+        """Jacobian of the map, EQ 12 (vegas_map.py:60-74)."""
+        return ops.map_forward(y, self.x_edges, self.dx_edges, want_x=False)[1]
+
+    def get_X_and_Jac(self, y):
+        """Both in a single pass over y (what the integrator uses)."""
+        x, jac, _ = ops.map_forward(y, self.x_edges, self.dx_edges)
+        return x, jac
+
+    def _get_interval_ID(self, y):
+        """floor(y*Ni) as int64, EQ 10 (vegas_map.py:76-85)."""
+        ids = ops.map_forward(y, self.x_edges, self.dx_edges, want_x=False, want_jac=False, want_ids=True)[2]
+        return ids.to(torch.int64)
+
+    def _get_interval_offset(self, y):
+        """y*Ni - floor(y*Ni), EQ 11 (vegas_map.py:87-97)."""
+        return ops.map_forward(y, self.x_edges, self.dx_edges, want_x=False, want_jac=False, want_offset=True)[3]
+
+    # -- histogram ----------------------------------------------------------------------------
+    def accumulate_weight(self, y, jf_vec2):
+        """weights[d, k] += jf^2 and counts[d, k] += 1 for every sample (vegas_map.py:99-111)."""
+        ops.map_accumulate(y, jf_vec2, self.weights, self.counts)
+
+    @staticmethod
+    def _smooth_map(weights, counts, alpha):
+        """Smoothed, compressed weights, EQ 18-22; None if a dimension sums to zero (vegas_map.py:113-172)."""
+        smoothed, status = ops.map_smooth(weights, counts, alpha)
+        if int(status[0].item()) != 0:
+            return None
+        return smoothed
+
+    def _reset_weight(self):
+        """Zero the histogram (vegas_map.py:174-183)."""
+        self.weights = torch.zeros((self.dim, self.N_intervals), dtype=self.dtype, device=self.device)
+        self.counts = torch.zeros((self.dim, self.N_intervals), dtype=torch.int64, device=self.device)
+
+    # -- rebinning ----------------------------------------------------------------------------
+    def update_map(self, check=True):
+        """Adapt the edges to the accumulated weights, section II C (vegas_map.py:185-261).
+
+        The kernels never synchronise: problems are reported through a device status word.  With
+        `check=True` (default, reference behaviour) the word is read back here and turned into the
+        reference's warnings / RuntimeError; the integrator passes `check=False` and calls
+        `check_status()` at its own synchronisation points."""
+        ops.map_update(self.x_edges, self.dx_edges, self.weights, self.counts, self.alpha, self._status)
+        if check:
+            self.check_status()
+
+    def check_status(self, status=None):
+        """Raise / warn like vegas_map.py:188-196,240-257 from a status word (device read-back)."""
+        st = (self._status if status is None else status)
+        st = st.tolist() if isinstance(st, torch.Tensor) else list(st)
+        if st[0]:
+            msg = ("Cannot update the VEGASMap. This can happen with an integrand "
+                   "which evaluates to zero everywhere.")
+            logger.warning(msg)
+            warnings.warn(msg, RuntimeWarning)
+        if st[1]:
+            num_edges = self.x_edges.shape[1]
+            msg = f"{st[1]} out of {num_edges * self.dim} calculated VEGASMap edges were infinite"
+            logger.warning(msg)
+            warnings.warn(msg, RuntimeWarning)
+        if st[2]:
+            raise RuntimeError("Could not replace all infinite edges")

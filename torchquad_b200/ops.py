@@ -1,0 +1,409 @@
+"""Tensor-level wrappers of the C ABI (include/tqb200.h) plus the autograd glue of the unfused path.
+
+Every function takes CUDA tensors, launches on the current stream and returns without synchronising.
+Autograd: the reference gets gradients for free because it is written in differentiable ATen ops; here
+the three places where a gradient crosses one of our kernels get an explicit backward
+(Monte Carlo samples wrt the domain, per-cube sums wrt jf, grid points wrt the 1-D nodes, weighted
+contraction / column sums wrt the integrand values) -- pinned by tests mirroring
+/root/reference/tests/gradient_test.py:162-259.
+"""
+import torch
+
+from . import _lib
+from ._lib import call, dtype_code, ptr, require_cuda, stream_ptr, workspace
+
+
+def _ws(device):
+    ws = workspace(device)
+    return ws.data_ptr(), ws.numel()
+
+
+# ------------------------------------------------------------------------------------------- RNG / MC
+def philox_uniform(rows, dim, dtype, device, seed, call_idx, row_begin=0):
+    """U[0,1) block [rows, dim] of stream (seed, call_idx), global rows row_begin.. (rng.py:119-125)."""
+    out = torch.empty((rows, dim), dtype=dtype, device=device)
+    require_cuda(out)
+    if rows > 0:
+        with torch.cuda.device(out.device):
+            call("tq_philox_uniform", ptr(out), row_begin, row_begin + rows, dim, dtype_code(dtype),
+                 seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, stream_ptr(out.device))
+    return out
+
+
+class _MCSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, domain, rows, seed, call_idx, row_begin):
+        require_cuda(domain)
+        dom = domain.detach().contiguous()
+        dim = dom.shape[0]
+        out = torch.empty((rows, dim), dtype=dom.dtype, device=dom.device)
+        if rows > 0:
+            with torch.cuda.device(dom.device):
+                call("tq_mc_sample", ptr(out), ptr(dom), row_begin, row_begin + rows, dim, dtype_code(dom.dtype),
+                     seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, stream_ptr(dom.device))
+        ctx.meta = (rows, seed, call_idx, row_begin, dom.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        rows, seed, call_idx, row_begin, dtype = ctx.meta
+        g = grad_out.contiguous()
+        dim = g.shape[1]
+        gd = torch.zeros((dim, 2), dtype=torch.float64, device=g.device)
+        if rows > 0:
+            with torch.cuda.device(g.device):
+                wsp, wsn = _ws(g.device)
+                call("tq_mc_sample_backward", ptr(g), row_begin, row_begin + rows, dim, dtype_code(dtype),
+                     seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, ptr(gd), wsp, wsn, stream_ptr(g.device))
+        return gd.to(dtype), None, None, None, None
+
+
+def mc_sample(domain, rows, seed, call_idx, row_begin=0):
+    """points = u*(b-a)+a for the [dim,2] domain (monte_carlo.py:84-106); differentiable wrt domain."""
+    return _MCSample.apply(domain, rows, seed, call_idx, row_begin)
+
+
+def sum_columns(f, want_sumsq=False):
+    """fp64 column sums (and sums of squares) of f[rows] or f[rows, cols]; no autograd."""
+    require_cuda(f)
+    f2 = f.detach().contiguous()
+    rows = f2.shape[0]
+    cols = 1 if f2.dim() == 1 else int(f2[0].numel()) if rows > 0 else int(torch.Size(f2.shape[1:]).numel())
+    s = torch.zeros(cols, dtype=torch.float64, device=f2.device)
+    q = torch.zeros(cols, dtype=torch.float64, device=f2.device) if want_sumsq else None
+    if rows > 0:
+        with torch.cuda.device(f2.device):
+            wsp, wsn = _ws(f2.device)
+            call("tq_sum_columns", ptr(f2), rows, cols, dtype_code(f2.dtype), ptr(s), ptr(q), wsp, wsn,
+                 stream_ptr(f2.device))
+    return s, q
+
+
+class _ReduceSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f):
+        s, _ = sum_columns(f)
+        ctx.shape = f.shape
+        return s.to(f.dtype).reshape(f.shape[1:])
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.unsqueeze(0).expand(ctx.shape)
+
+
+def reduce_sum(f):
+    """sum(f, axis=0) accumulated in fp64 and rounded once to f.dtype (monte_carlo.py:77); differentiable."""
+    return _ReduceSum.apply(f)
+
+
+class _ReduceSumF64(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f):
+        s, _ = sum_columns(f)
+        ctx.shape, ctx.dtype = f.shape, f.dtype
+        return s.reshape(f.shape[1:])
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dtype).unsqueeze(0).expand(ctx.shape)
+
+
+def reduce_sum_f64(f):
+    """Like reduce_sum but returns the unrounded fp64 sums (for accumulation over chunks and ranks)."""
+    return _ReduceSumF64.apply(f)
+
+
+class _AllReduceSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        from . import distributed as tqdist
+
+        out = t.detach().clone()
+        tqdist.all_reduce_sum_(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        # every rank holds the same replicated result; each rank backpropagates its own contribution
+        return g
+
+
+def all_reduce_sum_autograd(t):
+    """Sum over ranks that keeps the local autograd graph (d(total)/d(local part) = 1)."""
+    return _AllReduceSum.apply(t)
+
+
+# ------------------------------------------------------------------------------------------- VEGAS map
+def map_forward(y, x_edges, dx_edges, want_x=True, want_jac=True, want_ids=False, want_offset=False):
+    """(x, jac, ids[, offset]) of vegas_map.py:44-97 in one pass."""
+    require_cuda(y, x_edges, dx_edges)
+    y = y.contiguous()
+    rows, dim = y.shape
+    ni = dx_edges.shape[1]
+    x = torch.empty_like(y) if want_x else None
+    jac = torch.empty(rows, dtype=y.dtype, device=y.device) if want_jac else None
+    ids = torch.empty((rows, dim), dtype=torch.int32, device=y.device) if want_ids else None
+    off = torch.empty_like(y) if want_offset else None
+    if rows > 0:
+        with torch.cuda.device(y.device):
+            call("tq_vegas_map_forward", ptr(y), ptr(x_edges), ptr(dx_edges), ptr(x), ptr(jac), ptr(ids), ptr(off), rows,
+                 dim, ni, dtype_code(y.dtype), stream_ptr(y.device))
+    if want_offset:
+        return x, jac, ids, off
+    return x, jac, ids
+
+
+def map_accumulate(y, jf2, weights, counts):
+    """weights[d,k] += jf2, counts[d,k] += 1 in place (vegas_map.py:99-111)."""
+    require_cuda(y, jf2, weights, counts)
+    y = y.contiguous()
+    jf2 = jf2.detach().contiguous()
+    rows, dim = y.shape
+    if rows > 0:
+        with torch.cuda.device(y.device):
+            call("tq_vegas_map_accumulate", ptr(y), ptr(jf2), ptr(weights), ptr(counts), rows, dim, weights.shape[1],
+                 dtype_code(y.dtype), stream_ptr(y.device))
+
+
+def _map_scratch(dim, ni, dtype, device):
+    nbytes = _lib.load().tq_vegas_map_workspace_bytes(dim, ni, dtype_code(dtype))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def map_smooth(weights, counts, alpha):
+    """_smooth_map (vegas_map.py:113-172).  Returns (smoothed, status[4] int32 device tensor)."""
+    require_cuda(weights, counts)
+    dim, ni = weights.shape
+    out = torch.empty_like(weights)
+    status = torch.zeros(4, dtype=torch.int32, device=weights.device)
+    scratch = _map_scratch(dim, ni, weights.dtype, weights.device)
+    with torch.cuda.device(weights.device):
+        call("tq_vegas_map_smooth", ptr(weights.contiguous()), ptr(counts.contiguous()), ptr(out), dim, ni, float(alpha),
+             dtype_code(weights.dtype), ptr(status), ptr(scratch), scratch.numel(), stream_ptr(weights.device))
+    return out, status
+
+
+def map_update(x_edges, dx_edges, weights, counts, alpha, status):
+    """update_map (vegas_map.py:185-261) in place; `status` is an int32[4] device tensor (see header)."""
+    require_cuda(x_edges, dx_edges, weights, counts, status)
+    dim, ni = weights.shape
+    scratch = _map_scratch(dim, ni, weights.dtype, weights.device)
+    with torch.cuda.device(weights.device):
+        call("tq_vegas_map_update", ptr(x_edges), ptr(dx_edges), ptr(weights), ptr(counts), dim, ni, float(alpha),
+             dtype_code(weights.dtype), ptr(status), ptr(scratch), scratch.numel(), stream_ptr(weights.device))
+
+
+# ------------------------------------------------------------------------------------------- stratification
+def strat_nh(dh, nevals_exp):
+    """nh (int64 [C]) and its exclusive scan offsets (int64 [C+1]) (vegas_stratification.py:92-103)."""
+    require_cuda(dh)
+    n = dh.shape[0]
+    nh = torch.empty(n, dtype=torch.int64, device=dh.device)
+    offsets = torch.empty(n + 1, dtype=torch.int64, device=dh.device)
+    with torch.cuda.device(dh.device):
+        wsp, wsn = _ws(dh.device)
+        call("tq_vegas_strat_nh", ptr(dh.contiguous()), n, float(nevals_exp), dtype_code(dh.dtype), ptr(nh), ptr(offsets),
+             wsp, wsn, stream_ptr(dh.device))
+    return nh, offsets
+
+
+def strat_offsets(nh):
+    """Exclusive scan of a user-provided nh (int64 [C]) -> offsets int64 [C+1]."""
+    require_cuda(nh)
+    nh = nh.contiguous()
+    n = nh.shape[0]
+    offsets = torch.empty(n + 1, dtype=torch.int64, device=nh.device)
+    with torch.cuda.device(nh.device):
+        wsp, wsn = _ws(nh.device)
+        call("tq_vegas_strat_offsets", ptr(nh), n, ptr(offsets), wsp, wsn, stream_ptr(nh.device))
+    return offsets
+
+
+def strat_sample(offsets, n_strat, dim, dtype, row_begin, row_end, u_in=None, seed=0, call_idx=0):
+    """y rows [row_begin,row_end) of vegas_stratification.py:140-165 (injected `u_in` or cube-keyed Philox)."""
+    require_cuda(offsets, u_in)
+    rows = row_end - row_begin
+    y = torch.empty((rows, dim), dtype=dtype, device=offsets.device)
+    if u_in is not None:
+        u_in = u_in.contiguous()
+        if tuple(u_in.shape) != (rows, dim) or u_in.dtype != dtype:
+            raise ValueError(f"rng.uniform returned shape {tuple(u_in.shape)} / {u_in.dtype}, expected {(rows, dim)} / {dtype}")
+    if rows > 0:
+        with torch.cuda.device(offsets.device):
+            call("tq_vegas_strat_sample", ptr(offsets), offsets.shape[0] - 1, n_strat, dim, dtype_code(dtype), ptr(u_in),
+                 seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, row_begin, row_end, ptr(y), stream_ptr(offsets.device))
+    return y
+
+
+class _StratAccumulate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, jf, offsets, row_base, cube_begin, cube_end):
+        require_cuda(jf, offsets)
+        v = jf.detach().contiguous()
+        n_cubes = offsets.shape[0] - 1
+        JF = torch.zeros(n_cubes, dtype=v.dtype, device=v.device)
+        JF2 = torch.zeros(n_cubes, dtype=v.dtype, device=v.device)
+        with torch.cuda.device(v.device):
+            call("tq_vegas_strat_accumulate", ptr(v), row_base, ptr(offsets), cube_begin, cube_end, ptr(JF), ptr(JF2),
+                 dtype_code(v.dtype), stream_ptr(v.device))
+        ctx.save_for_backward(offsets)
+        ctx.meta = (row_base, v.shape[0])
+        ctx.mark_non_differentiable(JF2)
+        return JF, JF2
+
+    @staticmethod
+    def backward(ctx, gJF, _gJF2):
+        (offsets,) = ctx.saved_tensors
+        row_base, rows = ctx.meta
+        g = torch.empty(rows, dtype=gJF.dtype, device=gJF.device)
+        if rows > 0:
+            with torch.cuda.device(g.device):
+                call("tq_vegas_strat_accumulate_backward", ptr(gJF.contiguous()), ptr(offsets), offsets.shape[0] - 1,
+                     row_base, row_base + rows, ptr(g), dtype_code(g.dtype), stream_ptr(g.device))
+        return g, None, None, None, None
+
+
+def strat_accumulate(jf, offsets, row_base=0, cube_begin=0, cube_end=None):
+    """JF[c], JF2[c] over each cube's rows in order (vegas_stratification.py:46-70); JF differentiable wrt jf.
+
+    JF/JF2 are full-length [C] tensors, zero outside [cube_begin, cube_end); the sum of squares is not
+    differentiated (the reference detaches everything derived from it, vegas.py:298-299)."""
+    cube_end = offsets.shape[0] - 1 if cube_end is None else cube_end
+    return _StratAccumulate.apply(jf, offsets, row_base, cube_begin, cube_end)
+
+
+def strat_update(JF, JF2, nh, v_cubes, beta):
+    """Estimator + update_DH: returns (dh [C], scalars fp64 [3] = I, sigma2, sum d^beta)."""
+    require_cuda(JF, JF2, nh)
+    n = JF.shape[0]
+    dh = torch.empty(n, dtype=JF.dtype, device=JF.device)
+    scalars = torch.zeros(3, dtype=torch.float64, device=JF.device)
+    with torch.cuda.device(JF.device):
+        wsp, wsn = _ws(JF.device)
+        call("tq_vegas_strat_update", ptr(JF.detach().contiguous()), ptr(JF2.detach().contiguous()), ptr(nh), n,
+             float(v_cubes), float(beta), dtype_code(JF.dtype), ptr(dh), ptr(scalars), wsp, wsn, stream_ptr(JF.device))
+    return dh, scalars
+
+
+# ------------------------------------------------------------------------------------------- Newton-Cotes
+class _GridPoints(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, nodes, p_begin, p_end):
+        require_cuda(nodes)
+        nd = nodes.detach().contiguous()
+        dim, n = nd.shape
+        pts = torch.empty((p_end - p_begin, dim), dtype=nd.dtype, device=nd.device)
+        if p_end > p_begin:
+            with torch.cuda.device(nd.device):
+                call("tq_nc_grid_points", ptr(nd), n, dim, p_begin, p_end, ptr(pts), dtype_code(nd.dtype),
+                     stream_ptr(nd.device))
+        ctx.meta = (n, dim, p_begin, p_end, nd.dtype)
+        return pts
+
+    @staticmethod
+    def backward(ctx, g):
+        n, dim, p_begin, p_end, dtype = ctx.meta
+        g = g.contiguous()
+        gn = torch.zeros((dim, n), dtype=torch.float64, device=g.device)
+        with torch.cuda.device(g.device):
+            call("tq_nc_grid_points_backward", ptr(g), n, dim, p_begin, p_end, ptr(gn), dtype_code(dtype),
+                 stream_ptr(g.device))
+        return gn.to(dtype), None, None
+
+
+def nc_grid_points(nodes, p_begin=0, p_end=None):
+    """points[p, d] = nodes[d, i_d(p)] (integration_grid.py:98-99 ordering); differentiable wrt nodes."""
+    dim, n = nodes.shape
+    p_end = n**dim if p_end is None else p_end
+    return _GridPoints.apply(nodes, p_begin, p_end)
+
+
+def nc_point_weights(w, p_begin, p_end):
+    require_cuda(w)
+    w = w.contiguous()
+    dim, n = w.shape
+    out = torch.empty(p_end - p_begin, dtype=w.dtype, device=w.device)
+    if p_end > p_begin:
+        with torch.cuda.device(w.device):
+            call("tq_nc_point_weights", ptr(w), n, dim, p_begin, p_end, ptr(out), dtype_code(w.dtype), stream_ptr(w.device))
+    return out
+
+
+class _Contract(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, w, p_begin, p_end, keep_f64):
+        require_cuda(f, w)
+        fv = f.detach().contiguous()
+        wv = w.detach().contiguous()
+        dim, n = wv.shape
+        rows = p_end - p_begin
+        if fv.shape[0] != rows:
+            raise ValueError(f"expected {rows} function values, got {fv.shape[0]}")
+        cols = 1 if fv.dim() == 1 else int(torch.Size(fv.shape[1:]).numel())
+        out = torch.zeros(cols, dtype=torch.float64, device=fv.device)
+        if rows > 0:
+            with torch.cuda.device(fv.device):
+                wsp, wsn = _ws(fv.device)
+                call("tq_nc_contract", ptr(fv), ptr(wv), n, dim, p_begin, p_end, cols, dtype_code(fv.dtype), ptr(out),
+                     wsp, wsn, stream_ptr(fv.device))
+        ctx.save_for_backward(wv)
+        ctx.meta = (p_begin, p_end, f.shape, fv.dtype)
+        out = out if keep_f64 else out.to(fv.dtype)
+        return out.reshape(f.shape[1:])
+
+    @staticmethod
+    def backward(ctx, g):
+        (wv,) = ctx.saved_tensors
+        p_begin, p_end, shape, dtype = ctx.meta
+        W = nc_point_weights(wv, p_begin, p_end)
+        gf = W.reshape([-1] + [1] * (len(shape) - 1)) * g.to(dtype).unsqueeze(0)
+        return gf.expand(shape), None, None, None, None
+
+
+def nc_contract(f, w, p_begin=0, p_end=None):
+    """sum_p f[p, ...] * prod_d w[d, i_d(p)] in fp64, rounded once; differentiable wrt f."""
+    dim, n = w.shape
+    p_end = n**dim if p_end is None else p_end
+    return _Contract.apply(f, w, p_begin, p_end, False)
+
+
+def nc_contract_f64(f, w, p_begin, p_end):
+    """Same contraction, unrounded fp64 partial sums (for accumulation over chunks and ranks)."""
+    return _Contract.apply(f, w, p_begin, p_end, True)
+
+
+# ------------------------------------------------------------------------------------------- fused
+def fused_mc(fn_struct, dtype, device, row_begin, row_end, seed, call_idx):
+    """{sum f, sum f^2} (fp64 [2]) of a built-in integrand over rows of the row-keyed stream."""
+    out = torch.zeros(2, dtype=torch.float64, device=device)
+    require_cuda(out)
+    with torch.cuda.device(out.device):
+        wsp, wsn = _ws(out.device)
+        call("tq_fused_mc", fn_struct, dtype_code(dtype), row_begin, row_end, seed & 0xFFFFFFFFFFFFFFFF,
+             call_idx & 0xFFFFFFFF, ptr(out), wsp, wsn, stream_ptr(out.device))
+    return out
+
+
+def fused_nc(fn_struct, nodes, w, p_begin, p_end):
+    require_cuda(nodes, w)
+    dim, n = nodes.shape
+    out = torch.zeros(1, dtype=torch.float64, device=nodes.device)
+    with torch.cuda.device(nodes.device):
+        wsp, wsn = _ws(nodes.device)
+        call("tq_fused_nc", fn_struct, ptr(nodes.contiguous()), ptr(w.contiguous()), n, dtype_code(nodes.dtype), p_begin,
+             p_end, ptr(out), wsp, wsn, stream_ptr(nodes.device))
+    return out
+
+
+def fused_vegas(fn_struct, x_edges, dx_edges, weights, counts, row_begin, row_end, seed, call_idx,
+                offsets=None, n_strat=1, JF=None, JF2=None):
+    """One fused VEGAS pass (warm-up when offsets is None).  Returns fp64 [2] = {sum jf, sum jf^2} (warm-up only)."""
+    require_cuda(x_edges, dx_edges, weights, counts, offsets, JF, JF2)
+    out = torch.zeros(2, dtype=torch.float64, device=x_edges.device)
+    n_cubes = 0 if offsets is None else offsets.shape[0] - 1
+    with torch.cuda.device(x_edges.device):
+        wsp, wsn = _ws(x_edges.device)
+        call("tq_fused_vegas", fn_struct, dtype_code(x_edges.dtype), ptr(offsets), n_cubes, n_strat, row_begin, row_end,
+             ptr(x_edges), ptr(dx_edges), dx_edges.shape[1], ptr(weights), ptr(counts), ptr(JF), ptr(JF2),
+             seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, ptr(out), wsp, wsn, stream_ptr(x_edges.device))
+    return out
