@@ -40,7 +40,7 @@ def same(a, b, what):
 
 
 def npy(t):
-    return t.detach().cpu().numpy()
+    return t.detach().cpu().numpy().copy()  # copy: the reference mutates some tensors in place later
 
 
 class Injected:

@@ -448,6 +448,15 @@ def mc_result(f, domain):
     return res.squeeze() if one_d else res
 
 
+def mc_integrate(fn, dim, N, domain, seed=None):
+    """MonteCarlo.integrate with the reference's own RNG (monte_carlo.py:20-58, rng.py:119-125):
+    torch.manual_seed + torch.rand on the CPU.  Used as the CPU baseline of bench.py."""
+    if seed is not None:
+        torch.random.manual_seed(seed)
+    u = torch.rand(size=[N, dim], dtype=domain.dtype)
+    return mc_result(fn(mc_sample_points(u, domain)), domain)
+
+
 # --------------------------------------------------------------------------
 # Newton-Cotes grids  (integration_grid.py, grid_integrator.py, trapezoid/simpson/boole.py)
 # --------------------------------------------------------------------------

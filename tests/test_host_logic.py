@@ -1,0 +1,162 @@
+"""Host-side logic of the drop-in classes that needs no GPU: input validation, N adjustment, domain set-up,
+rule weight patterns, the VEGAS schedule, sharding arithmetic and the built-in integrands' closed forms.
+Mirrors the host-side assertions of /root/reference/tests (cited per test)."""
+import math
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import torchquad_b200 as tq
+from oracle import ref_oracle as O
+from torchquad_b200 import distributed as tqdist
+from torchquad_b200 import integrands as F
+from torchquad_b200.integration.utils import (_check_integration_domain, _linspace_with_grads,
+                                              _setup_integration_domain)
+
+
+def test_check_inputs_and_domain_validation():
+    """/root/reference/torchquad/integration/base_integrator.py:93-116, utils.py:162-206."""
+    chk = tq.BaseIntegrator._check_inputs
+    with pytest.raises(ValueError):
+        chk(dim=0)
+    with pytest.raises(ValueError):
+        chk(N=0)
+    with pytest.raises(ValueError):
+        chk(N=10.0)
+    with pytest.raises(ValueError):
+        chk(dim=3, integration_domain=[[0, 1]] * 2)
+    with pytest.raises(ValueError):
+        _check_integration_domain([[1.0, 0.0]])
+    with pytest.raises(ValueError):
+        _check_integration_domain([[0.0, 1.0, 2.0]])
+    with pytest.raises(ValueError):
+        _check_integration_domain(torch.tensor([[1.0, 0.0]]))
+    with pytest.raises(ValueError):
+        _check_integration_domain(torch.zeros(3))
+    assert _check_integration_domain([[0, 1], [2, 3]]) == 2
+    assert _check_integration_domain(torch.tensor([[0.0, 1.0]] * 4)) == 4
+
+
+def test_setup_integration_domain_dtype_rules():
+    """/root/reference/tests/utils_integration_test.py:123-180 (torch backend rows)."""
+    torch.set_default_dtype(torch.float64)
+    try:
+        d = _setup_integration_domain(2, None, None)
+        assert d.dtype == torch.float64 and d.tolist() == [[-1.0, 1.0]] * 2
+        d = _setup_integration_domain(1, [[0, 3]], "torch")
+        assert d.dtype == torch.float64 and d.shape == (1, 2)
+        given = torch.tensor([[0.0, 1.0]], dtype=torch.float32)
+        assert _setup_integration_domain(1, given, None) is given
+        with pytest.raises(ValueError):
+            _setup_integration_domain(2, [[0, 1]], None)
+        with pytest.raises(ValueError):
+            _setup_integration_domain(1, [[0, 1]], "numpy")
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
+def test_linspace_with_grads_endpoints_exact():
+    """/root/reference/tests/utils_integration_test.py:47-72."""
+    for rg in (False, True):
+        a = torch.tensor(-2.0, dtype=torch.float64, requires_grad=rg)
+        b = torch.tensor(7.0, dtype=torch.float64, requires_grad=rg)
+        g = _linspace_with_grads(a, b, 11, rg)
+        assert g.shape == (11,) and float(g[0]) == -2.0 and float(g[-1]) == 7.0
+        assert g.requires_grad == rg
+
+
+@pytest.mark.parametrize("rule,cls", [("trapezoid", tq.Trapezoid), ("simpson", tq.Simpson), ("boole", tq.Boole)])
+def test_adjust_n_and_rule_weights(rule, cls):
+    """_adjust_N (simpson.py:54-81, boole.py:56-84) and the 1-D weight patterns against the oracle's
+    axis-by-axis stencil (trapezoid.py:28-37, simpson.py:30-46, boole.py:30-48)."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for dim, N in [(1, 2), (1, 401), (2, 16), (2, 1000), (3, 1_076_890), (6, 31**6), (6, 33**6), (10, 3**10)]:
+            assert cls._adjust_N(dim, N) == O.nc_adjust_n(rule, dim, N)
+    n = {"trapezoid": 8, "simpson": 9, "boole": 9}[rule]
+    w = cls._rule_weights_1d(n, torch.float64, "cpu")
+    f = torch.rand(n, dtype=torch.float64)
+    hs = torch.tensor([0.37], dtype=torch.float64)
+    want = O.nc_result(rule, f, 1, n, hs)
+    got = (f * w).sum() * hs[0] / cls._rule_denominator
+    assert abs(float(got) - float(want)) < 1e-15 * max(1.0, abs(float(want)))
+    # tensor product: sum_p f(p) prod_d w[i_d] prod_d h_d/c == oracle in 3-D
+    f3 = torch.rand(n**3, dtype=torch.float64)
+    hs3 = torch.tensor([0.1, 0.2, 0.3], dtype=torch.float64)
+    W = torch.einsum("i,j,k->ijk", w, w, w).reshape(-1)
+    got3 = (f3 * W).sum() * torch.prod(hs3 / cls._rule_denominator)
+    assert abs(float(got3) - float(O.nc_result(rule, f3, 3, n, hs3))) < 1e-14
+    if rule != "trapezoid":
+        assert cls._get_minimal_N(3) == {"simpson": 27, "boole": 125}[rule]
+
+
+def test_vegas_schedule_matches_oracle_decisions():
+    """_check_abort_conditions / weighted mean (vegas.py:161-209,318-362) on synthetic iteration records:
+    the host-side numpy arithmetic must take the same decisions as the reference's tensor arithmetic."""
+    rng = np.random.default_rng(0)
+    for dt, npdt in [(torch.float64, np.float64), (torch.float32, np.float32)]:
+        for trial in range(20):
+            res = [1.0 + 0.01 * rng.standard_normal() for _ in range(5)]
+            sig = [abs(1e-4 * (1 + rng.standard_normal())) for _ in range(5)]
+            if trial % 7 == 0:
+                sig[2] = 0.0
+            run = O.VegasRun(lambda x: x[:, 0], 2, 100_000, torch.tensor([[0.0, 1.0]] * 2, dtype=dt), None)
+            run.results = [torch.tensor(r, dtype=dt) for r in res]
+            run.sigma2 = [torch.tensor(s, dtype=dt) for s in sig]
+            run.it, run.fevals = 5, 20_000 + trial * 1000
+            v = tq.VEGAS()
+            v.dtype, v._np, v.device = dt, npdt, torch.device("cpu")
+            v.results = [torch.tensor(r, dtype=dt) for r in res]
+            v.sigma2 = [torch.tensor(s, dtype=dt) for s in sig]
+            v.it, v._nr_of_fevals, v.N = 5, run.fevals, 100_000
+            v._max_iterations, v._eps_rel, v._eps_abs = 20, 0, 0
+            v._starting_N = v._N_increment = 100_000 // 25
+            v._map_status = []
+            want_mean = run.result()
+            assert torch.equal(v._get_result(), want_mean)
+            stop_ref = run.check_abort()
+            stop = v._check_abort_conditions()
+            assert stop == stop_ref and v._starting_N == run.starting_N, (trial, dt)
+
+
+def test_shard_ranges_partition_exactly():
+    for total in [0, 1, 7, 1000, 10**9 + 7]:
+        for world in [1, 2, 3, 8]:
+            spans = [tqdist.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def test_builtin_integrands_closed_forms_and_struct():
+    a, u = [1.3, 0.7, 2.1], [0.3, 0.6, 0.45]
+    for cls, fam in [(F.GenzOscillatory, "oscillatory"), (F.GenzProductPeak, "product_peak"), (F.GenzCornerPeak, "corner_peak"),
+                     (F.GenzGaussian, "gaussian"), (F.GenzC0, "c0"), (F.GenzDiscontinuous, "discontinuous")]:
+        fn = cls(3, a=a, u=u)
+        assert abs(fn.exact() - O.genz_exact(fam, a, u)) <= 1e-14 * abs(fn.exact())
+        x = torch.rand(64, 3, dtype=torch.float64)
+        assert torch.allclose(fn(x), O.genz(fam, x, a, u), rtol=1e-14, atol=0)
+        s = fn.to_struct([0.0, 1.0, 2.0], [1.0, 2.0, 3.0], 6.0)
+        assert s.dim == 3 and s.family == F.FAMILY[fn.family] and list(s.a)[:3] == a and s.scale == 6.0
+        assert list(s.start)[:3] == [0.0, 1.0, 2.0] and list(s.size)[:3] == [1.0, 2.0, 3.0]
+    assert abs(F.SumOfSines(10).exact() - 20 * math.sin(0.5) ** 2) < 1e-15
+    assert abs(F.Polynomial(2, [1.0, 2.0, 3.0]).exact() - 2 * (1 + 1 + 1)) < 1e-15
+    x = torch.rand(10, 4, dtype=torch.float64)
+    assert torch.allclose(F.ProductOfCosines(4)(x), O.test_integrand("product_cos", x))
+    assert torch.allclose(F.SumOfExp(4)(x), O.test_integrand("exponential", x))
+    with pytest.raises(ValueError):
+        F.GenzGaussian(40)
+    with pytest.raises(ValueError):
+        F.GenzGaussian(3, a=[1.0, 2.0])
+
+
+def test_stratification_configuration_matches_reference_formula():
+    """N_strat / N_cubes / V_cubes (vegas_stratification.py:27-31) and map size (vegas.py:117) for BASELINE configs."""
+    for N, dim, ns, ni in [(10**6, 4, 10, 4000), (2_500_000_000, 8, 8, 10**7), (10**10, 16, 3, 4 * 10**7)]:
+        inc = N // 25
+        assert O.strat_config(inc, dim)[0] == ns and max(2, inc // 10) == ni
+        s = tq.VEGASStratification.__new__(tq.VEGASStratification)
+        n_strat = int((inc / 4.0) ** (1.0 / dim))
+        assert n_strat == ns

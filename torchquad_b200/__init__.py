@@ -22,6 +22,10 @@ from .utils.set_log_level import set_log_level
 from .utils.set_precision import set_precision
 from .utils.set_up_backend import set_up_backend
 
+import os as _os
+
+set_log_level(_os.environ.get("TORCHQUAD_LOG_LEVEL", "WARNING"))
+
 __all__ = [
     "__version__", "GridIntegrator", "BaseIntegrator", "IntegrationGrid", "MonteCarlo", "Trapezoid", "Simpson",
     "Boole", "NewtonCotes", "VEGAS", "VEGASMap", "VEGASStratification", "RNG", "enable_cuda", "set_precision",
