@@ -115,7 +115,7 @@ def test_map_forward_accumulate_update_sequence(cuda, golden, tag):
         ops.map_update(gxe, gdxe, gw, gc, 0.5, status)
         assert status.tolist() == [0, 0, 0, 0]
         want_xe, want_dxe = torch.from_numpy(g[f"xe{it}"]), torch.from_numpy(g[f"dxe{it}"])
-        assert float((gxe.cpu() - want_xe).abs().max()) <= (1e-14 if tag == "f64" else 2e-7)
+        assert float((gxe.cpu() - want_xe).abs().max()) <= (1e-14 if tag == "f64" else 1e-6)  # reference rebins with an fp32 cumsum
         assert rel_err(gdxe, want_dxe) <= (1e-11 if tag == "f64" else 5e-4)
         assert torch.equal(gxe[:, [0, -1]].cpu(), want_xe[:, [0, -1]])  # outer edges exactly 0 and 1
         assert int(gc.abs().sum()) == 0 and float(gw.abs().sum()) == 0.0  # reset
