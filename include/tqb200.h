@@ -198,6 +198,12 @@ TQ_API int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int6
                    void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
                    size_t ws_bytes, void* stream);
 
+/* Get (and, when bytes > 0, set) the device's L2 fetch granularity hint (cudaLimitMaxL2FetchGranularity:
+ * 32, 64 or 128).  The VEGAS kernels gather map edges and update histogram bins at random positions of
+ * tables that exceed L2 when the reference's map size formula is used (Ni = N/250 per dimension); with
+ * the default 128-byte granularity every 8/16-byte access moves 128 bytes of HBM. */
+TQ_API int tq_l2_fetch_granularity(int32_t bytes, int32_t* previous_host);
+
 /* Peak-rate microbenchmarks used by bench.py for the fused-path roofline denominators:
  * kind 0 = dependent-free FP32 FMA chains, 1 = FP64 FMA chains, 2 = Philox4x32-10 blocks.
  * Performs iters*threads*ops_per_iter operations; returns ops per launch through ops_out_host. */

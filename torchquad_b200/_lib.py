@@ -61,6 +61,7 @@ PROTOTYPES = {
     "tq_fused_nc": (ctypes.c_int, [_P_INTEGRAND, c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_p, c_p, c_sz, c_p]),
     "tq_fused_vegas": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_p, c_i64, c_i32, c_i64, c_i64, c_p, c_p, c_i64, c_p, c_p,
                                       c_p, c_p, c_u64, c_u32, c_p, c_p, c_sz, c_p]),
+    "tq_l2_fetch_granularity": (ctypes.c_int, [c_i32, ctypes.POINTER(c_i32)]),
     "tq_peak_microbench": (ctypes.c_int, [c_i32, c_i64, c_p, ctypes.POINTER(c_f64), c_p]),
 }
 
@@ -143,6 +144,14 @@ def call(name, *args):
         raise RuntimeError(f"{name} failed ({rc}): {lib.tq_last_error().decode()}")
     launch_count += 1
     return rc
+
+
+def l2_fetch_granularity(device, nbytes=0):
+    """Return the current L2 fetch granularity hint of `device`; set it first when nbytes > 0."""
+    prev = c_i32()
+    with torch.cuda.device(device):
+        call("tq_l2_fetch_granularity", nbytes, ctypes.byref(prev))
+    return prev.value
 
 
 def device_info():

@@ -4,19 +4,20 @@
 
 namespace tq {
 
-// One thread per (row, Philox block): thread i of the flat index space writes the LANES consecutive
-// elements out[row*dim + blk*LANES ...], so a warp always covers one contiguous span of the row-major
-// output (128-bit stores when dim % LANES == 0, narrower ones otherwise).
-// The (row, blk) split of the flat index uses one 64-bit division per CTA tile and a 24-bit
-// multiply-shift per item (exact for item offsets < 2^16 and nblk <= 32).
+// One thread per (row, Philox block) item.  A CTA produces a tile of `tile_rows` complete rows in shared
+// memory (item i of the tile covers elements [q*dim + blk*LANES, +LANES) of the tile, q = i / nblk) and then
+// streams the tile to HBM with 128-bit stores, so every store instruction of a warp covers 512 contiguous
+// bytes whatever `dim` is.  Instruction issue (INT32 Philox rounds) is within ~1.3x of the HBM write time,
+// so index arithmetic is kept 32-bit: the (q, blk) split is a 24-bit multiply-shift (exact for i < 2^16).
 template <typename T, bool AFFINE>
 __global__ void __launch_bounds__(256)
 uniform_kernel(T* __restrict__ out, const T* __restrict__ domain, int64_t row_begin, int64_t nrows,
-               int dim, int nblk, uint32_t magic, uint64_t seed, uint32_t call) {
+               int dim, int nblk, uint32_t magic, uint64_t seed, uint32_t call, int tile_rows) {
     constexpr int LANES = U01<T>::LANES;
-    constexpr int ITEMS = 4;
-    constexpr int TILE = 256 * ITEMS;
-    __shared__ T s_start[TQ_MAX_DIM], s_size[TQ_MAX_DIM];
+    constexpr int V = 16 / sizeof(T);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* tile = reinterpret_cast<T*>(smem_raw);
+    __shared__ T s_start[TQ_MAX_DIM * 4], s_size[TQ_MAX_DIM * 4];
     if (AFFINE) {
         if (threadIdx.x < dim) {
             T a = domain[2 * threadIdx.x], b = domain[2 * threadIdx.x + 1];
@@ -25,43 +26,51 @@ uniform_kernel(T* __restrict__ out, const T* __restrict__ domain, int64_t row_be
         }
         __syncthreads();
     }
-    const int64_t total = nrows * nblk;
-    const bool vec_ok = (dim % LANES == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    for (int64_t base = (int64_t)blockIdx.x * TILE; base < total; base += (int64_t)gridDim.x * TILE) {
-        const int64_t row0 = base / nblk;
-        const uint32_t rem0 = (uint32_t)(base - row0 * nblk);
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const uint32_t l = threadIdx.x + k * 256;
-            if (base + l >= total) break;
-            const uint32_t ll = rem0 + l;
-            const uint32_t q = (uint32_t)(((uint64_t)ll * magic) >> 24);
-            const uint32_t blk = ll - q * nblk;
-            const int64_t r = row0 + q;  // local row
-            const uint64_t grow = (uint64_t)(row_begin + r);
+    const bool lanes_aligned = (dim % LANES) == 0;
+    const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const int64_t ntiles = (nrows + tile_rows - 1) / tile_rows;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t r0 = t * tile_rows;
+        const int rows_here = (int)(nrows - r0 < tile_rows ? nrows - r0 : tile_rows);
+        const uint32_t items = (uint32_t)rows_here * (uint32_t)nblk;
+        const uint64_t grow0 = (uint64_t)(row_begin + r0);
+        for (uint32_t i = threadIdx.x; i < items; i += 256) {
+            const uint32_t q = (uint32_t)(((uint64_t)i * magic) >> 24);
+            const uint32_t blk = i - q * nblk;
+            const uint64_t grow = grow0 + q;
             T u[LANES];
             philox_block<T>(seed, call, (uint32_t)grow, (uint32_t)(grow >> 32), blk, u);
             const int d0 = blk * LANES;
             if (AFFINE) {
 #pragma unroll
                 for (int j = 0; j < LANES; ++j) {
-                    int d = d0 + j;
-                    if (d < dim) u[j] = add_rn(mul_rn(u[j], s_size[d]), s_start[d]);
+                    const int d = d0 + j;
+                    if (lanes_aligned || d < dim) u[j] = add_rn(mul_rn(u[j], s_size[d]), s_start[d]);
                 }
             }
-            T* p = out + r * dim + d0;
-            if (vec_ok) {
-                if constexpr (LANES == 4) {
-                    *reinterpret_cast<float4*>(p) = make_float4(u[0], u[1], u[2], u[3]);
-                } else {
-                    *reinterpret_cast<double2*>(p) = make_double2(u[0], u[1]);
-                }
+            T* p = tile + q * dim + d0;
+            if (lanes_aligned) {
+                if constexpr (LANES == 4) *reinterpret_cast<float4*>(p) = make_float4(u[0], u[1], u[2], u[3]);
+                else *reinterpret_cast<double2*>(p) = make_double2(u[0], u[1]);
             } else {
 #pragma unroll
                 for (int j = 0; j < LANES; ++j)
                     if (d0 + j < dim) p[j] = u[j];
             }
         }
+        __syncthreads();
+        const uint32_t n_el = (uint32_t)rows_here * (uint32_t)dim;
+        T* g = out + r0 * dim;
+        if (out_aligned && ((r0 * dim) % V) == 0) {
+            const uint32_t nvec = n_el / V;
+            const uint4* src = reinterpret_cast<const uint4*>(tile);
+            uint4* dst = reinterpret_cast<uint4*>(g);
+            for (uint32_t i = threadIdx.x; i < nvec; i += 256) __stcs(dst + i, src[i]);
+            for (uint32_t i = nvec * V + threadIdx.x; i < n_el; i += 256) g[i] = tile[i];
+        } else {
+            for (uint32_t i = threadIdx.x; i < n_el; i += 256) g[i] = tile[i];
+        }
+        __syncthreads();
     }
 }
 
@@ -72,12 +81,23 @@ static int launch_uniform(T* out, const T* domain, int64_t row_begin, int64_t ro
     if (nrows <= 0) return TQ_OK;
     const int nblk = (dim + U01<T>::LANES - 1) / U01<T>::LANES;
     const uint32_t magic = (uint32_t)((1u << 24) / (uint32_t)nblk) + 1u;
-    const int64_t items = nrows * nblk;
-    const int grid = grid_for((items + 3) / 4, 256, 8);
-    if (domain)
-        uniform_kernel<T, true><<<grid, 256, 0, st>>>(out, domain, row_begin, nrows, dim, nblk, magic, seed, call);
-    else
-        uniform_kernel<T, false><<<grid, 256, 0, st>>>(out, nullptr, row_begin, nrows, dim, nblk, magic, seed, call);
+    // tile: <= 32 KB of shared memory, a multiple of 4 rows (keeps 16-byte alignment of every tile), < 2^16 items
+    int tile_rows = (int)((32 * 1024) / ((size_t)dim * sizeof(T)));
+    if (tile_rows * nblk > 65532) tile_rows = 65532 / nblk;
+    tile_rows &= ~3;
+    if (tile_rows < 4) tile_rows = 4;
+    if (tile_rows > nrows) tile_rows = (int)((nrows + 3) & ~(int64_t)3);
+    const size_t smem = (size_t)tile_rows * dim * sizeof(T);
+    const int64_t ntiles = (nrows + tile_rows - 1) / tile_rows;
+    const int64_t cap = (int64_t)num_sms() * 6;
+    const int grid = (int)(ntiles < cap ? ntiles : cap);
+    if (domain) {
+        cudaFuncSetAttribute(uniform_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        uniform_kernel<T, true><<<grid, 256, smem, st>>>(out, domain, row_begin, nrows, dim, nblk, magic, seed, call, tile_rows);
+    } else {
+        cudaFuncSetAttribute(uniform_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        uniform_kernel<T, false><<<grid, 256, smem, st>>>(out, nullptr, row_begin, nrows, dim, nblk, magic, seed, call, tile_rows);
+    }
     return check_launch("uniform_kernel");
 }
 

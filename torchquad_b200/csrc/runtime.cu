@@ -82,6 +82,18 @@ int tq_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     return TQ_OK;
 }
 
+int tq_l2_fetch_granularity(int32_t bytes, int32_t* previous_host) {
+    size_t prev = 0;
+    cudaError_t e = cudaDeviceGetLimit(&prev, cudaLimitMaxL2FetchGranularity);
+    if (e != cudaSuccess) { tq::set_error("cudaDeviceGetLimit: %s", cudaGetErrorString(e)); return (int)e; }
+    if (previous_host) *previous_host = (int32_t)prev;
+    if (bytes > 0) {
+        e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes);
+        if (e != cudaSuccess) { tq::set_error("cudaDeviceSetLimit: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    return TQ_OK;
+}
+
 int tq_peak_microbench(int32_t kind, int64_t iters, double* sink, double* ops_out_host, void* stream) {
     const int block = 256;
     const int grid = tq::num_sms() * 8;

@@ -379,13 +379,14 @@ int tq_vegas_map_accumulate(const void* y, const void* jf2, void* weights, int64
     const size_t elt = dtype == TQ_F64 ? 8 : 4;
     const int64_t bins = (int64_t)dim * n_intervals;
     const size_t smem = (size_t)bins * (elt + 4);
-    // Privatise in shared memory only when every CTA amortises zero+flush of the whole histogram.
-    int64_t ctas = (rows * dim) / (8 * bins);
-    if (ctas > num_sms()) ctas = num_sms();
-    if (smem <= 200 * 1024 && ctas >= 1) {
+    // Privatise in shared memory only for small maps (<= 4096 bins: same-address contention would serialise
+    // the L2 atomics) and when every CTA amortises zero+flush; larger maps stay L2-resident (see fused.cu).
+    int64_t ctas = (rows * dim) / (16 * bins);
+    if (ctas > (int64_t)num_sms() * 4) ctas = (int64_t)num_sms() * 4;
+    if (bins <= 4096 && ctas >= 1) {
         const int64_t rows_per_cta = (rows + ctas - 1) / ctas;
         TQ_DISPATCH_DTYPE(dtype, {
-            cudaFuncSetAttribute(map_accumulate_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(map_accumulate_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
             map_accumulate_smem_kernel<T><<<(int)ctas, 512, smem, st>>>((const T*)y, (const T*)jf2, (T*)weights,
                                                                        (unsigned long long*)counts, rows, dim,
                                                                        n_intervals, rows_per_cta);

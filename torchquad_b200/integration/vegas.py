@@ -16,6 +16,7 @@ sample set and all-reduce [weights | counts | JF | JF2] once per iteration.
 import numpy as np
 import torch
 
+from .. import _lib
 from .. import distributed as tqdist
 from .. import ops
 from ..integrands import BuiltinIntegrand
@@ -28,7 +29,20 @@ from .vegas_stratification import VEGASStratification
 
 
 class VEGAS(BaseIntegrator):
-    """VEGAS Enhanced, arXiv:2009.05112.  Same surface as the reference class."""
+    """VEGAS Enhanced, arXiv:2009.05112.  Same surface as the reference class.
+
+    Extension attributes (defaults reproduce the reference):
+      max_map_intervals  cap on the map size per dimension.  The reference uses Ni = (N // (max_it + 5)) // 10
+                         (vegas.py:117), i.e. 1e7 .. 4e7 bins per dimension for N = 2.5e9 .. 1e10: tables far
+                         larger than L2 that turn every bin lookup and histogram update into a random HBM
+                         access (and collapse numerically in fp32).  None keeps the formula.
+      l2_fetch_bytes     L2 fetch granularity hint used while a large map is in flight (None: leave as is;
+                         measured on B200: 32 vs the default 64 makes no difference, profiles/README.md).
+    """
+
+    max_map_intervals = None
+    l2_fetch_bytes = None
+    _large_map_bytes = 64 << 20
 
     def __init__(self):
         super().__init__()
@@ -75,6 +89,8 @@ class VEGAS(BaseIntegrator):
                                            float(self._volume.item()))
 
         N_intervals = max(2, self._N_increment // 10)  # vegas.py:117
+        if self.max_map_intervals is not None:
+            N_intervals = max(2, min(N_intervals, int(self.max_map_intervals)))
         self.map = VEGASMap(N_intervals, dim, "torch", self.dtype, device=self.device)
         self.strat = VEGASStratification(self._N_increment, dim=dim, rng=self.rng, backend="torch", dtype=self.dtype,
                                          device=self.device)
@@ -84,16 +100,24 @@ class VEGAS(BaseIntegrator):
         self._host_block = None
         self._map_status = []
 
-        if use_warmup:
-            self._warmup_grid(5, self._starting_N // 5)
-
-        while True:
-            self.it += 1
-            self.results.append(0)
-            self.sigma2.append(0)
-            self._run_iteration()
-            if self._check_abort_conditions():
-                break
+        # random-access regime: shrink the L2 fetch granularity while the big tables are in flight
+        restore_l2 = None
+        if (self.l2_fetch_bytes and self.device.type == "cuda"
+                and dim * N_intervals * (2 * domain.element_size() + 8) > self._large_map_bytes):
+            restore_l2 = _lib.l2_fetch_granularity(self.device, int(self.l2_fetch_bytes))
+        try:
+            if use_warmup:
+                self._warmup_grid(5, self._starting_N // 5)
+            while True:
+                self.it += 1
+                self.results.append(0)
+                self.sigma2.append(0)
+                self._run_iteration()
+                if self._check_abort_conditions():
+                    break
+        finally:
+            if restore_l2:
+                _lib.l2_fetch_granularity(self.device, restore_l2)
         self._flush_map_status()
         logger.debug("VEGAS finished")
         return self._get_result()
