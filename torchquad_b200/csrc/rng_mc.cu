@@ -4,73 +4,84 @@
 
 namespace tq {
 
-// One thread per (row, Philox block) item.  A CTA produces a tile of `tile_rows` complete rows in shared
-// memory (item i of the tile covers elements [q*dim + blk*LANES, +LANES) of the tile, q = i / nblk) and then
-// streams the tile to HBM with 128-bit stores, so every store instruction of a warp covers 512 contiguous
-// bytes whatever `dim` is.  Instruction issue (INT32 Philox rounds) is within ~1.3x of the HBM write time,
-// so index arithmetic is kept 32-bit: the (q, blk) split is a 24-bit multiply-shift (exact for i < 2^16).
+// One thread per (row, Philox block) item, with the block index FIXED per thread: thread t of a CTA owns
+// Philox block `t % nblk` of rows `t / nblk + k*rows_per_pass`, so everything that depends on the column
+// (domain start/size, number of valid lanes, store width) is loop-invariant and lives in registers, the row
+// advances by a constant stride, and the threads of a warp still write one contiguous span of the row-major
+// output.  Why this shape: on B200 the kernel is bound by instruction issue, not by HBM -- IMAD.WIDE (2 per
+// Philox round) is quarter rate, which caps the chip at ~4.8e11 Philox blocks/s = 7.6 TB/s of uniforms
+// (tq_peak_microbench kind 2), so every ALU-pipe instruction spent on indexing or predicates costs bandwidth.
+// Conversion: u = m * 2^-24 (m < 2^24, exact) and x = u*size + start; the exact power-of-two scale is folded
+// into `size` on the host side of the loop (RN(m*2^-24*size) is unchanged), keeping bit parity with
+// mul-then-add of the reference (monte_carlo.py:106).
+template <typename T> struct RawBits;
+template <> struct RawBits<float> {
+    __device__ __forceinline__ static void get(const uint4& r, float* m) {
+        m[0] = __uint2float_rn(r.x >> 8); m[1] = __uint2float_rn(r.y >> 8);
+        m[2] = __uint2float_rn(r.z >> 8); m[3] = __uint2float_rn(r.w >> 8);
+    }
+    static constexpr float SCALE = 5.9604644775390625e-08f;  // 2^-24
+};
+template <> struct RawBits<double> {
+    __device__ __forceinline__ static void get(const uint4& r, double* m) {
+        m[0] = __ull2double_rn((((unsigned long long)r.y << 32) | r.x) >> 11);
+        m[1] = __ull2double_rn((((unsigned long long)r.w << 32) | r.z) >> 11);
+    }
+    static constexpr double SCALE = 1.1102230246251565e-16;  // 2^-53
+};
+
 template <typename T, bool AFFINE>
 __global__ void __launch_bounds__(256)
 uniform_kernel(T* __restrict__ out, const T* __restrict__ domain, int64_t row_begin, int64_t nrows,
-               int dim, int nblk, uint32_t magic, uint64_t seed, uint32_t call, int tile_rows) {
+               int dim, int nblk, uint64_t seed, uint32_t call) {
     constexpr int LANES = U01<T>::LANES;
-    constexpr int V = 16 / sizeof(T);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* tile = reinterpret_cast<T*>(smem_raw);
-    __shared__ T s_start[TQ_MAX_DIM * 4], s_size[TQ_MAX_DIM * 4];
-    if (AFFINE) {
-        if (threadIdx.x < dim) {
-            T a = domain[2 * threadIdx.x], b = domain[2 * threadIdx.x + 1];
-            s_start[threadIdx.x] = a;
-            s_size[threadIdx.x] = sub_rn(b, a);
+    const int rows_per_pass = 256 / nblk;
+    const int rloc = threadIdx.x / nblk;
+    const int blk = threadIdx.x - rloc * nblk;
+    if (rloc >= rows_per_pass) return;  // idle tail threads when 256 % nblk != 0 (no barriers below)
+    const int d0 = blk * LANES;
+    const int nvalid = dim - d0 < LANES ? dim - d0 : LANES;
+    T sz[LANES], st[LANES];
+#pragma unroll
+    for (int j = 0; j < LANES; ++j) {
+        sz[j] = RawBits<T>::SCALE;
+        st[j] = (T)0;
+        if (AFFINE && j < nvalid) {
+            const T a = domain[2 * (d0 + j)], b = domain[2 * (d0 + j) + 1];
+            sz[j] = mul_rn(sub_rn(b, a), RawBits<T>::SCALE);  // exact: power-of-two scaling
+            st[j] = a;
         }
-        __syncthreads();
     }
-    const bool lanes_aligned = (dim % LANES) == 0;
-    const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    const int64_t ntiles = (nrows + tile_rows - 1) / tile_rows;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t r0 = t * tile_rows;
-        const int rows_here = (int)(nrows - r0 < tile_rows ? nrows - r0 : tile_rows);
-        const uint32_t items = (uint32_t)rows_here * (uint32_t)nblk;
-        const uint64_t grow0 = (uint64_t)(row_begin + r0);
-        for (uint32_t i = threadIdx.x; i < items; i += 256) {
-            const uint32_t q = (uint32_t)(((uint64_t)i * magic) >> 24);
-            const uint32_t blk = i - q * nblk;
-            const uint64_t grow = grow0 + q;
-            T u[LANES];
-            philox_block<T>(seed, call, (uint32_t)grow, (uint32_t)(grow >> 32), blk, u);
-            const int d0 = blk * LANES;
-            if (AFFINE) {
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const int64_t stride = (int64_t)gridDim.x * rows_per_pass;
+    int64_t row = (int64_t)blockIdx.x * rows_per_pass + rloc;
+    T* p = out + row * dim + d0;
+    const int64_t pstride = stride * dim;
+    // store width: 16 B when the column block is complete and every row start is 16-byte aligned, else 8 B
+    // pairs when rows start 8-byte aligned, else scalars (decided once per thread)
+    const bool base16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const int mode = (nvalid == LANES && base16 && (dim % LANES) == 0) ? 2
+                   : (sizeof(T) == 4 && base16 && (dim % 2) == 0 && (nvalid % 2) == 0) ? 1 : 0;
+    for (; row < nrows; row += stride, p += pstride) {
+        const uint64_t grow = (uint64_t)(row_begin + row);
+        const uint4 r = Philox::run((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)blk, call, k0, k1);
+        T v[LANES];
+        RawBits<T>::get(r, v);
 #pragma unroll
-                for (int j = 0; j < LANES; ++j) {
-                    const int d = d0 + j;
-                    if (lanes_aligned || d < dim) u[j] = add_rn(mul_rn(u[j], s_size[d]), s_start[d]);
-                }
+        for (int j = 0; j < LANES; ++j) v[j] = AFFINE ? add_rn(mul_rn(v[j], sz[j]), st[j]) : mul_rn(v[j], sz[j]);
+        if (mode == 2) {
+            if constexpr (LANES == 4) __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+            else __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1]));
+        } else if (mode == 1) {
+            if constexpr (LANES == 4) {
+                __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+                if (nvalid == 4) __stcs(reinterpret_cast<float2*>(p) + 1, make_float2(v[2], v[3]));
             }
-            T* p = tile + q * dim + d0;
-            if (lanes_aligned) {
-                if constexpr (LANES == 4) *reinterpret_cast<float4*>(p) = make_float4(u[0], u[1], u[2], u[3]);
-                else *reinterpret_cast<double2*>(p) = make_double2(u[0], u[1]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < LANES; ++j)
-                    if (d0 + j < dim) p[j] = u[j];
-            }
-        }
-        __syncthreads();
-        const uint32_t n_el = (uint32_t)rows_here * (uint32_t)dim;
-        T* g = out + r0 * dim;
-        if (out_aligned && ((r0 * dim) % V) == 0) {
-            const uint32_t nvec = n_el / V;
-            const uint4* src = reinterpret_cast<const uint4*>(tile);
-            uint4* dst = reinterpret_cast<uint4*>(g);
-            for (uint32_t i = threadIdx.x; i < nvec; i += 256) __stcs(dst + i, src[i]);
-            for (uint32_t i = nvec * V + threadIdx.x; i < n_el; i += 256) g[i] = tile[i];
         } else {
-            for (uint32_t i = threadIdx.x; i < n_el; i += 256) g[i] = tile[i];
+#pragma unroll
+            for (int j = 0; j < LANES; ++j)
+                if (j < nvalid) p[j] = v[j];
         }
-        __syncthreads();
     }
 }
 
@@ -80,24 +91,14 @@ static int launch_uniform(T* out, const T* domain, int64_t row_begin, int64_t ro
     const int64_t nrows = row_end - row_begin;
     if (nrows <= 0) return TQ_OK;
     const int nblk = (dim + U01<T>::LANES - 1) / U01<T>::LANES;
-    const uint32_t magic = (uint32_t)((1u << 24) / (uint32_t)nblk) + 1u;
-    // tile: <= 32 KB of shared memory, a multiple of 4 rows (keeps 16-byte alignment of every tile), < 2^16 items
-    int tile_rows = (int)((32 * 1024) / ((size_t)dim * sizeof(T)));
-    if (tile_rows * nblk > 65532) tile_rows = 65532 / nblk;
-    tile_rows &= ~3;
-    if (tile_rows < 4) tile_rows = 4;
-    if (tile_rows > nrows) tile_rows = (int)((nrows + 3) & ~(int64_t)3);
-    const size_t smem = (size_t)tile_rows * dim * sizeof(T);
-    const int64_t ntiles = (nrows + tile_rows - 1) / tile_rows;
-    const int64_t cap = (int64_t)num_sms() * 6;
-    const int grid = (int)(ntiles < cap ? ntiles : cap);
-    if (domain) {
-        cudaFuncSetAttribute(uniform_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        uniform_kernel<T, true><<<grid, 256, smem, st>>>(out, domain, row_begin, nrows, dim, nblk, magic, seed, call, tile_rows);
-    } else {
-        cudaFuncSetAttribute(uniform_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        uniform_kernel<T, false><<<grid, 256, smem, st>>>(out, nullptr, row_begin, nrows, dim, nblk, magic, seed, call, tile_rows);
-    }
+    const int rows_per_pass = 256 / nblk;
+    const int64_t passes = (nrows + rows_per_pass - 1) / rows_per_pass;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    const int grid = (int)(passes < cap ? passes : cap);
+    if (domain)
+        uniform_kernel<T, true><<<grid, 256, 0, st>>>(out, domain, row_begin, nrows, dim, nblk, seed, call);
+    else
+        uniform_kernel<T, false><<<grid, 256, 0, st>>>(out, nullptr, row_begin, nrows, dim, nblk, seed, call);
     return check_launch("uniform_kernel");
 }
 
