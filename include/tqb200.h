@@ -186,15 +186,20 @@ TQ_API int tq_fused_mc(const tq_integrand* fn_host, int32_t dtype, int64_t row_b
 /* Newton-Cotes: out_f64[0] = sum_p f(nodes[., i(p)]) * prod_d w[d, i_d(p)]. */
 TQ_API int tq_fused_nc(const tq_integrand* fn_host, const void* nodes, const void* w, int32_t n, int32_t dtype,
                 int64_t p_begin, int64_t p_end, double* out_f64, void* ws, size_t ws_bytes, void* stream);
+/* {x_edges[d,k], dx_edges[d,k]} interleaved as pairs [dim, Ni] (float2 / double2): the layout the fused
+ * kernel gathers from, one 8/16-byte load per dimension instead of two. */
+TQ_API int tq_vegas_map_pack_edges(const void* x_edges, const void* dx_edges, void* edges_packed, int32_t dim,
+                            int64_t n_intervals, int32_t dtype, void* stream);
 /* One VEGAS pass without writing samples: generate -> map -> evaluate -> accumulate.
  *   stratified (offsets != NULL): rows [row_begin,row_end) of the cube-sorted order (vegas.py:268-291);
  *     JF/JF2 (pre-zeroed by the caller) receive the per-cube sums.
  *   warm-up (offsets == NULL): rows are plain samples y = u*0.999999 (vegas.py:236); out_f64 receives
  *     {sum jf, sum jf^2}.
+ *   edges_packed: see tq_vegas_map_pack_edges.
  *   weights/counts (map histogram, vegas_map.py:99-111) are accumulated unless weights == NULL. */
 TQ_API int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
-                   int32_t n_strat, int64_t row_begin, int64_t row_end, const void* x_edges,
-                   const void* dx_edges, int64_t n_intervals, void* weights, int64_t* counts, void* JF,
+                   int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_packed,
+                   int64_t n_intervals, void* weights, int64_t* counts, void* JF,
                    void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
                    size_t ws_bytes, void* stream);
 

@@ -34,3 +34,13 @@ elif what == "mc_sample":
     for _ in range(3):
         p = ops.mc_sample(dom, 10**8, 1, 0, 0)
     torch.cuda.synchronize()
+elif what == "vegas8cap":
+    dom = torch.tensor([[0.0, 1.0]] * 8, dtype=torch.float64, device=dev)
+    v = tq.VEGAS(); v.max_map_intervals = 4096
+    r = v.integrate(F.GenzOscillatory(8, a=0.5, u=0.3), 8, N=2_500_000_000, integration_domain=dom, seed=1)
+    print(float(r))
+elif what == "vegas16cap":
+    dom = torch.tensor([[0.0, 1.0]] * 16, dtype=torch.float32, device=dev)
+    v = tq.VEGAS(); v.max_map_intervals = 4096
+    r = v.integrate(F.GenzProductPeak(16, a=2.0, u=0.5), 16, N=10**10, integration_domain=dom, seed=1)
+    print(float(r), v._nr_of_fevals)

@@ -59,7 +59,8 @@ PROTOTYPES = {
     "tq_nc_point_weights": (ctypes.c_int, [c_p, c_i32, c_i32, c_i64, c_i64, c_p, c_i32, c_p]),
     "tq_fused_mc": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_i64, c_i64, c_u64, c_u32, c_p, c_p, c_sz, c_p]),
     "tq_fused_nc": (ctypes.c_int, [_P_INTEGRAND, c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_p, c_p, c_sz, c_p]),
-    "tq_fused_vegas": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_p, c_i64, c_i32, c_i64, c_i64, c_p, c_p, c_i64, c_p, c_p,
+    "tq_vegas_map_pack_edges": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
+    "tq_fused_vegas": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_p, c_i64, c_i32, c_i64, c_i64, c_p, c_i64, c_p, c_p,
                                       c_p, c_p, c_u64, c_u32, c_p, c_p, c_sz, c_p]),
     "tq_l2_fetch_granularity": (ctypes.c_int, [c_i32, ctypes.POINTER(c_i32)]),
     "tq_peak_microbench": (ctypes.c_int, [c_i32, c_i64, c_p, ctypes.POINTER(c_f64), c_p]),

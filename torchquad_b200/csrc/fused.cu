@@ -171,28 +171,49 @@ fused_nc_kernel(const tq_integrand P, const T* __restrict__ nodes, const T* __re
 
 // ------------------------------------------------------------------ fused VEGAS pass
 // One thread per sample row.  Each CTA owns a contiguous chunk of the (cube-sorted) rows and walks it in
-// tiles of FV_BLOCK rows: the slice of `offsets` a tile needs (<= FV_BLOCK/2+2 entries because nh >= 2) is
-// staged in shared memory, so the row -> cube lookup is a short shared-memory binary search; only the first
-// tile of a chunk pays a global binary search.  Bin ids of the row are parked in shared memory until jf is
-// known, then the f^2 histogram is updated (shared-memory privatised when the whole map fits, L2
-// reductions otherwise); per-cube sums go through shared accumulators and one global add per cube and tile.
+// tiles of FV_BLOCK rows.  Per tile, one thread per overlapped cube (<= FV_BLOCK/2 + 2 because nh >= 2) reads
+// its two offsets and writes its slice index into s_cube[row] for the rows it owns, so the row -> cube lookup
+// is one shared-memory byte; only the first tile of a chunk pays a global binary search, later tiles start
+// from the previous tile's last cube.  Shared buffers are double-buffered: one barrier per tile.
+// Bin ids of a row are parked in shared memory until jf is known, then the f^2 histogram is updated
+// (L2 reductions; shared-memory privatised only for tiny maps).  Per-cube sums: rows of a cube are
+// consecutive lanes, so a key-segmented warp shuffle reduction leaves one partial per (cube, warp), added to
+// JF/JF2 with one L2 reduction each -- no shared-memory atomics.
+// Map edges arrive packed as {x_edge[k], dx_edge[k]} pairs: one 8/16-byte gather per dimension.
 constexpr int FV_BLOCK = 256;
-constexpr int FV_SLICE = FV_BLOCK / 2 + 4;  // +1 cube of slack: the walk may start one cube early
+constexpr int FV_SLICE = FV_BLOCK / 2 + 4;
+
+template <typename T> struct Pair2;
+template <> struct Pair2<float> { using type = float2; };
+template <> struct Pair2<double> { using type = double2; };
+
+template <typename T>
+__device__ __forceinline__ void segmented_warp_sum2(unsigned key, T& a, T& b) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned k2 = __shfl_down_sync(0xffffffffu, key, off);
+        const T a2 = __shfl_down_sync(0xffffffffu, a, off);
+        const T b2 = __shfl_down_sync(0xffffffffu, b, off);
+        if (lane + off < 32 && k2 == key) { a += a2; b += b2; }
+    }
+}
 
 template <int FAM, typename T, bool STRAT>
 __global__ void __launch_bounds__(FV_BLOCK)
 fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, int64_t n_cubes, int n_strat,
-                   int64_t row_begin, int64_t row_end, int64_t rows_per_cta, const T* __restrict__ xe,
-                   const T* __restrict__ dxe, long long ni, T* __restrict__ weights,
+                   int64_t row_begin, int64_t row_end, int64_t rows_per_cta,
+                   const typename Pair2<T>::type* __restrict__ edges, long long ni, T* __restrict__ weights,
                    unsigned long long* __restrict__ counts, T* __restrict__ JF, T* __restrict__ JF2, uint64_t seed,
                    uint32_t call, bool hist_smem, double* partials, unsigned int* ticket, double* out) {
     constexpr int LANES = U01<T>::LANES;
+    using P2 = typename Pair2<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ FnShared<T> S;
     __shared__ double sh[32 * 2];
-    __shared__ long long s_off[FV_SLICE];
-    __shared__ T s_jf[FV_SLICE], s_jf2[FV_SLICE];
-    __shared__ long long s_cube_cur;
+    __shared__ long long s_off[2][FV_SLICE];
+    __shared__ unsigned char s_cube[2][FV_BLOCK];
+    __shared__ long long s_first_cube;
     stage_integrand<T>(P, S);
     const int dim = S.dim;
     int* s_ids = reinterpret_cast<int*>(smem_raw);                        // [dim][FV_BLOCK]
@@ -211,41 +232,38 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
                 const long long mid = (lo + hi + 1) >> 1;
                 if (__ldg(&offsets[mid]) <= r_lo) lo = mid; else hi = mid - 1;
             }
-            s_cube_cur = lo;
+            s_first_cube = lo;
         }
     }
     __syncthreads();
+    long long c_lo = STRAT && r_lo < r_hi ? s_first_cube : 0;
     const T nif = (T)ni;
     const T nsf = (T)n_strat;
     double acc[2] = {0.0, 0.0};
-    for (int64_t rb = r_lo; rb < r_hi; rb += FV_BLOCK) {
+    int buf = 0;
+    for (int64_t rb = r_lo; rb < r_hi; rb += FV_BLOCK, buf ^= 1) {
+        const int64_t re = rb + FV_BLOCK < r_hi ? rb + FV_BLOCK : r_hi;
         const int64_t row = rb + threadIdx.x;
-        const bool active = row < r_hi;
-        long long c_lo = 0;
-        int ci = 0;
+        const bool active = row < re;
         if (STRAT) {
-            c_lo = s_cube_cur;
-            for (int i = threadIdx.x; i < FV_SLICE; i += blockDim.x) {
-                const long long c = c_lo + i;
-                s_off[i] = __ldg(&offsets[c <= n_cubes ? c : n_cubes]);
-                s_jf[i] = (T)0;
-                s_jf2[i] = (T)0;
+            if (threadIdx.x < FV_SLICE) {
+                const long long c = c_lo + threadIdx.x;
+                const long long lo = __ldg(&offsets[c < n_cubes ? c : n_cubes]);
+                const long long hi = __ldg(&offsets[c + 1 < n_cubes ? c + 1 : n_cubes]);
+                s_off[buf][threadIdx.x] = lo;
+                const long long a = lo > rb ? lo : rb, b = hi < re ? hi : re;
+                for (long long r = a; r < b; ++r) s_cube[buf][r - rb] = (unsigned char)threadIdx.x;
             }
             __syncthreads();
-            if (active) {
-                int lo = 0, hi = FV_SLICE - 2;  // largest i with s_off[i] <= row (entries past the end repeat M)
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (s_off[mid] <= row) lo = mid; else hi = mid - 1;
-                }
-                ci = lo;
-            }
         }
+        T jf = (T)0, jf2 = (T)0;
+        unsigned key = 0xffffu;
         if (active) {
             uint32_t i0, i1, c = 0;
             if (STRAT) {
-                i0 = (uint32_t)(c_lo + ci);
-                i1 = (uint32_t)(row - s_off[ci]);
+                key = s_cube[buf][threadIdx.x];
+                i0 = (uint32_t)(c_lo + key);
+                i1 = (uint32_t)(row - s_off[buf][key]);
                 c = i0;
             } else {
                 i0 = (uint32_t)(uint64_t)row;
@@ -276,25 +294,17 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
                         long long k = (long long)fl;
                         k = k < 0 ? 0 : (k >= ni ? ni - 1 : k);
                         const T o = sub_rn(t, fl);
-                        const T dxv = __ldg(&dxe[(int64_t)d * ni + k]);
-                        const T xv = __ldg(&xe[(int64_t)d * (ni + 1) + k]);
-                        const T x = add_rn(xv, mul_rn(dxv, o));
-                        jac = mul_rn(jac, mul_rn(nif, dxv));
+                        const P2 e = __ldg(&edges[(int64_t)d * ni + k]);
+                        const T x = add_rn(e.x, mul_rn(e.y, o));
+                        jac = mul_rn(jac, mul_rn(nif, e.y));
                         s_ids[d * FV_BLOCK + threadIdx.x] = (int)k;
                         fn.step(add_rn(mul_rn(x, S.size[d]), S.start[d]), d, S);
                     }
                 }
             }
             const T f = mul_rn(fn.finish(S), S.scale);
-            const T jf = mul_rn(f, jac);
-            const T jf2 = mul_rn(jf, jf);
-            if (STRAT) {
-                atomicAdd(&s_jf[ci], jf);
-                atomicAdd(&s_jf2[ci], jf2);
-            } else {
-                acc[0] += (double)jf;
-                acc[1] += (double)jf2;
-            }
+            jf = mul_rn(f, jac);
+            jf2 = mul_rn(jf, jf);
             if (do_hist) {
                 if (hist_smem) {
                     for (int d = 0; d < dim; ++d) {
@@ -312,18 +322,17 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
             }
         }
         if (STRAT) {
-            __syncthreads();
-            // flush per-cube sums of this tile; cubes straddling tiles/CTAs accumulate through the atomics
-            const int64_t last_row = (rb + FV_BLOCK < r_hi ? rb + FV_BLOCK : r_hi) - 1;
-            for (int i = threadIdx.x; i < FV_SLICE - 1; i += blockDim.x) {
-                const long long c = c_lo + i;
-                if (c < n_cubes && s_off[i] <= last_row && s_off[i + 1] > rb) {
-                    atomicAdd(&JF[c], s_jf[i]);
-                    atomicAdd(&JF2[c], s_jf2[i]);
-                }
+            const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+            T a = jf, b = jf2;
+            segmented_warp_sum2<T>(key, a, b);
+            if (active && ((threadIdx.x & 31) == 0 || prev != key)) {
+                atomicAdd(&JF[c_lo + key], a);
+                atomicAdd(&JF2[c_lo + key], b);
             }
-            if (row == last_row) s_cube_cur = c_lo + ci;
-            __syncthreads();
+            c_lo += s_cube[buf][(int)(re - rb) - 1];  // cube of the tile's last row: where the next tile starts
+        } else {
+            acc[0] += (double)jf;
+            acc[1] += (double)jf2;
         }
     }
     if (do_hist && hist_smem) {
@@ -337,6 +346,21 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
         }
     }
     if (!STRAT) grid_sum_finish<2>(acc, sh, partials, ticket, out);
+}
+
+// {x_edges[d,k], dx_edges[d,k]} -> packed pairs [dim, Ni]
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_edges_kernel(const T* __restrict__ xe, const T* __restrict__ dxe, typename Pair2<T>::type* __restrict__ out,
+                  int dim, long long ni) {
+    const int64_t total = (int64_t)dim * ni;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = i / ni, k = i - d * ni;
+        typename Pair2<T>::type e;
+        e.x = xe[d * (ni + 1) + k];
+        e.y = dxe[i];
+        out[i] = e;
+    }
 }
 
 #define TQ_DISPATCH_FAMILY(fam, ...)                                                                  \
@@ -413,9 +437,20 @@ int tq_fused_nc(const tq_integrand* fn_host, const void* nodes, const void* w, i
     return check_launch("fused_nc_kernel");
 }
 
+int tq_vegas_map_pack_edges(const void* x_edges, const void* dx_edges, void* edges_packed, int32_t dim,
+                            int64_t n_intervals, int32_t dtype, void* stream) {
+    TQ_REQUIRE(dim >= 1 && n_intervals >= 1, "tq_vegas_map_pack_edges: bad shape");
+    const int grid = grid_for((int64_t)dim * n_intervals, 256, 8);
+    TQ_DISPATCH_DTYPE(dtype, {
+        pack_edges_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x_edges, (const T*)dx_edges,
+                                                                 (typename Pair2<T>::type*)edges_packed, dim, n_intervals);
+    });
+    return check_launch("pack_edges_kernel");
+}
+
 int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
-                   int32_t n_strat, int64_t row_begin, int64_t row_end, const void* x_edges,
-                   const void* dx_edges, int64_t n_intervals, void* weights, int64_t* counts, void* JF,
+                   int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_packed,
+                   int64_t n_intervals, void* weights, int64_t* counts, void* JF,
                    void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
                    size_t ws_bytes, void* stream) {
     int rc = check_integrand("tq_fused_vegas", fn_host);
@@ -462,13 +497,13 @@ int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* of
             if (strat) {
                 cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, true><<<(unsigned)ctas, FV_BLOCK, smem, st>>>(
-                    *fn_host, (const long long*)offsets, n_cubes, n_strat, row_begin, row_end, rows_per_cta, (const T*)x_edges,
-                    (const T*)dx_edges, n_intervals, (T*)weights, (unsigned long long*)counts, (T*)JF, (T*)JF2, seed, call_idx,
-                    hist_smem, partials, ticket, out_f64);
+                    *fn_host, (const long long*)offsets, n_cubes, n_strat, row_begin, row_end, rows_per_cta,
+                    (const typename Pair2<T>::type*)edges_packed, n_intervals, (T*)weights, (unsigned long long*)counts,
+                    (T*)JF, (T*)JF2, seed, call_idx, hist_smem, partials, ticket, out_f64);
             } else {
                 cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, false><<<(unsigned)ctas, FV_BLOCK, smem, st>>>(
-                    *fn_host, nullptr, 0, 1, row_begin, row_end, rows_per_cta, (const T*)x_edges, (const T*)dx_edges,
+                    *fn_host, nullptr, 0, 1, row_begin, row_end, rows_per_cta, (const typename Pair2<T>::type*)edges_packed,
                     n_intervals, (T*)weights, (unsigned long long*)counts, nullptr, nullptr, seed, call_idx, hist_smem,
                     partials, ticket, out_f64);
             }

@@ -148,7 +148,7 @@ class VEGAS(BaseIntegrator):
         for _ in range(warmup_N_it):
             begin, end = self._rank_rows(N_samples)
             if self._fused:
-                ops.fused_vegas(self._fn_struct, self.map.x_edges, self.map.dx_edges, self.map.weights, self.map.counts,
+                ops.fused_vegas(self._fn_struct, self.map.packed_edges(), self.map.weights, self.map.counts,
                                 begin, end, self.rng.seed, self.rng.next_call())
                 self._nr_of_fevals += N_samples
             else:
@@ -181,7 +181,7 @@ class VEGAS(BaseIntegrator):
         grad_path = False
         if self._fused:
             JFs = torch.zeros((2, strat.N_cubes), dtype=self.dtype, device=self.device)
-            ops.fused_vegas(self._fn_struct, vmap.x_edges, vmap.dx_edges,
+            ops.fused_vegas(self._fn_struct, vmap.packed_edges(),
                             vmap.weights if self.use_grid_improve else None, vmap.counts, begin, end, self.rng.seed,
                             self.rng.next_call(), offsets=offsets, n_strat=strat.N_strat, JF=JFs[0], JF2=JFs[1])
             self._nr_of_fevals += M

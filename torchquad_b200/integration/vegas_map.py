@@ -84,6 +84,11 @@ class VEGASMap:
         if check:
             self.check_status()
 
+    def packed_edges(self):
+        """{x_edges, dx_edges} interleaved [dim, Ni, 2] for the fused kernel (re-packed from the public tensors)."""
+        self._edges2 = ops.pack_edges(self.x_edges, self.dx_edges, getattr(self, "_edges2", None))
+        return self._edges2
+
     def check_status(self, status=None):
         """Raise / warn like vegas_map.py:188-196,240-257 from a status word (device read-back)."""
         st = (self._status if status is None else status)

@@ -395,15 +395,27 @@ def fused_nc(fn_struct, nodes, w, p_begin, p_end):
     return out
 
 
-def fused_vegas(fn_struct, x_edges, dx_edges, weights, counts, row_begin, row_end, seed, call_idx,
+def pack_edges(x_edges, dx_edges, out=None):
+    """Interleave {x_edges[d,k], dx_edges[d,k]} into [dim, Ni, 2] (the fused kernel's gather layout)."""
+    require_cuda(x_edges, dx_edges)
+    dim, ni = dx_edges.shape
+    if out is None:
+        out = torch.empty((dim, ni, 2), dtype=dx_edges.dtype, device=dx_edges.device)
+    with torch.cuda.device(dx_edges.device):
+        call("tq_vegas_map_pack_edges", ptr(x_edges), ptr(dx_edges), ptr(out), dim, ni, dtype_code(dx_edges.dtype),
+             stream_ptr(dx_edges.device))
+    return out
+
+
+def fused_vegas(fn_struct, edges_packed, weights, counts, row_begin, row_end, seed, call_idx,
                 offsets=None, n_strat=1, JF=None, JF2=None):
     """One fused VEGAS pass (warm-up when offsets is None).  Returns fp64 [2] = {sum jf, sum jf^2} (warm-up only)."""
-    require_cuda(x_edges, dx_edges, weights, counts, offsets, JF, JF2)
-    out = torch.zeros(2, dtype=torch.float64, device=x_edges.device)
+    require_cuda(edges_packed, weights, counts, offsets, JF, JF2)
+    out = torch.zeros(2, dtype=torch.float64, device=edges_packed.device)
     n_cubes = 0 if offsets is None else offsets.shape[0] - 1
-    with torch.cuda.device(x_edges.device):
-        wsp, wsn = _ws(x_edges.device)
-        call("tq_fused_vegas", fn_struct, dtype_code(x_edges.dtype), ptr(offsets), n_cubes, n_strat, row_begin, row_end,
-             ptr(x_edges), ptr(dx_edges), dx_edges.shape[1], ptr(weights), ptr(counts), ptr(JF), ptr(JF2),
-             seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, ptr(out), wsp, wsn, stream_ptr(x_edges.device))
+    with torch.cuda.device(edges_packed.device):
+        wsp, wsn = _ws(edges_packed.device)
+        call("tq_fused_vegas", fn_struct, dtype_code(edges_packed.dtype), ptr(offsets), n_cubes, n_strat, row_begin, row_end,
+             ptr(edges_packed), edges_packed.shape[1], ptr(weights), ptr(counts), ptr(JF), ptr(JF2),
+             seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, ptr(out), wsp, wsn, stream_ptr(edges_packed.device))
     return out
