@@ -114,9 +114,20 @@ TQ_API int tq_sum_columns(const void* f, int64_t rows, int64_t cols, int32_t dty
 TQ_API int tq_vegas_map_forward(const void* y, const void* x_edges, const void* dx_edges, void* x, void* jac,
                          int32_t* ids, void* offset, int64_t rows, int32_t dim, int64_t n_intervals,
                          int32_t dtype, void* stream);
+/* Same pass with the edges packed as {x_edge, dx_edge} pairs (tq_vegas_map_pack_edges; one gather per element)
+ * and, when `domain` ([dim,2], nullable) is given, the unit-cube -> domain transform x*size + start of
+ * vegas.py:109-110 applied in the same kernel. */
+TQ_API int tq_vegas_map_forward_packed(const void* y, const void* edges_packed, const void* domain, void* x, void* jac,
+                                int32_t* ids, int64_t rows, int32_t dim, int64_t n_intervals, int32_t dtype,
+                                void* stream);
 /* accumulate_weight (:99-111): weights[d,k] += jf2[r], counts[d,k] += 1 (int64, bit-exact). */
 TQ_API int tq_vegas_map_accumulate(const void* y, const void* jf2, void* weights, int64_t* counts, int64_t rows,
                             int32_t dim, int64_t n_intervals, int32_t dtype, void* stream);
+/* The tail of an unfused VEGAS pass in one kernel (vegas.py:104-112,284-290): jf = (f*volume)*jac,
+ * weights[d,k] += jf^2, counts[d,k] += 1, and jf written to jf_out (nullable) for tq_vegas_strat_accumulate. */
+TQ_API int tq_vegas_accumulate_fused(const void* y, const void* f, const void* jac, double volume, void* jf_out, void* weights,
+                              int64_t* counts, int64_t rows, int32_t dim, int64_t n_intervals, int32_t dtype,
+                              void* stream);
 /* Scratch bytes tq_vegas_map_smooth / tq_vegas_map_update need for a [dim, Ni] map (pass as ws). */
 TQ_API size_t tq_vegas_map_workspace_bytes(int32_t dim, int64_t n_intervals, int32_t dtype);
 /* _smooth_map (:113-172) written to `smoothed[dim, Ni]`; status[0] = 1 when a dimension sums to zero

@@ -47,6 +47,25 @@ __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(
 __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
 
+// Exact 32-bit division by a runtime constant (Granlund-Montgomery round-up form): q = x / d for all x.
+struct FastDiv {
+    uint32_t d, m, s;
+    __host__ __device__ void set(uint32_t d_) {
+        d = d_;
+        if (d_ <= 1) { m = 0; s = 0; return; }
+        uint32_t l = 0;
+        while ((1ull << l) < d_) ++l;  // ceil(log2 d)
+        m = (uint32_t)((((1ull << l) - d_) << 32) / d_ + 1);
+        s = l;
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t x) const {
+        if (d <= 1) return x;
+        const uint32_t t = __umulhi(m, x);
+        return (t + ((x - t) >> 1)) >> (s - 1);
+    }
+};
+
+
 // ---------------------------------------------------------------- Philox4x32-10
 // Salmon et al. SC'11.  key = 64-bit seed, counter = 4 x u32.  Known-answer vectors are checked in
 // tests/test_philox.py against oracle/ref_oracle.py:philox4x32_10.

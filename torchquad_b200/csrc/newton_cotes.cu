@@ -13,26 +13,74 @@ struct GridIndex {
     int dim;
 };
 
-// One thread per (row, d) element so that the row-major store is coalesced; the digit is extracted with a
-// division by the precomputed stride n^(dim-1-d).
-template <typename T>
-__global__ void __launch_bounds__(256)
-grid_points_kernel(const T* __restrict__ nodes, uint32_t n, int dim, int64_t p_begin, int64_t p_end,
-                   T* __restrict__ out) {
-    __shared__ uint64_t s_stride[TQ_MAX_DIM];
-    if (threadIdx.x == 0) {
-        uint64_t s = 1;
-        for (int d = dim - 1; d >= 0; --d) { s_stride[d] = s; s *= n; }
+// Mixed-radix walker: digit i_d(p) = (p / stride_d) % n of a point index that advances by a constant step.
+// Keeps (q = digit, r = p % stride_d); adding the step is a handful of adds/compares, no division.
+struct DigitWalker {
+    uint64_t stride, r, step_r;
+    uint32_t q, step_q, n;
+    __device__ __forceinline__ void init(uint64_t p, uint64_t stride_, uint32_t n_, uint64_t step) {
+        stride = stride_;
+        n = n_;
+        const uint64_t t = p / stride_;
+        r = p - t * stride_;
+        q = (uint32_t)(t % n_);
+        const uint64_t ts = step / stride_;
+        step_r = step - ts * stride_;
+        step_q = (uint32_t)(ts % n_);
     }
-    __syncthreads();
-    const int64_t total = (p_end - p_begin) * dim;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = e / dim;
-        const int d = (int)(e - r * dim);
-        const uint64_t p = (uint64_t)(p_begin + r);
-        const uint32_t i = (uint32_t)((p / s_stride[d]) % n);
-        out[e] = __ldg(&nodes[(int64_t)d * n + i]);
+    __device__ __forceinline__ void advance() {
+        r += step_r;
+        uint32_t carry = 0;
+        if (r >= stride) { r -= stride; carry = 1; }
+        q += step_q + carry;
+        if (q >= n) q -= n;
+        if (q >= n) q -= n;
+    }
+};
+
+// Thread t owns the vector of V consecutive dimensions `t % nvb` of rows t / nvb + k*rows_per_pass: the
+// columns (hence the digit walkers and the store width) are loop-invariant, a warp writes one contiguous
+// span of the row-major output, and no division is executed inside the loop.
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+grid_points_kernel(const T* __restrict__ nodes, uint32_t n, int dim, int nvb, int64_t p_begin, int64_t p_end,
+                   T* __restrict__ out, bool vec_ok) {
+    const int rows_per_pass = 256 / nvb;
+    const int rloc = threadIdx.x / nvb;
+    const int vb = threadIdx.x - rloc * nvb;
+    if (rloc >= rows_per_pass) return;
+    const int d0 = vb * V;
+    const int nvalid = dim - d0 < V ? dim - d0 : V;
+    const int64_t nrows = p_end - p_begin;
+    const int64_t step = (int64_t)gridDim.x * rows_per_pass;
+    int64_t row = (int64_t)blockIdx.x * rows_per_pass + rloc;
+    if (row >= nrows) return;
+    DigitWalker w[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        uint64_t stride = 1;
+        const int d = d0 + j < dim ? d0 + j : dim - 1;
+        for (int i = dim - 1; i > d; --i) stride *= n;
+        w[j].init((uint64_t)(p_begin + row), stride, n, (uint64_t)step);
+    }
+    T* p = out + row * dim + d0;
+    const int64_t pstep = step * dim;
+    const bool vec = vec_ok && nvalid == V;
+    for (; row < nrows; row += step, p += pstep) {
+        alignas(16) T v[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int d = d0 + j < dim ? d0 + j : dim - 1;
+            v[j] = __ldg(&nodes[(int64_t)d * n + w[j].q]);
+            w[j].advance();
+        }
+        if (vec) {
+            __stcs(reinterpret_cast<uint4*>(p), *reinterpret_cast<uint4*>(v));
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                if (j < nvalid) p[j] = v[j];
+        }
     }
 }
 
@@ -112,19 +160,76 @@ point_weights_kernel(const T* __restrict__ w, uint32_t n, int dim, int64_t p_beg
 }
 
 // cols == 1 contraction: fp64 accumulation of f[p]*W[p], deterministic two-stage reduction.
-template <typename T>
+// Each thread handles vectors of V consecutive points (32 bytes: two 128-bit loads of f) advancing by a constant step.
+// The point index is carried as (hi, last) = (p / n, p % n) without division; the weight of the leading
+// dim-1 digits (the digits of hi, extracted with multiply-shift divisions) is formed once per vector and the
+// last digit steps through the vector, with a carry when the vector crosses a row of the last dimension.
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
 contract1_kernel(const T* __restrict__ f, const T* __restrict__ w, uint32_t n, int dim, int64_t p_begin,
-                 int64_t p_end, double* partials, unsigned int* ticket, double* out, bool use_smem) {
+                 int64_t p_end, FastDiv fd, double* partials, unsigned int* ticket, double* out, bool use_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double sh[32];
     const T* sw = stage_weights<T>(w, reinterpret_cast<T*>(smem_raw), dim, n, use_smem);
-    const GridIndex gi{n, dim};
+    const T* wl = sw + (dim - 1) * n;
+    const int64_t npts = p_end - p_begin;
+    const int64_t nvec = (npts + V - 1) / V;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;  // in vectors
+    int64_t vi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double acc[1] = {0.0};
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < p_end - p_begin;
-         r += (int64_t)gridDim.x * blockDim.x) {
-        const T wt = point_weight<T>(sw, gi, (uint64_t)(p_begin + r));
-        acc[0] += (double)__ldcs(&f[r]) * (double)wt;
+    if (vi < nvec) {
+        const uint64_t p0 = (uint64_t)(p_begin + vi * V);
+        uint64_t hi = p0 / n;
+        uint32_t last = (uint32_t)(p0 - hi * n);
+        const uint64_t sp = (uint64_t)step * V;
+        const uint64_t step_hi = sp / n;
+        const uint32_t step_last = (uint32_t)(sp - step_hi * n);
+        auto prefix_of = [&](uint64_t h) {
+            T pr = (T)1;
+            if (h <= 0xffffffffull) {
+                uint32_t q = (uint32_t)h;
+                for (int d = dim - 2; d >= 0; --d) {
+                    const uint32_t t = fd.div(q);
+                    pr *= sw[d * n + (q - t * n)];
+                    q = t;
+                }
+            } else {
+                for (int d = dim - 2; d >= 0; --d) {
+                    const uint64_t t = h / n;
+                    pr *= sw[d * n + (uint32_t)(h - t * n)];
+                    h = t;
+                }
+            }
+            return pr;
+        };
+        for (; vi < nvec; vi += step) {
+            const int64_t r = vi * V;
+            alignas(16) T fv[V];
+            if (V > 1 && r + V <= npts) {
+#pragma unroll
+                for (int q = 0; q < (int)(V * sizeof(T) / 16); ++q)
+                    reinterpret_cast<uint4*>(fv)[q] = __ldcs(reinterpret_cast<const uint4*>(f + r) + q);
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) fv[j] = r + j < npts ? f[r + j] : (T)0;
+            }
+            T prefix = prefix_of(hi);
+            uint32_t l = last;
+            uint64_t h = hi;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                if (l >= n) {  // crossed into the next row of the last dimension
+                    l = 0;
+                    ++h;
+                    prefix = prefix_of(h);
+                }
+                acc[0] += (double)fv[j] * (double)(prefix * wl[l]);
+                ++l;
+            }
+            hi += step_hi;
+            last += step_last;
+            if (last >= n) { last -= n; ++hi; }
+        }
     }
     grid_sum_finish<1>(acc, sh, partials, ticket, out);
 }
@@ -186,9 +291,16 @@ int tq_nc_grid_points(const void* nodes, int32_t n, int32_t dim, int64_t p_begin
     int rc = check_grid_args("tq_nc_grid_points", n, dim, p_begin, p_end);
     if (rc) return rc;
     if (p_end == p_begin) return TQ_OK;
-    const int grid = grid_for((p_end - p_begin) * dim, 256, 8);
     TQ_DISPATCH_DTYPE(dtype, {
-        grid_points_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)nodes, (uint32_t)n, dim, p_begin, p_end, (T*)points);
+        constexpr int V = 16 / sizeof(T);
+        const int nvb = (dim + V - 1) / V;
+        const int rows_per_pass = 256 / nvb;
+        const int64_t passes = (p_end - p_begin + rows_per_pass - 1) / rows_per_pass;
+        const int64_t cap = (int64_t)num_sms() * 8;
+        const int grid = (int)(passes < cap ? passes : cap);
+        const bool vec_ok = (dim % V) == 0 && (reinterpret_cast<uintptr_t>(points) & 15) == 0;
+        grid_points_kernel<T, V><<<grid, 256, 0, as_stream(stream)>>>((const T*)nodes, (uint32_t)n, dim, nvb, p_begin, p_end,
+                                                                     (T*)points, vec_ok);
     });
     return check_launch("grid_points_kernel");
 }
@@ -235,14 +347,23 @@ int tq_nc_contract(const void* f, const void* w, int32_t n, int32_t dim, int64_t
     cudaStream_t st = as_stream(stream);
     const int64_t rows = p_end - p_begin;
     if (cols == 1) {
-        const int grid = grid_for(rows, 256, 4);
+        const int grid = grid_for((rows + 7) / 8, 256, 4);
         double* partials = wk.take<double>((size_t)grid);
         if (!ticket || !partials) { set_error("tq_nc_contract: workspace too small"); return TQ_ERR_WORKSPACE; }
+        const bool aligned = (reinterpret_cast<uintptr_t>(f) & 15) == 0;
         TQ_DISPATCH_DTYPE(dtype, {
+            constexpr int V = 32 / sizeof(T);
             const bool use_smem = (size_t)dim * n * sizeof(T) <= NC_TABLE_SMEM;
             const size_t smem = use_smem ? (size_t)dim * n * sizeof(T) : 0;
-            cudaFuncSetAttribute(contract1_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NC_TABLE_SMEM);
-            contract1_kernel<T><<<grid, 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, partials, ticket, out_f64, use_smem);
+            FastDiv fd;
+            fd.set((uint32_t)n);
+            if (aligned) {
+                cudaFuncSetAttribute(contract1_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NC_TABLE_SMEM);
+                contract1_kernel<T, V><<<grid, 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, fd, partials, ticket, out_f64, use_smem);
+            } else {
+                cudaFuncSetAttribute(contract1_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NC_TABLE_SMEM);
+                contract1_kernel<T, 1><<<grid, 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, fd, partials, ticket, out_f64, use_smem);
+            }
         });
         return check_launch("contract1_kernel");
     }

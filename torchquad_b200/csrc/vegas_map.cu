@@ -18,48 +18,158 @@ __device__ __forceinline__ long long bin_of(T y, T nif, long long ni, T& offset)
     return k;
 }
 
-template <typename T>
+// Tile kernel.  Phase 1: one thread per 16-byte vector of the row-major tile (coalesced 128-bit loads of y and
+// stores of x / ids / offsets); every element looks up its bin, gathers the two edge values (L1/L2 resident
+// for ordinary map sizes) and parks its Jacobian factor Ni*dx in shared memory (rows padded to an odd
+// stride).  Phase 2: one thread per row multiplies the factors left to right (the reference's order,
+// vegas_map.py:70-73) and writes jac coalesced.  HBM traffic = the algorithmic 2*dim*s + s bytes per row.
+constexpr int MF_TILE_ELEMS = 2048;
+
+template <typename T> struct EdgePair;
+template <> struct EdgePair<float> { using type = float2; };
+template <> struct EdgePair<double> { using type = double2; };
+
+// PACKED: edges come as {x_edge, dx_edge} pairs [dim, Ni] (one gather per element; tq_vegas_map_pack_edges) and
+// `domain` (nullable, [dim, 2]) applies the integrator's unit-cube -> domain transform x*size + start of
+// vegas.py:109-110 in the same pass (mul then add, like the torch expression it replaces).
+template <typename T, int V, bool PACKED>
 __global__ void __launch_bounds__(256)
 map_forward_kernel(const T* __restrict__ y, const T* __restrict__ xe, const T* __restrict__ dxe,
-                   T* __restrict__ x, T* __restrict__ jac, int32_t* __restrict__ ids, T* __restrict__ off,
-                   int64_t rows, int dim, long long ni) {
-    const T nif = (T)ni;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
-         r += (int64_t)gridDim.x * blockDim.x) {
-        T j = (T)1;
-        for (int d = 0; d < dim; ++d) {
-            T o;
-            const long long k = bin_of<T>(y[r * dim + d], nif, ni, o);
-            const T dxv = __ldg(&dxe[(int64_t)d * ni + k]);
-            if (x) {
-                const T xv = __ldg(&xe[(int64_t)d * (ni + 1) + k]);
-                x[r * dim + d] = add_rn(xv, mul_rn(dxv, o));
-            }
-            j = mul_rn(j, mul_rn(nif, dxv));
-            if (ids) ids[r * dim + d] = (int32_t)k;
-            if (off) off[r * dim + d] = o;
+                   const T* __restrict__ domain, T* __restrict__ x, T* __restrict__ jac, int32_t* __restrict__ ids,
+                   T* __restrict__ off, int64_t rows, int dim, long long ni, int tile_rows, uint32_t magic) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_fac = reinterpret_cast<T*>(smem_raw);  // [tile_rows][dimp]
+    const int dimp = dim | 1;
+    T* s_dom = s_fac + (size_t)tile_rows * dimp;  // [2][dim] start, size (only with a domain)
+    if (domain) {
+        for (int d = threadIdx.x; d < dim; d += 256) {
+            const T a = domain[2 * d], b = domain[2 * d + 1];
+            s_dom[d] = a;
+            s_dom[dim + d] = sub_rn(b, a);
         }
-        if (jac) jac[r] = j;
+        __syncthreads();
+    }
+    const typename EdgePair<T>::type* ep = reinterpret_cast<const typename EdgePair<T>::type*>(xe);
+    const T nif = (T)ni;
+    const int64_t ntiles = (rows + tile_rows - 1) / tile_rows;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t r0 = t * tile_rows;
+        const int rows_here = (int)(rows - r0 < tile_rows ? rows - r0 : tile_rows);
+        const int n_el = rows_here * dim;
+        const int64_t e0 = r0 * dim;
+        for (int v = threadIdx.x * V; v < n_el; v += 256 * V) {
+            alignas(16) T yv[V], xv[V], ov[V];
+            alignas(16) int kv[V];
+            if (V > 1 && v + V <= n_el) {
+                *reinterpret_cast<uint4*>(yv) = __ldcs(reinterpret_cast<const uint4*>(y + e0 + v));
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) yv[j] = v + j < n_el ? y[e0 + v + j] : (T)0;
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const uint32_t e = (uint32_t)(v + j);
+                const uint32_t r = (uint32_t)(((uint64_t)e * magic) >> 24);  // e / dim, exact for e < 2^16
+                const int d = (int)(e - r * dim);
+                T o;
+                const long long k = bin_of<T>(yv[j], nif, ni, o);
+                if (v + j < n_el) {
+                    T xev, dxv;
+                    if (PACKED) {
+                        const typename EdgePair<T>::type e2 = __ldg(&ep[(int64_t)d * ni + k]);
+                        xev = e2.x;
+                        dxv = e2.y;
+                    } else {
+                        dxv = __ldg(&dxe[(int64_t)d * ni + k]);
+                        xev = x ? __ldg(&xe[(int64_t)d * (ni + 1) + k]) : (T)0;
+                    }
+                    if (x) {
+                        T xx = add_rn(xev, mul_rn(dxv, o));
+                        if (domain) xx = add_rn(mul_rn(xx, s_dom[dim + d]), s_dom[d]);
+                        xv[j] = xx;
+                    }
+                    s_fac[r * dimp + d] = mul_rn(nif, dxv);
+                }
+                kv[j] = (int)k;
+                ov[j] = o;
+            }
+            if (V > 1 && v + V <= n_el) {
+                if (x) __stcs(reinterpret_cast<uint4*>(x + e0 + v), *reinterpret_cast<uint4*>(xv));
+                if (off) __stcs(reinterpret_cast<uint4*>(off + e0 + v), *reinterpret_cast<uint4*>(ov));
+                if (ids) {
+                    if (V == 4) __stcs(reinterpret_cast<int4*>(ids + e0 + v), *reinterpret_cast<int4*>(kv));
+                    else __stcs(reinterpret_cast<int2*>(ids + e0 + v), *reinterpret_cast<int2*>(kv));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    if (v + j < n_el) {
+                        if (x) x[e0 + v + j] = xv[j];
+                        if (off) off[e0 + v + j] = ov[j];
+                        if (ids) ids[e0 + v + j] = kv[j];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (jac) {
+            for (int r = threadIdx.x; r < rows_here; r += 256) {
+                T j = (T)1;
+                for (int d = 0; d < dim; ++d) j = mul_rn(j, s_fac[r * dimp + d]);
+                jac[r0 + r] = j;
+            }
+        }
+        __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------ accumulate (weights += jf2, counts += 1)
-// Large maps: straight L2 reductions (RED.ADD.F32/F64 + RED.ADD.U64), one thread per (row, dim) element so
-// the y reads are coalesced.
-template <typename T>
+// L2 reductions (RED.ADD.F32/F64 + RED.ADD.U64), one thread per 16-byte vector of the row-major y tile
+// (coalesced 128-bit loads; (row, dim) of an element from a multiply-shift, no division).
+// FUSED: the weight is jf^2 with jf = (f*volume)*jac formed here (vegas.py:104-112,284-287), and jf is
+// written out for the per-cube sums -- this replaces three torch elementwise passes of the unfused path.
+template <typename T, int V, bool FUSED>
 __global__ void __launch_bounds__(256)
-map_accumulate_global_kernel(const T* __restrict__ y, const T* __restrict__ jf2, T* __restrict__ weights,
-                             unsigned long long* __restrict__ counts, int64_t rows, int dim, long long ni) {
+map_accumulate_global_kernel(const T* __restrict__ y, const T* __restrict__ jf2_or_f, const T* __restrict__ jacp,
+                             T volume, T* __restrict__ jf_out, T* __restrict__ weights,
+                             unsigned long long* __restrict__ counts, int64_t rows, int dim, long long ni,
+                             int tile_rows, uint32_t magic) {
     const T nif = (T)ni;
-    const int64_t total = rows * dim;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = e / dim;
-        const int d = (int)(e - r * dim);
-        T o;
-        const long long k = bin_of<T>(y[e], nif, ni, o);
-        atomicAdd(&weights[(int64_t)d * ni + k], jf2[r]);
-        atomicAdd(&counts[(int64_t)d * ni + k], 1ull);
+    const int64_t ntiles = (rows + tile_rows - 1) / tile_rows;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t r0 = t * tile_rows;
+        const int rows_here = (int)(rows - r0 < tile_rows ? rows - r0 : tile_rows);
+        const int n_el = rows_here * dim;
+        const int64_t e0 = r0 * dim;
+        for (int v = threadIdx.x * V; v < n_el; v += 256 * V) {
+            alignas(16) T yv[V];
+            if (V > 1 && v + V <= n_el) {
+                *reinterpret_cast<uint4*>(yv) = __ldcs(reinterpret_cast<const uint4*>(y + e0 + v));
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) yv[j] = v + j < n_el ? y[e0 + v + j] : (T)0;
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                if (v + j < n_el) {
+                    const uint32_t e = (uint32_t)(v + j);
+                    const uint32_t r = (uint32_t)(((uint64_t)e * magic) >> 24);
+                    const int d = (int)(e - r * dim);
+                    T o;
+                    const long long k = bin_of<T>(yv[j], nif, ni, o);
+                    T wgt;
+                    if (FUSED) {
+                        const T jf = mul_rn(mul_rn(__ldg(&jf2_or_f[r0 + r]), volume), __ldg(&jacp[r0 + r]));
+                        wgt = mul_rn(jf, jf);
+                        if (d == 0 && jf_out) jf_out[r0 + r] = jf;
+                    } else {
+                        wgt = __ldg(&jf2_or_f[r0 + r]);
+                    }
+                    atomicAdd(&weights[(int64_t)d * ni + k], wgt);
+                    atomicAdd(&counts[(int64_t)d * ni + k], 1ull);
+                }
+            }
+        }
     }
 }
 
@@ -351,6 +461,65 @@ static int run_smooth(const T* weights, const long long* counts, T* smoothed_out
     return check_launch("map smoothing");
 }
 
+template <bool PACKED>
+static int launch_map_forward(const void* y, const void* xe, const void* dxe, const void* domain, void* x, void* jac,
+                              int32_t* ids, void* offset, int64_t rows, int32_t dim, int64_t n_intervals, int32_t dtype,
+                              void* stream) {
+    TQ_REQUIRE(dim >= 1 && n_intervals >= 1 && rows >= 0, "tq_vegas_map_forward: bad shape");
+    TQ_REQUIRE(ids == nullptr || n_intervals <= 0x7fffffffLL, "tq_vegas_map_forward: ids need Ni < 2^31");
+    if (rows == 0) return TQ_OK;
+    TQ_REQUIRE(dim <= 255, "tq_vegas_map_forward: dim %d too large (max 255)", dim);
+    int tile_rows = MF_TILE_ELEMS / dim;
+    if (tile_rows < 4) tile_rows = 4;
+    tile_rows &= ~3;  // every tile starts 16-byte aligned
+    const uint32_t magic = (uint32_t)((1u << 24) / (uint32_t)dim) + 1u;
+    const int64_t ntiles = (rows + tile_rows - 1) / tile_rows;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    const int grid = (int)(ntiles < cap ? ntiles : cap);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(offset)) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(ids) & 7) == 0 && (dtype == TQ_F64 || (reinterpret_cast<uintptr_t>(ids) & 15) == 0);
+    TQ_DISPATCH_DTYPE(dtype, {
+        const size_t smem = ((size_t)tile_rows * (dim | 1) + 2 * (size_t)dim) * sizeof(T);
+        constexpr int VW = 16 / sizeof(T);
+        if (aligned)
+            map_forward_kernel<T, VW, PACKED><<<grid, 256, smem, as_stream(stream)>>>(
+                (const T*)y, (const T*)xe, (const T*)dxe, (const T*)domain, (T*)x, (T*)jac, ids, (T*)offset, rows, dim,
+                n_intervals, tile_rows, magic);
+        else
+            map_forward_kernel<T, 1, PACKED><<<grid, 256, smem, as_stream(stream)>>>(
+                (const T*)y, (const T*)xe, (const T*)dxe, (const T*)domain, (T*)x, (T*)jac, ids, (T*)offset, rows, dim,
+                n_intervals, tile_rows, magic);
+    });
+    return check_launch("map_forward_kernel");
+}
+
+template <bool FUSED>
+static int launch_accumulate_global(const void* y, const void* a, const void* jac, double volume, void* jf_out,
+                                    void* weights, int64_t* counts, int64_t rows, int32_t dim, int64_t n_intervals,
+                                    int32_t dtype, cudaStream_t st) {
+    TQ_REQUIRE(dim <= 255, "tq_vegas_map_accumulate: dim %d too large (max 255)", dim);
+    int tile_rows = MF_TILE_ELEMS / dim;
+    if (tile_rows < 4) tile_rows = 4;
+    tile_rows &= ~3;
+    const uint32_t magic = (uint32_t)((1u << 24) / (uint32_t)dim) + 1u;
+    const int64_t ntiles = (rows + tile_rows - 1) / tile_rows;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    const int grid = (int)(ntiles < cap ? ntiles : cap);
+    const bool aligned = (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    TQ_DISPATCH_DTYPE(dtype, {
+        constexpr int VW = 16 / sizeof(T);
+        if (aligned)
+            map_accumulate_global_kernel<T, VW, FUSED><<<grid, 256, 0, st>>>((const T*)y, (const T*)a, (const T*)jac, (T)volume,
+                                                                            (T*)jf_out, (T*)weights, (unsigned long long*)counts,
+                                                                            rows, dim, n_intervals, tile_rows, magic);
+        else
+            map_accumulate_global_kernel<T, 1, FUSED><<<grid, 256, 0, st>>>((const T*)y, (const T*)a, (const T*)jac, (T)volume,
+                                                                           (T*)jf_out, (T*)weights, (unsigned long long*)counts,
+                                                                           rows, dim, n_intervals, tile_rows, magic);
+    });
+    return check_launch("map_accumulate_global_kernel");
+}
+
 }  // namespace tq
 
 using namespace tq;
@@ -360,15 +529,13 @@ extern "C" {
 int tq_vegas_map_forward(const void* y, const void* x_edges, const void* dx_edges, void* x, void* jac,
                          int32_t* ids, void* offset, int64_t rows, int32_t dim, int64_t n_intervals,
                          int32_t dtype, void* stream) {
-    TQ_REQUIRE(dim >= 1 && n_intervals >= 1 && rows >= 0, "tq_vegas_map_forward: bad shape");
-    TQ_REQUIRE(ids == nullptr || n_intervals <= 0x7fffffffLL, "tq_vegas_map_forward: ids need Ni < 2^31");
-    if (rows == 0) return TQ_OK;
-    const int grid = grid_for(rows, 256, 8);
-    TQ_DISPATCH_DTYPE(dtype, {
-        map_forward_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)y, (const T*)x_edges, (const T*)dx_edges,
-                                                                  (T*)x, (T*)jac, ids, (T*)offset, rows, dim, n_intervals);
-    });
-    return check_launch("map_forward_kernel");
+    return launch_map_forward<false>(y, x_edges, dx_edges, nullptr, x, jac, ids, offset, rows, dim, n_intervals, dtype, stream);
+}
+
+int tq_vegas_map_forward_packed(const void* y, const void* edges_packed, const void* domain, void* x, void* jac,
+                                int32_t* ids, int64_t rows, int32_t dim, int64_t n_intervals, int32_t dtype,
+                                void* stream) {
+    return launch_map_forward<true>(y, edges_packed, nullptr, domain, x, jac, ids, nullptr, rows, dim, n_intervals, dtype, stream);
 }
 
 int tq_vegas_map_accumulate(const void* y, const void* jf2, void* weights, int64_t* counts, int64_t rows,
@@ -393,12 +560,16 @@ int tq_vegas_map_accumulate(const void* y, const void* jf2, void* weights, int64
         });
         return check_launch("map_accumulate_smem_kernel");
     }
-    const int grid = grid_for(rows * dim, 256, 8);
-    TQ_DISPATCH_DTYPE(dtype, {
-        map_accumulate_global_kernel<T><<<grid, 256, 0, st>>>((const T*)y, (const T*)jf2, (T*)weights,
-                                                             (unsigned long long*)counts, rows, dim, n_intervals);
-    });
-    return check_launch("map_accumulate_global_kernel");
+    return launch_accumulate_global<false>(y, jf2, nullptr, 1.0, nullptr, weights, counts, rows, dim, n_intervals, dtype, st);
+}
+
+int tq_vegas_accumulate_fused(const void* y, const void* f, const void* jac, double volume, void* jf_out, void* weights,
+                              int64_t* counts, int64_t rows, int32_t dim, int64_t n_intervals, int32_t dtype,
+                              void* stream) {
+    TQ_REQUIRE(dim >= 1 && n_intervals >= 1 && rows >= 0, "tq_vegas_accumulate_fused: bad shape");
+    if (rows == 0) return TQ_OK;
+    return launch_accumulate_global<true>(y, f, jac, volume, jf_out, weights, counts, rows, dim, n_intervals, dtype,
+                                          as_stream(stream));
 }
 
 size_t tq_vegas_map_workspace_bytes(int32_t dim, int64_t n_intervals, int32_t dtype) {

@@ -3,6 +3,7 @@
 // Replaces torchquad/integration/vegas_stratification.py (get_NH :92-103, _get_indices/get_Y :105-165,
 // accumulate_weight :46-70, update_DH :72-90) and the estimator of vegas.py:293-303.
 #include "common.cuh"
+#include "strat_tile.cuh"
 
 namespace tq {
 
@@ -146,66 +147,127 @@ __device__ __forceinline__ int cube_in_slice(const long long* s_off, int count, 
 }
 
 // ---- get_Y
+// Each CTA walks a contiguous chunk of rows in tiles of ST_ROWS (row -> cube through StratTile).  Inside a
+// tile, thread t owns Philox block `t % nblk` (LANES consecutive dimensions) of rows t / nblk + k*rows_per_pass:
+// the column block is loop-invariant (digit divisor, store width) and a warp writes one contiguous span of y.
 template <typename T>
 __global__ void __launch_bounds__(256)
-strat_sample_kernel(const long long* __restrict__ offsets, int64_t n_cubes, int n_strat, int dim,
+strat_sample_kernel(const long long* __restrict__ offsets, int64_t n_cubes, int n_strat, int dim, int nblk,
                     const T* __restrict__ u_in, uint64_t seed, uint32_t call, int64_t row_begin, int64_t row_end,
-                    T* __restrict__ y) {
+                    int64_t rows_per_cta, FastDiv fdn, T* __restrict__ y) {
     constexpr int LANES = U01<T>::LANES;
-    __shared__ long long s_off[ST_TILE / 2 + 4];
-    __shared__ long long s_bounds[2];
+    __shared__ StratTile st;
+    const int rows_per_pass = 256 / nblk;
+    const int rloc = threadIdx.x / nblk;
+    const int blk = threadIdx.x - rloc * nblk;
+    const bool worker = rloc < rows_per_pass;
+    const int d0 = blk * LANES;
+    const int nvalid = dim - d0 < LANES ? dim - d0 : LANES;
+    // n_strat^d0, saturated: the first digit of this thread's block is (cube / div0) % n_strat
+    unsigned long long pw = 1;
+    for (int i = 0; i < d0 && pw <= 0xffffffffull; ++i) pw *= (unsigned long long)n_strat;
+    FastDiv fd0;
+    fd0.set(pw > 0xffffffffull ? 0xffffffffu : (uint32_t)pw);
+    const uint32_t ns = (uint32_t)n_strat;
     const T nsf = (T)n_strat;
-    for (int64_t rb = row_begin + (int64_t)blockIdx.x * ST_TILE; rb < row_end; rb += (int64_t)gridDim.x * ST_TILE) {
-        const int64_t re = rb + ST_TILE < row_end ? rb + ST_TILE : row_end;
-        const CubeSlice sl = load_cube_slice(offsets, n_cubes, rb, re - 1, s_off, s_bounds);
-        for (int64_t row = rb + threadIdx.x; row < re; row += blockDim.x) {
-            const int ci = cube_in_slice(s_off, sl.count, row);
-            const uint32_t cube = (uint32_t)(sl.c_lo + ci);
-            const uint32_t k = (uint32_t)(row - s_off[ci]);
-            T* out = y + (row - row_begin) * dim;
-            const T* uin = u_in ? u_in + (row - row_begin) * dim : nullptr;
-            uint32_t c = cube;
-            for (int d0 = 0; d0 < dim; d0 += LANES) {
-                T u[LANES];
-                if (uin) {
+    const bool base16 = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(u_in)) & 15) == 0;
+    const int mode = (nvalid == LANES && base16 && (dim % LANES) == 0) ? 2 : 0;
+    const int64_t r_lo = row_begin + (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r_hi = r_lo + rows_per_cta < row_end ? r_lo + rows_per_cta : row_end;
+    if (threadIdx.x == 0 && r_lo < r_hi) st.first = cube_of_row(offsets, n_cubes, r_lo);
+    __syncthreads();
+    long long c_lo = r_lo < r_hi ? st.first : 0;
+    int buf = 0;
+    for (int64_t rb = r_lo; rb < r_hi; rb += ST_ROWS, buf ^= 1) {
+        const int64_t re = rb + ST_ROWS < r_hi ? rb + ST_ROWS : r_hi;
+        strat_tile_fill(st, buf, offsets, n_cubes, c_lo, rb, re);
+        const int n_here = (int)(re - rb);
+        if (worker) {
+            for (int rl = rloc; rl < n_here; rl += rows_per_pass) {
+                const int ci = st.cube[buf][rl];
+                const uint32_t cube = (uint32_t)(c_lo + ci);
+                const int64_t row = rb + rl;
+                const uint32_t k = (uint32_t)(row - st.off[buf][ci]);
+                T* out = y + (row - row_begin) * dim + d0;
+                alignas(16) T u[LANES];
+                if (u_in) {
+                    const T* uin = u_in + (row - row_begin) * dim + d0;
+                    if (mode == 2) *reinterpret_cast<uint4*>(u) = __ldcs(reinterpret_cast<const uint4*>(uin));
+                    else {
 #pragma unroll
-                    for (int j = 0; j < LANES; ++j) u[j] = (d0 + j < dim) ? uin[d0 + j] : (T)0;
+                        for (int j = 0; j < LANES; ++j) u[j] = j < nvalid ? uin[j] : (T)0;
+                    }
                 } else {
-                    philox_block<T>(seed, call, cube, k, (uint32_t)(d0 / LANES), u);
+                    philox_block<T>(seed, call, cube, k, (uint32_t)blk, u);
                 }
+                uint32_t c = fd0.div(cube);
 #pragma unroll
                 for (int j = 0; j < LANES; ++j) {
-                    if (d0 + j < dim) {
-                        const uint32_t q = c / (uint32_t)n_strat;
-                        const uint32_t p = c - q * (uint32_t)n_strat;
-                        c = q;
-                        T v = div_rn(add_rn((T)p, u[j]), nsf);
-                        if (v >= (T)1) v = (T)0.999999;
-                        out[d0 + j] = v;
-                    }
+                    const uint32_t q = fdn.div(c);
+                    const uint32_t p = c - q * ns;
+                    c = q;
+                    T v = div_rn(add_rn((T)p, u[j]), nsf);
+                    if (v >= (T)1) v = (T)0.999999;
+                    u[j] = v;
+                }
+                if (mode == 2) {
+                    __stcs(reinterpret_cast<uint4*>(out), *reinterpret_cast<uint4*>(u));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < LANES; ++j)
+                        if (j < nvalid) out[j] = u[j];
                 }
             }
         }
-        __syncthreads();
+        c_lo += st.cube[buf][n_here - 1];
     }
 }
 
 // ---- accumulate_weight: one thread per cube, rows summed in order (bit-identical to the CPU scatter_add_).
+// Cubes holding more than ST_HEAVY rows (peaked dh) would serialise one thread for a long time; those are
+// summed by the whole warp instead (stride-32 coalesced loads, fp64 accumulation, one rounding), which is
+// within 1 ulp of the exact sum rather than bit-identical to the reference's sequential order.
+constexpr long long ST_HEAVY = 256;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 strat_accumulate_kernel(const T* __restrict__ jf, int64_t row_base, const long long* __restrict__ offsets,
                         int64_t cube_begin, int64_t cube_end, T* __restrict__ JF, T* __restrict__ JF2) {
-    for (int64_t c = cube_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cube_end;
-         c += (int64_t)gridDim.x * blockDim.x) {
-        const long long r0 = offsets[c] - row_base, r1 = offsets[c + 1] - row_base;
-        T s = (T)0, q = (T)0;
-        for (long long r = r0; r < r1; ++r) {
-            const T v = jf[r];
-            s = add_rn(s, v);
-            q = add_rn(q, mul_rn(v, v));
+    const int lane = threadIdx.x & 31;
+    for (int64_t cw = cube_begin + (int64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); cw < cube_end;
+         cw += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = cw + lane;
+        const bool valid = c < cube_end;
+        const long long r0 = valid ? offsets[c] - row_base : 0, r1 = valid ? offsets[c + 1] - row_base : 0;
+        const bool heavy = r1 - r0 > ST_HEAVY;
+        if (valid && !heavy) {
+            T s = (T)0, q = (T)0;
+            for (long long r = r0; r < r1; ++r) {
+                const T v = jf[r];
+                s = add_rn(s, v);
+                q = add_rn(q, mul_rn(v, v));
+            }
+            JF[c] = s;
+            JF2[c] = q;
         }
-        JF[c] = s;
-        JF2[c] = q;
+        unsigned m = __ballot_sync(0xffffffffu, heavy);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const long long R0 = __shfl_sync(0xffffffffu, r0, src), R1 = __shfl_sync(0xffffffffu, r1, src);
+            double s = 0.0, q = 0.0;
+            for (long long r = R0 + lane; r < R1; r += 32) {
+                const double v = (double)jf[r];
+                s += v;
+                q += v * v;
+            }
+            s = warp_sum(s);
+            q = warp_sum(q);
+            if (lane == 0) {
+                JF[cw + src] = (T)s;
+                JF2[cw + src] = (T)q;
+            }
+        }
     }
 }
 
@@ -311,10 +373,20 @@ int tq_vegas_strat_sample(const int64_t* offsets, int64_t n_cubes, int32_t n_str
     TQ_REQUIRE(n_strat >= 1 && dim >= 1, "tq_vegas_strat_sample: bad n_strat/dim");
     TQ_REQUIRE(row_end >= row_begin && row_begin >= 0, "tq_vegas_strat_sample: bad row range");
     if (row_end == row_begin) return TQ_OK;
-    const int grid = grid_for(row_end - row_begin, ST_TILE, 8);
+    const int64_t nrows = row_end - row_begin;
+    const int64_t tiles = (nrows + ST_ROWS - 1) / ST_ROWS;
+    int64_t ctas = tiles < (int64_t)num_sms() * 8 ? tiles : (int64_t)num_sms() * 8;
+    int64_t rows_per_cta = (nrows + ctas - 1) / ctas;
+    rows_per_cta = ((rows_per_cta + ST_ROWS - 1) / ST_ROWS) * ST_ROWS;
+    ctas = (nrows + rows_per_cta - 1) / rows_per_cta;
     TQ_DISPATCH_DTYPE(dtype, {
-        strat_sample_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const long long*)offsets, n_cubes, n_strat, dim,
-                                                                   (const T*)u_in, seed, call_idx, row_begin, row_end, (T*)y);
+        const int nblk = (dim + U01<T>::LANES - 1) / U01<T>::LANES;
+        TQ_REQUIRE(nblk <= 128, "tq_vegas_strat_sample: dim %d too large", dim);
+        FastDiv fdn;
+        fdn.set((uint32_t)n_strat);
+        strat_sample_kernel<T><<<(unsigned)ctas, 256, 0, as_stream(stream)>>>((const long long*)offsets, n_cubes, n_strat, dim, nblk,
+                                                                             (const T*)u_in, seed, call_idx, row_begin, row_end,
+                                                                             rows_per_cta, fdn, (T*)y);
     });
     return check_launch("strat_sample_kernel");
 }

@@ -80,6 +80,11 @@ class VEGAS(BaseIntegrator):
         self._volume = torch.prod(self._sizes)
         self._user_fn = fn
         self._fn = lambda x: fn(x * self._sizes + self._starts) * self._volume
+        # Without a gradient through the domain, the unit-cube -> domain transform and the f*volume*jac tail
+        # are fused into the map kernels (same mul/add order as the torch expressions above).
+        self._domain = domain
+        self._fuse_tail = not domain.requires_grad
+        self._volume_host = float(self._volume.detach()) if self._fuse_tail else None
 
         self._fused = (isinstance(fn, BuiltinIntegrand) and type(rng) is RNG and fn.dim == dim
                        and not domain.requires_grad)
@@ -158,12 +163,16 @@ class VEGAS(BaseIntegrator):
                 else:
                     yrnd = self.rng.uniform(size=[N_samples, self._dim], dtype=self.dtype).to(self.device) * 0.999999
                     yrnd = yrnd[begin:end]
-                x, jac = self.map.get_X_and_Jac(yrnd)
-                f_eval = self._eval(x).squeeze()
+                f_raw, jac = self._map_and_eval(yrnd)
                 if tqdist.is_enabled():
                     self._nr_of_fevals += N_samples - (end - begin)
-                jf_vec2 = ((f_eval * jac) ** 2).detach()
-                self.map.accumulate_weight(yrnd, jf_vec2)
+                if f_raw is not None and not (torch.is_grad_enabled() and f_raw.requires_grad):
+                    ops.accumulate_fused(yrnd, f_raw, jac, self._volume_host, self.map.weights, self.map.counts,
+                                         want_jf=False)
+                else:
+                    f_eval = self._last_f_eval
+                    jf_vec2 = ((f_eval * jac) ** 2).detach()
+                    self.map.accumulate_weight(yrnd, jf_vec2)
             self._reduce_map_stats()
             self._update_map()
 
@@ -196,16 +205,19 @@ class VEGAS(BaseIntegrator):
                 u = self.rng.uniform(size=[M, self._dim], dtype=self.dtype).to(self.device)
                 y = ops.strat_sample(offsets, strat.N_strat, self._dim, self.dtype, begin, end,
                                      u_in=u[begin:end].contiguous())
-            x, jac = vmap.get_X_and_Jac(y)
-            f_eval = self._eval(x).squeeze()
+            f_raw, jac = self._map_and_eval(y)
             if tqdist.is_enabled():
                 self._nr_of_fevals += M - (end - begin)
-            if f_eval.dim() == 0:
-                f_eval = f_eval.reshape(1)
-            jf_vec = f_eval * jac
-            jf_vec2 = (jf_vec**2).detach()
-            if self.use_grid_improve:
-                vmap.accumulate_weight(y, jf_vec2)
+            if f_raw is not None and not (torch.is_grad_enabled() and f_raw.requires_grad):
+                if self.use_grid_improve:
+                    jf_vec = ops.accumulate_fused(y, f_raw, jac, self._volume_host, vmap.weights, vmap.counts)
+                else:
+                    jf_vec = (f_raw * self._volume.detach()) * jac
+            else:
+                f_eval = self._last_f_eval
+                jf_vec = f_eval * jac
+                if self.use_grid_improve:
+                    vmap.accumulate_weight(y, (jf_vec**2).detach())
             grad_path = torch.is_grad_enabled() and jf_vec.requires_grad
             JF, JF2 = ops.strat_accumulate(jf_vec, offsets, row_base=begin, cube_begin=cube_lo, cube_end=cube_hi)
             if tqdist.is_enabled():
@@ -229,6 +241,29 @@ class VEGAS(BaseIntegrator):
         self.sigma2[-1] = scal[1].to(self.dtype)
         if self.use_grid_improve:
             self._update_map()
+
+    def _map_and_eval(self, y):
+        """y -> (raw integrand values, jac).  Fused tail: x comes out of the map kernel already in domain
+        coordinates and the raw values are returned for `accumulate_fused`; otherwise (gradient through the
+        domain) the reference's torch expressions are used and (None, jac) is returned with the scaled values
+        left in `self._last_f_eval`."""
+        if self._fuse_tail:
+            x, jac, _ = ops.map_forward_packed(y, self.map.packed_edges(), self._domain.detach())
+            f_raw, n = self.evaluate_integrand(self._user_fn, x)
+            self._nr_of_fevals += n
+            f_raw = f_raw.reshape(-1) if f_raw.numel() == n else f_raw.squeeze()
+            if f_raw.dtype != self.dtype:
+                f_raw = f_raw.to(self.dtype)
+            if torch.is_grad_enabled() and f_raw.requires_grad:
+                self._last_f_eval = f_raw * self._volume
+                return f_raw, jac
+            return f_raw, jac
+        x, jac = self.map.get_X_and_Jac(y)
+        f_eval = self._eval(x).squeeze()
+        if f_eval.dim() == 0:
+            f_eval = f_eval.reshape(1)
+        self._last_f_eval = f_eval
+        return None, jac
 
     def _cube_aligned_shard(self, offsets):
         """(M, cube_lo, cube_hi, row_lo, row_hi) of this rank: contiguous cube ranges balanced by rows.

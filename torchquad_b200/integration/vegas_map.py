@@ -29,6 +29,7 @@ class VEGASMap:
         edges = torch.linspace(0.0, 1.0, N_intervals + 1, dtype=dtype, device=self.device)
         self.x_edges = edges.reshape(1, -1).repeat(dim, 1).contiguous()
         self._status = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._edges2, self._edges2_stale = None, True
         self._reset_weight()
 
     # -- bin lookup ---------------------------------------------------------------------------
@@ -81,13 +82,20 @@ class VEGASMap:
         reference's warnings / RuntimeError; the integrator passes `check=False` and calls
         `check_status()` at its own synchronisation points."""
         ops.map_update(self.x_edges, self.dx_edges, self.weights, self.counts, self.alpha, self._status)
+        self._edges2_stale = True
         if check:
             self.check_status()
 
     def packed_edges(self):
-        """{x_edges, dx_edges} interleaved [dim, Ni, 2] for the fused kernel (re-packed from the public tensors)."""
-        self._edges2 = ops.pack_edges(self.x_edges, self.dx_edges, getattr(self, "_edges2", None))
+        """{x_edges, dx_edges} interleaved [dim, Ni, 2]: the gather layout of the fused / packed kernels.
+        Cached; `update_map` invalidates it (call `invalidate_packed()` after editing the edges by hand)."""
+        if self._edges2 is None or self._edges2_stale:
+            self._edges2 = ops.pack_edges(self.x_edges, self.dx_edges, self._edges2)
+            self._edges2_stale = False
         return self._edges2
+
+    def invalidate_packed(self):
+        self._edges2_stale = True
 
     def check_status(self, status=None):
         """Raise / warn like vegas_map.py:188-196,240-257 from a status word (device read-back)."""
