@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--workload", default="mc10", choices=sorted(WORKLOADS))
     ap.add_argument("--no-unfused", action="store_true", help="skip the unfused torch-callable arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--map-cap", type=int, default=None,
+                    help="VEGAS workloads: cap the map at this many intervals per dimension (VEGAS.max_map_intervals); "
+                         "default keeps the reference's Ni = N/250")
     return ap.parse_args()
 
 
@@ -56,11 +59,11 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------ integrands
-def make_integrand(name, dim):
+def make_integrand(name, dim, fast_math=False):
     from torchquad_b200 import integrands as F
 
     if name == "sum_sin":
-        return F.SumOfSines(dim)
+        return F.SumOfSines(dim, fast_math=fast_math)
     if name == "prod_cos":
         return F.ProductOfCosines(dim)
     if name == "genz_gaussian":
@@ -223,7 +226,7 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------------ our arm
-def build_steps(wl, device, world):
+def build_steps(wl, device, world, map_cap=None):
     """Returns (fused_step, e2e_step, unfused_step, evals_per_step_per_job, info)."""
     import torchquad_b200 as tq
 
@@ -267,6 +270,7 @@ def build_steps(wl, device, world):
         evals = lambda: integ._nr_of_fevals  # noqa: E731
     else:
         integ = tq.VEGAS()
+        integ.max_map_intervals = map_cap
 
         def fused():
             state["seed"] += 1
@@ -281,7 +285,25 @@ def build_steps(wl, device, world):
             return float(integ.integrate(call, dim, N=N, integration_domain=dom_host, seed=state["seed"], backend="torch"))
 
         evals = lambda: integ._nr_of_fevals  # noqa: E731
-    return fused, e2e, unfused, evals, {"dtype": dt, "dim": dim, "exact": fn.exact()}
+    info = {"dtype": dt, "dim": dim, "exact": fn.exact(), "integrator": integ}
+    if wl["kind"] == "mc":
+        fast_fn = make_integrand(wl["integrand"], dim, fast_math=True)
+
+        def fused_fast():
+            state["seed"] += 1
+            return integ.integrate(fast_fn, dim, N=N, integration_domain=dom_dev, seed=state["seed"])
+
+        info["fused_fast"] = fused_fast
+    return fused, e2e, unfused, evals, info
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised in
+# profiles/r1 (same launch shapes as kernel_rooflines below / the default workload).
+NCU_TRAFFIC = {
+    "fused_mc_kernel": 28_160,            # profiles/r1/prof_fused_mc.txt (1e9 evals: no sample traffic)
+    "sum1_kernel": 865_042_944,           # profiles/r1/prof_sum1.txt (2e8 fp32 values = 800 MB algorithmic)
+    "uniform_kernel": 8_028_438_320,      # profiles/r1/prof_uniform_f32_d10.txt (2e8 x 10 fp32 = 8.0 GB algorithmic)
+}
 
 
 def measured_peaks():
@@ -339,8 +361,8 @@ def kernel_rooflines(wl, device, clocks_mhz):
         out["roofline_unfused"] = {
             "kernel": "uniform_kernel<T,true> (tq_mc_sample: Philox + affine map, points written to HBM)",
             "bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": bytes_alg / t / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-            "launch_ms": t * 1e3, "algorithmic_bytes_per_launch": bytes_alg,
+            "frac": bytes_alg / t / 1e9 / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get("uniform_kernel"),
+            "peak_source": peak_src, "launch_ms": t * 1e3, "algorithmic_bytes_per_launch": bytes_alg,
         }
         del buf
         f = torch.rand(rows, dtype=dt, device=device)
@@ -348,7 +370,8 @@ def kernel_rooflines(wl, device, clocks_mhz):
         out["roofline_reduce"] = {
             "kernel": "sum1_kernel<T> (tq_sum_columns: fp64-accumulated reduction of f)", "bound": "hbm",
             "achieved": rows * f.element_size() / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": rows * f.element_size() / t / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+            "frac": rows * f.element_size() / t / 1e9 / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get("sum1_kernel"),
+            "peak_source": peak_src,
             "launch_ms": t * 1e3,
         }
     return out
@@ -374,7 +397,7 @@ def run_ours(args, wl):
         tq.distributed.enable()
         barrier = dist.barrier
     flush = torch.zeros(128 << 20, dtype=torch.float32, device=device)
-    fused, e2e, unfused, evals, info = build_steps(wl, device, world)
+    fused, e2e, unfused, evals, info = build_steps(wl, device, world, args.map_cap)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -391,8 +414,16 @@ def run_ours(args, wl):
     e2e_steps = max(2, args.steps // 2)
     n_evals_e2e = evals()
 
+    fast = None
+    if "fused_fast" in info:
+        f_steps = max(2, args.steps // 2)
+        t_fast = max_over_ranks(sum(timed_steps(info["fused_fast"], f_steps, 1, flush, barrier)), device, world)
+        fast = {"value": evals() * f_steps / t_fast, "unit": "evals/s", "ms_per_step": t_fast / f_steps * 1e3,
+                "last_integral": float(info["fused_fast"]()),
+                "note": "same fused kernel with sin() evaluated by the SFU (__sinf, abs error ~5e-7): opt-in "
+                        "SumOfSines(dim, fast_math=True); not used for `value`"}
     unf = None
-    if not args.no_unfused and wl["kind"] in ("mc", "boole"):
+    if not args.no_unfused and wl["kind"] in ("mc", "boole", "vegas") and wl["N"] <= 3 * 10**9:
         u_steps = 2
         t_unf = max_over_ranks(sum(timed_steps(unfused, u_steps, 1, flush, barrier)), device, world)
         unf = {"value": evals() * u_steps / t_unf, "unit": "evals/s", "ms_per_step": t_unf / u_steps * 1e3,
@@ -425,10 +456,16 @@ def run_ours(args, wl):
         ach = n_evals * args.steps / t_fused * blocks_per_eval
         line["roofline"] = {"kernel": "fused_mc_kernel<SUM_SIN,float>", "bound": "int32/fp32 issue (no tensor, no HBM traffic)",
                             "achieved": ach / 1e9, "peak": micro["philox_blocks_per_s"] / 1e9, "unit": "G Philox blocks/s",
-                            "frac": ach / micro["philox_blocks_per_s"], "traffic": None,
+                            "frac": ach / micro["philox_blocks_per_s"], "traffic": NCU_TRAFFIC.get("fused_mc_kernel"),
                             "note": "peak = Philox-only microbenchmark on this GPU; the kernel also evaluates dim sin() per eval"}
+    if wl["kind"] == "vegas":
+        line["config"]["map_intervals"] = info["integrator"].map.N_intervals
+        line["config"]["n_cubes"] = info["integrator"].strat.N_cubes
+        line["config"]["iterations"] = info["integrator"].it
     if roof:
         line.update({k: v for k, v in roof.items()})
+    if fast:
+        line["fast_math"] = fast
     if unf:
         line["unfused"] = unf
     if not args.no_cpu_baseline and world == 1:

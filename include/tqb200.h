@@ -58,7 +58,12 @@ extern "C" {
 #define TQ_F_SUM_EXP 7
 #define TQ_F_PROD_COS 8
 #define TQ_F_POLYNOMIAL 9
-#define TQ_F_COUNT 10
+/* fp32 fast-math variants (MUFU.SIN/COS/EX2 via __sinf/__cosf/__expf, |abs error| <= ~5e-7 on the
+ * reference test domains); identical to the precise family in fp64. */
+#define TQ_F_SUM_SIN_FAST 10
+#define TQ_F_SUM_EXP_FAST 11
+#define TQ_F_PROD_COS_FAST 12
+#define TQ_F_COUNT 13
 
 /* Parameters of a built-in integrand, passed by value from the host.  `a`/`u` are the Genz difficulty
  * and shift vectors; `coeff[0..ncoeff)` the polynomial coefficients (same for each dimension).

@@ -291,6 +291,19 @@ def test_fused_integrands_match_torch_formulation_and_exact(cuda, cls, kw, tag):
         assert abs(fn.exact() - O.genz_exact(cls.family[5:], fn.a, fn.u)) <= 1e-13 * abs(fn.exact())
 
 
+def test_fast_math_variants_stay_within_fp32_tolerance(cuda):
+    """Opt-in SFU evaluation of sin/cos/exp (fp32): the estimate moves by far less than the 1e-5 bar."""
+    dom = torch.tensor([[0.0, 1.0]] * 6, dtype=torch.float32, device=cuda)
+    for cls in (F.SumOfSines, F.SumOfExp, F.ProductOfCosines):
+        a = float(tq.MonteCarlo().integrate(cls(6), 6, N=2_000_000, integration_domain=dom, seed=4))
+        b = float(tq.MonteCarlo().integrate(cls(6, fast_math=True), 6, N=2_000_000, integration_domain=dom, seed=4))
+        assert abs(a - b) <= 2e-6 * abs(a), (cls.__name__, a, b)
+    d64 = dom.double()
+    a = float(tq.MonteCarlo().integrate(F.SumOfSines(6), 6, N=100_000, integration_domain=d64, seed=4))
+    b = float(tq.MonteCarlo().integrate(F.SumOfSines(6, fast_math=True), 6, N=100_000, integration_domain=d64, seed=4))
+    assert a == b  # fp64 has no fast variant
+
+
 def test_fused_polynomial(cuda):
     fn = F.Polynomial(3, [1.0, -2.0, 0.5, 3.0])
     dom = torch.tensor([[0.0, 1.0]] * 3, dtype=torch.float64, device=cuda)

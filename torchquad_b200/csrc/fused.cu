@@ -51,7 +51,7 @@ struct Integrand {
     T acc;
     bool inside;
     __device__ __forceinline__ void init() {
-        acc = (FAM == TQ_F_GENZ_PRODUCT_PEAK || FAM == TQ_F_PROD_COS) ? (T)1 : (T)0;
+        acc = (FAM == TQ_F_GENZ_PRODUCT_PEAK || FAM == TQ_F_PROD_COS || FAM == TQ_F_PROD_COS_FAST) ? (T)1 : (T)0;
         inside = true;
     }
     __device__ __forceinline__ void step(T x, int d, const FnShared<T>& S) {
@@ -74,6 +74,12 @@ struct Integrand {
             acc += exp(x);
         } else if constexpr (FAM == TQ_F_PROD_COS) {
             acc *= cos(x);
+        } else if constexpr (FAM == TQ_F_SUM_SIN_FAST) {
+            if constexpr (sizeof(T) == 4) acc += __sinf(x); else acc += sin(x);
+        } else if constexpr (FAM == TQ_F_SUM_EXP_FAST) {
+            if constexpr (sizeof(T) == 4) acc += __expf(x); else acc += exp(x);
+        } else if constexpr (FAM == TQ_F_PROD_COS_FAST) {
+            if constexpr (sizeof(T) == 4) acc *= __cosf(x); else acc *= cos(x);
         } else if constexpr (FAM == TQ_F_POLYNOMIAL) {
             T h = S.coeff[S.ncoeff - 1];
             for (int k = S.ncoeff - 2; k >= 0; --k) h = h * x + S.coeff[k];
@@ -375,6 +381,9 @@ pack_edges_kernel(const T* __restrict__ xe, const T* __restrict__ dxe, typename 
         case TQ_F_SUM_EXP: { constexpr int FAM = TQ_F_SUM_EXP; __VA_ARGS__; break; }                        \
         case TQ_F_PROD_COS: { constexpr int FAM = TQ_F_PROD_COS; __VA_ARGS__; break; }                      \
         case TQ_F_POLYNOMIAL: { constexpr int FAM = TQ_F_POLYNOMIAL; __VA_ARGS__; break; }                  \
+        case TQ_F_SUM_SIN_FAST: { constexpr int FAM = TQ_F_SUM_SIN_FAST; __VA_ARGS__; break; }              \
+        case TQ_F_SUM_EXP_FAST: { constexpr int FAM = TQ_F_SUM_EXP_FAST; __VA_ARGS__; break; }              \
+        case TQ_F_PROD_COS_FAST: { constexpr int FAM = TQ_F_PROD_COS_FAST; __VA_ARGS__; break; }            \
         default: tq::set_error("unknown integrand family %d", (int)(fam)); return TQ_ERR_INVALID_ARGUMENT;  \
     }
 
