@@ -142,9 +142,11 @@ TQ_API int tq_vegas_map_smooth(const void* weights, const int64_t* counts, void*
                         size_t ws_bytes, void* stream);
 /* update_map (:185-261): smooth, equal-mass rebin (fp64 prefix sums), inf repair, dx = diff(x), reset
  * of weights/counts.  status (device int32[4]): [0]=1 update skipped (zero dimension), [1]=number of
- * non-finite edges that were repaired, [2]=1 unrepairable (reference raises RuntimeError), [3]=unused. */
-TQ_API int tq_vegas_map_update(void* x_edges, void* dx_edges, void* weights, int64_t* counts, int32_t dim,
-                        int64_t n_intervals, double alpha, int32_t dtype, int32_t* status, void* ws,
+ * non-finite edges that were repaired, [2]=1 unrepairable (reference raises RuntimeError), [3]=unused.
+ * edges_packed (nullable): also receives the new edges as {x_edge, dx_edge} pairs (tq_vegas_map_pack_edges).
+ * Maps of up to 32768 intervals per dimension run the whole update in a single launch. */
+TQ_API int tq_vegas_map_update(void* x_edges, void* dx_edges, void* weights, int64_t* counts, void* edges_packed,
+                        int32_t dim, int64_t n_intervals, double alpha, int32_t dtype, int32_t* status, void* ws,
                         size_t ws_bytes, void* stream);
 
 /* ---- VEGAS stratification (torchquad/integration/vegas_stratification.py) -----------------------

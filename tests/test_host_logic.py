@@ -113,7 +113,7 @@ def test_vegas_schedule_matches_oracle_decisions():
             v.it, v._nr_of_fevals, v.N = 5, run.fevals, 100_000
             v._max_iterations, v._eps_rel, v._eps_abs = 20, 0, 0
             v._starting_N = v._N_increment = 100_000 // 25
-            v._map_status = []
+            v._status_used, v._status_buf = 0, torch.zeros((4, 4), dtype=torch.int32)
             want_mean = run.result()
             assert torch.equal(v._get_result(), want_mean)
             stop_ref = run.check_abort()

@@ -48,7 +48,7 @@ PROTOTYPES = {
     "tq_vegas_map_accumulate": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
     "tq_vegas_map_workspace_bytes": (c_sz, [c_i32, c_i64, c_i32]),
     "tq_vegas_map_smooth": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_f64, c_i32, c_p, c_p, c_sz, c_p]),
-    "tq_vegas_map_update": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i32, c_i64, c_f64, c_i32, c_p, c_p, c_sz, c_p]),
+    "tq_vegas_map_update": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_i32, c_i64, c_f64, c_i32, c_p, c_p, c_sz, c_p]),
     "tq_vegas_strat_nh": (ctypes.c_int, [c_p, c_i64, c_f64, c_i32, c_p, c_p, c_p, c_sz, c_p]),
     "tq_vegas_strat_offsets": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_sz, c_p]),
     "tq_vegas_strat_sample": (ctypes.c_int, [c_p, c_i64, c_i32, c_i32, c_i32, c_p, c_u64, c_u32, c_i64, c_i64, c_p, c_p]),

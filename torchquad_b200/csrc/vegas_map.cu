@@ -390,7 +390,8 @@ __device__ __forceinline__ T repaired_edge(const T* __restrict__ xn, long long e
 template <typename T>
 __global__ void __launch_bounds__(256)
 map_finalize_kernel(const T* __restrict__ x_new, T* __restrict__ xe, T* __restrict__ dxe, T* __restrict__ weights,
-                    long long* __restrict__ counts, long long ni, int32_t* status) {
+                    long long* __restrict__ counts, typename EdgePair<T>::type* __restrict__ packed, long long ni,
+                    int32_t* status) {
     const int d = blockIdx.y;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < ni) {
@@ -407,7 +408,135 @@ map_finalize_kernel(const T* __restrict__ x_new, T* __restrict__ xe, T* __restri
     if (e < ni) {
         bool b2, s2;
         const T vn = repaired_edge<T>(xn, e + 1, ni, b2, s2);
-        dxe[(int64_t)d * ni + e] = sub_rn(vn, v);
+        const T dv = sub_rn(vn, v);
+        dxe[(int64_t)d * ni + e] = dv;
+        if (packed) {
+            typename EdgePair<T>::type pr;
+            pr.x = v;
+            pr.y = dv;
+            packed[(int64_t)d * ni + e] = pr;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ small maps: the whole update in ONE launch
+// For maps up to MAP_SMALL_NI intervals per dimension (every case where VEGAS is launch-latency bound) one CTA
+// per dimension runs average -> smooth -> fp64 prefix -> new edges -> repair/diff/reset back to back with CTA
+// barriers instead of seven launches.  The "any dimension sums to zero" decision needs all row sums; each
+// CTA recomputes them (dim * Ni reads, tiny at these sizes) instead of synchronising across CTAs.
+constexpr long long MAP_SMALL_NI = 32768;
+constexpr int MAP_SMALL_DIM = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+map_update_small_kernel(T* __restrict__ xe, T* __restrict__ dxe, T* __restrict__ weights, long long* __restrict__ counts,
+                        typename EdgePair<T>::type* __restrict__ packed, T* __restrict__ avg, T* __restrict__ smoothed,
+                        double* __restrict__ S, T* __restrict__ x_new, int dim, long long ni, T alpha,
+                        int32_t* status, bool do_edges) {
+    __shared__ double sh[33];
+    __shared__ double s_tot[MAP_SMALL_DIM];
+    __shared__ double s_total2;
+    const int d = blockIdx.x;
+    const int tid = threadIdx.x;
+    for (int dd = 0; dd < dim; ++dd) {
+        const T* w = weights + (int64_t)dd * ni;
+        const long long* c = counts + (int64_t)dd * ni;
+        double part[1] = {0.0};
+        for (long long j = tid; j < ni; j += blockDim.x) {
+            const T a = filled_average<T>(w, c, j, ni);
+            if (dd == d) avg[(int64_t)d * ni + j] = a;
+            part[0] += (double)a;
+        }
+        block_sum<1>(part, sh);
+        if (tid == 0) s_tot[dd] = part[0];
+        __syncthreads();
+    }
+    bool any_zero = false;
+    for (int dd = 0; dd < dim; ++dd) any_zero |= ((T)s_tot[dd] == (T)0);
+    if (any_zero) {
+        if (d == 0 && tid == 0) status[0] = 1;
+        if (do_edges) {
+            for (long long j = tid; j < ni; j += blockDim.x) {
+                weights[(int64_t)d * ni + j] = (T)0;
+                counts[(int64_t)d * ni + j] = 0;
+            }
+        }
+        return;
+    }
+    // smoothing + compression (vegas_map.py:146-170)
+    const T* a = avg + (int64_t)d * ni;
+    T* sm = smoothed + (int64_t)d * ni;
+    const T denom = mul_rn((T)8, (T)s_tot[d]);
+    double part[1] = {0.0};
+    for (long long j = tid; j < ni; j += blockDim.x) {
+        T v;
+        if (j == 0) v = add_rn(mul_rn((T)7, a[0]), a[1]);
+        else if (j == ni - 1) v = add_rn(a[ni - 2], mul_rn((T)7, a[ni - 1]));
+        else v = add_rn(add_rn(a[j - 1], mul_rn((T)6, a[j])), a[j + 1]);
+        v = div_rn(v, denom);
+        if (v != (T)0) {
+            const T base = div_rn(sub_rn(v, (T)1), log(v));
+            v = (alpha == (T)0.5) ? sqrt(base) : pow(base, alpha);
+        }
+        sm[j] = v;
+        part[0] += (double)v;
+    }
+    block_sum<1>(part, sh);
+    if (tid == 0) s_total2 = part[0];
+    __syncthreads();
+    if (!do_edges) return;
+    // fp64 inclusive prefix sums
+    double* Sd = S + (int64_t)d * ni;
+    double carry = 0.0;
+    for (long long base = 0; base < ni; base += blockDim.x) {
+        const long long j = base + tid;
+        const double v = j < ni ? (double)sm[j] : 0.0;
+        double total;
+        const double ex = block_excl_scan<double>(v, sh, total);
+        if (j < ni) Sd[j] = carry + ex + v;
+        carry += total;
+    }
+    __syncthreads();
+    // new inner edges (vegas_map.py:214-239)
+    const T* x_old = xe + (int64_t)d * (ni + 1);
+    const T* dx_old = dxe + (int64_t)d * ni;
+    T* xn = x_new + (int64_t)d * (ni + 1);
+    const T delta_t = div_rn((T)s_total2, (T)ni);
+    const double delta = (double)delta_t;
+    if (tid == 0) { xn[0] = x_old[0]; xn[ni] = x_old[ni]; }
+    for (long long m = tid; m <= ni - 2; m += blockDim.x) {
+        long long lo = 0, hi = ni - 1;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            const long long k = (long long)(__ddiv_rn(Sd[mid], delta));
+            if (k > m) hi = mid; else lo = mid + 1;
+        }
+        const long long idx = lo;
+        const double below = idx > 0 ? Sd[idx - 1] : 0.0;
+        const T acc = (T)((double)(m + 1) * delta - below);
+        xn[m + 1] = add_rn(x_old[idx], mul_rn(div_rn(acc, sm[idx]), dx_old[idx]));
+    }
+    __syncthreads();
+    // repair, diff, pack, reset (vegas_map.py:240-261)
+    for (long long e = tid; e <= ni; e += blockDim.x) {
+        bool bad, still;
+        const T v = repaired_edge<T>(xn, e, ni, bad, still);
+        if (bad) atomicAdd(&status[1], 1);
+        if (still) status[2] = 1;
+        xe[(int64_t)d * (ni + 1) + e] = v;
+        if (e < ni) {
+            bool b2, s2;
+            const T dv = sub_rn(repaired_edge<T>(xn, e + 1, ni, b2, s2), v);
+            dxe[(int64_t)d * ni + e] = dv;
+            if (packed) {
+                typename EdgePair<T>::type pr;
+                pr.x = v;
+                pr.y = dv;
+                packed[(int64_t)d * ni + e] = pr;
+            }
+            weights[(int64_t)d * ni + e] = (T)0;
+            counts[(int64_t)d * ni + e] = 0;
+        }
     }
 }
 
@@ -582,16 +711,22 @@ int tq_vegas_map_smooth(const void* weights, const int64_t* counts, void* smooth
     TQ_REQUIRE(dim >= 1 && dim <= 65535 && n_intervals >= 2, "tq_vegas_map_smooth: need dim >= 1 and Ni >= 2");
     Workspace w(ws, ws_bytes);
     MapScratch s;
+    cudaStream_t st = as_stream(stream);
     TQ_DISPATCH_DTYPE(dtype, {
         if (!carve<T>(w, dim, n_intervals, s, false)) { set_error("tq_vegas_map_smooth: workspace too small"); return TQ_ERR_WORKSPACE; }
-        return run_smooth<T>((const T*)weights, (const long long*)counts, (T*)smoothed, s, dim, n_intervals, alpha, status,
-                             as_stream(stream));
+        if (n_intervals <= MAP_SMALL_NI && dim <= MAP_SMALL_DIM) {
+            cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st);
+            map_update_small_kernel<T><<<dim, 1024, 0, st>>>(nullptr, nullptr, (T*)weights, (long long*)counts, nullptr, (T*)s.avg,
+                                                            (T*)smoothed, nullptr, nullptr, dim, n_intervals, (T)alpha, status, false);
+            return check_launch("map_update_small_kernel");
+        }
+        return run_smooth<T>((const T*)weights, (const long long*)counts, (T*)smoothed, s, dim, n_intervals, alpha, status, st);
     });
     return TQ_OK;
 }
 
-int tq_vegas_map_update(void* x_edges, void* dx_edges, void* weights, int64_t* counts, int32_t dim,
-                        int64_t n_intervals, double alpha, int32_t dtype, int32_t* status, void* ws,
+int tq_vegas_map_update(void* x_edges, void* dx_edges, void* weights, int64_t* counts, void* edges_packed,
+                        int32_t dim, int64_t n_intervals, double alpha, int32_t dtype, int32_t* status, void* ws,
                         size_t ws_bytes, void* stream) {
     TQ_REQUIRE(dim >= 1 && dim <= 65535 && n_intervals >= 2, "tq_vegas_map_update: need dim >= 1 and Ni >= 2");
     Workspace w(ws, ws_bytes);
@@ -599,7 +734,15 @@ int tq_vegas_map_update(void* x_edges, void* dx_edges, void* weights, int64_t* c
     cudaStream_t st = as_stream(stream);
     const long long ni = n_intervals;
     TQ_DISPATCH_DTYPE(dtype, {
+        using P2 = typename EdgePair<T>::type;
         if (!carve<T>(w, dim, ni, s, true)) { set_error("tq_vegas_map_update: workspace too small (need %zu bytes)", map_scratch_bytes(dim, ni, sizeof(T))); return TQ_ERR_WORKSPACE; }
+        if (ni <= MAP_SMALL_NI && dim <= MAP_SMALL_DIM) {
+            cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st);
+            map_update_small_kernel<T><<<dim, 1024, 0, st>>>((T*)x_edges, (T*)dx_edges, (T*)weights, (long long*)counts,
+                                                            (P2*)edges_packed, (T*)s.avg, (T*)s.smoothed, s.S, (T*)s.x_new, dim, ni,
+                                                            (T)alpha, status, true);
+            return check_launch("map_update_small_kernel");
+        }
         int rc = run_smooth<T>((const T*)weights, (const long long*)counts, (T*)s.smoothed, s, dim, ni, alpha, status, st);
         if (rc) return rc;
         dim3 grid(s.ntiles, dim);
@@ -609,7 +752,7 @@ int tq_vegas_map_update(void* x_edges, void* dx_edges, void* weights, int64_t* c
                                                    (const T*)dx_edges, (T*)s.x_new, ni, status);
         dim3 grid_f((unsigned)((ni + 1 + 255) / 256), dim);
         map_finalize_kernel<T><<<grid_f, 256, 0, st>>>((const T*)s.x_new, (T*)x_edges, (T*)dx_edges, (T*)weights,
-                                                      (long long*)counts, ni, status);
+                                                      (long long*)counts, (P2*)edges_packed, ni, status);
     });
     return check_launch("map update");
 }

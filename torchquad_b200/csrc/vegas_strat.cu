@@ -70,6 +70,29 @@ nh_scan_kernel(const T* __restrict__ dh, int64_t n_cubes, T nev, const long long
     }
 }
 
+// Small stratifications (the launch-latency-bound regime): get_NH + scan in ONE CTA.
+constexpr int64_t ST_SMALL_CUBES = 32768;
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+nh_small_kernel(const T* __restrict__ dh, int64_t n_cubes, T nev, long long* __restrict__ nh,
+                long long* __restrict__ offsets) {
+    __shared__ long long sh[33];
+    long long carry = 0;
+    for (int64_t base = 0; base < n_cubes; base += blockDim.x) {
+        const int64_t c = base + threadIdx.x;
+        const long long v = c < n_cubes ? nh_of<T>(dh[c], nev) : 0;
+        long long total;
+        const long long ex = block_excl_scan<long long>(v, sh, total);
+        if (c < n_cubes) {
+            nh[c] = v;
+            offsets[c] = carry + ex;
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0) offsets[n_cubes] = carry;
+}
+
 // ---- exclusive scan of a caller-provided nh
 __global__ void __launch_bounds__(256)
 i64_tile_sum_kernel(const long long* __restrict__ v, int64_t n, long long* __restrict__ tile_sums) {
@@ -317,6 +340,42 @@ strat_update_kernel(const T* __restrict__ JF, const T* __restrict__ JF2, const l
     grid_sum_finish<3>(acc, sh, partials, ticket, scalars);
 }
 
+// Small stratifications: estimator, d^beta, its sum and the normalisation in ONE CTA.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+strat_update_small_kernel(const T* __restrict__ JF, const T* __restrict__ JF2, const long long* __restrict__ nh,
+                          int64_t n_cubes, T V, T V2, T beta, T* __restrict__ dh, double* scalars) {
+    __shared__ double sh[32 * 3];
+    __shared__ double s_sum;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int64_t c = threadIdx.x; c < n_cubes; c += blockDim.x) {
+        const T n = (T)nh[c];
+        const T inv = div_rn((T)1, n);
+        const T jf = JF[c], jf2 = JF2[c];
+        const T ih = mul_rn(jf, mul_rn(inv, V));
+        const T sig2 = fabs(sub_rn(mul_rn(mul_rn(jf2, inv), V2), mul_rn(ih, ih)));
+        acc[0] += (double)ih;
+        acc[1] += (double)mul_rn(sig2, inv);
+        const T m = div_rn(mul_rn(V, jf), n);
+        T dv = sub_rn(div_rn(mul_rn(V2, jf2), n), mul_rn(m, m));
+        if (dv < (T)0) dv = (T)0;
+        const T p = pow(dv, beta);
+        dh[c] = p;
+        acc[2] += (double)p;
+    }
+    block_sum<3>(acc, sh);
+    if (threadIdx.x == 0) {
+        scalars[0] = acc[0];
+        scalars[1] = acc[1];
+        scalars[2] = acc[2];
+        s_sum = acc[2];
+    }
+    __syncthreads();
+    const T s = (T)s_sum;
+    if (s == (T)0) return;
+    for (int64_t c = threadIdx.x; c < n_cubes; c += blockDim.x) dh[c] = div_rn(dh[c], s);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 strat_normalise_kernel(T* __restrict__ dh, int64_t n_cubes, const double* __restrict__ scalars) {
@@ -342,6 +401,12 @@ int tq_vegas_strat_nh(const void* dh, int64_t n_cubes, double nevals_exp, int32_
     long long* tile_sums = w.take<long long>((size_t)ntiles);
     if (!tile_sums) { set_error("tq_vegas_strat_nh: workspace too small for %lld cubes", (long long)n_cubes); return TQ_ERR_WORKSPACE; }
     cudaStream_t st = as_stream(stream);
+    if (n_cubes <= ST_SMALL_CUBES) {
+        TQ_DISPATCH_DTYPE(dtype, {
+            nh_small_kernel<T><<<1, 1024, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, (long long*)nh, (long long*)offsets);
+        });
+        return check_launch("nh_small_kernel");
+    }
     TQ_DISPATCH_DTYPE(dtype, {
         nh_tile_sum_kernel<T><<<(unsigned)ntiles, 256, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, tile_sums);
         i64_tile_scan_kernel<<<1, 256, 0, st>>>(tile_sums, ntiles, (long long*)offsets + n_cubes);
@@ -427,6 +492,13 @@ int tq_vegas_strat_update(const void* JF, const void* JF2, const int64_t* nh, in
     double* partials = w.take<double>((size_t)grid * 3);
     if (!ticket || !partials) { set_error("tq_vegas_strat_update: workspace too small"); return TQ_ERR_WORKSPACE; }
     cudaStream_t st = as_stream(stream);
+    if (n_cubes <= ST_SMALL_CUBES) {
+        TQ_DISPATCH_DTYPE(dtype, {
+            strat_update_small_kernel<T><<<1, 1024, 0, st>>>((const T*)JF, (const T*)JF2, (const long long*)nh, n_cubes,
+                                                            (T)v_cubes, (T)(v_cubes * v_cubes), (T)beta, (T*)dh, scalars_f64);
+        });
+        return check_launch("strat_update_small_kernel");
+    }
     TQ_DISPATCH_DTYPE(dtype, {
         strat_update_kernel<T><<<grid, 256, 0, st>>>((const T*)JF, (const T*)JF2, (const long long*)nh, n_cubes,
                                                     (T)v_cubes, (T)(v_cubes * v_cubes), (T)beta, (T*)dh, partials, ticket,

@@ -103,7 +103,9 @@ class VEGAS(BaseIntegrator):
         self.sigma2 = []   # per-iteration variances (0-dim tensors, detached)
         self.it = 0
         self._host_block = None
-        self._map_status = []
+        # one status word per map update, written by the kernels, read back in one go at the sync points
+        self._status_buf = torch.zeros((max_iterations + 16, 4), dtype=torch.int32, device=self.device)
+        self._status_used = 0
 
         # random-access regime: shrink the L2 fetch granularity while the big tables are in flight
         restore_l2 = None
@@ -136,15 +138,17 @@ class VEGAS(BaseIntegrator):
             tqdist.all_reduce_sum_(self.map.weights, self.map.counts)
 
     def _update_map(self):
-        self.map.update_map(check=False)
-        self._map_status.append(self.map._status.clone())
+        if self._status_used == self._status_buf.shape[0]:
+            self._flush_map_status()
+        self.map.update_map(check=False, status=self._status_buf[self._status_used])
+        self._status_used += 1
 
     def _flush_map_status(self):
         """Turn accumulated device status words into the reference's warnings / errors (one read-back)."""
-        if not self._map_status:
+        if not self._status_used:
             return
-        words = torch.stack(self._map_status).tolist()
-        self._map_status = []
+        words = self._status_buf[: self._status_used].tolist()
+        self._status_used = 0
         for w in words:
             self.map.check_status(w)
 
@@ -233,12 +237,13 @@ class VEGAS(BaseIntegrator):
         # estimator + damped-variance update in one kernel (vegas.py:293-303, vegas_stratification.py:72-90)
         strat.update_DH()
         scal = strat.last_scalars
+        # scal[0], scal[1] are fp64 views (no kernel); they are rounded to the working dtype when read back
         if grad_path:
             inv = 1.0 / neval.to(self.dtype)
             self.results[-1] = (strat.JF * (inv * strat.V_cubes)).sum()
         else:
-            self.results[-1] = scal[0].to(self.dtype)
-        self.sigma2[-1] = scal[1].to(self.dtype)
+            self.results[-1] = scal[0]
+        self.sigma2[-1] = scal[1]
         if self.use_grid_improve:
             self._update_map()
 
@@ -281,9 +286,10 @@ class VEGAS(BaseIntegrator):
     # ------------------------------------------------------------------ schedule (host)
     def _host_values(self):
         """(results, sigma2) of the current block as numpy scalars of the working dtype (one read-back)."""
-        packed = torch.stack([torch.stack([r.detach() for r in self.results]),
-                              torch.stack([s.detach() for s in self.sigma2])]).cpu().numpy()
-        return [self._np(v) for v in packed[0]], [self._np(v) for v in packed[1]]
+        packed = torch.stack([r.detach().to(torch.float64) for r in self.results]
+                             + [s.detach().to(torch.float64) for s in self.sigma2]).cpu().numpy()
+        k = len(self.results)
+        return [self._np(v) for v in packed[:k]], [self._np(v) for v in packed[k:]]
 
     @staticmethod
     def _weighted_mean(results, sigma2):

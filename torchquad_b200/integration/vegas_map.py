@@ -74,17 +74,20 @@ class VEGASMap:
         self.counts = torch.zeros((self.dim, self.N_intervals), dtype=torch.int64, device=self.device)
 
     # -- rebinning ----------------------------------------------------------------------------
-    def update_map(self, check=True):
+    def update_map(self, check=True, status=None):
         """Adapt the edges to the accumulated weights, section II C (vegas_map.py:185-261).
 
         The kernels never synchronise: problems are reported through a device status word.  With
         `check=True` (default, reference behaviour) the word is read back here and turned into the
         reference's warnings / RuntimeError; the integrator passes `check=False` and calls
         `check_status()` at its own synchronisation points."""
-        ops.map_update(self.x_edges, self.dx_edges, self.weights, self.counts, self.alpha, self._status)
-        self._edges2_stale = True
+        st = self._status if status is None else status
+        keep_packed = self._edges2 is not None  # refresh the packed copy in the same launch once it exists
+        ops.map_update(self.x_edges, self.dx_edges, self.weights, self.counts, self.alpha, st,
+                       edges_packed=self._edges2 if keep_packed else None)
+        self._edges2_stale = not keep_packed
         if check:
-            self.check_status()
+            self.check_status(st)
 
     def packed_edges(self):
         """{x_edges, dx_edges} interleaved [dim, Ni, 2]: the gather layout of the fused / packed kernels.

@@ -214,14 +214,16 @@ def map_smooth(weights, counts, alpha):
     return out, status
 
 
-def map_update(x_edges, dx_edges, weights, counts, alpha, status):
-    """update_map (vegas_map.py:185-261) in place; `status` is an int32[4] device tensor (see header)."""
-    require_cuda(x_edges, dx_edges, weights, counts, status)
+def map_update(x_edges, dx_edges, weights, counts, alpha, status, edges_packed=None):
+    """update_map (vegas_map.py:185-261) in place; `status` is an int32[4] device tensor (see header);
+    `edges_packed` ([dim, Ni, 2], optional) receives the new edges in the packed gather layout."""
+    require_cuda(x_edges, dx_edges, weights, counts, status, edges_packed)
     dim, ni = weights.shape
     scratch = _map_scratch(dim, ni, weights.dtype, weights.device)
     with torch.cuda.device(weights.device):
-        call("tq_vegas_map_update", ptr(x_edges), ptr(dx_edges), ptr(weights), ptr(counts), dim, ni, float(alpha),
-             dtype_code(weights.dtype), ptr(status), ptr(scratch), scratch.numel(), stream_ptr(weights.device))
+        call("tq_vegas_map_update", ptr(x_edges), ptr(dx_edges), ptr(weights), ptr(counts), ptr(edges_packed), dim, ni,
+             float(alpha), dtype_code(weights.dtype), ptr(status), ptr(scratch), scratch.numel(),
+             stream_ptr(weights.device))
 
 
 # ------------------------------------------------------------------------------------------- stratification
@@ -308,7 +310,7 @@ def strat_update(JF, JF2, nh, v_cubes, beta):
     require_cuda(JF, JF2, nh)
     n = JF.shape[0]
     dh = torch.empty(n, dtype=JF.dtype, device=JF.device)
-    scalars = torch.zeros(3, dtype=torch.float64, device=JF.device)
+    scalars = torch.empty(3, dtype=torch.float64, device=JF.device)  # fully written by the kernel
     with torch.cuda.device(JF.device):
         wsp, wsn = _ws(JF.device)
         call("tq_vegas_strat_update", ptr(JF.detach().contiguous()), ptr(JF2.detach().contiguous()), ptr(nh), n,
@@ -442,7 +444,8 @@ def fused_vegas(fn_struct, edges_packed, weights, counts, row_begin, row_end, se
                 offsets=None, n_strat=1, JF=None, JF2=None):
     """One fused VEGAS pass (warm-up when offsets is None).  Returns fp64 [2] = {sum jf, sum jf^2} (warm-up only)."""
     require_cuda(edges_packed, weights, counts, offsets, JF, JF2)
-    out = torch.zeros(2, dtype=torch.float64, device=edges_packed.device)
+    # only the warm-up pass reduces {sum jf, sum jf^2}; the stratified pass writes JF/JF2
+    out = torch.empty(2, dtype=torch.float64, device=edges_packed.device) if offsets is None else None
     n_cubes = 0 if offsets is None else offsets.shape[0] - 1
     with torch.cuda.device(edges_packed.device):
         wsp, wsn = _ws(edges_packed.device)
