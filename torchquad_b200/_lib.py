@@ -69,6 +69,7 @@ PROTOTYPES = {
 }
 
 _cdll = None
+_fns = {}
 _lock = threading.Lock()
 _workspaces = {}
 launch_count = 0  # kernels-launching C-ABI calls issued by this process (bench.py reports it)
@@ -92,6 +93,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+            _fns[name] = fn
         _cdll = lib
     return _cdll
 
@@ -124,7 +126,31 @@ def ptr(t):
 
 
 def stream_ptr(device=None):
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw cudaStream_t of torch's current stream on `device` (the C ABI launches on the caller's stream)."""
+    idx = device.index if device is not None and device.index is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
+class on_device:
+    """`with on_device(dev):` -- make `dev` the current CUDA device for the C-ABI call; free when it already is."""
+
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.prev = -1
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def workspace(device):
@@ -141,10 +167,13 @@ def workspace(device):
 def call(name, *args):
     """Invoke a C-ABI entry point and turn a non-zero status into RuntimeError."""
     global launch_count
-    lib = load()
-    rc = getattr(lib, name)(*args)
+    fn = _fns.get(name)
+    if fn is None:
+        load()
+        fn = _fns[name]
+    rc = fn(*args)
     if rc != 0:
-        raise RuntimeError(f"{name} failed ({rc}): {lib.tq_last_error().decode()}")
+        raise RuntimeError(f"{name} failed ({rc}): {_cdll.tq_last_error().decode()}")
     launch_count += 1
     return rc
 
@@ -152,7 +181,7 @@ def call(name, *args):
 def l2_fetch_granularity(device, nbytes=0):
     """Return the current L2 fetch granularity hint of `device`; set it first when nbytes > 0."""
     prev = c_i32()
-    with torch.cuda.device(device):
+    with on_device(device):
         call("tq_l2_fetch_granularity", nbytes, ctypes.byref(prev))
     return prev.value
 

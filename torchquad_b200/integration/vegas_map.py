@@ -30,6 +30,7 @@ class VEGASMap:
         self.x_edges = edges.reshape(1, -1).repeat(dim, 1).contiguous()
         self._status = torch.zeros(4, dtype=torch.int32, device=self.device)
         self._edges2, self._edges2_stale = None, True
+        self._scratch = None
         self._reset_weight()
 
     # -- bin lookup ---------------------------------------------------------------------------
@@ -83,8 +84,10 @@ class VEGASMap:
         `check_status()` at its own synchronisation points."""
         st = self._status if status is None else status
         keep_packed = self._edges2 is not None  # refresh the packed copy in the same launch once it exists
+        if self._scratch is None:
+            self._scratch = ops.map_scratch(self.dim, self.N_intervals, self.dtype, self.device)
         ops.map_update(self.x_edges, self.dx_edges, self.weights, self.counts, self.alpha, st,
-                       edges_packed=self._edges2 if keep_packed else None)
+                       edges_packed=self._edges2 if keep_packed else None, scratch=self._scratch)
         self._edges2_stale = not keep_packed
         if check:
             self.check_status(st)

@@ -10,7 +10,7 @@ contraction / column sums wrt the integrand values) -- pinned by tests mirroring
 import torch
 
 from . import _lib
-from ._lib import call, dtype_code, ptr, require_cuda, stream_ptr, workspace
+from ._lib import call, dtype_code, on_device, ptr, require_cuda, stream_ptr, workspace
 
 
 def _ws(device):
@@ -24,7 +24,7 @@ def philox_uniform(rows, dim, dtype, device, seed, call_idx, row_begin=0):
     out = torch.empty((rows, dim), dtype=dtype, device=device)
     require_cuda(out)
     if rows > 0:
-        with torch.cuda.device(out.device):
+        with on_device(out.device):
             call("tq_philox_uniform", ptr(out), row_begin, row_begin + rows, dim, dtype_code(dtype),
                  seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, stream_ptr(out.device))
     return out
@@ -38,7 +38,7 @@ class _MCSample(torch.autograd.Function):
         dim = dom.shape[0]
         out = torch.empty((rows, dim), dtype=dom.dtype, device=dom.device)
         if rows > 0:
-            with torch.cuda.device(dom.device):
+            with on_device(dom.device):
                 call("tq_mc_sample", ptr(out), ptr(dom), row_begin, row_begin + rows, dim, dtype_code(dom.dtype),
                      seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, stream_ptr(dom.device))
         ctx.meta = (rows, seed, call_idx, row_begin, dom.dtype)
@@ -51,7 +51,7 @@ class _MCSample(torch.autograd.Function):
         dim = g.shape[1]
         gd = torch.zeros((dim, 2), dtype=torch.float64, device=g.device)
         if rows > 0:
-            with torch.cuda.device(g.device):
+            with on_device(g.device):
                 wsp, wsn = _ws(g.device)
                 call("tq_mc_sample_backward", ptr(g), row_begin, row_begin + rows, dim, dtype_code(dtype),
                      seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, ptr(gd), wsp, wsn, stream_ptr(g.device))
@@ -72,7 +72,7 @@ def sum_columns(f, want_sumsq=False):
     s = torch.zeros(cols, dtype=torch.float64, device=f2.device)
     q = torch.zeros(cols, dtype=torch.float64, device=f2.device) if want_sumsq else None
     if rows > 0:
-        with torch.cuda.device(f2.device):
+        with on_device(f2.device):
             wsp, wsn = _ws(f2.device)
             call("tq_sum_columns", ptr(f2), rows, cols, dtype_code(f2.dtype), ptr(s), ptr(q), wsp, wsn,
                  stream_ptr(f2.device))
@@ -145,7 +145,7 @@ def map_forward(y, x_edges, dx_edges, want_x=True, want_jac=True, want_ids=False
     ids = torch.empty((rows, dim), dtype=torch.int32, device=y.device) if want_ids else None
     off = torch.empty_like(y) if want_offset else None
     if rows > 0:
-        with torch.cuda.device(y.device):
+        with on_device(y.device):
             call("tq_vegas_map_forward", ptr(y), ptr(x_edges), ptr(dx_edges), ptr(x), ptr(jac), ptr(ids), ptr(off), rows,
                  dim, ni, dtype_code(y.dtype), stream_ptr(y.device))
     if want_offset:
@@ -162,7 +162,7 @@ def map_forward_packed(y, edges_packed, domain=None, want_ids=False):
     jac = torch.empty(rows, dtype=y.dtype, device=y.device)
     ids = torch.empty((rows, dim), dtype=torch.int32, device=y.device) if want_ids else None
     if rows > 0:
-        with torch.cuda.device(y.device):
+        with on_device(y.device):
             call("tq_vegas_map_forward_packed", ptr(y), ptr(edges_packed), ptr(domain), ptr(x), ptr(jac), ptr(ids), rows,
                  dim, edges_packed.shape[1], dtype_code(y.dtype), stream_ptr(y.device))
     return x, jac, ids
@@ -178,7 +178,7 @@ def accumulate_fused(y, f, jac, volume, weights, counts, want_jf=True):
         raise ValueError(f"integrand values must have shape ({rows},) and dtype {y.dtype}, got {tuple(f.shape)} / {f.dtype}")
     jf = torch.empty(rows, dtype=y.dtype, device=y.device) if want_jf else None
     if rows > 0:
-        with torch.cuda.device(y.device):
+        with on_device(y.device):
             call("tq_vegas_accumulate_fused", ptr(y), ptr(f), ptr(jac), float(volume), ptr(jf), ptr(weights), ptr(counts),
                  rows, dim, weights.shape[1], dtype_code(y.dtype), stream_ptr(y.device))
     return jf
@@ -191,7 +191,7 @@ def map_accumulate(y, jf2, weights, counts):
     jf2 = jf2.detach().contiguous()
     rows, dim = y.shape
     if rows > 0:
-        with torch.cuda.device(y.device):
+        with on_device(y.device):
             call("tq_vegas_map_accumulate", ptr(y), ptr(jf2), ptr(weights), ptr(counts), rows, dim, weights.shape[1],
                  dtype_code(y.dtype), stream_ptr(y.device))
 
@@ -208,19 +208,25 @@ def map_smooth(weights, counts, alpha):
     out = torch.empty_like(weights)
     status = torch.zeros(4, dtype=torch.int32, device=weights.device)
     scratch = _map_scratch(dim, ni, weights.dtype, weights.device)
-    with torch.cuda.device(weights.device):
+    with on_device(weights.device):
         call("tq_vegas_map_smooth", ptr(weights.contiguous()), ptr(counts.contiguous()), ptr(out), dim, ni, float(alpha),
              dtype_code(weights.dtype), ptr(status), ptr(scratch), scratch.numel(), stream_ptr(weights.device))
     return out, status
 
 
-def map_update(x_edges, dx_edges, weights, counts, alpha, status, edges_packed=None):
+def map_scratch(dim, ni, dtype, device):
+    """Scratch buffer for map_smooth / map_update of a [dim, ni] map (reusable across calls on one stream)."""
+    return _map_scratch(dim, ni, dtype, device)
+
+
+def map_update(x_edges, dx_edges, weights, counts, alpha, status, edges_packed=None, scratch=None):
     """update_map (vegas_map.py:185-261) in place; `status` is an int32[4] device tensor (see header);
     `edges_packed` ([dim, Ni, 2], optional) receives the new edges in the packed gather layout."""
     require_cuda(x_edges, dx_edges, weights, counts, status, edges_packed)
     dim, ni = weights.shape
-    scratch = _map_scratch(dim, ni, weights.dtype, weights.device)
-    with torch.cuda.device(weights.device):
+    if scratch is None:
+        scratch = _map_scratch(dim, ni, weights.dtype, weights.device)
+    with on_device(weights.device):
         call("tq_vegas_map_update", ptr(x_edges), ptr(dx_edges), ptr(weights), ptr(counts), ptr(edges_packed), dim, ni,
              float(alpha), dtype_code(weights.dtype), ptr(status), ptr(scratch), scratch.numel(),
              stream_ptr(weights.device))
@@ -233,7 +239,7 @@ def strat_nh(dh, nevals_exp):
     n = dh.shape[0]
     nh = torch.empty(n, dtype=torch.int64, device=dh.device)
     offsets = torch.empty(n + 1, dtype=torch.int64, device=dh.device)
-    with torch.cuda.device(dh.device):
+    with on_device(dh.device):
         wsp, wsn = _ws(dh.device)
         call("tq_vegas_strat_nh", ptr(dh.contiguous()), n, float(nevals_exp), dtype_code(dh.dtype), ptr(nh), ptr(offsets),
              wsp, wsn, stream_ptr(dh.device))
@@ -246,7 +252,7 @@ def strat_offsets(nh):
     nh = nh.contiguous()
     n = nh.shape[0]
     offsets = torch.empty(n + 1, dtype=torch.int64, device=nh.device)
-    with torch.cuda.device(nh.device):
+    with on_device(nh.device):
         wsp, wsn = _ws(nh.device)
         call("tq_vegas_strat_offsets", ptr(nh), n, ptr(offsets), wsp, wsn, stream_ptr(nh.device))
     return offsets
@@ -262,7 +268,7 @@ def strat_sample(offsets, n_strat, dim, dtype, row_begin, row_end, u_in=None, se
         if tuple(u_in.shape) != (rows, dim) or u_in.dtype != dtype:
             raise ValueError(f"rng.uniform returned shape {tuple(u_in.shape)} / {u_in.dtype}, expected {(rows, dim)} / {dtype}")
     if rows > 0:
-        with torch.cuda.device(offsets.device):
+        with on_device(offsets.device):
             call("tq_vegas_strat_sample", ptr(offsets), offsets.shape[0] - 1, n_strat, dim, dtype_code(dtype), ptr(u_in),
                  seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, row_begin, row_end, ptr(y), stream_ptr(offsets.device))
     return y
@@ -276,7 +282,7 @@ class _StratAccumulate(torch.autograd.Function):
         n_cubes = offsets.shape[0] - 1
         JF = torch.zeros(n_cubes, dtype=v.dtype, device=v.device)
         JF2 = torch.zeros(n_cubes, dtype=v.dtype, device=v.device)
-        with torch.cuda.device(v.device):
+        with on_device(v.device):
             call("tq_vegas_strat_accumulate", ptr(v), row_base, ptr(offsets), cube_begin, cube_end, ptr(JF), ptr(JF2),
                  dtype_code(v.dtype), stream_ptr(v.device))
         ctx.save_for_backward(offsets)
@@ -290,7 +296,7 @@ class _StratAccumulate(torch.autograd.Function):
         row_base, rows = ctx.meta
         g = torch.empty(rows, dtype=gJF.dtype, device=gJF.device)
         if rows > 0:
-            with torch.cuda.device(g.device):
+            with on_device(g.device):
                 call("tq_vegas_strat_accumulate_backward", ptr(gJF.contiguous()), ptr(offsets), offsets.shape[0] - 1,
                      row_base, row_base + rows, ptr(g), dtype_code(g.dtype), stream_ptr(g.device))
         return g, None, None, None, None
@@ -311,7 +317,7 @@ def strat_update(JF, JF2, nh, v_cubes, beta):
     n = JF.shape[0]
     dh = torch.empty(n, dtype=JF.dtype, device=JF.device)
     scalars = torch.empty(3, dtype=torch.float64, device=JF.device)  # fully written by the kernel
-    with torch.cuda.device(JF.device):
+    with on_device(JF.device):
         wsp, wsn = _ws(JF.device)
         call("tq_vegas_strat_update", ptr(JF.detach().contiguous()), ptr(JF2.detach().contiguous()), ptr(nh), n,
              float(v_cubes), float(beta), dtype_code(JF.dtype), ptr(dh), ptr(scalars), wsp, wsn, stream_ptr(JF.device))
@@ -327,7 +333,7 @@ class _GridPoints(torch.autograd.Function):
         dim, n = nd.shape
         pts = torch.empty((p_end - p_begin, dim), dtype=nd.dtype, device=nd.device)
         if p_end > p_begin:
-            with torch.cuda.device(nd.device):
+            with on_device(nd.device):
                 call("tq_nc_grid_points", ptr(nd), n, dim, p_begin, p_end, ptr(pts), dtype_code(nd.dtype),
                      stream_ptr(nd.device))
         ctx.meta = (n, dim, p_begin, p_end, nd.dtype)
@@ -338,7 +344,7 @@ class _GridPoints(torch.autograd.Function):
         n, dim, p_begin, p_end, dtype = ctx.meta
         g = g.contiguous()
         gn = torch.zeros((dim, n), dtype=torch.float64, device=g.device)
-        with torch.cuda.device(g.device):
+        with on_device(g.device):
             call("tq_nc_grid_points_backward", ptr(g), n, dim, p_begin, p_end, ptr(gn), dtype_code(dtype),
                  stream_ptr(g.device))
         return gn.to(dtype), None, None
@@ -357,7 +363,7 @@ def nc_point_weights(w, p_begin, p_end):
     dim, n = w.shape
     out = torch.empty(p_end - p_begin, dtype=w.dtype, device=w.device)
     if p_end > p_begin:
-        with torch.cuda.device(w.device):
+        with on_device(w.device):
             call("tq_nc_point_weights", ptr(w), n, dim, p_begin, p_end, ptr(out), dtype_code(w.dtype), stream_ptr(w.device))
     return out
 
@@ -375,7 +381,7 @@ class _Contract(torch.autograd.Function):
         cols = 1 if fv.dim() == 1 else int(torch.Size(fv.shape[1:]).numel())
         out = torch.zeros(cols, dtype=torch.float64, device=fv.device)
         if rows > 0:
-            with torch.cuda.device(fv.device):
+            with on_device(fv.device):
                 wsp, wsn = _ws(fv.device)
                 call("tq_nc_contract", ptr(fv), ptr(wv), n, dim, p_begin, p_end, cols, dtype_code(fv.dtype), ptr(out),
                      wsp, wsn, stream_ptr(fv.device))
@@ -410,7 +416,7 @@ def fused_mc(fn_struct, dtype, device, row_begin, row_end, seed, call_idx):
     """{sum f, sum f^2} (fp64 [2]) of a built-in integrand over rows of the row-keyed stream."""
     out = torch.zeros(2, dtype=torch.float64, device=device)
     require_cuda(out)
-    with torch.cuda.device(out.device):
+    with on_device(out.device):
         wsp, wsn = _ws(out.device)
         call("tq_fused_mc", fn_struct, dtype_code(dtype), row_begin, row_end, seed & 0xFFFFFFFFFFFFFFFF,
              call_idx & 0xFFFFFFFF, ptr(out), wsp, wsn, stream_ptr(out.device))
@@ -421,7 +427,7 @@ def fused_nc(fn_struct, nodes, w, p_begin, p_end):
     require_cuda(nodes, w)
     dim, n = nodes.shape
     out = torch.zeros(1, dtype=torch.float64, device=nodes.device)
-    with torch.cuda.device(nodes.device):
+    with on_device(nodes.device):
         wsp, wsn = _ws(nodes.device)
         call("tq_fused_nc", fn_struct, ptr(nodes.contiguous()), ptr(w.contiguous()), n, dtype_code(nodes.dtype), p_begin,
              p_end, ptr(out), wsp, wsn, stream_ptr(nodes.device))
@@ -434,7 +440,7 @@ def pack_edges(x_edges, dx_edges, out=None):
     dim, ni = dx_edges.shape
     if out is None:
         out = torch.empty((dim, ni, 2), dtype=dx_edges.dtype, device=dx_edges.device)
-    with torch.cuda.device(dx_edges.device):
+    with on_device(dx_edges.device):
         call("tq_vegas_map_pack_edges", ptr(x_edges), ptr(dx_edges), ptr(out), dim, ni, dtype_code(dx_edges.dtype),
              stream_ptr(dx_edges.device))
     return out
@@ -447,7 +453,7 @@ def fused_vegas(fn_struct, edges_packed, weights, counts, row_begin, row_end, se
     # only the warm-up pass reduces {sum jf, sum jf^2}; the stratified pass writes JF/JF2
     out = torch.empty(2, dtype=torch.float64, device=edges_packed.device) if offsets is None else None
     n_cubes = 0 if offsets is None else offsets.shape[0] - 1
-    with torch.cuda.device(edges_packed.device):
+    with on_device(edges_packed.device):
         wsp, wsn = _ws(edges_packed.device)
         call("tq_fused_vegas", fn_struct, dtype_code(edges_packed.dtype), ptr(offsets), n_cubes, n_strat, row_begin, row_end,
              ptr(edges_packed), edges_packed.shape[1], ptr(weights), ptr(counts), ptr(JF), ptr(JF2),
