@@ -1,0 +1,150 @@
+"""Behavioural pins taken from the reference's own test-suite (/root/reference/tests), re-expressed against the
+drop-in surface on CUDA.  Each test cites the reference test it mirrors."""
+import math
+import warnings
+
+import pytest
+import torch
+
+import torchquad_b200 as tq
+from torchquad_b200.integration.integration_grid import IntegrationGrid
+from torchquad_b200.integration.utils import _add_at_indices
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _quiet():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        yield
+
+
+def test_calculate_result_accepts_keywords_and_reports_missing_values(cuda):
+    """boole_test.py:112-169, monte_carlo_test.py:136-182."""
+    dom = torch.tensor([[0.0, 1.0]], device=cuda)
+    b = tq.Boole()
+    pts, hs, n = b.calculate_grid(125, dom)
+    vals, _ = b.evaluate_integrand(lambda x: torch.rand(x.shape, device=x.device), pts)
+    r1 = b.calculate_result(vals, 1, n, hs, dom)
+    r2 = b.calculate_result(function_values=vals, dim=1, n_per_dim=n, hs=hs, integration_domain=dom)
+    r3 = b.calculate_result(vals, dim=1, n_per_dim=n, hs=hs, integration_domain=dom)
+    assert torch.allclose(r1, r2, rtol=1e-10) and torch.allclose(r1, r3, rtol=1e-10)
+    with pytest.raises(ValueError, match="function_values argument not found"):
+        b.calculate_result(dim=1, n_per_dim=5, hs=torch.tensor([0.25], device=cuda), integration_domain=dom)
+    with pytest.raises(ValueError, match="Please provide function_values"):
+        b.calculate_result()
+    mc = tq.MonteCarlo()
+    p = mc.calculate_sample_points(1000, dom, seed=0)
+    v, _ = mc.evaluate_integrand(lambda x: x[:, 0] * 2, p)
+    m1 = mc.calculate_result(v, dom)
+    m2 = mc.calculate_result(function_values=v, integration_domain=dom)
+    assert torch.equal(m1, m2) and abs(float(m1) - 1.0) < 0.1
+    with pytest.raises(ValueError, match="function_values argument not found"):
+        mc.calculate_result(integration_domain=dom)
+
+
+def test_vectorisation_check_and_seed_rng_conflict(cuda):
+    """base_integrator.py:70-75 and vegas.py:98-101 / monte_carlo.py:99-100."""
+    dom = torch.tensor([[0.0, 1.0]] * 2, device=cuda)
+    with pytest.raises(ValueError, match="only returned"):
+        tq.MonteCarlo().integrate(lambda x: x[:1, 0], 2, N=100, integration_domain=dom, seed=0)
+    with pytest.raises(ValueError, match="seed and rng cannot both be passed"):
+        tq.VEGAS().integrate(lambda x: x[:, 0], 2, N=1000, integration_domain=dom, seed=0, rng=tq.RNG(seed=1))
+    with pytest.raises(ValueError, match="seed and rng cannot both be passed"):
+        tq.MonteCarlo().integrate(lambda x: x[:, 0], 2, N=1000, integration_domain=dom, seed=0, rng=tq.RNG(seed=1))
+    with pytest.raises(ValueError):
+        tq.MonteCarlo().integrate(lambda x: x[:, 0], 2, N=0, integration_domain=dom)
+    with pytest.raises(ValueError):
+        tq.Trapezoid().integrate(lambda x: x[:, 0], 3, N=100, integration_domain=dom)  # dim mismatch
+
+
+def test_add_at_indices_cases(cuda):
+    """utils_integration_test.py:83-115."""
+    t = torch.zeros(500, device=cuda)
+    _add_at_indices(t, torch.arange(500, device=cuda), torch.arange(500.0, device=cuda))
+    assert torch.equal(t, torch.arange(500.0, device=cuda))
+    t = torch.zeros(3, device=cuda)
+    _add_at_indices(t, torch.zeros(500, dtype=torch.int64, device=cuda), torch.ones(500, device=cuda), is_sorted=True)
+    assert t.tolist() == [500.0, 0.0, 0.0]
+    t = torch.zeros(3, device=cuda)
+    _add_at_indices(t, torch.tensor([2, 1, 1, 2], device=cuda), torch.tensor([1.0, 2.0, 3.0, 4.0], device=cuda))
+    assert t.tolist() == [0.0, 5.0, 5.0]
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_integration_grid_properties(cuda, dt):
+    """integration_grid_test.py:48-95."""
+    for N, dom in [(10, [[0.0, 1.0]]), (18**2, [[0.0, 2.0], [-2.0, 1.0]]), (17**3 + 5, [[0.0, 2.0], [-2.0, 1.0], [0.5, 1.0]])]:
+        domain = torch.tensor(dom, dtype=dt, device=cuda)
+        g = IntegrationGrid(N, domain)
+        n = int(N ** (1 / len(dom)) + 1e-8)
+        assert g._N == n and g.points.shape == (n ** len(dom), len(dom)) and g.points.dtype == dt and g.h.dtype == dt
+        for d in range(len(dom)):
+            width = dom[d][1] - dom[d][0]
+            assert abs(float(g.h[d]) - width / (n - 1)) < 2e-8 * max(1.0, width) * (1e3 if dt == torch.float32 else 1)
+            assert float(g.points[:, d].min()) == dom[d][0] and float(g.points[:, d].max()) == dom[d][1]
+        assert g._runtime >= 0
+    with pytest.raises(ValueError):
+        IntegrationGrid(1, torch.tensor([[0.0, 1.0]], device=cuda))
+    with pytest.raises(ValueError):
+        IntegrationGrid(7, torch.tensor([[0.0, 1.0]] * 3, device=cuda))
+    # integer domains are promoted to float64 (issue #180 of the reference)
+    gi = IntegrationGrid(9, torch.tensor([[0, 2]], device=cuda))
+    assert gi.points.dtype == torch.float64
+
+
+def test_standard_integrands_meet_the_reference_bounds(cuda):
+    """The loose accuracy bounds of vegas_test.py:17-68 / monte_carlo_test.py / trapezoid_test.py on a few of the
+    reference's analytic test functions (helper_functions.py:19-327), fp64."""
+    tq.set_up_backend("torch", "float64")
+    try:
+        one_d = [
+            (lambda x: x[:, 0] * 0 + 2.0, [[0.0, 1.0]], 2.0),                      # constant
+            (lambda x: 3.0 * x[:, 0] + 2.0, [[0.0, 1.0]], 3.5),                    # degree 1
+            (lambda x: 4.0 * x[:, 0] ** 2 + 3.0 * x[:, 0] + 2.0, [[0.0, 2.0]], 4.0 * 8 / 3 + 6.0 + 4.0),
+            (lambda x: torch.exp(x[:, 0]), [[-2.0, 2.0]], math.exp(2) - math.exp(-2)),
+            (lambda x: torch.sin(x[:, 0]), [[0.0, 2 * math.pi]], 0.0),
+        ]
+        for fn, dom, exact in one_d:
+            assert abs(float(tq.VEGAS().integrate(fn, 1, N=10000, integration_domain=dom, seed=0)) - exact) < 5e-3 * max(1, abs(exact))
+            assert abs(float(tq.MonteCarlo().integrate(fn, 1, N=100000, integration_domain=dom, seed=0)) - exact) < 0.1
+            assert abs(float(tq.Trapezoid().integrate(fn, 1, N=100001, integration_domain=dom)) - exact) < 1e-5
+            assert abs(float(tq.Simpson().integrate(fn, 1, N=10001, integration_domain=dom)) - exact) < 1e-8
+        three_d = (lambda x: torch.sum(torch.exp(x), dim=1), [[0.0, 1.0]] * 3, 3 * (math.e - 1))
+        fn, dom, exact = three_d
+        assert abs(float(tq.VEGAS().integrate(fn, 3, N=10000, integration_domain=dom, seed=0)) - exact) < 0.61
+        assert abs(float(tq.Boole().integrate(fn, 3, N=17**3, integration_domain=dom)) - exact) < 1e-9
+        ten_d = (lambda x: torch.sum(torch.sin(x), dim=1), [[0.0, 1.0]] * 10, 20 * math.sin(0.5) ** 2)
+        fn, dom, exact = ten_d
+        assert abs(float(tq.VEGAS().integrate(fn, 10, N=10000, integration_domain=dom, seed=0)) - exact) < 12.5
+        assert abs(float(tq.MonteCarlo().integrate(fn, 10, N=100000, integration_domain=dom, seed=0)) - exact) < 0.05
+    finally:
+        torch.set_default_dtype(torch.float32)
+        torch.set_default_device("cpu")
+
+
+def test_vegas_options(cuda):
+    """use_warmup / use_grid_improve / max_iterations / eps_abs paths of vegas.py:30-159,161-209."""
+    dom = torch.tensor([[0.0, 1.0]] * 3, dtype=torch.float64, device=cuda)
+    fn = lambda x: torch.exp(-torch.sum(9.0 * (x - 0.5) ** 2, dim=1))  # noqa: E731
+    exact = (math.sqrt(math.pi) / 3 * math.erf(1.5)) ** 3
+    base = tq.VEGAS()
+    r = base.integrate(fn, 3, N=100_000, integration_domain=dom, seed=2)
+    assert abs(float(r) - exact) < 5 * float(base._get_error()) and base.it == 10
+    a = tq.VEGAS()
+    ra = a.integrate(fn, 3, N=100_000, integration_domain=dom, seed=2, use_warmup=False)
+    assert abs(float(ra) - exact) < 6 * float(a._get_error())
+    b = tq.VEGAS()
+    rb = b.integrate(fn, 3, N=100_000, integration_domain=dom, seed=2, use_grid_improve=False)
+    assert abs(float(rb) - exact) < 6 * float(b._get_error()) and float(b._get_error()) > float(base._get_error())
+    c = tq.VEGAS()
+    c.integrate(fn, 3, N=100_000, integration_domain=dom, seed=2, max_iterations=5)
+    assert c.it == 5
+    d = tq.VEGAS()
+    d.integrate(fn, 3, N=1_000_000, integration_domain=dom, seed=2, eps_abs=1e-2)
+    assert d.it == 5  # tolerance met at the first check
+    e = tq.VEGAS()
+    e.max_map_intervals = 64
+    re = e.integrate(fn, 3, N=100_000, integration_domain=dom, seed=2)
+    assert e.map.N_intervals == 64 and abs(float(re) - exact) < 6 * float(e._get_error())
