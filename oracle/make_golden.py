@@ -233,6 +233,32 @@ def case_nc(tag, dtype):
     np.savez_compressed(os.path.join(OUT, f"newton_cotes_{tag}.npz"), **out)
 
 
+def case_gauss():
+    """GaussLegendre (fp64, the only dtype the reference supports here: its weights are float64 numpy arrays)."""
+    out = {}
+    dtype = torch.float64
+    for dim, N, dom in [(1, 60, [[0.0, 5.0]]), (2, 8**2, [[0.0, 1.0], [-2.0, 0.5]]), (3, 5**3 + 3, [[0.0, 1.0], [1.0, 3.0], [-1.0, 1.0]])]:
+        domain = torch.tensor(dom, dtype=dtype)
+        gl = torchquad.GaussLegendre()
+        pts, hs, n = gl.calculate_grid(N, domain)
+        W = gl._weights(n, dim, "torch")
+        opts, oW, on = O.gauss_grid(N, domain)
+        same(pts, opts, "gauss points")
+        same(W, oW, "gauss weights")
+        assert n == on
+        f = torch.prod(torch.cos(pts), dim=1) + torch.sum(pts**3, dim=1)
+        ref = gl.integrate(lambda x: torch.prod(torch.cos(x), dim=1) + torch.sum(x**3, dim=1), dim, N, domain)
+        same(ref, O.gauss_result(f, oW, dim, n, domain), "gauss result")
+        fv = torch.stack([f, torch.sum(torch.exp(pts), dim=1)], dim=1)
+        refv = gl.integrate(lambda x: torch.stack([torch.prod(torch.cos(x), dim=1) + torch.sum(x**3, dim=1),
+                                                   torch.sum(torch.exp(x), dim=1)], dim=1), dim, N, domain)
+        same(refv, O.gauss_result(fv, oW, dim, n, domain), "gauss vector result")
+        k = f"d{dim}"
+        out.update({f"{k}_domain": npy(domain), f"{k}_N": np.int64(N), f"{k}_n": np.int64(n), f"{k}_points": npy(pts),
+                    f"{k}_W": npy(W), f"{k}_f": npy(f), f"{k}_result": npy(ref), f"{k}_fv": npy(fv), f"{k}_resultv": npy(refv)})
+    np.savez_compressed(os.path.join(OUT, "gauss_legendre_f64.npz"), **out)
+
+
 def case_reference_records():
     """Scalar records of the reference's own end-to-end runs with ITS RNG (torch CPU mt19937)."""
     torchquad.set_up_backend("torch", "float64", torch_enable_cuda=False)
@@ -266,5 +292,7 @@ if __name__ == "__main__":
         case_mc(tag, dt)
         case_nc(tag, dt)
         print("golden", tag, "ok (oracle == reference bitwise)")
+    case_gauss()
+    print("golden gauss ok (oracle == reference bitwise)")
     case_reference_records()
     print("wrote", sorted(os.listdir(OUT)))

@@ -512,6 +512,35 @@ def nc_result(rule, f, dim, n, hs):
 
 
 # --------------------------------------------------------------------------
+# Gauss-Legendre  (torchquad/integration/gaussian.py)
+# --------------------------------------------------------------------------
+def gauss_grid(N, domain):
+    """points [n^dim, dim], product weights [n^dim], n (gaussian.py:44-69,110-129,159-162;
+    integration_grid.py:64-99 with the Gauss `_grid_func`)."""
+    dim = domain.shape[0]
+    n = int(N ** (1.0 / dim) + 1e-8)
+    roots, weights = np.polynomial.legendre.leggauss(n)
+    roots, weights = torch.tensor(roots), torch.tensor(weights)
+    g = [((domain[d][1] - domain[d][0]) / 2) * roots + ((domain[d][0] + domain[d][1]) / 2) for d in range(dim)]
+    pts = torch.stack([m.ravel() for m in torch.meshgrid(*g, indexing="ij")], dim=1)
+    W = torch.prod(torch.stack(list(torch.meshgrid(*([weights] * dim), indexing="ij")), dim=0), dim=0).ravel()
+    return pts, W, n
+
+
+def gauss_result(f, W, dim, n, domain):
+    """evaluate_integrand's `result *= weights` (base_integrator.py:77-89) followed by the Gaussian composite
+    rule 0.5*(b-a)*sum per axis (gaussian.py:131-144, grid_integrator.py:70-88)."""
+    one_d = f.dim() == 1 or (f.dim() == 2 and f.shape[1] == 1)
+    if f.dim() == 1:
+        f = f.unsqueeze(1)
+    f = f * W.reshape([-1] + [1] * (f.dim() - 1))
+    a = f.movedim(0, -1).reshape(list(f.shape[1:]) + [n] * dim)
+    for cur in range(dim):
+        a = 0.5 * (domain[cur][1] - domain[cur][0]) * torch.sum(a, dim=a.dim() - 1)
+    return a.squeeze() if one_d else a
+
+
+# --------------------------------------------------------------------------
 # Built-in integrands: Genz families (Genz 1984/1987; not in the reference, SURVEY 8d)
 # and the reference's test integrands (tests/integration_test_functions.py:146-325).
 # Each returns (f(x), exact integral over [0,1]^d or the given domain when known).

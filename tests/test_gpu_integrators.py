@@ -243,6 +243,41 @@ def test_newton_cotes_polynomial_exactness(cuda):
     assert abs(float(r10) - 10 / 3) < 5e-9
 
 
+def test_gauss_legendre_matches_reference_fixture_and_exactness(cuda, golden):
+    """GaussLegendre against the reference fixture; exactness up to degree 2n-1
+    (/root/reference/tests/gauss_test.py:9-49)."""
+    g = golden("gauss_legendre_f64")
+    fn = lambda x: torch.prod(torch.cos(x), dim=1) + torch.sum(x**3, dim=1)  # noqa: E731
+    for dim in (1, 2, 3):
+        k = f"d{dim}"
+        dom = torch.from_numpy(g[f"{k}_domain"]).to(cuda)
+        gl = tq.GaussLegendre()
+        pts, hs, n = gl.calculate_grid(int(g[f"{k}_N"]), dom)
+        assert n == int(g[f"{k}_n"])
+        assert torch.allclose(pts.cpu(), torch.from_numpy(g[f"{k}_points"]), rtol=0, atol=1e-15)
+        assert torch.allclose(gl._weights(n, dim, device=cuda).cpu(), torch.from_numpy(g[f"{k}_W"]), rtol=1e-14)
+        r = gl.integrate(fn, dim, int(g[f"{k}_N"]), dom)
+        assert r.dtype == torch.float64 and abs(float(r) - float(g[f"{k}_result"])) <= 1e-13 * max(1, abs(float(g[f"{k}_result"])))
+        rv = gl.integrate(lambda x: torch.stack([fn(x), torch.sum(torch.exp(x), dim=1)], dim=1), dim, int(g[f"{k}_N"]), dom)
+        assert torch.allclose(rv.cpu(), torch.from_numpy(g[f"{k}_resultv"]), rtol=1e-13)
+        # reference-style split-phase use: weights applied to the values, then calculate_result
+        vals, _ = gl.evaluate_integrand(fn, pts, weights=gl._weights(n, dim, device=cuda))
+        r2 = gl.calculate_result(vals, dim, n, hs, dom)
+        assert abs(float(r2) - float(r)) <= 1e-13 * max(1, abs(float(r)))
+    dom1 = torch.tensor([[0.0, 2.0]], dtype=torch.float64, device=cuda)
+    assert abs(float(tq.GaussLegendre().integrate(lambda x: x[:, 0] ** 3 - x[:, 0] + 2.0, 1, 2, dom1)) - 6.0) < 8e-15
+    assert abs(float(tq.GaussLegendre().integrate(lambda x: torch.sin(x[:, 0]), 1, 60, torch.tensor([[0.0, 5.0]], dtype=torch.float64, device=cuda)))
+               - (1 - math.cos(5.0))) < 7e-11
+    # fused functor and multi-chunk paths
+    dom4 = torch.tensor([[0.0, 1.0]] * 4, dtype=torch.float64, device=cuda)
+    pc = F.ProductOfCosines(4)
+    a = tq.GaussLegendre().integrate(pc, 4, 12**4, dom4)
+    b = tq.GaussLegendre().integrate(lambda x: pc(x), 4, 12**4, dom4)
+    assert abs(float(a) - pc.exact()) < 1e-14 and abs(float(b) - pc.exact()) < 1e-14
+    base = tq.Gaussian().integrate(lambda x: x[:, 0] ** 2, 1, 8, None)  # parent class integrates on [-1, 1]
+    assert abs(float(base) - 2.0 / 3.0) < 1e-6
+
+
 @pytest.mark.parametrize("tag", ["f32", "f64"])
 def test_newton_cotes_fused_and_chunked_equal_plain(cuda, tag):
     dt = DT[tag]

@@ -9,6 +9,7 @@ __version__ = "0.1.0"
 
 from . import distributed, integrands  # noqa: F401
 from .integration.base_integrator import BaseIntegrator
+from .integration.gaussian import Gaussian, GaussLegendre
 from .integration.grid_integrator import GridIntegrator
 from .integration.integration_grid import IntegrationGrid
 from .integration.monte_carlo import MonteCarlo
@@ -28,6 +29,6 @@ set_log_level(_os.environ.get("TORCHQUAD_LOG_LEVEL", "WARNING"))
 
 __all__ = [
     "__version__", "GridIntegrator", "BaseIntegrator", "IntegrationGrid", "MonteCarlo", "Trapezoid", "Simpson",
-    "Boole", "NewtonCotes", "VEGAS", "VEGASMap", "VEGASStratification", "RNG", "enable_cuda", "set_precision",
+    "Boole", "NewtonCotes", "GaussLegendre", "Gaussian", "VEGAS", "VEGASMap", "VEGASStratification", "RNG", "enable_cuda", "set_precision",
     "set_log_level", "set_up_backend", "integrands", "distributed",
 ]

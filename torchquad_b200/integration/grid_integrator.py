@@ -47,7 +47,7 @@ class GridIntegrator(BaseIntegrator):
         w = self._rule_weights_1d(n, dtype, device)
         return w.reshape(1, n).repeat(dim, 1).contiguous()
 
-    def _scale(self, hs):
+    def _scale(self, hs, domain=None):
         """prod_d h_d / c, multiplied in the order the reference applies its passes."""
         s = hs[0] / self._rule_denominator
         for d in range(1, hs.shape[0]):
@@ -68,9 +68,10 @@ class GridIntegrator(BaseIntegrator):
         chunk_rows = max(1, self.max_points_bytes // (dim * domain.element_size()))
         if not fused and world == 1 and total_points <= chunk_rows:
             grid_points, hs, n_per_dim = self.calculate_grid(N, domain)
-            function_values, num_points = self.evaluate_integrand(
-                fn, grid_points, weights=self._weights(n_per_dim, dim, "torch"))
+            function_values, num_points = self.evaluate_integrand(fn, grid_points)
             self._nr_of_fevals = num_points
+            if hasattr(self, "integrate_values"):  # Gaussian rules: weights go into the contraction kernel
+                return self._squeeze_1d(function_values, self.integrate_values, dim, n_per_dim, domain)
             return self.calculate_result(function_values, dim, n_per_dim, hs, domain)
 
         # sharded / chunked / fused: contiguous point ranges of the same grid
@@ -96,13 +97,22 @@ class GridIntegrator(BaseIntegrator):
         if world > 1:
             total = ops.all_reduce_sum_autograd(total)
         self._nr_of_fevals = total_points
-        return total.to(domain.dtype) * self._scale(hs)
+        return total.to(domain.dtype) * self._scale(hs, domain)
+
+    @staticmethod
+    def _squeeze_1d(function_values, fn, *args):
+        """The 1-D squeeze rule of the reference's decorator (utils.py:235-277) around `fn(values, *args)`."""
+        from .utils import _split_function_values
+
+        values, one_d = _split_function_values(function_values)
+        result = fn(values, *args)
+        return torch.squeeze(result) if one_d else result
 
     @expand_func_values_and_squeeze_integral
     def calculate_result(self, function_values, dim, n_per_dim, hs, integration_domain):
         """Apply the composite rule to values on the full grid (grid_integrator.py:57-91)."""
         table = self._weight_table(n_per_dim, dim, function_values.dtype, function_values.device)
-        return ops.nc_contract(function_values, table) * self._scale(hs)
+        return ops.nc_contract(function_values, table) * self._scale(hs, integration_domain)
 
     def calculate_grid(self, N, integration_domain, disable_integration_domain_check=False):
         """(points [n^dim, dim], h [dim], n) (grid_integrator.py:93-127)."""
