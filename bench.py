@@ -166,8 +166,9 @@ def max_over_ranks(x, device, world):
 
 
 # ------------------------------------------------------------------------------------ reference / CPU arm
-def cpu_reference_rate(wl, budget_s=12.0):
-    """Reference algorithm on the host cores (oracle port, torch CPU ops = the reference's arithmetic)."""
+def cpu_reference_runner(wl):
+    """(run, sample description): one bounded repetition of the reference algorithm on the host cores
+    (oracle port: torch CPU ops = the reference's own arithmetic).  run() returns the evaluations it did."""
     from oracle import ref_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)
@@ -182,8 +183,8 @@ def cpu_reference_rate(wl, budget_s=12.0):
             O.mc_integrate(fn, dim, n, dom, seed=0)
             return n
 
-        sample = f"MonteCarlo {dim}-D N={n:.0e} per repetition"
-    elif wl["kind"] == "boole":
+        return run, f"MonteCarlo {dim}-D N={n:.0e} per repetition"
+    if wl["kind"] == "boole":
         npd = 17
 
         def run():
@@ -191,38 +192,45 @@ def cpu_reference_rate(wl, budget_s=12.0):
             O.nc_result("boole", fn(pts), dim, n_, hs)
             return npd**dim
 
-        sample = f"Boole {dim}-D n={npd} per dim per repetition"
-    else:
-        n = min(wl["N"], 2 * 10**6 if dim > 4 else 10**6)
+        return run, f"Boole {dim}-D n={npd} per dim per repetition"
+    n = min(wl["N"], 2 * 10**6 if dim > 4 else 10**6)
 
-        def run():
-            g = torch.Generator().manual_seed(0)
-            r = O.VegasRun(fn, dim, n, dom, lambda size, dtype: torch.rand(size, dtype=dtype, generator=g))
-            r.run()
-            return r.fevals
+    def run():
+        g = torch.Generator().manual_seed(0)
+        r = O.VegasRun(fn, dim, n, dom, lambda size, dtype: torch.rand(size, dtype=dtype, generator=g))
+        r.run()
+        return r.fevals
 
-        sample = f"VEGAS {dim}-D N={n:.0e} per repetition"
-    run()  # warm-up (thread pool, allocator)
-    evals, t0 = 0, time.perf_counter()
-    reps = 0
-    while time.perf_counter() - t0 < budget_s or reps < 2:
+    return run, f"VEGAS {dim}-D N={n:.0e} per repetition"
+
+
+def cpu_reference_rate(wl, budget_s=12.0, steps=None, warmup=1):
+    """Time the reference algorithm on the host: `steps` repetitions when given, else a time budget."""
+    run, sample = cpu_reference_runner(wl)
+    for _ in range(max(1, warmup)):
+        run()  # warm-up (thread pool, allocator)
+    evals, reps, t0 = 0, 0, time.perf_counter()
+    while (reps < steps) if steps else (time.perf_counter() - t0 < budget_s or reps < 2):
         evals += run()
         reps += 1
     dt_s = time.perf_counter() - t0
     return {"value": evals / dt_s, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{sample} x {reps} repetitions ({dt_s:.1f} s); oracle/ref_oracle.py restates the reference over the same ATen CPU kernels"}
+            "sample": f"{sample} x {reps} repetitions ({dt_s:.1f} s); oracle/ref_oracle.py restates the reference over the same ATen CPU kernels",
+            "ms_per_step": dt_s / reps * 1e3}
 
 
 def run_reference(args, wl):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    base = cpu_reference_rate(wl, budget_s=max(4.0, 2.0 * args.steps))
+    base = cpu_reference_rate(wl, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": "integrand evals/s", "value": base["value"], "unit": "evals/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base.pop("ms_per_step"),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if wl["dtype"] == "float32" else "f64",
-        "data": "synthetic", "config": {"workload": args.workload, **{k: wl[k] for k in ("kind", "dim", "N", "integrand")}},
+        "data": "synthetic",
+        "config": {"workload": args.workload, "kind": wl["kind"], "dim": wl["dim"], "N_per_gpu": wl["N"],
+                   "integrand": wl["integrand"], "path": "reference algorithm on the host cores, bounded sample per step"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -487,7 +495,9 @@ def run_ours(args, wl):
     if unf:
         line["unfused"] = unf
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_reference_rate(wl)
+        base = cpu_reference_rate(wl)
+        base.pop("ms_per_step", None)
+        line["cpu_baseline"] = base
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
