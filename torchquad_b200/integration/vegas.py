@@ -99,6 +99,15 @@ class VEGAS(BaseIntegrator):
         self.map = VEGASMap(N_intervals, dim, "torch", self.dtype, device=self.device)
         self.strat = VEGASStratification(self._N_increment, dim=dim, rng=self.rng, backend="torch", dtype=self.dtype,
                                          device=self.device)
+        # Multi-GPU: the float statistics of a pass live in ONE buffer [weights | JF | JF2] so that a pass needs
+        # one all-reduce for them plus one for the int64 counts.
+        self._stats = None
+        if tqdist.is_enabled():
+            n_w = dim * N_intervals
+            self._stats = torch.zeros(n_w + 2 * self.strat.N_cubes, dtype=self.dtype, device=self.device)
+            self.map.weights = self._stats[:n_w].view(dim, N_intervals)
+            self._stats_w = self._stats[:n_w]
+            self._stats_jf = self._stats[n_w:].view(2, self.strat.N_cubes)
         self.results = []  # per-iteration integral estimates (0-dim tensors)
         self.sigma2 = []   # per-iteration variances (0-dim tensors, detached)
         self.it = 0
@@ -133,9 +142,14 @@ class VEGAS(BaseIntegrator):
     def _rank_rows(self, total):
         return tqdist.shard_range(total)
 
-    def _reduce_map_stats(self):
-        if tqdist.is_enabled():
-            tqdist.all_reduce_sum_(self.map.weights, self.map.counts)
+    def _reduce_stats(self, with_cubes):
+        """Sum the pass statistics over the ranks: [weights | JF | JF2] in one collective, counts in another."""
+        if self._stats is None:
+            return
+        if with_cubes:
+            tqdist.all_reduce_sum_(self._stats, self.map.counts)
+        else:
+            tqdist.all_reduce_sum_(self._stats_w, self.map.counts)
 
     def _update_map(self):
         if self._status_used == self._status_buf.shape[0]:
@@ -177,7 +191,7 @@ class VEGAS(BaseIntegrator):
                     f_eval = self._last_f_eval
                     jf_vec2 = ((f_eval * jac) ** 2).detach()
                     self.map.accumulate_weight(yrnd, jf_vec2)
-            self._reduce_map_stats()
+            self._reduce_stats(with_cubes=False)
             self._update_map()
 
     def _run_iteration(self):
@@ -193,13 +207,15 @@ class VEGAS(BaseIntegrator):
             cube_lo, cube_hi = 0, strat.N_cubes
         grad_path = False
         if self._fused:
-            JFs = torch.zeros((2, strat.N_cubes), dtype=self.dtype, device=self.device)
+            if self._stats is not None:
+                JFs = self._stats_jf.zero_()
+            else:
+                JFs = torch.zeros((2, strat.N_cubes), dtype=self.dtype, device=self.device)
             ops.fused_vegas(self._fn_struct, vmap.packed_edges(),
                             vmap.weights if self.use_grid_improve else None, vmap.counts, begin, end, self.rng.seed,
                             self.rng.next_call(), offsets=offsets, n_strat=strat.N_strat, JF=JFs[0], JF2=JFs[1])
             self._nr_of_fevals += M
-            if tqdist.is_enabled():
-                tqdist.all_reduce_sum_(JFs)
+            self._reduce_stats(with_cubes=True)
             strat.JF, strat.JF2 = JFs[0], JFs[1]
         else:
             if type(self.rng) is RNG:
@@ -224,15 +240,15 @@ class VEGAS(BaseIntegrator):
                     vmap.accumulate_weight(y, (jf_vec**2).detach())
             grad_path = torch.is_grad_enabled() and jf_vec.requires_grad
             JF, JF2 = ops.strat_accumulate(jf_vec, offsets, row_base=begin, cube_begin=cube_lo, cube_end=cube_hi)
-            if tqdist.is_enabled():
-                both = torch.stack([JF.detach(), JF2])
-                tqdist.all_reduce_sum_(both)
+            if self._stats is not None:
+                both = self._stats_jf
+                both[0].copy_(JF.detach())
+                both[1].copy_(JF2)
+                self._reduce_stats(with_cubes=True)
                 JF = JF + (both[0] - JF.detach()) if grad_path else both[0]
                 JF2 = both[1]
             strat.JF, strat.JF2 = JF, JF2
             strat.strat_counts = neval.to(self.dtype)
-        if self.use_grid_improve:
-            self._reduce_map_stats()
 
         # estimator + damped-variance update in one kernel (vegas.py:293-303, vegas_stratification.py:72-90)
         strat.update_DH()
