@@ -1,0 +1,104 @@
+"""Edge cases of the drop-in surface: minimal sizes, odd shapes, large dimension counts, ragged tails."""
+import math
+import warnings
+
+import pytest
+import torch
+
+import torchquad_b200 as tq
+from oracle import ref_oracle as O
+from torchquad_b200 import integrands as F
+from torchquad_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _quiet():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        yield
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_minimal_sizes(cuda, dt):
+    dom = torch.tensor([[0.0, 2.0]], dtype=dt, device=cuda)
+    one = tq.MonteCarlo().integrate(lambda x: x[:, 0] * 0 + 3.0, 1, N=1, integration_domain=dom, seed=0)
+    assert float(one) == 6.0
+    assert float(tq.MonteCarlo().integrate(F.Polynomial(1, [3.0]), 1, N=1, integration_domain=dom, seed=0)) == 6.0
+    assert abs(float(tq.Trapezoid().integrate(lambda x: x[:, 0], 1, N=2, integration_domain=dom)) - 2.0) < 1e-6
+    assert abs(float(tq.Simpson().integrate(lambda x: x[:, 0] ** 2, 1, N=None, integration_domain=dom)) - 8 / 3) < 1e-5
+    assert abs(float(tq.Boole().integrate(lambda x: x[:, 0] ** 4, 1, N=None, integration_domain=dom)) - 32 / 5) < 1e-4
+    # the smallest VEGAS run the reference can do: N=125 -> 5 evaluations per iteration, 2 map intervals
+    v = tq.VEGAS()
+    r = v.integrate(lambda x: x[:, 0] * 0 + 1.0, 1, N=125, integration_domain=dom, seed=0)
+    assert v.map.N_intervals == 2 and v.strat.N_cubes == 1 and abs(float(r) - 2.0) < 1e-5
+    with pytest.raises(ZeroDivisionError):  # N_strat = 0, exactly like the reference (vegas_stratification.py:27-31)
+        tq.VEGAS().integrate(lambda x: x[:, 0], 1, N=26, integration_domain=dom, seed=0)
+
+
+def test_many_dimensions_unfused(cuda):
+    """Unfused kernels are not limited to TQ_MAX_DIM (only the fused functors are)."""
+    dim = 40
+    dom = torch.tensor([[0.0, 1.0]] * dim, dtype=torch.float64, device=cuda)
+    fn = lambda x: torch.sum(x, dim=1)  # noqa: E731
+    r = tq.MonteCarlo().integrate(fn, dim, N=200_000, integration_domain=dom, seed=0)
+    assert abs(float(r) - dim / 2) < 0.05
+    pts = ops.mc_sample(dom, 1000, 5, 0, 0)
+    want = O.mc_sample_points(O.philox_uniform(5, 0, 0, 1000, dim, torch.float64), dom.cpu())
+    assert torch.equal(pts.cpu(), want)
+    v = tq.VEGAS()
+    rv = v.integrate(fn, dim, N=100_000, integration_domain=dom, seed=0)
+    assert abs(float(rv) - dim / 2) < 0.2 and v.strat.N_strat == 1
+    with pytest.raises(ValueError):
+        F.SumOfSines(dim)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+@pytest.mark.parametrize("dim", [1, 2, 3, 5, 7, 9, 31])
+def test_ragged_dims_sample_and_map(cuda, dt, dim):
+    """Every (dim, dtype) store-width path of the row-major producers against the oracle, odd row counts."""
+    rows = 1237
+    u = ops.philox_uniform(rows, dim, dt, cuda, 9, 2, 1000)
+    assert torch.equal(u.cpu(), O.philox_uniform(9, 2, 1000, rows, dim, dt))
+    ns = 3
+    n_cubes = ns ** min(dim, 6)
+    g = torch.Generator().manual_seed(dim)
+    nh = torch.randint(2, 6, (n_cubes,), generator=g)
+    offsets = ops.strat_offsets(nh.to(cuda))
+    M = int(offsets[-1])
+    y = ops.strat_sample(offsets, ns, dim, dt, 0, M, seed=4, call_idx=1)
+    assert y.shape == (M, dim) and float(y.min()) >= 0 and float(y.max()) < 1
+    # same rows from an arbitrary sub-range; digits follow the cube index (dim 0 fastest)
+    a, b = M // 5, min(M, M // 5 + 333)
+    assert torch.equal(ops.strat_sample(offsets, ns, dim, dt, a, b, seed=4, call_idx=1), y[a:b])
+    cube = torch.repeat_interleave(torch.arange(n_cubes), nh)
+    digits = O.strat_cube_digits(n_cubes, ns, dim)[cube]
+    assert torch.equal(torch.floor(y.cpu().double() * ns).long().clamp(max=ns - 1)[:, : min(dim, 6)], digits[:, : min(dim, 6)])
+    xe, dxe, w, c = (t.to(cuda) for t in O.map_init(11, dim, dt))
+    x, jac, ids = ops.map_forward(y, xe, dxe, want_ids=True)
+    assert torch.equal(x.cpu(), O.map_get_x(y.cpu(), xe.cpu(), dxe.cpu()))
+    assert torch.equal(ids.cpu().long(), O.interval_id(y.cpu(), 11))
+    nodes = torch.linspace(0, 1, 4, dtype=dt, device=cuda).repeat(min(dim, 6), 1).contiguous()
+    total = 4 ** min(dim, 6)
+    lo, hi = min(2, total - 1), total - 1
+    pts = ops.nc_grid_points(nodes, lo, hi)
+    mesh = torch.stack([m.ravel() for m in torch.meshgrid(*[nodes[0].cpu()] * min(dim, 6), indexing="ij")], dim=1)
+    assert torch.equal(pts.cpu(), mesh[lo:hi])
+
+
+def test_results_do_not_depend_on_launch_geometry(cuda):
+    """Row sub-ranges, chunk sizes and grid sizes must not change what is computed (fp64: to rounding)."""
+    fn = F.GenzC0(3, a=[1.0, 2.0, 3.0], u=[0.2, 0.5, 0.8])
+    s = fn.to_struct([0.0] * 3, [1.0] * 3, 1.0)
+    full = ops.fused_mc(s, torch.float64, cuda, 0, 1_000_003, 3, 0)
+    parts = sum(ops.fused_mc(s, torch.float64, cuda, a, b, 3, 0) for a, b in [(0, 1), (1, 17), (17, 999_999), (999_999, 1_000_003)])
+    assert torch.allclose(full, parts, rtol=1e-13)
+    nodes = torch.linspace(0, 1, 13, dtype=torch.float64, device=cuda).repeat(3, 1).contiguous()
+    table = tq.Simpson()._weight_table(13, 3, torch.float64, cuda)
+    whole = ops.fused_nc(s, nodes, table, 0, 13**3)
+    split = ops.fused_nc(s, nodes, table, 0, 1000) + ops.fused_nc(s, nodes, table, 1000, 13**3)
+    assert torch.allclose(whole, split, rtol=1e-13)
+    f = torch.rand(13**3, dtype=torch.float64, device=cuda)
+    both = float(ops.nc_contract_f64(f[:777].contiguous(), table, 0, 777) + ops.nc_contract_f64(f[777:].contiguous(), table, 777, 13**3))
+    assert abs(float(ops.nc_contract(f, table)) - both) <= 1e-14 * abs(both)

@@ -238,11 +238,11 @@ extern "C" {
 
 int tq_philox_uniform(void* out, int64_t row_begin, int64_t row_end, int32_t dim, int32_t dtype,
                       uint64_t seed, uint32_t call_idx, void* stream) {
-    TQ_REQUIRE(dim >= 1 && dim <= TQ_MAX_DIM * 4, "tq_philox_uniform: dim %d out of range", dim);
+    TQ_REQUIRE(dim >= 1 && dim <= 512, "tq_philox_uniform: dim %d out of range (max 512)", dim);
     TQ_REQUIRE(row_end >= row_begin && row_begin >= 0, "tq_philox_uniform: bad row range");
     TQ_DISPATCH_DTYPE(dtype, {
         const int nblk = (dim + U01<T>::LANES - 1) / U01<T>::LANES;
-        TQ_REQUIRE(nblk <= 32, "tq_philox_uniform: dim %d too large", dim);
+        TQ_REQUIRE(nblk <= 256, "tq_philox_uniform: dim %d too large", dim);
         return launch_uniform<T>((T*)out, nullptr, row_begin, row_end, dim, seed, call_idx, as_stream(stream));
     });
     return TQ_OK;
@@ -250,7 +250,7 @@ int tq_philox_uniform(void* out, int64_t row_begin, int64_t row_end, int32_t dim
 
 int tq_mc_sample(void* out, const void* domain, int64_t row_begin, int64_t row_end, int32_t dim,
                  int32_t dtype, uint64_t seed, uint32_t call_idx, void* stream) {
-    TQ_REQUIRE(dim >= 1 && dim <= TQ_MAX_DIM, "tq_mc_sample: dim %d out of range (max %d)", dim, TQ_MAX_DIM);
+    TQ_REQUIRE(dim >= 1 && dim <= 512, "tq_mc_sample: dim %d out of range (max 512)", dim);
     TQ_REQUIRE(row_end >= row_begin && row_begin >= 0, "tq_mc_sample: bad row range");
     TQ_REQUIRE(domain != nullptr, "tq_mc_sample: domain is NULL");
     TQ_DISPATCH_DTYPE(dtype, {
@@ -262,7 +262,7 @@ int tq_mc_sample(void* out, const void* domain, int64_t row_begin, int64_t row_e
 int tq_mc_sample_backward(const void* grad_out, int64_t row_begin, int64_t row_end, int32_t dim,
                           int32_t dtype, uint64_t seed, uint32_t call_idx, double* grad_domain_f64,
                           void* ws, size_t ws_bytes, void* stream) {
-    TQ_REQUIRE(dim >= 1 && dim <= TQ_MAX_DIM, "tq_mc_sample_backward: dim %d out of range", dim);
+    TQ_REQUIRE(dim >= 1 && dim <= 512, "tq_mc_sample_backward: dim %d out of range (max 512)", dim);
     const int64_t nrows = row_end - row_begin;
     TQ_REQUIRE(nrows >= 0, "tq_mc_sample_backward: bad row range");
     Workspace w(ws, ws_bytes);
