@@ -187,6 +187,9 @@ fused_nc_kernel(const tq_integrand P, const T* __restrict__ nodes, const T* __re
 // JF/JF2 with one L2 reduction each -- no shared-memory atomics.
 // Map edges arrive packed as {x_edge[k], dx_edge[k]} pairs: one 8/16-byte gather per dimension.
 constexpr int FV_BLOCK = 256;
+#ifndef FV_MIN_CTAS
+#define FV_MIN_CTAS 6
+#endif
 constexpr int FV_SLICE = FV_BLOCK / 2 + 4;
 
 template <typename T> struct Pair2;
@@ -206,7 +209,7 @@ __device__ __forceinline__ void segmented_warp_sum2(unsigned key, T& a, T& b) {
 }
 
 template <int FAM, typename T, bool STRAT>
-__global__ void __launch_bounds__(FV_BLOCK)
+__global__ void __launch_bounds__(FV_BLOCK, FV_MIN_CTAS)
 fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, int64_t n_cubes, int n_strat,
                    int64_t row_begin, int64_t row_end, int64_t rows_per_cta,
                    const typename Pair2<T>::type* __restrict__ edges, long long ni, T* __restrict__ weights,
