@@ -18,10 +18,8 @@ from .integration.rng import RNG
 from .integration.vegas import VEGAS
 from .integration.vegas_map import VEGASMap
 from .integration.vegas_stratification import VEGASStratification
-from .utils.enable_cuda import enable_cuda
+from .utils.config import enable_cuda, set_precision, set_up_backend
 from .utils.set_log_level import set_log_level
-from .utils.set_precision import set_precision
-from .utils.set_up_backend import set_up_backend
 
 import os as _os
 

@@ -6,8 +6,7 @@ import warnings
 import torch
 
 from ..utils.set_log_level import logger
-from ..utils.set_precision import _get_precision  # noqa: F401  (kept for API parity)
-from ..utils.set_up_backend import _get_default_backend
+from ..utils.config import _get_default_backend, _get_precision  # noqa: F401  (_get_precision: API parity)
 
 
 def _infer_backend(x):
