@@ -221,6 +221,47 @@ TQ_API int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int6
                    void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
                    size_t ws_bytes, void* stream);
 
+/* ---- whole fused VEGAS run in one call (host loop in C++) ----------------------------------------
+ * Runs VEGAS.integrate's warm-up, iterations and chi^2 / budget schedule (vegas.py:137-209,211-315) for a
+ * built-in integrand, calling the step kernels above; sample-for-sample identical to driving them one by
+ * one.  All device buffers are owned by the caller (no allocation); records/status need
+ * TQ_VEGAS_MAX_PASSES*4 entries.  JF and JF2 must be contiguous ([2, n_cubes], JF2 = JF + n_cubes). */
+#define TQ_VEGAS_MAX_PASSES 128
+typedef struct tq_vegas_state {
+    void* x_edges;      /* [dim, Ni+1] */
+    void* dx_edges;     /* [dim, Ni] */
+    void* edges_packed; /* [dim, Ni, 2], already packed for the initial map */
+    void* weights;      /* [dim, Ni], zero */
+    int64_t* counts;    /* [dim, Ni], zero */
+    void* dh;           /* [n_cubes], initial 1/n_cubes */
+    int64_t* nh;        /* [n_cubes] */
+    int64_t* offsets;   /* [n_cubes + 1] */
+    void* JF;           /* [2, n_cubes] */
+    void* JF2;
+    double* records;    /* [TQ_VEGAS_MAX_PASSES * 4]: per iteration I, sigma^2, sum d^beta, unused */
+    int32_t* status;    /* [TQ_VEGAS_MAX_PASSES * 4]: per map update, see tq_vegas_map_update */
+    void* map_ws;       /* tq_vegas_map_workspace_bytes(dim, Ni, dtype) */
+    size_t map_ws_bytes;
+    void* ws;           /* tq_workspace_bytes(), zero-initialised */
+    size_t ws_bytes;
+} tq_vegas_state;
+typedef struct tq_vegas_result {
+    int32_t it;          /* iterations performed (VEGAS.it) */
+    int32_t n_block;     /* entries of results / sigma2: the last block of up to 5 iterations */
+    int64_t fevals;      /* VEGAS._nr_of_fevals */
+    int64_t starting_N;  /* per-iteration budget when the run stopped */
+    int32_t calls_used;  /* next free call index of the Philox stream */
+    int32_t n_passes;    /* map updates performed = valid status words */
+    double results[8];
+    double sigma2[8];
+    int32_t status[TQ_VEGAS_MAX_PASSES * 4];
+} tq_vegas_result;
+TQ_API int tq_vegas_run_fused(const tq_integrand* fn_host, int32_t dtype, int64_t N, int32_t max_iterations,
+                       double eps_rel, double eps_abs, int32_t use_grid_improve, int32_t use_warmup,
+                       int64_t n_intervals, int32_t n_strat, int64_t n_cubes, double v_cubes, double alpha,
+                       double beta, uint64_t seed, uint32_t first_call, const tq_vegas_state* state,
+                       tq_vegas_result* result_host, void* stream);
+
 /* Get (and, when bytes > 0, set) the device's L2 fetch granularity hint (cudaLimitMaxL2FetchGranularity:
  * 32, 64 or 128).  The VEGAS kernels gather map edges and update histogram bins at random positions of
  * tables that exceed L2 when the reference's map size formula is used (Ni = N/250 per dimension); with

@@ -31,6 +31,26 @@ class tq_integrand(ctypes.Structure):
 
 
 _P_INTEGRAND = ctypes.POINTER(tq_integrand)
+TQ_VEGAS_MAX_PASSES = 128
+
+
+class tq_vegas_state(ctypes.Structure):
+    """Mirror of `struct tq_vegas_state`: caller-owned device buffers of a fused VEGAS run."""
+
+    _fields_ = [
+        ("x_edges", c_p), ("dx_edges", c_p), ("edges_packed", c_p), ("weights", c_p), ("counts", c_p),
+        ("dh", c_p), ("nh", c_p), ("offsets", c_p), ("JF", c_p), ("JF2", c_p), ("records", c_p), ("status", c_p),
+        ("map_ws", c_p), ("map_ws_bytes", c_sz), ("ws", c_p), ("ws_bytes", c_sz),
+    ]
+
+
+class tq_vegas_result(ctypes.Structure):
+    """Mirror of `struct tq_vegas_result` (host memory)."""
+
+    _fields_ = [
+        ("it", c_i32), ("n_block", c_i32), ("fevals", c_i64), ("starting_N", c_i64), ("calls_used", c_i32),
+        ("n_passes", c_i32), ("results", c_f64 * 8), ("sigma2", c_f64 * 8), ("status", c_i32 * (TQ_VEGAS_MAX_PASSES * 4)),
+    ]
 
 # name -> (restype, argtypes); must list every symbol of include/tqb200.h (checked by tests/test_abi.py)
 PROTOTYPES = {
@@ -64,6 +84,9 @@ PROTOTYPES = {
     "tq_vegas_map_pack_edges": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
     "tq_fused_vegas": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_p, c_i64, c_i32, c_i64, c_i64, c_p, c_i64, c_p, c_p,
                                       c_p, c_p, c_u64, c_u32, c_p, c_p, c_sz, c_p]),
+    "tq_vegas_run_fused": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_i64, c_i32, c_f64, c_f64, c_i32, c_i32, c_i64, c_i32, c_i64,
+                                          c_f64, c_f64, c_f64, c_u64, c_u32, ctypes.POINTER(tq_vegas_state),
+                                          ctypes.POINTER(tq_vegas_result), c_p]),
     "tq_l2_fetch_granularity": (ctypes.c_int, [c_i32, ctypes.POINTER(c_i32)]),
     "tq_peak_microbench": (ctypes.c_int, [c_i32, c_i64, c_p, ctypes.POINTER(c_f64), c_p]),
 }

@@ -1,0 +1,176 @@
+// Host-side VEGAS+ loop for the fused path: one C-ABI call runs warm-up, all iterations and the
+// chi^2 / budget schedule of torchquad/integration/vegas.py:137-209,211-315 without returning to Python
+// between passes.  Small problems (the reference's own N = 1e6 configuration is ~0.5 ms of GPU work) are
+// bound by per-launch host overhead; from C++ a pass costs a handful of launches and one 8-byte read-back.
+// The kernels are exactly those of the step-by-step API (this file only calls public tq_* entry points), so a
+// run is sample-for-sample identical to the Python-driven loop (tests/test_gpu_integrators.py).
+#include <math.h>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tq {
+
+static inline float tsqrt(float x) { return sqrtf(x); }
+static inline double tsqrt(double x) { return sqrt(x); }
+
+// vegas.py:318-362 in the working precision T (the reference does this arithmetic on 0-dim tensors of dtype T).
+template <typename T>
+struct Block {
+    std::vector<T> res, sig;
+    T mean() const {
+        bool zero = false;
+        for (T s : sig) zero |= (s == (T)0);
+        if (zero) {
+            T acc = (T)0;
+            for (T r : res) acc += r;
+            return acc / (T)res.size();
+        }
+        T num = (T)0, den = (T)0;
+        for (size_t k = 0; k < res.size(); ++k) {
+            num += res[k] / sig[k];
+            den += (T)1 / sig[k];
+        }
+        return num / den;
+    }
+    T error() const {
+        T inv = (T)0;
+        for (T s : sig)
+            if (s != (T)0) inv += (T)1 / s;
+        return inv == (T)0 ? sig[0] : (T)1 / tsqrt(inv);
+    }
+    T chisq(T m) const {
+        T acc = res[0] * (T)0;
+        for (size_t k = 0; k < res.size(); ++k)
+            if (res[k] != m) acc += (res[k] - m) * (res[k] - m) / sig[k];
+        return acc;
+    }
+};
+
+template <typename T>
+static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t max_it, double eps_rel, double eps_abs,
+                     bool grid_improve, bool warmup, int64_t ni, int32_t n_strat, int64_t n_cubes, double v_cubes,
+                     double alpha, double beta, uint64_t seed, uint32_t call, const tq_vegas_state* s,
+                     tq_vegas_result* out, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    const int dim = fn->dim;
+    const size_t elt = sizeof(T);
+    const int64_t increment = N / (max_it + 5);  // vegas.py:90-91
+    int64_t starting = increment;
+    int64_t fevals = 0;
+    int passes = 0;
+    const int max_passes = TQ_VEGAS_MAX_PASSES;
+    auto update_map = [&]() -> int {
+        if (passes >= max_passes) { set_error("tq_vegas_run_fused: more than %d passes", max_passes); return TQ_ERR_UNSUPPORTED; }
+        int rc = tq_vegas_map_update(s->x_edges, s->dx_edges, s->weights, s->counts, s->edges_packed, dim, ni, alpha, dtype,
+                                     s->status + 4 * passes, s->map_ws, s->map_ws_bytes, stream);
+        ++passes;
+        return rc;
+    };
+    if (warmup) {  // vegas.py:211-266: 5 unstratified passes of starting//5 samples, results discarded
+        const int64_t ns = starting / 5;
+        for (int w = 0; w < 5; ++w) {
+            int rc = tq_fused_vegas(fn, dtype, nullptr, 0, 1, 0, ns, s->edges_packed, ni, s->weights, s->counts, nullptr, nullptr,
+                                    seed, call++, s->records, s->ws, s->ws_bytes, stream);
+            if (rc) return rc;
+            fevals += ns;
+            if ((rc = update_map())) return rc;
+        }
+    }
+    Block<T> blk;
+    int it = 0;
+    int first_rec = 0;  // record index of the first iteration of the current block
+    while (true) {
+        ++it;
+        int rc = tq_vegas_strat_nh(s->dh, n_cubes, (double)starting, dtype, s->nh, s->offsets, s->ws, s->ws_bytes, stream);
+        if (rc) return rc;
+        long long M = 0;
+        cudaMemcpyAsync(&M, s->offsets + n_cubes, sizeof(long long), cudaMemcpyDeviceToHost, st);
+        cudaMemsetAsync(s->JF, 0, 2 * (size_t)n_cubes * elt, st);
+        cudaError_t e = cudaStreamSynchronize(st);  // the one sync of the iteration (M sizes the launch)
+        if (e != cudaSuccess) { set_error("tq_vegas_run_fused: %s", cudaGetErrorString(e)); return (int)e; }
+        rc = tq_fused_vegas(fn, dtype, s->offsets, n_cubes, n_strat, 0, M, s->edges_packed, ni, grid_improve ? s->weights : nullptr,
+                            s->counts, s->JF, s->JF2, seed, call++, nullptr, s->ws, s->ws_bytes, stream);
+        if (rc) return rc;
+        fevals += M;
+        if (it > TQ_VEGAS_MAX_PASSES) { set_error("tq_vegas_run_fused: too many iterations"); return TQ_ERR_UNSUPPORTED; }
+        rc = tq_vegas_strat_update(s->JF, s->JF2, s->nh, n_cubes, v_cubes, beta, dtype, s->dh, s->records + 4 * (it - 1), s->ws,
+                                   s->ws_bytes, stream);
+        if (rc) return rc;
+        if (grid_improve && (rc = update_map())) return rc;
+        if (it % 5 > 0) continue;
+        // vegas.py:161-209 on the block of the last (up to) five iterations
+        const int nrec = it - first_rec;
+        std::vector<double> rec(4 * nrec);
+        cudaMemcpyAsync(rec.data(), s->records + 4 * first_rec, rec.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("tq_vegas_run_fused: %s", cudaGetErrorString(e)); return (int)e; }
+        blk.res.clear();
+        blk.sig.clear();
+        for (int k = 0; k < nrec; ++k) {
+            blk.res.push_back((T)rec[4 * k]);
+            blk.sig.push_back((T)rec[4 * k + 1]);
+        }
+        const T mean = blk.mean();
+        const T res_abs = (T)fabs((double)mean);
+        const T err = blk.error();
+        const T chi2 = blk.chisq(mean);
+        bool stop = false;
+        if ((err <= (T)eps_rel * res_abs || err <= (T)eps_abs) && chi2 / (T)5 < (T)1) stop = true;
+        if (!stop) {
+            if (chi2 / (T)5 < (T)1) {
+                if (res_abs == (T)0) {
+                    starting += increment;
+                } else {
+                    const T acc = err / res_abs;
+                    const T scaled = (T)starting * tsqrt((T)(acc / (T)(eps_rel + 1e-8)));
+                    const int64_t alt = isfinite((double)scaled) && (double)scaled < 9.0e18 ? (int64_t)scaled : INT64_MAX;
+                    starting = starting + increment < alt ? starting + increment : alt;
+                }
+            } else if (chi2 / (T)5 > (T)1) {
+                starting += increment;
+            }
+            if (fevals + starting * 5 > N) stop = true;
+            else if (it + 5 > max_it) stop = true;
+        }
+        if (stop) break;
+        first_rec = it;
+    }
+    out->it = it;
+    out->n_block = (int32_t)blk.res.size();
+    out->fevals = fevals;
+    out->starting_N = starting;
+    out->calls_used = (int32_t)(call);
+    out->n_passes = passes;
+    for (size_t k = 0; k < blk.res.size() && k < 8; ++k) {
+        out->results[k] = (double)blk.res[k];
+        out->sigma2[k] = (double)blk.sig[k];
+    }
+    if (passes > 0) {
+        cudaMemcpyAsync(out->status, s->status, 4 * (size_t)passes * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("tq_vegas_run_fused: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    return TQ_OK;
+}
+
+}  // namespace tq
+
+extern "C" int tq_vegas_run_fused(const tq_integrand* fn_host, int32_t dtype, int64_t N, int32_t max_iterations,
+                                  double eps_rel, double eps_abs, int32_t use_grid_improve, int32_t use_warmup,
+                                  int64_t n_intervals, int32_t n_strat, int64_t n_cubes, double v_cubes, double alpha,
+                                  double beta, uint64_t seed, uint32_t first_call, const tq_vegas_state* state,
+                                  tq_vegas_result* result_host, void* stream) {
+    TQ_REQUIRE(fn_host && state && result_host, "tq_vegas_run_fused: NULL argument");
+    TQ_REQUIRE(N >= 1 && max_iterations >= 1 && max_iterations + 5 <= TQ_VEGAS_MAX_PASSES,
+               "tq_vegas_run_fused: max_iterations must be in [1, %d]", TQ_VEGAS_MAX_PASSES - 5);
+    TQ_REQUIRE(n_cubes >= 1 && n_strat >= 1 && n_intervals >= 2, "tq_vegas_run_fused: bad map / stratification sizes");
+    if (dtype == TQ_F32)
+        return tq::run_fused<float>(fn_host, dtype, N, max_iterations, eps_rel, eps_abs, use_grid_improve != 0, use_warmup != 0,
+                                    n_intervals, n_strat, n_cubes, v_cubes, alpha, beta, seed, first_call, state, result_host, stream);
+    if (dtype == TQ_F64)
+        return tq::run_fused<double>(fn_host, dtype, N, max_iterations, eps_rel, eps_abs, use_grid_improve != 0, use_warmup != 0,
+                                     n_intervals, n_strat, n_cubes, v_cubes, alpha, beta, seed, first_call, state, result_host, stream);
+    tq::set_error("tq_vegas_run_fused: unsupported dtype %d", dtype);
+    return TQ_ERR_INVALID_ARGUMENT;
+}

@@ -42,6 +42,7 @@ class VEGAS(BaseIntegrator):
 
     max_map_intervals = None
     l2_fetch_bytes = None
+    native_loop = True  # fused single-GPU runs: drive all passes from C++ (tq_vegas_run_fused)
     _large_map_bytes = 64 << 20
 
     def __init__(self):
@@ -116,6 +117,10 @@ class VEGAS(BaseIntegrator):
         self._status_buf = torch.zeros((max_iterations + 16, 4), dtype=torch.int32, device=self.device)
         self._status_used = 0
 
+        if (self._fused and self.native_loop and not tqdist.is_enabled()
+                and max_iterations + 5 <= _lib.TQ_VEGAS_MAX_PASSES):
+            return self._integrate_native_loop(N, use_warmup)
+
         # random-access regime: shrink the L2 fetch granularity while the big tables are in flight
         restore_l2 = None
         if (self.l2_fetch_bytes and self.device.type == "cuda"
@@ -137,6 +142,27 @@ class VEGAS(BaseIntegrator):
         self._flush_map_status()
         logger.debug("VEGAS finished")
         return self._get_result()
+
+    def _integrate_native_loop(self, N, use_warmup):
+        """Fused single-GPU run with the pass loop and schedule in C++ (csrc/vegas_driver.cu): same kernels, same
+        Philox call indices and therefore the same samples as the Python-driven loop below."""
+        first_call = self.rng._call
+        res = ops.vegas_run_fused(self._fn_struct, self.map, self.strat, N, self._max_iterations, self._eps_rel,
+                                  self._eps_abs, self.use_grid_improve, use_warmup, self.rng.seed, first_call)
+        self.rng._call = res.calls_used
+        self.it = res.it
+        self._nr_of_fevals = res.fevals
+        self._starting_N = res.starting_N
+        self.results = [torch.tensor(res.results[k], dtype=torch.float64, device=self.device) for k in range(res.n_block)]
+        self.sigma2 = [torch.tensor(res.sigma2[k], dtype=torch.float64, device=self.device) for k in range(res.n_block)]
+        self._host_cache = ([self._np(res.results[k]) for k in range(res.n_block)],
+                            [self._np(res.sigma2[k]) for k in range(res.n_block)])
+        self.map._edges2_stale = False
+        for p in range(res.n_passes):
+            self.map.check_status(list(res.status[4 * p: 4 * p + 4]))
+        with np.errstate(all="ignore"):
+            mean = self._weighted_mean(*self._host_cache)
+        return torch.tensor(mean, dtype=self.dtype, device=self.device)
 
     # ------------------------------------------------------------------ passes
     def _rank_rows(self, total):

@@ -459,3 +459,33 @@ def fused_vegas(fn_struct, edges_packed, weights, counts, row_begin, row_end, se
              ptr(edges_packed), edges_packed.shape[1], ptr(weights), ptr(counts), ptr(JF), ptr(JF2),
              seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, ptr(out), wsp, wsn, stream_ptr(edges_packed.device))
     return out
+
+
+def vegas_run_fused(fn_struct, vmap, strat, N, max_iterations, eps_rel, eps_abs, use_grid_improve, use_warmup, seed,
+                    first_call):
+    """Whole fused VEGAS run through `tq_vegas_run_fused` (host loop in C++).  `vmap` / `strat` are the
+    VEGASMap / VEGASStratification objects whose tensors hold the state (mutated in place).
+    Returns the filled `tq_vegas_result`; synchronises (the schedule needs the per-block estimates)."""
+    dev, dt = vmap.device, vmap.dtype
+    n_cubes = strat.N_cubes
+    JFs = torch.zeros((2, n_cubes), dtype=dt, device=dev)
+    nh = torch.empty(n_cubes, dtype=torch.int64, device=dev)
+    offsets = torch.empty(n_cubes + 1, dtype=torch.int64, device=dev)
+    records = torch.zeros(_lib.TQ_VEGAS_MAX_PASSES * 4, dtype=torch.float64, device=dev)
+    status = torch.zeros(_lib.TQ_VEGAS_MAX_PASSES * 4, dtype=torch.int32, device=dev)
+    scratch = _map_scratch(vmap.dim, vmap.N_intervals, dt, dev)
+    ws = workspace(dev)
+    packed = vmap.packed_edges()
+    state = _lib.tq_vegas_state(
+        ptr(vmap.x_edges), ptr(vmap.dx_edges), ptr(packed), ptr(vmap.weights), ptr(vmap.counts), ptr(strat.dh), ptr(nh),
+        ptr(offsets), ptr(JFs[0]), ptr(JFs[1]), ptr(records), ptr(status), ptr(scratch), scratch.numel(), ws.data_ptr(),
+        ws.numel())
+    result = _lib.tq_vegas_result()
+    with on_device(dev):
+        call("tq_vegas_run_fused", fn_struct, dtype_code(dt), N, max_iterations, float(eps_rel), float(eps_abs),
+             int(bool(use_grid_improve)), int(bool(use_warmup)), vmap.N_intervals, strat.N_strat, n_cubes,
+             float(strat.V_cubes), float(vmap.alpha), float(strat.beta), seed & 0xFFFFFFFFFFFFFFFF, first_call & 0xFFFFFFFF,
+             state, result, stream_ptr(dev))
+    strat.JF, strat.JF2, strat._nh, strat._offsets = JFs[0], JFs[1], nh, offsets
+    strat.strat_counts = nh.to(dt)
+    return result
