@@ -175,7 +175,8 @@ TQ_API int tq_vegas_strat_accumulate_backward(const void* grad_JF, const int64_t
                                        int64_t row_begin, int64_t row_end, void* grad_jf, int32_t dtype,
                                        void* stream);
 /* Iteration estimator (vegas.py:293-303) + update_DH (vegas_stratification.py:72-90) in one pass:
- *   scalars_f64[0] = I_it = sum JF*V/n, [1] = sigma2_it = sum |JF2*V^2/n - ih^2|/n, [2] = sum d^beta;
+ *   scalars_f64[0] = I_it = sum JF*V/n, [1] = sigma2_it = sum |JF2*V^2/n - ih^2|/n, [2] = sum d^beta,
+ *   [3] = sum nh (the pass's sample count, exact below 2^53) -- scalars_f64 holds FOUR doubles;
  *   dh[c] = d^beta / sum (left unnormalised when the sum is 0). */
 TQ_API int tq_vegas_strat_update(const void* JF, const void* JF2, const int64_t* nh, int64_t n_cubes,
                           double v_cubes, double beta, int32_t dtype, void* dh, double* scalars_f64,

@@ -270,6 +270,7 @@ def test_strat_sequence_matches_golden(cuda, golden, tag):
         want_dh = torch.from_numpy(g[f"dh{it}"])
         assert rel_err(dh, want_dh) <= (1e-13 if tag == "f64" else 3e-6)
         assert abs(float(scal[0]) - float(g[f"I{it}"])) <= RTOL[tag] * abs(float(g[f"I{it}"]))
+        assert float(scal[3]) == float(nh.sum())
         assert abs(float(scal[1]) - float(g[f"s2{it}"])) <= RTOL[tag] * 10 * abs(float(g[f"s2{it}"]))
         dh = want_dh.to(cuda)  # continue from the golden state so nh stays bit-comparable
     nhp, _ = ops.strat_nh(dev(g["dhp"], cuda), 54321)

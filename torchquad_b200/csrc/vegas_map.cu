@@ -4,6 +4,9 @@
 // gather/scatter/cumsum ATen launches; here each step is one pass over its data.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace tq {
 
 // ------------------------------------------------------------------ forward (get_X + get_Jac + ids)
@@ -420,117 +423,174 @@ map_finalize_kernel(const T* __restrict__ x_new, T* __restrict__ xe, T* __restri
 }
 
 // ------------------------------------------------------------------ small maps: the whole update in ONE launch
-// For maps up to MAP_SMALL_NI intervals per dimension (every case where VEGAS is launch-latency bound) one CTA
-// per dimension runs average -> smooth -> fp64 prefix -> new edges -> repair/diff/reset back to back with CTA
-// barriers instead of seven launches.  The "any dimension sums to zero" decision needs all row sums; each
-// CTA recomputes them (dim * Ni reads, tiny at these sizes) instead of synchronising across CTAs.
+// For maps up to MAP_SMALL_NI intervals per dimension (every case where VEGAS is launch-latency bound) one
+// thread-block CLUSTER per dimension runs average -> smooth -> fp64 prefix -> new edges -> repair/diff/reset
+// back to back, with cluster barriers and distributed shared memory instead of seven launches.  Each CTA owns
+// a contiguous slice of the dimension's bins and each thread `per` consecutive bins, kept in registers from
+// the smoothing to the prefix sums.  The "any dimension sums to zero" decision needs all row sums; each
+// cluster recomputes them (dim * Ni reads per cluster, tiny at these sizes) instead of synchronising across
+// clusters.
 constexpr long long MAP_SMALL_NI = 32768;
 constexpr int MAP_SMALL_DIM = 64;
+constexpr int MAP_CL = 8;          // CTAs per cluster = per dimension
+constexpr int MAP_CL_THREADS = 512;
+constexpr int MAP_CL_ITEMS = 8;    // MAP_SMALL_NI / (MAP_CL * MAP_CL_THREADS)
+constexpr int MAP_COARSE = 32;     // stride of the shared-memory search table over the prefix sums
 
 template <typename T>
-__global__ void __launch_bounds__(1024)
+__global__ void __cluster_dims__(MAP_CL, 1, 1) __launch_bounds__(MAP_CL_THREADS)
 map_update_small_kernel(T* __restrict__ xe, T* __restrict__ dxe, T* __restrict__ weights, long long* __restrict__ counts,
                         typename EdgePair<T>::type* __restrict__ packed, T* __restrict__ avg, T* __restrict__ smoothed,
                         double* __restrict__ S, T* __restrict__ x_new, int dim, long long ni, T alpha,
                         int32_t* status, bool do_edges) {
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ double sh[33];
+    __shared__ double s_part[MAP_SMALL_DIM];  // this CTA's share of every dimension's row sum
     __shared__ double s_tot[MAP_SMALL_DIM];
-    __shared__ double s_total2;
-    const int d = blockIdx.x;
+    __shared__ double s_slice;                // this CTA's share of the smoothed row sum
+    __shared__ double s_coarse[MAP_SMALL_NI / MAP_COARSE];
+    const int d = blockIdx.x / MAP_CL;
+    const unsigned rank = cluster.block_rank();
     const int tid = threadIdx.x;
+    const int per = (int)((ni + MAP_CL * MAP_CL_THREADS - 1) / (MAP_CL * MAP_CL_THREADS));
+    const long long slice = (long long)per * MAP_CL_THREADS;
+    const long long j_lo = (long long)rank * slice;
+    const long long j_hi = j_lo + slice < ni ? j_lo + slice : ni;
+    // ---- averages with the zero-count fill; row sums of every dimension (vegas_map.py:118-144,150)
     for (int dd = 0; dd < dim; ++dd) {
         const T* w = weights + (int64_t)dd * ni;
         const long long* c = counts + (int64_t)dd * ni;
         double part[1] = {0.0};
-        for (long long j = tid; j < ni; j += blockDim.x) {
+        for (long long j = j_lo + tid; j < j_hi; j += MAP_CL_THREADS) {
             const T a = filled_average<T>(w, c, j, ni);
             if (dd == d) avg[(int64_t)d * ni + j] = a;
             part[0] += (double)a;
         }
         block_sum<1>(part, sh);
-        if (tid == 0) s_tot[dd] = part[0];
-        __syncthreads();
+        if (tid == 0) s_part[dd] = part[0];
     }
+    cluster.sync();  // also publishes this cluster's avg[] slices to its other CTAs
+    if (tid < dim) {
+        double t = 0.0;
+        for (unsigned r = 0; r < MAP_CL; ++r) t += cluster.map_shared_rank(s_part, r)[tid];
+        s_tot[tid] = t;
+    }
+    __syncthreads();
     bool any_zero = false;
     for (int dd = 0; dd < dim; ++dd) any_zero |= ((T)s_tot[dd] == (T)0);
-    if (any_zero) {
-        if (d == 0 && tid == 0) status[0] = 1;
+    if (any_zero) {  // the reference skips the whole update (vegas_map.py:192-197), keeping only the reset
+        if (blockIdx.x == 0 && tid == 0) status[0] = 1;
         if (do_edges) {
-            for (long long j = tid; j < ni; j += blockDim.x) {
+            for (long long j = j_lo + tid; j < j_hi; j += MAP_CL_THREADS) {
                 weights[(int64_t)d * ni + j] = (T)0;
                 counts[(int64_t)d * ni + j] = 0;
             }
         }
+        cluster.sync();  // no CTA may exit while its shared memory is still being read
         return;
     }
-    // smoothing + compression (vegas_map.py:146-170)
+    // ---- smoothing + compression (vegas_map.py:146-170); thread owns bins [jt, jt + per)
     const T* a = avg + (int64_t)d * ni;
     T* sm = smoothed + (int64_t)d * ni;
     const T denom = mul_rn((T)8, (T)s_tot[d]);
-    double part[1] = {0.0};
-    for (long long j = tid; j < ni; j += blockDim.x) {
-        T v;
-        if (j == 0) v = add_rn(mul_rn((T)7, a[0]), a[1]);
-        else if (j == ni - 1) v = add_rn(a[ni - 2], mul_rn((T)7, a[ni - 1]));
-        else v = add_rn(add_rn(a[j - 1], mul_rn((T)6, a[j])), a[j + 1]);
-        v = div_rn(v, denom);
-        if (v != (T)0) {
-            const T base = div_rn(sub_rn(v, (T)1), log(v));
-            v = (alpha == (T)0.5) ? sqrt(base) : pow(base, alpha);
+    const long long jt = j_lo + (long long)tid * per;
+    T v[MAP_CL_ITEMS];
+    double run = 0.0;
+#pragma unroll
+    for (int i = 0; i < MAP_CL_ITEMS; ++i) {
+        const long long j = jt + i;
+        v[i] = (T)0;
+        if (i < per && j < ni) {
+            T x;
+            if (j == 0) x = add_rn(mul_rn((T)7, a[0]), a[1]);
+            else if (j == ni - 1) x = add_rn(a[ni - 2], mul_rn((T)7, a[ni - 1]));
+            else x = add_rn(add_rn(a[j - 1], mul_rn((T)6, a[j])), a[j + 1]);
+            x = div_rn(x, denom);
+            if (x != (T)0) {
+                const T base = div_rn(sub_rn(x, (T)1), log(x));
+                x = (alpha == (T)0.5) ? sqrt(base) : pow(base, alpha);  // ATen evaluates x**0.5 as sqrt
+            }
+            v[i] = x;
+            sm[j] = x;
+            run += (double)x;
         }
-        sm[j] = v;
-        part[0] += (double)v;
     }
-    block_sum<1>(part, sh);
-    if (tid == 0) s_total2 = part[0];
-    __syncthreads();
-    if (!do_edges) return;
-    // fp64 inclusive prefix sums
+    if (!do_edges) {
+        cluster.sync();
+        return;
+    }
+    // ---- fp64 inclusive prefix sums (vegas_map.py:207-213): CTA scan + rank-ordered slice totals
+    double total;
+    double ex = block_excl_scan<double>(run, sh, total);
+    if (tid == 0) s_slice = total;
+    cluster.sync();
+    double row_total = 0.0;
+    for (unsigned r = 0; r < MAP_CL; ++r) {
+        const double t = *cluster.map_shared_rank(&s_slice, r);
+        if (r < rank) ex += t;
+        row_total += t;
+    }
     double* Sd = S + (int64_t)d * ni;
-    double carry = 0.0;
-    for (long long base = 0; base < ni; base += blockDim.x) {
-        const long long j = base + tid;
-        const double v = j < ni ? (double)sm[j] : 0.0;
-        double total;
-        const double ex = block_excl_scan<double>(v, sh, total);
-        if (j < ni) Sd[j] = carry + ex + v;
-        carry += total;
+#pragma unroll
+    for (int i = 0; i < MAP_CL_ITEMS; ++i) {
+        const long long j = jt + i;
+        if (i < per && j < ni) {
+            ex += (double)v[i];
+            Sd[j] = ex;
+        }
     }
-    __syncthreads();
-    // new inner edges (vegas_map.py:214-239)
+    cluster.sync();
+    // ---- new inner edges (vegas_map.py:214-239): two-level search, coarse table in shared memory
     const T* x_old = xe + (int64_t)d * (ni + 1);
     const T* dx_old = dxe + (int64_t)d * ni;
     T* xn = x_new + (int64_t)d * (ni + 1);
-    const T delta_t = div_rn((T)s_total2, (T)ni);
+    const T delta_t = div_rn((T)row_total, (T)ni);
     const double delta = (double)delta_t;
-    if (tid == 0) { xn[0] = x_old[0]; xn[ni] = x_old[ni]; }
-    for (long long m = tid; m <= ni - 2; m += blockDim.x) {
-        long long lo = 0, hi = ni - 1;
+    const long long last = ni - 2;  // largest searchable index
+    const int nblk = (int)((last + MAP_COARSE) / MAP_COARSE);  // blocks of MAP_COARSE covering [0, last]
+    for (int b = tid; b < nblk; b += MAP_CL_THREADS) {
+        const long long e = (long long)b * MAP_COARSE + MAP_COARSE - 1;
+        s_coarse[b] = Sd[e < last ? e : last];
+    }
+    if (rank == 0 && tid == 0) { xn[0] = x_old[0]; xn[ni] = x_old[ni]; }
+    __syncthreads();
+    for (long long m = j_lo + tid; m < j_hi && m <= last; m += MAP_CL_THREADS) {
+        // smallest j in [0, last] with trunc(S_j / delta) > m; ni - 1 when there is none
+        int lo = 0, hi = nblk;
         while (lo < hi) {
-            const long long mid = (lo + hi) >> 1;
-            const long long k = (long long)(__ddiv_rn(Sd[mid], delta));
-            if (k > m) hi = mid; else lo = mid + 1;
+            const int mid = (lo + hi) >> 1;
+            if ((long long)__ddiv_rn(s_coarse[mid], delta) > m) hi = mid; else lo = mid + 1;
         }
-        const long long idx = lo;
+        long long idx = ni - 1;
+        if (lo < nblk) {
+            long long flo = (long long)lo * MAP_COARSE, fhi = flo + MAP_COARSE - 1;
+            if (fhi > last) fhi = last;
+            while (flo < fhi) {
+                const long long mid = (flo + fhi) >> 1;
+                if ((long long)__ddiv_rn(Sd[mid], delta) > m) fhi = mid; else flo = mid + 1;
+            }
+            idx = flo;
+        }
         const double below = idx > 0 ? Sd[idx - 1] : 0.0;
         const T acc = (T)((double)(m + 1) * delta - below);
         xn[m + 1] = add_rn(x_old[idx], mul_rn(div_rn(acc, sm[idx]), dx_old[idx]));
     }
-    __syncthreads();
-    // repair, diff, pack, reset (vegas_map.py:240-261)
-    for (long long e = tid; e <= ni; e += blockDim.x) {
+    cluster.sync();
+    // ---- repair, diff, pack, reset (vegas_map.py:240-261)
+    const long long e_hi = (j_lo < ni && j_hi == ni) ? ni + 1 : j_hi;  // edge ni goes with the last non-empty slice
+    for (long long e = j_lo + tid; e < e_hi; e += MAP_CL_THREADS) {
         bool bad, still;
-        const T v = repaired_edge<T>(xn, e, ni, bad, still);
+        const T val = repaired_edge<T>(xn, e, ni, bad, still);
         if (bad) atomicAdd(&status[1], 1);
         if (still) status[2] = 1;
-        xe[(int64_t)d * (ni + 1) + e] = v;
+        xe[(int64_t)d * (ni + 1) + e] = val;
         if (e < ni) {
             bool b2, s2;
-            const T dv = sub_rn(repaired_edge<T>(xn, e + 1, ni, b2, s2), v);
+            const T dv = sub_rn(repaired_edge<T>(xn, e + 1, ni, b2, s2), val);
             dxe[(int64_t)d * ni + e] = dv;
             if (packed) {
                 typename EdgePair<T>::type pr;
-                pr.x = v;
+                pr.x = val;
                 pr.y = dv;
                 packed[(int64_t)d * ni + e] = pr;
             }
@@ -716,7 +776,7 @@ int tq_vegas_map_smooth(const void* weights, const int64_t* counts, void* smooth
         if (!carve<T>(w, dim, n_intervals, s, false)) { set_error("tq_vegas_map_smooth: workspace too small"); return TQ_ERR_WORKSPACE; }
         if (n_intervals <= MAP_SMALL_NI && dim <= MAP_SMALL_DIM) {
             cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st);
-            map_update_small_kernel<T><<<dim, 1024, 0, st>>>(nullptr, nullptr, (T*)weights, (long long*)counts, nullptr, (T*)s.avg,
+            map_update_small_kernel<T><<<dim * MAP_CL, MAP_CL_THREADS, 0, st>>>(nullptr, nullptr, (T*)weights, (long long*)counts, nullptr, (T*)s.avg,
                                                             (T*)smoothed, nullptr, nullptr, dim, n_intervals, (T)alpha, status, false);
             return check_launch("map_update_small_kernel");
         }
@@ -738,7 +798,7 @@ int tq_vegas_map_update(void* x_edges, void* dx_edges, void* weights, int64_t* c
         if (!carve<T>(w, dim, ni, s, true)) { set_error("tq_vegas_map_update: workspace too small (need %zu bytes)", map_scratch_bytes(dim, ni, sizeof(T))); return TQ_ERR_WORKSPACE; }
         if (ni <= MAP_SMALL_NI && dim <= MAP_SMALL_DIM) {
             cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st);
-            map_update_small_kernel<T><<<dim, 1024, 0, st>>>((T*)x_edges, (T*)dx_edges, (T*)weights, (long long*)counts,
+            map_update_small_kernel<T><<<dim * MAP_CL, MAP_CL_THREADS, 0, st>>>((T*)x_edges, (T*)dx_edges, (T*)weights, (long long*)counts,
                                                             (P2*)edges_packed, (T*)s.avg, (T*)s.smoothed, s.S, (T*)s.x_new, dim, ni,
                                                             (T)alpha, status, true);
             return check_launch("map_update_small_kernel");

@@ -5,6 +5,9 @@
 #include "common.cuh"
 #include "strat_tile.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace tq {
 
 constexpr int ST_TILE = 1024;  // cubes (or rows) per CTA tile: 256 threads x 4
@@ -70,27 +73,50 @@ nh_scan_kernel(const T* __restrict__ dh, int64_t n_cubes, T nev, const long long
     }
 }
 
-// Small stratifications (the launch-latency-bound regime): get_NH + scan in ONE CTA.
+// Small stratifications (the launch-latency-bound regime): get_NH + scan in ONE launch by one thread-block
+// cluster.  Each of the SMALL_CL x SMALL_THREADS threads owns `per` consecutive cubes; CTA totals cross the
+// cluster through distributed shared memory, so the whole scan costs one CTA scan and one cluster barrier.
 constexpr int64_t ST_SMALL_CUBES = 32768;
+constexpr int SMALL_CL = 8;         // CTAs per cluster (portable maximum)
+constexpr int SMALL_THREADS = 512;  // threads per CTA
+constexpr int SMALL_ITEMS = 8;      // ST_SMALL_CUBES / (SMALL_CL * SMALL_THREADS)
 
 template <typename T>
-__global__ void __launch_bounds__(1024)
+__global__ void __cluster_dims__(SMALL_CL, 1, 1) __launch_bounds__(SMALL_THREADS)
 nh_small_kernel(const T* __restrict__ dh, int64_t n_cubes, T nev, long long* __restrict__ nh,
                 long long* __restrict__ offsets) {
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ long long sh[33];
-    long long carry = 0;
-    for (int64_t base = 0; base < n_cubes; base += blockDim.x) {
-        const int64_t c = base + threadIdx.x;
-        const long long v = c < n_cubes ? nh_of<T>(dh[c], nev) : 0;
-        long long total;
-        const long long ex = block_excl_scan<long long>(v, sh, total);
-        if (c < n_cubes) {
-            nh[c] = v;
-            offsets[c] = carry + ex;
-        }
-        carry += total;
+    __shared__ long long s_total;
+    const unsigned rank = cluster.block_rank();
+    const int per = (int)((n_cubes + SMALL_CL * SMALL_THREADS - 1) / (SMALL_CL * SMALL_THREADS));
+    const int64_t c0 = ((int64_t)rank * SMALL_THREADS + threadIdx.x) * per;
+    long long v[SMALL_ITEMS], run = 0;
+#pragma unroll
+    for (int i = 0; i < SMALL_ITEMS; ++i) {
+        v[i] = (i < per && c0 + i < n_cubes) ? nh_of<T>(dh[c0 + i], nev) : 0;
+        run += v[i];
     }
-    if (threadIdx.x == 0) offsets[n_cubes] = carry;
+    long long total;
+    long long ex = block_excl_scan<long long>(run, sh, total);
+    if (threadIdx.x == 0) s_total = total;
+    cluster.sync();
+    long long all = 0;
+    for (unsigned r = 0; r < SMALL_CL; ++r) {
+        const long long t = *cluster.map_shared_rank(&s_total, r);
+        if (r < rank) ex += t;
+        all += t;
+    }
+    cluster.sync();  // no CTA may exit while its shared memory is still being read
+#pragma unroll
+    for (int i = 0; i < SMALL_ITEMS; ++i) {
+        if (i < per && c0 + i < n_cubes) {
+            nh[c0 + i] = v[i];
+            offsets[c0 + i] = ex;
+        }
+        ex += v[i];
+    }
+    if (rank == 0 && threadIdx.x == 0) offsets[n_cubes] = all;
 }
 
 // ---- exclusive scan of a caller-provided nh
@@ -317,11 +343,12 @@ __global__ void __launch_bounds__(256)
 strat_update_kernel(const T* __restrict__ JF, const T* __restrict__ JF2, const long long* __restrict__ nh,
                     int64_t n_cubes, T V, T V2, T beta, T* __restrict__ dh, double* partials, unsigned int* ticket,
                     double* scalars) {
-    __shared__ double sh[32 * 3];
-    double acc[3] = {0.0, 0.0, 0.0};
+    __shared__ double sh[32 * 4];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cubes;
          c += (int64_t)gridDim.x * blockDim.x) {
-        const T n = (T)nh[c];
+        const long long nc = nh[c];
+        const T n = (T)nc;
         const T inv = div_rn((T)1, n);
         const T jf = JF[c], jf2 = JF2[c];
         // vegas.py:293-303
@@ -336,44 +363,70 @@ strat_update_kernel(const T* __restrict__ JF, const T* __restrict__ JF2, const l
         const T p = pow(dv, beta);
         dh[c] = p;
         acc[2] += (double)p;
+        acc[3] += (double)nc;
     }
-    grid_sum_finish<3>(acc, sh, partials, ticket, scalars);
+    grid_sum_finish<4>(acc, sh, partials, ticket, scalars);
 }
 
-// Small stratifications: estimator, d^beta, its sum and the normalisation in ONE CTA.
+// Small stratifications: estimator, d^beta, its sum and the normalisation in ONE launch by one cluster
+// (fp64 pow on a single SM was the whole cost of the one-CTA version).  The d^beta values stay in registers
+// between the reduction and the normalisation; the sums cross the cluster through distributed shared memory
+// in rank order, so every CTA normalises by the same value.
 template <typename T>
-__global__ void __launch_bounds__(1024)
+__global__ void __cluster_dims__(SMALL_CL, 1, 1) __launch_bounds__(SMALL_THREADS)
 strat_update_small_kernel(const T* __restrict__ JF, const T* __restrict__ JF2, const long long* __restrict__ nh,
                           int64_t n_cubes, T V, T V2, T beta, T* __restrict__ dh, double* scalars) {
-    __shared__ double sh[32 * 3];
-    __shared__ double s_sum;
-    double acc[3] = {0.0, 0.0, 0.0};
-    for (int64_t c = threadIdx.x; c < n_cubes; c += blockDim.x) {
-        const T n = (T)nh[c];
-        const T inv = div_rn((T)1, n);
-        const T jf = JF[c], jf2 = JF2[c];
-        const T ih = mul_rn(jf, mul_rn(inv, V));
-        const T sig2 = fabs(sub_rn(mul_rn(mul_rn(jf2, inv), V2), mul_rn(ih, ih)));
-        acc[0] += (double)ih;
-        acc[1] += (double)mul_rn(sig2, inv);
-        const T m = div_rn(mul_rn(V, jf), n);
-        T dv = sub_rn(div_rn(mul_rn(V2, jf2), n), mul_rn(m, m));
-        if (dv < (T)0) dv = (T)0;
-        const T p = pow(dv, beta);
-        dh[c] = p;
-        acc[2] += (double)p;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double sh[32 * 4];
+    __shared__ double s_part[4];
+    const unsigned rank = cluster.block_rank();
+    const int64_t t = (int64_t)rank * SMALL_THREADS + threadIdx.x;
+    T p[SMALL_ITEMS];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < SMALL_ITEMS; ++i) {
+        const int64_t c = (int64_t)i * SMALL_CL * SMALL_THREADS + t;
+        p[i] = (T)0;
+        if (c < n_cubes) {
+            const long long nc = nh[c];
+            const T n = (T)nc;
+            const T inv = div_rn((T)1, n);
+            const T jf = JF[c], jf2 = JF2[c];
+            const T ih = mul_rn(jf, mul_rn(inv, V));
+            const T sig2 = fabs(sub_rn(mul_rn(mul_rn(jf2, inv), V2), mul_rn(ih, ih)));
+            acc[0] += (double)ih;
+            acc[1] += (double)mul_rn(sig2, inv);
+            const T m = div_rn(mul_rn(V, jf), n);
+            T dv = sub_rn(div_rn(mul_rn(V2, jf2), n), mul_rn(m, m));
+            if (dv < (T)0) dv = (T)0;
+            p[i] = pow(dv, beta);
+            acc[2] += (double)p[i];
+            acc[3] += (double)nc;
+        }
     }
-    block_sum<3>(acc, sh);
+    block_sum<4>(acc, sh);
     if (threadIdx.x == 0) {
-        scalars[0] = acc[0];
-        scalars[1] = acc[1];
-        scalars[2] = acc[2];
-        s_sum = acc[2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_part[k] = acc[k];
     }
-    __syncthreads();
-    const T s = (T)s_sum;
-    if (s == (T)0) return;
-    for (int64_t c = threadIdx.x; c < n_cubes; c += blockDim.x) dh[c] = div_rn(dh[c], s);
+    cluster.sync();
+    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+    for (unsigned r = 0; r < SMALL_CL; ++r) {
+        const double* rp = cluster.map_shared_rank(s_part, r);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tot[k] += rp[k];
+    }
+    cluster.sync();
+    if (rank == 0 && threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) scalars[k] = tot[k];
+    }
+    const T s = (T)tot[2];
+#pragma unroll
+    for (int i = 0; i < SMALL_ITEMS; ++i) {
+        const int64_t c = (int64_t)i * SMALL_CL * SMALL_THREADS + t;
+        if (c < n_cubes) dh[c] = s == (T)0 ? p[i] : div_rn(p[i], s);  // vegas_stratification.py:89-90
+    }
 }
 
 template <typename T>
@@ -403,7 +456,7 @@ int tq_vegas_strat_nh(const void* dh, int64_t n_cubes, double nevals_exp, int32_
     cudaStream_t st = as_stream(stream);
     if (n_cubes <= ST_SMALL_CUBES) {
         TQ_DISPATCH_DTYPE(dtype, {
-            nh_small_kernel<T><<<1, 1024, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, (long long*)nh, (long long*)offsets);
+            nh_small_kernel<T><<<SMALL_CL, SMALL_THREADS, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, (long long*)nh, (long long*)offsets);
         });
         return check_launch("nh_small_kernel");
     }
@@ -489,12 +542,12 @@ int tq_vegas_strat_update(const void* JF, const void* JF2, const int64_t* nh, in
     Workspace w(ws, ws_bytes);
     unsigned int* ticket = w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
     const int grid = grid_for(n_cubes, 256, 4);
-    double* partials = w.take<double>((size_t)grid * 3);
+    double* partials = w.take<double>((size_t)grid * 4);
     if (!ticket || !partials) { set_error("tq_vegas_strat_update: workspace too small"); return TQ_ERR_WORKSPACE; }
     cudaStream_t st = as_stream(stream);
     if (n_cubes <= ST_SMALL_CUBES) {
         TQ_DISPATCH_DTYPE(dtype, {
-            strat_update_small_kernel<T><<<1, 1024, 0, st>>>((const T*)JF, (const T*)JF2, (const long long*)nh, n_cubes,
+            strat_update_small_kernel<T><<<SMALL_CL, SMALL_THREADS, 0, st>>>((const T*)JF, (const T*)JF2, (const long long*)nh, n_cubes,
                                                             (T)v_cubes, (T)(v_cubes * v_cubes), (T)beta, (T*)dh, scalars_f64);
         });
         return check_launch("strat_update_small_kernel");

@@ -35,7 +35,7 @@ class VEGASStratification:
         self.strat_counts = torch.zeros([self.N_cubes], dtype=dtype, device=self.device)
         self._nh = None        # int64 counts of the current iteration
         self._offsets = None   # their exclusive scan, [N_cubes + 1]
-        self.last_scalars = None  # fp64 [3]: I_it, sigma2_it, sum d^beta of the last update_DH
+        self.last_scalars = None  # fp64 [4]: I_it, sigma2_it, sum d^beta, sum nh of the last update_DH
 
     # -- sample counts ------------------------------------------------------------------------
     def get_NH(self, nevals_exp):

@@ -312,11 +312,11 @@ def strat_accumulate(jf, offsets, row_base=0, cube_begin=0, cube_end=None):
 
 
 def strat_update(JF, JF2, nh, v_cubes, beta):
-    """Estimator + update_DH: returns (dh [C], scalars fp64 [3] = I, sigma2, sum d^beta)."""
+    """Estimator + update_DH: returns (dh [C], scalars fp64 [4] = I, sigma2, sum d^beta, sum nh)."""
     require_cuda(JF, JF2, nh)
     n = JF.shape[0]
     dh = torch.empty(n, dtype=JF.dtype, device=JF.device)
-    scalars = torch.empty(3, dtype=torch.float64, device=JF.device)  # fully written by the kernel
+    scalars = torch.empty(4, dtype=torch.float64, device=JF.device)  # fully written by the kernel
     with on_device(JF.device):
         wsp, wsn = _ws(JF.device)
         call("tq_vegas_strat_update", ptr(JF.detach().contiguous()), ptr(JF2.detach().contiguous()), ptr(nh), n,
