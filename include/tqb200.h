@@ -211,7 +211,9 @@ TQ_API int tq_vegas_map_pack_edges(const void* x_edges, const void* dx_edges, vo
                             int64_t n_intervals, int32_t dtype, void* stream);
 /* One VEGAS pass without writing samples: generate -> map -> evaluate -> accumulate.
  *   stratified (offsets != NULL): rows [row_begin,row_end) of the cube-sorted order (vegas.py:268-291);
- *     JF/JF2 (pre-zeroed by the caller) receive the per-cube sums.
+ *     JF/JF2 (pre-zeroed by the caller) receive the per-cube sums.  row_begin == 0 and row_end < 0 selects the
+ *     whole pass [0, offsets[n_cubes]) with the count read ON THE DEVICE (no host read-back of get_NH's total);
+ *     -row_end is then the caller's estimate of that count and only sizes the grid.
  *   warm-up (offsets == NULL): rows are plain samples y = u*0.999999 (vegas.py:236); out_f64 receives
  *     {sum jf, sum jf^2}.
  *   edges_packed: see tq_vegas_map_pack_edges.

@@ -15,7 +15,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "libtqb200.so")
-SOURCES = ["runtime.cu", "rng_mc.cu", "vegas_map.cu", "vegas_strat.cu", "newton_cotes.cu", "fused.cu", "vegas_driver.cu"]
+SOURCES = ["runtime.cu", "rng_mc.cu", "vegas_map.cu", "vegas_strat.cu", "newton_cotes.cu", "fused.cu", "vegas_small.cu",
+           "vegas_driver.cu"]
 NVCC_FLAGS = [
     *os.environ.get("TQ_NVCC_EXTRA", "").split(),
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

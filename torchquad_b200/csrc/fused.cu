@@ -211,7 +211,7 @@ __device__ __forceinline__ void segmented_warp_sum2(unsigned key, T& a, T& b) {
 template <int FAM, typename T, bool STRAT>
 __global__ void __launch_bounds__(FV_BLOCK, FV_MIN_CTAS)
 fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, int64_t n_cubes, int n_strat,
-                   int64_t row_begin, int64_t row_end, int64_t rows_per_cta,
+                   int64_t row_begin, int64_t row_end, bool rows_from_offsets, int64_t rows_per_cta,
                    const typename Pair2<T>::type* __restrict__ edges, long long ni, T* __restrict__ weights,
                    unsigned long long* __restrict__ counts, T* __restrict__ JF, T* __restrict__ JF2, uint64_t seed,
                    uint32_t call, bool hist_smem, double* partials, unsigned int* ticket, double* out) {
@@ -222,7 +222,6 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
     __shared__ double sh[32 * 2];
     __shared__ long long s_off[2][FV_SLICE];
     __shared__ unsigned char s_cube[2][FV_BLOCK];
-    __shared__ long long s_first_cube;
     stage_integrand<T>(P, S);
     const int dim = S.dim;
     int* s_ids = reinterpret_cast<int*>(smem_raw);                        // [dim][FV_BLOCK]
@@ -232,24 +231,30 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
     if (do_hist && hist_smem) {
         for (int i = threadIdx.x; i < dim * (int)ni; i += blockDim.x) { s_w[i] = (T)0; s_c[i] = 0u; }
     }
-    const int64_t r_lo = row_begin + (int64_t)blockIdx.x * rows_per_cta;
-    const int64_t r_hi = r_lo + rows_per_cta < row_end ? r_lo + rows_per_cta : row_end;
-    if (STRAT) {
-        if (threadIdx.x == 0 && r_lo < r_hi) {
-            long long lo = 0, hi = n_cubes - 1;  // largest c with offsets[c] <= r_lo
-            while (lo < hi) {
-                const long long mid = (lo + hi + 1) >> 1;
-                if (__ldg(&offsets[mid]) <= r_lo) lo = mid; else hi = mid - 1;
-            }
-            s_first_cube = lo;
-        }
-    }
     __syncthreads();
-    long long c_lo = STRAT && r_lo < r_hi ? s_first_cube : 0;
+    if (STRAT && rows_from_offsets) row_end = __ldg(&offsets[n_cubes]);  // sample count of the pass, never read back
     const T nif = (T)ni;
     const T nsf = (T)n_strat;
     double acc[2] = {0.0, 0.0};
     int buf = 0;
+    // The host sizes the grid so that one chunk per CTA covers its row estimate; the stride loop keeps the pass
+    // complete when the device-side count exceeds it.
+    for (int64_t r_lo = row_begin + (int64_t)blockIdx.x * rows_per_cta; r_lo < row_end;
+         r_lo += (int64_t)gridDim.x * rows_per_cta) {
+    const int64_t r_hi = r_lo + rows_per_cta < row_end ? r_lo + rows_per_cta : row_end;
+    long long c_lo = 0;
+    if (STRAT) {
+        // largest c with offsets[c] <= r_lo, by a CTA-wide FV_BLOCK-ary search: every round all threads probe
+        // one point each, so 10^4 cubes take two load latencies instead of fourteen dependent ones.
+        long long hi = n_cubes;  // offsets[c_lo] <= r_lo < offsets[hi]
+        while (hi - c_lo > 1) {
+            const long long step = (hi - c_lo + FV_BLOCK - 1) / FV_BLOCK;
+            const long long p = c_lo + (long long)(threadIdx.x + 1) * step;
+            const int below = __syncthreads_count(p < hi && __ldg(&offsets[p]) <= r_lo);
+            c_lo += below * step;
+            if (c_lo + step < hi) hi = c_lo + step;
+        }
+    }
     for (int64_t rb = r_lo; rb < r_hi; rb += FV_BLOCK, buf ^= 1) {
         const int64_t re = rb + FV_BLOCK < r_hi ? rb + FV_BLOCK : r_hi;
         const int64_t row = rb + threadIdx.x;
@@ -343,6 +348,7 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
             acc[0] += (double)jf;
             acc[1] += (double)jf2;
         }
+    }
     }
     if (do_hist && hist_smem) {
         __syncthreads();
@@ -467,9 +473,14 @@ int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* of
                    size_t ws_bytes, void* stream) {
     int rc = check_integrand("tq_fused_vegas", fn_host);
     if (rc) return rc;
+    const bool strat = offsets != nullptr;
+    const bool rows_from_offsets = row_end < 0;  // count stays on the device; -row_end is the sizing estimate
+    if (rows_from_offsets) {
+        TQ_REQUIRE(strat && row_begin == 0, "tq_fused_vegas: a device-side row count needs a stratified pass from row 0");
+        row_end = -row_end;
+    }
     TQ_REQUIRE(row_end >= row_begin && row_begin >= 0, "tq_fused_vegas: bad row range");
     TQ_REQUIRE(n_intervals >= 1 && n_intervals < (1LL << 31), "tq_fused_vegas: n_intervals out of range");
-    const bool strat = offsets != nullptr;
     TQ_REQUIRE(!strat || (n_cubes >= 1 && n_cubes < (1LL << 31) && n_strat >= 1 && JF && JF2),
                "tq_fused_vegas: stratified pass needs n_cubes, n_strat, JF, JF2");
     TQ_REQUIRE(strat || out_f64 != nullptr, "tq_fused_vegas: warm-up pass needs out_f64");
@@ -507,15 +518,15 @@ int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* of
     TQ_DISPATCH_DTYPE(dtype, {
         TQ_DISPATCH_FAMILY(fn_host->family, {
             if (strat) {
-                cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
+                if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, true><<<(unsigned)ctas, FV_BLOCK, smem, st>>>(
-                    *fn_host, (const long long*)offsets, n_cubes, n_strat, row_begin, row_end, rows_per_cta,
+                    *fn_host, (const long long*)offsets, n_cubes, n_strat, row_begin, row_end, rows_from_offsets, rows_per_cta,
                     (const typename Pair2<T>::type*)edges_packed, n_intervals, (T*)weights, (unsigned long long*)counts,
                     (T*)JF, (T*)JF2, seed, call_idx, hist_smem, partials, ticket, out_f64);
             } else {
-                cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
+                if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, false><<<(unsigned)ctas, FV_BLOCK, smem, st>>>(
-                    *fn_host, nullptr, 0, 1, row_begin, row_end, rows_per_cta, (const typename Pair2<T>::type*)edges_packed,
+                    *fn_host, nullptr, 0, 1, row_begin, row_end, false, rows_per_cta, (const typename Pair2<T>::type*)edges_packed,
                     n_intervals, (T*)weights, (unsigned long long*)counts, nullptr, nullptr, seed, call_idx, hist_smem,
                     partials, ticket, out_f64);
             }

@@ -1,0 +1,53 @@
+// Device helpers shared by the VEGAS map / stratification kernels and their small-problem cluster versions.
+#pragma once
+#include "common.cuh"
+
+namespace tq {
+
+template <typename T> struct EdgePair;
+template <> struct EdgePair<float> { using type = float2; };
+template <> struct EdgePair<double> { using type = double2; };
+
+// get_NH for one cube: max(2, floor(dh * nevals_exp)) (vegas_stratification.py:92-103)
+template <typename T>
+__device__ __forceinline__ long long nh_of(T dh, T nev) {
+    T v = floor(mul_rn(dh, nev));
+    v = v < (T)2 ? (T)2 : v;  // clamp(min=2)
+    return (long long)v;
+}
+
+// Average with the zero-count fill of vegas_map.py:118-144 in closed form.  After t fill rounds a
+// zero-count bin at distance t from the nearest counted bin has taken that bin's average; the right
+// neighbour wins ties (its copy happens first in a round); bins farther than 10 keep their raw weight
+// (always 0 in practice because weights and counts are accumulated together).
+template <typename T>
+__device__ __forceinline__ T filled_average(const T* __restrict__ w, const long long* __restrict__ c, long long j,
+                                            long long ni) {
+    const long long cj = c[j];
+    if (cj != 0) return div_rn(w[j], (T)cj);
+    int dr = 0, dl = 0;
+    for (int t = 1; t <= 10; ++t)
+        if (j + t < ni && c[j + t] != 0) { dr = t; break; }
+    for (int t = 1; t <= 10; ++t)
+        if (j - t >= 0 && c[j - t] != 0) { dl = t; break; }
+    if (dr && (!dl || dr <= dl)) return div_rn(w[j + dr], (T)c[j + dr]);
+    if (dl) return div_rn(w[j - dl], (T)c[j - dl]);
+    return w[j];
+}
+
+// Non-finite repair of one new edge (vegas_map.py:240-257): the mean of its two neighbours.
+template <typename T>
+__device__ __forceinline__ T repaired_edge(const T* __restrict__ xn, long long e, long long ni, bool& was_bad,
+                                           bool& still_bad) {
+    T v = xn[e];
+    was_bad = false;
+    still_bad = false;
+    if (!isfinite(v)) {
+        was_bad = true;
+        if (e > 0 && e < ni) v = mul_rn((T)0.5, add_rn(xn[e - 1], xn[e + 1]));
+        still_bad = !isfinite(v);
+    }
+    return v;
+}
+
+}  // namespace tq

@@ -2,12 +2,15 @@
 // chi^2 / budget schedule of torchquad/integration/vegas.py:137-209,211-315 without returning to Python
 // between passes.  Small problems (the reference's own N = 1e6 configuration is ~0.5 ms of GPU work) are
 // bound by per-launch host overhead; from C++ a pass costs a handful of launches and one 8-byte read-back.
-// The kernels are exactly those of the step-by-step API (this file only calls public tq_* entry points), so a
-// run is sample-for-sample identical to the Python-driven loop (tests/test_gpu_integrators.py).
+// The kernels are exactly those of the step-by-step API, so a run draws the same samples as the Python-driven
+// loop (tests/test_gpu_integrators.py).  Nothing is read back inside a block of five iterations: the fused
+// pass takes its sample count from get_NH's offsets on the device, the stratification update records it next
+// to the iteration estimate, and the schedule reads the block's records in one copy.
 #include <math.h>
 #include <vector>
 
 #include "common.cuh"
+#include "internal.cuh"
 
 namespace tq {
 
@@ -62,11 +65,12 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
     const int max_passes = TQ_VEGAS_MAX_PASSES;
     auto update_map = [&]() -> int {
         if (passes >= max_passes) { set_error("tq_vegas_run_fused: more than %d passes", max_passes); return TQ_ERR_UNSUPPORTED; }
-        int rc = tq_vegas_map_update(s->x_edges, s->dx_edges, s->weights, s->counts, s->edges_packed, dim, ni, alpha, dtype,
-                                     s->status + 4 * passes, s->map_ws, s->map_ws_bytes, stream);
+        int rc = map_update_launch(s->x_edges, s->dx_edges, s->weights, s->counts, s->edges_packed, dim, ni, alpha, dtype,
+                                   s->status + 4 * passes, false, s->map_ws, s->map_ws_bytes, stream);
         ++passes;
         return rc;
     };
+    cudaMemsetAsync(s->status, 0, 4 * (size_t)max_passes * sizeof(int32_t), st);
     if (warmup) {  // vegas.py:211-266: 5 unstratified passes of starting//5 samples, results discarded
         const int64_t ns = starting / 5;
         for (int w = 0; w < 5; ++w) {
@@ -77,39 +81,67 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
             if ((rc = update_map())) return rc;
         }
     }
+    // Small problems: the stratification update, every dimension's map update and the NEXT pass's get_NH share one
+    // launch (vegas_small.cu); get_NH runs on its own only after the schedule may have changed the sample budget.
+    const bool small = small_strat_ok(n_cubes) && (!grid_improve || small_map_ok(dim, ni));
+    MapScratch scratch = {};
+    if (small && grid_improve && !map_scratch_carve(s->map_ws, s->map_ws_bytes, dim, ni, dtype, true, scratch)) {
+        set_error("tq_vegas_run_fused: map workspace too small");
+        return TQ_ERR_WORKSPACE;
+    }
+    const size_t jf_bytes = 2 * (size_t)n_cubes * elt;  // JF and JF2 are one [2, n_cubes] allocation (tq_vegas_state)
     Block<T> blk;
     int it = 0;
-    int first_rec = 0;  // record index of the first iteration of the current block
+    int first_rec = 0;      // record index of the first iteration of the current block
+    bool have_nh = false;   // nh/offsets of the coming pass already computed (and JF/JF2 zeroed) by the last update
     while (true) {
         ++it;
-        int rc = tq_vegas_strat_nh(s->dh, n_cubes, (double)starting, dtype, s->nh, s->offsets, s->ws, s->ws_bytes, stream);
-        if (rc) return rc;
-        long long M = 0;
-        cudaMemcpyAsync(&M, s->offsets + n_cubes, sizeof(long long), cudaMemcpyDeviceToHost, st);
-        cudaMemsetAsync(s->JF, 0, 2 * (size_t)n_cubes * elt, st);
-        cudaError_t e = cudaStreamSynchronize(st);  // the one sync of the iteration (M sizes the launch)
-        if (e != cudaSuccess) { set_error("tq_vegas_run_fused: %s", cudaGetErrorString(e)); return (int)e; }
-        rc = tq_fused_vegas(fn, dtype, s->offsets, n_cubes, n_strat, 0, M, s->edges_packed, ni, grid_improve ? s->weights : nullptr,
+        int rc = TQ_OK;
+        if (!have_nh) {  // get_NH's launch also zeroes JF/JF2 for this pass
+            rc = strat_nh_launch(s->dh, n_cubes, (double)starting, dtype, s->nh, s->offsets, s->JF, jf_bytes, s->ws, s->ws_bytes,
+                                 stream);
+            if (rc) return rc;
+        }
+        // sum nh <= starting * sum(dh) + 2 * n_cubes; the estimate only sizes the grid
+        const int64_t m_est = starting + 2 * n_cubes + 1024;
+        rc = tq_fused_vegas(fn, dtype, s->offsets, n_cubes, n_strat, 0, -m_est, s->edges_packed, ni, grid_improve ? s->weights : nullptr,
                             s->counts, s->JF, s->JF2, seed, call++, nullptr, s->ws, s->ws_bytes, stream);
         if (rc) return rc;
-        fevals += M;
         if (it > TQ_VEGAS_MAX_PASSES) { set_error("tq_vegas_run_fused: too many iterations"); return TQ_ERR_UNSUPPORTED; }
-        rc = tq_vegas_strat_update(s->JF, s->JF2, s->nh, n_cubes, v_cubes, beta, dtype, s->dh, s->records + 4 * (it - 1), s->ws,
-                                   s->ws_bytes, stream);
-        if (rc) return rc;
-        if (grid_improve && (rc = update_map())) return rc;
+        double* record = s->records + 4 * (it - 1);
+        if (small) {
+            have_nh = it % 5 > 0;  // inside a block the next pass keeps this one's budget
+            SmallStrat sa = {s->JF, s->JF2, s->nh, n_cubes, v_cubes, beta, s->dh, record, have_nh ? (double)starting : 0.0,
+                             s->offsets, s->JF, jf_bytes};
+            if (grid_improve) {
+                if (passes >= max_passes) { set_error("tq_vegas_run_fused: more than %d passes", max_passes); return TQ_ERR_UNSUPPORTED; }
+                SmallMap ma = {s->x_edges, s->dx_edges, s->weights, s->counts, s->edges_packed, scratch, dim, ni, alpha,
+                               s->status + 4 * passes, true};
+                ++passes;
+                rc = small_update_launch(&sa, &ma, dtype, stream);
+            } else {
+                rc = small_update_launch(&sa, nullptr, dtype, stream);
+            }
+            if (rc) return rc;
+        } else {
+            rc = tq_vegas_strat_update(s->JF, s->JF2, s->nh, n_cubes, v_cubes, beta, dtype, s->dh, record, s->ws, s->ws_bytes, stream);
+            if (rc) return rc;
+            if (grid_improve && (rc = update_map())) return rc;
+        }
         if (it % 5 > 0) continue;
         // vegas.py:161-209 on the block of the last (up to) five iterations
         const int nrec = it - first_rec;
         std::vector<double> rec(4 * nrec);
         cudaMemcpyAsync(rec.data(), s->records + 4 * first_rec, rec.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
-        e = cudaStreamSynchronize(st);
+        if (passes > 0) cudaMemcpyAsync(out->status, s->status, 4 * (size_t)passes * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { set_error("tq_vegas_run_fused: %s", cudaGetErrorString(e)); return (int)e; }
         blk.res.clear();
         blk.sig.clear();
         for (int k = 0; k < nrec; ++k) {
             blk.res.push_back((T)rec[4 * k]);
             blk.sig.push_back((T)rec[4 * k + 1]);
+            fevals += (int64_t)rec[4 * k + 3];  // sum nh of the pass (vegas.py:291)
         }
         const T mean = blk.mean();
         const T res_abs = (T)fabs((double)mean);
@@ -145,11 +177,6 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
     for (size_t k = 0; k < blk.res.size() && k < 8; ++k) {
         out->results[k] = (double)blk.res[k];
         out->sigma2[k] = (double)blk.sig[k];
-    }
-    if (passes > 0) {
-        cudaMemcpyAsync(out->status, s->status, 4 * (size_t)passes * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { set_error("tq_vegas_run_fused: %s", cudaGetErrorString(e)); return (int)e; }
     }
     return TQ_OK;
 }

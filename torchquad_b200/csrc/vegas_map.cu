@@ -3,9 +3,8 @@
 // _smooth_map :113-172, update_map :185-261).  The reference runs these as Python loops over dim with
 // gather/scatter/cumsum ATen launches; here each step is one pass over its data.
 #include "common.cuh"
-
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
+#include "internal.cuh"
+#include "vegas_dev.cuh"
 
 namespace tq {
 
@@ -27,10 +26,6 @@ __device__ __forceinline__ long long bin_of(T y, T nif, long long ni, T& offset)
 // stride).  Phase 2: one thread per row multiplies the factors left to right (the reference's order,
 // vegas_map.py:70-73) and writes jac coalesced.  HBM traffic = the algorithmic 2*dim*s + s bytes per row.
 constexpr int MF_TILE_ELEMS = 2048;
-
-template <typename T> struct EdgePair;
-template <> struct EdgePair<float> { using type = float2; };
-template <> struct EdgePair<double> { using type = double2; };
 
 // PACKED: edges come as {x_edge, dx_edge} pairs [dim, Ni] (one gather per element; tq_vegas_map_pack_edges) and
 // `domain` (nullable, [dim, 2]) applies the integrator's unit-cube -> domain transform x*size + start of
@@ -213,25 +208,6 @@ map_accumulate_smem_kernel(const T* __restrict__ y, const T* __restrict__ jf2, T
 // ------------------------------------------------------------------ smoothing pipeline
 constexpr int MAP_TILE = 1024;  // bins per CTA tile (256 threads x 4)
 
-// K1: average with the zero-count fill of vegas_map.py:118-144 in closed form.  After t fill rounds a
-// zero-count bin at distance t from the nearest counted bin has taken that bin's average; the right
-// neighbour wins ties (its copy happens first in a round); bins farther than 10 keep their raw weight
-// (always 0 in practice because weights and counts are accumulated together).
-template <typename T>
-__device__ __forceinline__ T filled_average(const T* __restrict__ w, const long long* __restrict__ c, long long j,
-                                            long long ni) {
-    const long long cj = c[j];
-    if (cj != 0) return div_rn(w[j], (T)cj);
-    int dr = 0, dl = 0;
-    for (int t = 1; t <= 10; ++t)
-        if (j + t < ni && c[j + t] != 0) { dr = t; break; }
-    for (int t = 1; t <= 10; ++t)
-        if (j - t >= 0 && c[j - t] != 0) { dl = t; break; }
-    if (dr && (!dl || dr <= dl)) return div_rn(w[j + dr], (T)c[j + dr]);
-    if (dl) return div_rn(w[j - dl], (T)c[j - dl]);
-    return w[j];
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 map_average_kernel(const T* __restrict__ weights, const long long* __restrict__ counts, T* __restrict__ avg,
@@ -375,21 +351,8 @@ map_edges_kernel(const T* __restrict__ smoothed, const double* __restrict__ S, c
     xn[m + 1] = add_rn(x_old[idx], mul_rn(div_rn(acc, sm), dxe[(int64_t)d * ni + idx]));
 }
 
-// K5: non-finite repair (vegas_map.py:240-257), dx = diff(x) (:259) and the weight/count reset (:261,:196).
-template <typename T>
-__device__ __forceinline__ T repaired_edge(const T* __restrict__ xn, long long e, long long ni, bool& was_bad,
-                                           bool& still_bad) {
-    T v = xn[e];
-    was_bad = false;
-    still_bad = false;
-    if (!isfinite(v)) {
-        was_bad = true;
-        if (e > 0 && e < ni) v = mul_rn((T)0.5, add_rn(xn[e - 1], xn[e + 1]));
-        still_bad = !isfinite(v);
-    }
-    return v;
-}
-
+// K5: non-finite repair (vegas_map.py:240-257, repaired_edge in vegas_dev.cuh), dx = diff(x) (:259) and the
+// weight/count reset (:261,:196).
 template <typename T>
 __global__ void __launch_bounds__(256)
 map_finalize_kernel(const T* __restrict__ x_new, T* __restrict__ xe, T* __restrict__ dxe, T* __restrict__ weights,
@@ -422,195 +385,6 @@ map_finalize_kernel(const T* __restrict__ x_new, T* __restrict__ xe, T* __restri
     }
 }
 
-// ------------------------------------------------------------------ small maps: the whole update in ONE launch
-// For maps up to MAP_SMALL_NI intervals per dimension (every case where VEGAS is launch-latency bound) one
-// thread-block CLUSTER per dimension runs average -> smooth -> fp64 prefix -> new edges -> repair/diff/reset
-// back to back, with cluster barriers and distributed shared memory instead of seven launches.  Each CTA owns
-// a contiguous slice of the dimension's bins and each thread `per` consecutive bins, kept in registers from
-// the smoothing to the prefix sums.  The "any dimension sums to zero" decision needs all row sums; each
-// cluster recomputes them (dim * Ni reads per cluster, tiny at these sizes) instead of synchronising across
-// clusters.
-constexpr long long MAP_SMALL_NI = 32768;
-constexpr int MAP_SMALL_DIM = 64;
-constexpr int MAP_CL = 8;          // CTAs per cluster = per dimension
-constexpr int MAP_CL_THREADS = 512;
-constexpr int MAP_CL_ITEMS = 8;    // MAP_SMALL_NI / (MAP_CL * MAP_CL_THREADS)
-constexpr int MAP_COARSE = 32;     // stride of the shared-memory search table over the prefix sums
-
-template <typename T>
-__global__ void __cluster_dims__(MAP_CL, 1, 1) __launch_bounds__(MAP_CL_THREADS)
-map_update_small_kernel(T* __restrict__ xe, T* __restrict__ dxe, T* __restrict__ weights, long long* __restrict__ counts,
-                        typename EdgePair<T>::type* __restrict__ packed, T* __restrict__ avg, T* __restrict__ smoothed,
-                        double* __restrict__ S, T* __restrict__ x_new, int dim, long long ni, T alpha,
-                        int32_t* status, bool do_edges) {
-    cg::cluster_group cluster = cg::this_cluster();
-    __shared__ double sh[33];
-    __shared__ double s_part[MAP_SMALL_DIM];  // this CTA's share of every dimension's row sum
-    __shared__ double s_tot[MAP_SMALL_DIM];
-    __shared__ double s_slice;                // this CTA's share of the smoothed row sum
-    __shared__ double s_coarse[MAP_SMALL_NI / MAP_COARSE];
-    const int d = blockIdx.x / MAP_CL;
-    const unsigned rank = cluster.block_rank();
-    const int tid = threadIdx.x;
-    const int per = (int)((ni + MAP_CL * MAP_CL_THREADS - 1) / (MAP_CL * MAP_CL_THREADS));
-    const long long slice = (long long)per * MAP_CL_THREADS;
-    const long long j_lo = (long long)rank * slice;
-    const long long j_hi = j_lo + slice < ni ? j_lo + slice : ni;
-    // ---- averages with the zero-count fill; row sums of every dimension (vegas_map.py:118-144,150)
-    for (int dd = 0; dd < dim; ++dd) {
-        const T* w = weights + (int64_t)dd * ni;
-        const long long* c = counts + (int64_t)dd * ni;
-        double part[1] = {0.0};
-        for (long long j = j_lo + tid; j < j_hi; j += MAP_CL_THREADS) {
-            const T a = filled_average<T>(w, c, j, ni);
-            if (dd == d) avg[(int64_t)d * ni + j] = a;
-            part[0] += (double)a;
-        }
-        block_sum<1>(part, sh);
-        if (tid == 0) s_part[dd] = part[0];
-    }
-    cluster.sync();  // also publishes this cluster's avg[] slices to its other CTAs
-    if (tid < dim) {
-        double t = 0.0;
-        for (unsigned r = 0; r < MAP_CL; ++r) t += cluster.map_shared_rank(s_part, r)[tid];
-        s_tot[tid] = t;
-    }
-    __syncthreads();
-    bool any_zero = false;
-    for (int dd = 0; dd < dim; ++dd) any_zero |= ((T)s_tot[dd] == (T)0);
-    if (any_zero) {  // the reference skips the whole update (vegas_map.py:192-197), keeping only the reset
-        if (blockIdx.x == 0 && tid == 0) status[0] = 1;
-        if (do_edges) {
-            for (long long j = j_lo + tid; j < j_hi; j += MAP_CL_THREADS) {
-                weights[(int64_t)d * ni + j] = (T)0;
-                counts[(int64_t)d * ni + j] = 0;
-            }
-        }
-        cluster.sync();  // no CTA may exit while its shared memory is still being read
-        return;
-    }
-    // ---- smoothing + compression (vegas_map.py:146-170); thread owns bins [jt, jt + per)
-    const T* a = avg + (int64_t)d * ni;
-    T* sm = smoothed + (int64_t)d * ni;
-    const T denom = mul_rn((T)8, (T)s_tot[d]);
-    const long long jt = j_lo + (long long)tid * per;
-    T v[MAP_CL_ITEMS];
-    double run = 0.0;
-#pragma unroll
-    for (int i = 0; i < MAP_CL_ITEMS; ++i) {
-        const long long j = jt + i;
-        v[i] = (T)0;
-        if (i < per && j < ni) {
-            T x;
-            if (j == 0) x = add_rn(mul_rn((T)7, a[0]), a[1]);
-            else if (j == ni - 1) x = add_rn(a[ni - 2], mul_rn((T)7, a[ni - 1]));
-            else x = add_rn(add_rn(a[j - 1], mul_rn((T)6, a[j])), a[j + 1]);
-            x = div_rn(x, denom);
-            if (x != (T)0) {
-                const T base = div_rn(sub_rn(x, (T)1), log(x));
-                x = (alpha == (T)0.5) ? sqrt(base) : pow(base, alpha);  // ATen evaluates x**0.5 as sqrt
-            }
-            v[i] = x;
-            sm[j] = x;
-            run += (double)x;
-        }
-    }
-    if (!do_edges) {
-        cluster.sync();
-        return;
-    }
-    // ---- fp64 inclusive prefix sums (vegas_map.py:207-213): CTA scan + rank-ordered slice totals
-    double total;
-    double ex = block_excl_scan<double>(run, sh, total);
-    if (tid == 0) s_slice = total;
-    cluster.sync();
-    double row_total = 0.0;
-    for (unsigned r = 0; r < MAP_CL; ++r) {
-        const double t = *cluster.map_shared_rank(&s_slice, r);
-        if (r < rank) ex += t;
-        row_total += t;
-    }
-    double* Sd = S + (int64_t)d * ni;
-#pragma unroll
-    for (int i = 0; i < MAP_CL_ITEMS; ++i) {
-        const long long j = jt + i;
-        if (i < per && j < ni) {
-            ex += (double)v[i];
-            Sd[j] = ex;
-        }
-    }
-    cluster.sync();
-    // ---- new inner edges (vegas_map.py:214-239): two-level search, coarse table in shared memory
-    const T* x_old = xe + (int64_t)d * (ni + 1);
-    const T* dx_old = dxe + (int64_t)d * ni;
-    T* xn = x_new + (int64_t)d * (ni + 1);
-    const T delta_t = div_rn((T)row_total, (T)ni);
-    const double delta = (double)delta_t;
-    const long long last = ni - 2;  // largest searchable index
-    const int nblk = (int)((last + MAP_COARSE) / MAP_COARSE);  // blocks of MAP_COARSE covering [0, last]
-    for (int b = tid; b < nblk; b += MAP_CL_THREADS) {
-        const long long e = (long long)b * MAP_COARSE + MAP_COARSE - 1;
-        s_coarse[b] = Sd[e < last ? e : last];
-    }
-    if (rank == 0 && tid == 0) { xn[0] = x_old[0]; xn[ni] = x_old[ni]; }
-    __syncthreads();
-    for (long long m = j_lo + tid; m < j_hi && m <= last; m += MAP_CL_THREADS) {
-        // smallest j in [0, last] with trunc(S_j / delta) > m; ni - 1 when there is none
-        int lo = 0, hi = nblk;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((long long)__ddiv_rn(s_coarse[mid], delta) > m) hi = mid; else lo = mid + 1;
-        }
-        long long idx = ni - 1;
-        if (lo < nblk) {
-            long long flo = (long long)lo * MAP_COARSE, fhi = flo + MAP_COARSE - 1;
-            if (fhi > last) fhi = last;
-            while (flo < fhi) {
-                const long long mid = (flo + fhi) >> 1;
-                if ((long long)__ddiv_rn(Sd[mid], delta) > m) fhi = mid; else flo = mid + 1;
-            }
-            idx = flo;
-        }
-        const double below = idx > 0 ? Sd[idx - 1] : 0.0;
-        const T acc = (T)((double)(m + 1) * delta - below);
-        xn[m + 1] = add_rn(x_old[idx], mul_rn(div_rn(acc, sm[idx]), dx_old[idx]));
-    }
-    cluster.sync();
-    // ---- repair, diff, pack, reset (vegas_map.py:240-261)
-    const long long e_hi = (j_lo < ni && j_hi == ni) ? ni + 1 : j_hi;  // edge ni goes with the last non-empty slice
-    for (long long e = j_lo + tid; e < e_hi; e += MAP_CL_THREADS) {
-        bool bad, still;
-        const T val = repaired_edge<T>(xn, e, ni, bad, still);
-        if (bad) atomicAdd(&status[1], 1);
-        if (still) status[2] = 1;
-        xe[(int64_t)d * (ni + 1) + e] = val;
-        if (e < ni) {
-            bool b2, s2;
-            const T dv = sub_rn(repaired_edge<T>(xn, e + 1, ni, b2, s2), val);
-            dxe[(int64_t)d * ni + e] = dv;
-            if (packed) {
-                typename EdgePair<T>::type pr;
-                pr.x = val;
-                pr.y = dv;
-                packed[(int64_t)d * ni + e] = pr;
-            }
-            weights[(int64_t)d * ni + e] = (T)0;
-            counts[(int64_t)d * ni + e] = 0;
-        }
-    }
-}
-
-struct MapScratch {
-    void* avg;       // T[dim*ni]   (reused as x_new: T[dim*(ni+1)] needs its own buffer)
-    void* smoothed;  // T[dim*ni]
-    void* x_new;     // T[dim*(ni+1)]
-    double* S;       // [dim*ni]
-    double* tile_sums;  // [dim*ntiles]
-    double* totals;     // [dim] (row sums of avg, then of smoothed)
-    double* totals2;
-    int ntiles;
-};
-
 static size_t map_scratch_bytes(int dim, long long ni, size_t elt) {
     const long long ntiles = (ni + MAP_TILE - 1) / MAP_TILE;
     size_t b = 0;
@@ -636,6 +410,11 @@ static bool carve(Workspace& w, int dim, long long ni, MapScratch& s, bool need_
     s.totals = w.take<double>(dim);
     s.totals2 = w.take<double>(dim);
     return s.avg && s.smoothed && s.tile_sums && s.totals && s.totals2 && (!need_edges || (s.x_new && s.S));
+}
+
+bool map_scratch_carve(void* ws, size_t ws_bytes, int dim, long long ni, int32_t dtype, bool need_edges, MapScratch& s) {
+    Workspace w(ws, ws_bytes);
+    return dtype == TQ_F64 ? carve<double>(w, dim, ni, s, need_edges) : carve<float>(w, dim, ni, s, need_edges);
 }
 
 template <typename T>
@@ -709,6 +488,39 @@ static int launch_accumulate_global(const void* y, const void* a, const void* ja
     return check_launch("map_accumulate_global_kernel");
 }
 
+// update_map; `clear_status` false when the caller has already zeroed status[0..4) (the native loop clears the
+// words of all its passes once).
+int map_update_launch(void* x_edges, void* dx_edges, void* weights, int64_t* counts, void* edges_packed, int32_t dim,
+                      int64_t n_intervals, double alpha, int32_t dtype, int32_t* status, bool clear_status, void* ws,
+                      size_t ws_bytes, void* stream) {
+    TQ_REQUIRE(dim >= 1 && dim <= 65535 && n_intervals >= 2, "tq_vegas_map_update: need dim >= 1 and Ni >= 2");
+    Workspace w(ws, ws_bytes);
+    MapScratch s;
+    cudaStream_t st = as_stream(stream);
+    const long long ni = n_intervals;
+    TQ_DISPATCH_DTYPE(dtype, {
+        using P2 = typename EdgePair<T>::type;
+        if (!carve<T>(w, dim, ni, s, true)) { set_error("tq_vegas_map_update: workspace too small (need %zu bytes)", map_scratch_bytes(dim, ni, sizeof(T))); return TQ_ERR_WORKSPACE; }
+        if (small_map_ok(dim, ni)) {
+            if (clear_status) cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st);
+            SmallMap a = {x_edges, dx_edges, weights, counts, edges_packed, s, dim, ni, alpha, status, true};
+            return small_update_launch(nullptr, &a, dtype, stream);
+        }
+        int rc = run_smooth<T>((const T*)weights, (const long long*)counts, (T*)s.smoothed, s, dim, ni, alpha, status, st);
+        if (rc) return rc;
+        dim3 grid(s.ntiles, dim);
+        map_prefix_kernel<T><<<grid, 256, 0, st>>>((const T*)s.smoothed, s.tile_sums, s.S, ni, s.ntiles, status);
+        dim3 grid_e((unsigned)((ni + 255) / 256), dim);
+        map_edges_kernel<T><<<grid_e, 256, 0, st>>>((const T*)s.smoothed, s.S, s.totals2, (const T*)x_edges,
+                                                   (const T*)dx_edges, (T*)s.x_new, ni, status);
+        dim3 grid_f((unsigned)((ni + 1 + 255) / 256), dim);
+        map_finalize_kernel<T><<<grid_f, 256, 0, st>>>((const T*)s.x_new, (T*)x_edges, (T*)dx_edges, (T*)weights,
+                                                      (long long*)counts, (P2*)edges_packed, ni, status);
+    });
+    return check_launch("map update");
+}
+
+
 }  // namespace tq
 
 using namespace tq;
@@ -774,11 +586,12 @@ int tq_vegas_map_smooth(const void* weights, const int64_t* counts, void* smooth
     cudaStream_t st = as_stream(stream);
     TQ_DISPATCH_DTYPE(dtype, {
         if (!carve<T>(w, dim, n_intervals, s, false)) { set_error("tq_vegas_map_smooth: workspace too small"); return TQ_ERR_WORKSPACE; }
-        if (n_intervals <= MAP_SMALL_NI && dim <= MAP_SMALL_DIM) {
+        if (small_map_ok(dim, n_intervals)) {
             cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st);
-            map_update_small_kernel<T><<<dim * MAP_CL, MAP_CL_THREADS, 0, st>>>(nullptr, nullptr, (T*)weights, (long long*)counts, nullptr, (T*)s.avg,
-                                                            (T*)smoothed, nullptr, nullptr, dim, n_intervals, (T)alpha, status, false);
-            return check_launch("map_update_small_kernel");
+            s.smoothed = smoothed;
+            SmallMap a = {nullptr, nullptr, const_cast<void*>(weights), const_cast<int64_t*>(counts), nullptr, s, dim, n_intervals,
+                          alpha, status, false};
+            return small_update_launch(nullptr, &a, dtype, stream);
         }
         return run_smooth<T>((const T*)weights, (const long long*)counts, (T*)smoothed, s, dim, n_intervals, alpha, status, st);
     });
@@ -788,33 +601,8 @@ int tq_vegas_map_smooth(const void* weights, const int64_t* counts, void* smooth
 int tq_vegas_map_update(void* x_edges, void* dx_edges, void* weights, int64_t* counts, void* edges_packed,
                         int32_t dim, int64_t n_intervals, double alpha, int32_t dtype, int32_t* status, void* ws,
                         size_t ws_bytes, void* stream) {
-    TQ_REQUIRE(dim >= 1 && dim <= 65535 && n_intervals >= 2, "tq_vegas_map_update: need dim >= 1 and Ni >= 2");
-    Workspace w(ws, ws_bytes);
-    MapScratch s;
-    cudaStream_t st = as_stream(stream);
-    const long long ni = n_intervals;
-    TQ_DISPATCH_DTYPE(dtype, {
-        using P2 = typename EdgePair<T>::type;
-        if (!carve<T>(w, dim, ni, s, true)) { set_error("tq_vegas_map_update: workspace too small (need %zu bytes)", map_scratch_bytes(dim, ni, sizeof(T))); return TQ_ERR_WORKSPACE; }
-        if (ni <= MAP_SMALL_NI && dim <= MAP_SMALL_DIM) {
-            cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st);
-            map_update_small_kernel<T><<<dim * MAP_CL, MAP_CL_THREADS, 0, st>>>((T*)x_edges, (T*)dx_edges, (T*)weights, (long long*)counts,
-                                                            (P2*)edges_packed, (T*)s.avg, (T*)s.smoothed, s.S, (T*)s.x_new, dim, ni,
-                                                            (T)alpha, status, true);
-            return check_launch("map_update_small_kernel");
-        }
-        int rc = run_smooth<T>((const T*)weights, (const long long*)counts, (T*)s.smoothed, s, dim, ni, alpha, status, st);
-        if (rc) return rc;
-        dim3 grid(s.ntiles, dim);
-        map_prefix_kernel<T><<<grid, 256, 0, st>>>((const T*)s.smoothed, s.tile_sums, s.S, ni, s.ntiles, status);
-        dim3 grid_e((unsigned)((ni + 255) / 256), dim);
-        map_edges_kernel<T><<<grid_e, 256, 0, st>>>((const T*)s.smoothed, s.S, s.totals2, (const T*)x_edges,
-                                                   (const T*)dx_edges, (T*)s.x_new, ni, status);
-        dim3 grid_f((unsigned)((ni + 1 + 255) / 256), dim);
-        map_finalize_kernel<T><<<grid_f, 256, 0, st>>>((const T*)s.x_new, (T*)x_edges, (T*)dx_edges, (T*)weights,
-                                                      (long long*)counts, (P2*)edges_packed, ni, status);
-    });
-    return check_launch("map update");
+    return map_update_launch(x_edges, dx_edges, weights, counts, edges_packed, dim, n_intervals, alpha, dtype, status,
+                             true, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -4,20 +4,12 @@
 // accumulate_weight :46-70, update_DH :72-90) and the estimator of vegas.py:293-303.
 #include "common.cuh"
 #include "strat_tile.cuh"
-
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
+#include "internal.cuh"
+#include "vegas_dev.cuh"
 
 namespace tq {
 
 constexpr int ST_TILE = 1024;  // cubes (or rows) per CTA tile: 256 threads x 4
-
-template <typename T>
-__device__ __forceinline__ long long nh_of(T dh, T nev) {
-    T v = floor(mul_rn(dh, nev));
-    v = v < (T)2 ? (T)2 : v;  // clamp(min=2)
-    return (long long)v;
-}
 
 // ---- get_NH + exclusive scan (3 phases: tile sums, scan of tile sums, tile scans)
 template <typename T>
@@ -71,52 +63,6 @@ nh_scan_kernel(const T* __restrict__ dh, int64_t n_cubes, T nev, const long long
         }
         ex += v[i];
     }
-}
-
-// Small stratifications (the launch-latency-bound regime): get_NH + scan in ONE launch by one thread-block
-// cluster.  Each of the SMALL_CL x SMALL_THREADS threads owns `per` consecutive cubes; CTA totals cross the
-// cluster through distributed shared memory, so the whole scan costs one CTA scan and one cluster barrier.
-constexpr int64_t ST_SMALL_CUBES = 32768;
-constexpr int SMALL_CL = 8;         // CTAs per cluster (portable maximum)
-constexpr int SMALL_THREADS = 512;  // threads per CTA
-constexpr int SMALL_ITEMS = 8;      // ST_SMALL_CUBES / (SMALL_CL * SMALL_THREADS)
-
-template <typename T>
-__global__ void __cluster_dims__(SMALL_CL, 1, 1) __launch_bounds__(SMALL_THREADS)
-nh_small_kernel(const T* __restrict__ dh, int64_t n_cubes, T nev, long long* __restrict__ nh,
-                long long* __restrict__ offsets) {
-    cg::cluster_group cluster = cg::this_cluster();
-    __shared__ long long sh[33];
-    __shared__ long long s_total;
-    const unsigned rank = cluster.block_rank();
-    const int per = (int)((n_cubes + SMALL_CL * SMALL_THREADS - 1) / (SMALL_CL * SMALL_THREADS));
-    const int64_t c0 = ((int64_t)rank * SMALL_THREADS + threadIdx.x) * per;
-    long long v[SMALL_ITEMS], run = 0;
-#pragma unroll
-    for (int i = 0; i < SMALL_ITEMS; ++i) {
-        v[i] = (i < per && c0 + i < n_cubes) ? nh_of<T>(dh[c0 + i], nev) : 0;
-        run += v[i];
-    }
-    long long total;
-    long long ex = block_excl_scan<long long>(run, sh, total);
-    if (threadIdx.x == 0) s_total = total;
-    cluster.sync();
-    long long all = 0;
-    for (unsigned r = 0; r < SMALL_CL; ++r) {
-        const long long t = *cluster.map_shared_rank(&s_total, r);
-        if (r < rank) ex += t;
-        all += t;
-    }
-    cluster.sync();  // no CTA may exit while its shared memory is still being read
-#pragma unroll
-    for (int i = 0; i < SMALL_ITEMS; ++i) {
-        if (i < per && c0 + i < n_cubes) {
-            nh[c0 + i] = v[i];
-            offsets[c0 + i] = ex;
-        }
-        ex += v[i];
-    }
-    if (rank == 0 && threadIdx.x == 0) offsets[n_cubes] = all;
 }
 
 // ---- exclusive scan of a caller-provided nh
@@ -368,67 +314,6 @@ strat_update_kernel(const T* __restrict__ JF, const T* __restrict__ JF2, const l
     grid_sum_finish<4>(acc, sh, partials, ticket, scalars);
 }
 
-// Small stratifications: estimator, d^beta, its sum and the normalisation in ONE launch by one cluster
-// (fp64 pow on a single SM was the whole cost of the one-CTA version).  The d^beta values stay in registers
-// between the reduction and the normalisation; the sums cross the cluster through distributed shared memory
-// in rank order, so every CTA normalises by the same value.
-template <typename T>
-__global__ void __cluster_dims__(SMALL_CL, 1, 1) __launch_bounds__(SMALL_THREADS)
-strat_update_small_kernel(const T* __restrict__ JF, const T* __restrict__ JF2, const long long* __restrict__ nh,
-                          int64_t n_cubes, T V, T V2, T beta, T* __restrict__ dh, double* scalars) {
-    cg::cluster_group cluster = cg::this_cluster();
-    __shared__ double sh[32 * 4];
-    __shared__ double s_part[4];
-    const unsigned rank = cluster.block_rank();
-    const int64_t t = (int64_t)rank * SMALL_THREADS + threadIdx.x;
-    T p[SMALL_ITEMS];
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int i = 0; i < SMALL_ITEMS; ++i) {
-        const int64_t c = (int64_t)i * SMALL_CL * SMALL_THREADS + t;
-        p[i] = (T)0;
-        if (c < n_cubes) {
-            const long long nc = nh[c];
-            const T n = (T)nc;
-            const T inv = div_rn((T)1, n);
-            const T jf = JF[c], jf2 = JF2[c];
-            const T ih = mul_rn(jf, mul_rn(inv, V));
-            const T sig2 = fabs(sub_rn(mul_rn(mul_rn(jf2, inv), V2), mul_rn(ih, ih)));
-            acc[0] += (double)ih;
-            acc[1] += (double)mul_rn(sig2, inv);
-            const T m = div_rn(mul_rn(V, jf), n);
-            T dv = sub_rn(div_rn(mul_rn(V2, jf2), n), mul_rn(m, m));
-            if (dv < (T)0) dv = (T)0;
-            p[i] = pow(dv, beta);
-            acc[2] += (double)p[i];
-            acc[3] += (double)nc;
-        }
-    }
-    block_sum<4>(acc, sh);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s_part[k] = acc[k];
-    }
-    cluster.sync();
-    double tot[4] = {0.0, 0.0, 0.0, 0.0};
-    for (unsigned r = 0; r < SMALL_CL; ++r) {
-        const double* rp = cluster.map_shared_rank(s_part, r);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tot[k] += rp[k];
-    }
-    cluster.sync();
-    if (rank == 0 && threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) scalars[k] = tot[k];
-    }
-    const T s = (T)tot[2];
-#pragma unroll
-    for (int i = 0; i < SMALL_ITEMS; ++i) {
-        const int64_t c = (int64_t)i * SMALL_CL * SMALL_THREADS + t;
-        if (c < n_cubes) dh[c] = s == (T)0 ? p[i] : div_rn(p[i], s);  // vegas_stratification.py:89-90
-    }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 strat_normalise_kernel(T* __restrict__ dh, int64_t n_cubes, const double* __restrict__ scalars) {
@@ -439,6 +324,28 @@ strat_normalise_kernel(T* __restrict__ dh, int64_t n_cubes, const double* __rest
         dh[c] = div_rn(dh[c], s);
 }
 
+// get_NH + offsets; `clear` (optional, 4-byte aligned) is zeroed on the same stream before the pass that
+// follows -- the native loop (vegas_driver.cu) folds its JF/JF2 reset into this launch.
+int strat_nh_launch(const void* dh, int64_t n_cubes, double nevals_exp, int32_t dtype, int64_t* nh, int64_t* offsets,
+                    void* clear, size_t clear_bytes, void* ws, size_t ws_bytes, void* stream) {
+    TQ_REQUIRE(n_cubes >= 1, "tq_vegas_strat_nh: n_cubes must be positive");
+    Workspace w(ws, ws_bytes);
+    w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
+    const int64_t ntiles = (n_cubes + ST_TILE - 1) / ST_TILE;
+    long long* tile_sums = w.take<long long>((size_t)ntiles);
+    if (!tile_sums) { set_error("tq_vegas_strat_nh: workspace too small for %lld cubes", (long long)n_cubes); return TQ_ERR_WORKSPACE; }
+    cudaStream_t st = as_stream(stream);
+    if (small_strat_ok(n_cubes)) return small_nh_launch(dh, n_cubes, nevals_exp, dtype, nh, offsets, clear, clear_bytes, stream);
+    if (clear && clear_bytes) cudaMemsetAsync(clear, 0, clear_bytes, st);
+    TQ_DISPATCH_DTYPE(dtype, {
+        nh_tile_sum_kernel<T><<<(unsigned)ntiles, 256, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, tile_sums);
+        i64_tile_scan_kernel<<<1, 256, 0, st>>>(tile_sums, ntiles, (long long*)offsets + n_cubes);
+        nh_scan_kernel<T><<<(unsigned)ntiles, 256, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, tile_sums,
+                                                           (long long*)nh, (long long*)offsets);
+    });
+    return check_launch("tq_vegas_strat_nh");
+}
+
 }  // namespace tq
 
 using namespace tq;
@@ -447,26 +354,7 @@ extern "C" {
 
 int tq_vegas_strat_nh(const void* dh, int64_t n_cubes, double nevals_exp, int32_t dtype, int64_t* nh,
                       int64_t* offsets, void* ws, size_t ws_bytes, void* stream) {
-    TQ_REQUIRE(n_cubes >= 1, "tq_vegas_strat_nh: n_cubes must be positive");
-    Workspace w(ws, ws_bytes);
-    w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
-    const int64_t ntiles = (n_cubes + ST_TILE - 1) / ST_TILE;
-    long long* tile_sums = w.take<long long>((size_t)ntiles);
-    if (!tile_sums) { set_error("tq_vegas_strat_nh: workspace too small for %lld cubes", (long long)n_cubes); return TQ_ERR_WORKSPACE; }
-    cudaStream_t st = as_stream(stream);
-    if (n_cubes <= ST_SMALL_CUBES) {
-        TQ_DISPATCH_DTYPE(dtype, {
-            nh_small_kernel<T><<<SMALL_CL, SMALL_THREADS, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, (long long*)nh, (long long*)offsets);
-        });
-        return check_launch("nh_small_kernel");
-    }
-    TQ_DISPATCH_DTYPE(dtype, {
-        nh_tile_sum_kernel<T><<<(unsigned)ntiles, 256, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, tile_sums);
-        i64_tile_scan_kernel<<<1, 256, 0, st>>>(tile_sums, ntiles, (long long*)offsets + n_cubes);
-        nh_scan_kernel<T><<<(unsigned)ntiles, 256, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, tile_sums,
-                                                           (long long*)nh, (long long*)offsets);
-    });
-    return check_launch("tq_vegas_strat_nh");
+    return strat_nh_launch(dh, n_cubes, nevals_exp, dtype, nh, offsets, nullptr, 0, ws, ws_bytes, stream);
 }
 
 int tq_vegas_strat_offsets(const int64_t* nh, int64_t n_cubes, int64_t* offsets, void* ws, size_t ws_bytes,
@@ -545,12 +433,9 @@ int tq_vegas_strat_update(const void* JF, const void* JF2, const int64_t* nh, in
     double* partials = w.take<double>((size_t)grid * 4);
     if (!ticket || !partials) { set_error("tq_vegas_strat_update: workspace too small"); return TQ_ERR_WORKSPACE; }
     cudaStream_t st = as_stream(stream);
-    if (n_cubes <= ST_SMALL_CUBES) {
-        TQ_DISPATCH_DTYPE(dtype, {
-            strat_update_small_kernel<T><<<SMALL_CL, SMALL_THREADS, 0, st>>>((const T*)JF, (const T*)JF2, (const long long*)nh, n_cubes,
-                                                            (T)v_cubes, (T)(v_cubes * v_cubes), (T)beta, (T*)dh, scalars_f64);
-        });
-        return check_launch("strat_update_small_kernel");
+    if (small_strat_ok(n_cubes)) {
+        SmallStrat a = {JF, JF2, const_cast<int64_t*>(nh), n_cubes, v_cubes, beta, dh, scalars_f64, 0.0, nullptr, nullptr, 0};
+        return small_update_launch(&a, nullptr, dtype, stream);
     }
     TQ_DISPATCH_DTYPE(dtype, {
         strat_update_kernel<T><<<grid, 256, 0, st>>>((const T*)JF, (const T*)JF2, (const long long*)nh, n_cubes,

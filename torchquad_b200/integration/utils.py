@@ -77,8 +77,9 @@ def _setup_integration_domain(dim, integration_domain, backend):
     return integration_domain
 
 
-def _check_integration_domain(integration_domain):
-    """Validate the domain and return its dimensionality (utils.py:162-206)."""
+def _check_integration_domain(integration_domain, check_values=True):
+    """Validate the domain and return its dimensionality (utils.py:162-206).  `check_values=False` skips the
+    device reduction + read-back of the bounds check for callers that inspect a host copy themselves."""
     if _infer_backend(integration_domain) == "builtins":
         dim = len(integration_domain)
         if dim < 1:
@@ -96,7 +97,7 @@ def _check_integration_domain(integration_domain):
         raise ValueError("integration_domain.shape[0] needs to be 1 or larger.")
     if num_bounds != 2:
         raise ValueError("integration_domain must have 2 values per boundary")
-    if _is_compiling(integration_domain):
+    if not check_values or _is_compiling(integration_domain):
         return dim
     if bool((integration_domain[:, 1] - integration_domain[:, 0]).min() < 0.0):
         raise ValueError("integration_domain has invalid boundary values")

@@ -23,7 +23,7 @@ from ..integrands import BuiltinIntegrand
 from ..utils.set_log_level import logger
 from .base_integrator import BaseIntegrator
 from .rng import RNG
-from .utils import _setup_integration_domain
+from .utils import _check_integration_domain, _setup_integration_domain
 from .vegas_map import VEGASMap
 from .vegas_stratification import VEGASStratification
 
@@ -53,7 +53,11 @@ class VEGAS(BaseIntegrator):
         """Integrate `fn` over the domain with at most ~N evaluations (vegas.py:30-159).
 
         Returns a 0-dim tensor of the domain's dtype on the domain's device."""
-        self._check_inputs(dim=dim, N=N, integration_domain=integration_domain)
+        # Input checks as in the reference; the domain's VALUES are checked below from the single host copy this
+        # method makes of them instead of through a separate device reduction + read-back.
+        self._check_inputs(dim=dim, N=N)
+        if integration_domain is not None and _check_integration_domain(integration_domain, check_values=False) != dim:
+            raise ValueError("The dimension of the integration domain must match the passed function dimensionality dim.")
         self._dim = dim
         self._nr_of_fevals = 0
         self._max_iterations = max_iterations
@@ -81,18 +85,22 @@ class VEGAS(BaseIntegrator):
         self._volume = torch.prod(self._sizes)
         self._user_fn = fn
         self._fn = lambda x: fn(x * self._sizes + self._starts) * self._volume
+        # One read-back brings the bounds and the volume to the host (the only synchronisation of the set-up).
+        host = torch.cat((domain.detach().reshape(-1), self._volume.detach().reshape(1))).tolist()
+        bounds = [(host[2 * i], host[2 * i + 1]) for i in range(dim)]
+        if any(hi < lo for lo, hi in bounds):
+            raise ValueError("integration_domain has invalid boundary values")
         # Without a gradient through the domain, the unit-cube -> domain transform and the f*volume*jac tail
         # are fused into the map kernels (same mul/add order as the torch expressions above).
         self._domain = domain
         self._fuse_tail = not domain.requires_grad
-        self._volume_host = float(self._volume.detach()) if self._fuse_tail else None
+        self._volume_host = host[-1] if self._fuse_tail else None
 
         self._fused = (isinstance(fn, BuiltinIntegrand) and type(rng) is RNG and fn.dim == dim
                        and not domain.requires_grad)
         if self._fused:
-            bounds = domain.detach().tolist()
-            self._fn_struct = fn.to_struct([b[0] for b in bounds], self._sizes.detach().tolist(),
-                                           float(self._volume.item()))
+            sizes = [float(self._np(hi) - self._np(lo)) for lo, hi in bounds]  # the working-dtype difference
+            self._fn_struct = fn.to_struct([lo for lo, _ in bounds], sizes, host[-1])
 
         N_intervals = max(2, self._N_increment // 10)  # vegas.py:117
         if self.max_map_intervals is not None:
@@ -113,13 +121,13 @@ class VEGAS(BaseIntegrator):
         self.sigma2 = []   # per-iteration variances (0-dim tensors, detached)
         self.it = 0
         self._host_block = None
-        # one status word per map update, written by the kernels, read back in one go at the sync points
-        self._status_buf = torch.zeros((max_iterations + 16, 4), dtype=torch.int32, device=self.device)
         self._status_used = 0
 
         if (self._fused and self.native_loop and not tqdist.is_enabled()
                 and max_iterations + 5 <= _lib.TQ_VEGAS_MAX_PASSES):
             return self._integrate_native_loop(N, use_warmup)
+        # one status word per map update, written by the kernels, read back in one go at the sync points
+        self._status_buf = torch.zeros((max_iterations + 16, 4), dtype=torch.int32, device=self.device)
 
         # random-access regime: shrink the L2 fetch granularity while the big tables are in flight
         restore_l2 = None
@@ -153,10 +161,11 @@ class VEGAS(BaseIntegrator):
         self.it = res.it
         self._nr_of_fevals = res.fevals
         self._starting_N = res.starting_N
-        self.results = [torch.tensor(res.results[k], dtype=torch.float64, device=self.device) for k in range(res.n_block)]
-        self.sigma2 = [torch.tensor(res.sigma2[k], dtype=torch.float64, device=self.device) for k in range(res.n_block)]
-        self._host_cache = ([self._np(res.results[k]) for k in range(res.n_block)],
-                            [self._np(res.sigma2[k]) for k in range(res.n_block)])
+        nb = res.n_block
+        block = torch.tensor(list(res.results[:nb]) + list(res.sigma2[:nb]), dtype=torch.float64, device=self.device)
+        self.results = list(block[:nb].unbind())  # 0-dim device tensors like the reference's, from one copy
+        self.sigma2 = list(block[nb:].unbind())
+        self._host_cache = ([self._np(res.results[k]) for k in range(nb)], [self._np(res.sigma2[k]) for k in range(nb)])
         self.map._edges2_stale = False
         for p in range(res.n_passes):
             self.map.check_status(list(res.status[4 * p: 4 * p + 4]))

@@ -6,6 +6,7 @@ All arithmetic is in libtqb200 (csrc/vegas_map.cu); the Python loops over `dim` 
 """
 import warnings
 
+import numpy as np
 import torch
 
 from .. import ops
@@ -24,14 +25,22 @@ class VEGASMap:
         self.backend = "torch"
         self.dtype = dtype
         self.device = torch.device(device) if device is not None else _default_device()
-        # Uniform start (vegas_map.py:32-39): dx = 1/Ni, edges from linspace (not a cumsum of dx).
-        self.dx_edges = torch.ones((dim, N_intervals), dtype=dtype, device=self.device) / N_intervals
+        # Uniform start (vegas_map.py:32-39): dx = 1/Ni (the quotient ones/Ni of the working dtype, computed once
+        # on the host), edges from linspace (not a cumsum of dx).
+        one = (np.float32 if dtype == torch.float32 else np.float64)(1.0)
+        self.dx_edges = torch.full((dim, N_intervals), float(one / type(one)(N_intervals)), dtype=dtype, device=self.device)
         edges = torch.linspace(0.0, 1.0, N_intervals + 1, dtype=dtype, device=self.device)
         self.x_edges = edges.reshape(1, -1).repeat(dim, 1).contiguous()
-        self._status = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._status_word = None
         self._edges2, self._edges2_stale = None, True
         self._scratch = None
         self._reset_weight()
+
+    @property
+    def _status(self):
+        if self._status_word is None:
+            self._status_word = torch.zeros(4, dtype=torch.int32, device=self.device)
+        return self._status_word
 
     # -- bin lookup ---------------------------------------------------------------------------
     def get_X(self, y):
@@ -71,8 +80,11 @@ class VEGASMap:
 
     def _reset_weight(self):
         """Zero the histogram (vegas_map.py:174-183)."""
-        self.weights = torch.zeros((self.dim, self.N_intervals), dtype=self.dtype, device=self.device)
-        self.counts = torch.zeros((self.dim, self.N_intervals), dtype=torch.int64, device=self.device)
+        n = self.dim * self.N_intervals
+        elt = 4 if self.dtype == torch.float32 else 8
+        raw = torch.zeros(n * (8 + elt), dtype=torch.uint8, device=self.device)  # one fill for both tables
+        self.counts = raw[: n * 8].view(torch.int64).view(self.dim, self.N_intervals)
+        self.weights = raw[n * 8:].view(self.dtype).view(self.dim, self.N_intervals)
 
     # -- rebinning ----------------------------------------------------------------------------
     def update_map(self, check=True, status=None):

@@ -4,6 +4,7 @@ Names follow the reference (tests/vegas_stratification_test.py): `N_strat, N_cub
 strat_counts`.  The reference materialises `repeat(arange(C), nh)` twice per iteration (a device->host sync
 each time); here rows locate their cube through the exclusive scan of `nh` (csrc/vegas_strat.cu).
 """
+import numpy as np
 import torch
 
 from .. import ops
@@ -29,13 +30,26 @@ class VEGASStratification:
         self.dtype = dtype
         self.backend = "torch"
         self.device = torch.device(device) if device is not None else _default_device()
-        self.JF = torch.zeros([self.N_cubes], dtype=dtype, device=self.device)
-        self.JF2 = torch.zeros([self.N_cubes], dtype=dtype, device=self.device)
-        self.dh = torch.ones([self.N_cubes], dtype=dtype, device=self.device) * 1.0 / self.N_cubes
-        self.strat_counts = torch.zeros([self.N_cubes], dtype=dtype, device=self.device)
+        zeros = torch.zeros((3, self.N_cubes), dtype=dtype, device=self.device)  # one fill; JF and JF2 stay adjacent
+        self.JF, self.JF2, self._strat_counts = zeros[0], zeros[1], zeros[2]
+        self._counts_stale = False  # set by the native loop: strat_counts = float(nh) is made on first access
+        # dh = ones * 1.0 / N_cubes (vegas_stratification.py:43): the working-dtype quotient, computed on the host
+        one = (np.float32 if dtype == torch.float32 else np.float64)(1.0)
+        self.dh = torch.full([self.N_cubes], float(one / type(one)(self.N_cubes)), dtype=dtype, device=self.device)
         self._nh = None        # int64 counts of the current iteration
         self._offsets = None   # their exclusive scan, [N_cubes + 1]
         self.last_scalars = None  # fp64 [4]: I_it, sigma2_it, sum d^beta, sum nh of the last update_DH
+
+    @property
+    def strat_counts(self):
+        """Samples per cube of the last pass as floats (the reference's attribute)."""
+        if self._counts_stale:
+            self._strat_counts, self._counts_stale = self._nh.to(self.dtype), False
+        return self._strat_counts
+
+    @strat_counts.setter
+    def strat_counts(self, value):
+        self._strat_counts, self._counts_stale = value, False
 
     # -- sample counts ------------------------------------------------------------------------
     def get_NH(self, nevals_exp):

@@ -468,11 +468,16 @@ def vegas_run_fused(fn_struct, vmap, strat, N, max_iterations, eps_rel, eps_abs,
     Returns the filled `tq_vegas_result`; synchronises (the schedule needs the per-block estimates)."""
     dev, dt = vmap.device, vmap.dtype
     n_cubes = strat.N_cubes
-    JFs = torch.zeros((2, n_cubes), dtype=dt, device=dev)
-    nh = torch.empty(n_cubes, dtype=torch.int64, device=dev)
-    offsets = torch.empty(n_cubes + 1, dtype=torch.int64, device=dev)
-    records = torch.zeros(_lib.TQ_VEGAS_MAX_PASSES * 4, dtype=torch.float64, device=dev)
-    status = torch.zeros(_lib.TQ_VEGAS_MAX_PASSES * 4, dtype=torch.int32, device=dev)
+    # JF and JF2 must be adjacent ([2, n_cubes]); the constructor's layout is, a user-replaced pair may not be
+    if strat.JF.data_ptr() + n_cubes * strat.JF.element_size() != strat.JF2.data_ptr() or strat.JF.dtype != dt:
+        pair = torch.empty((2, n_cubes), dtype=dt, device=dev)
+        strat.JF, strat.JF2 = pair[0], pair[1]
+    JFs = (strat.JF, strat.JF2)
+    # every buffer below is fully written on the device before it is read (the driver clears what it needs)
+    ints = torch.empty(2 * n_cubes + 1, dtype=torch.int64, device=dev)
+    nh, offsets = ints[:n_cubes], ints[n_cubes:]
+    records = torch.empty(_lib.TQ_VEGAS_MAX_PASSES * 4, dtype=torch.float64, device=dev)
+    status = torch.empty(_lib.TQ_VEGAS_MAX_PASSES * 4, dtype=torch.int32, device=dev)
     scratch = _map_scratch(vmap.dim, vmap.N_intervals, dt, dev)
     ws = workspace(dev)
     packed = vmap.packed_edges()
@@ -486,6 +491,6 @@ def vegas_run_fused(fn_struct, vmap, strat, N, max_iterations, eps_rel, eps_abs,
              int(bool(use_grid_improve)), int(bool(use_warmup)), vmap.N_intervals, strat.N_strat, n_cubes,
              float(strat.V_cubes), float(vmap.alpha), float(strat.beta), seed & 0xFFFFFFFFFFFFFFFF, first_call & 0xFFFFFFFF,
              state, result, stream_ptr(dev))
-    strat.JF, strat.JF2, strat._nh, strat._offsets = JFs[0], JFs[1], nh, offsets
-    strat.strat_counts = nh.to(dt)
+    strat._nh, strat._offsets = nh, offsets
+    strat._counts_stale = True  # strat_counts = float(nh) is materialised on first access
     return result
