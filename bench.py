@@ -106,6 +106,11 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            # nvidia-smi's start-up (NVML initialisation) stalls kernel launches for a while: wait for its first
+            # sample so that only the periodic queries overlap the timed region
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 10.0:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 

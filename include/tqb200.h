@@ -100,6 +100,13 @@ TQ_API int tq_philox_uniform(void* out, int64_t row_begin, int64_t row_end, int3
  * out[r, d] = u*(domain[d,1]-domain[d,0]) + domain[d,0] with u as above (mul then add, not fused). */
 TQ_API int tq_mc_sample(void* out, const void* domain, int64_t row_begin, int64_t row_end, int32_t dim,
                  int32_t dtype, uint64_t seed, uint32_t call_idx, void* stream);
+/* The same op for launches that are REPLAYED (CUDA-graph capture of a whole integrate() call, the counterpart
+ * of the reference's get_jit_compiled_integrate, monte_carlo.py:108-225): the stream call index used is
+ * call_idx + *call_offset_dev, read on the device, so a replay that follows an increment of that word draws
+ * fresh samples without a new launch configuration. */
+TQ_API int tq_mc_sample_replayable(void* out, const void* domain, int64_t row_begin, int64_t row_end, int32_t dim,
+                            int32_t dtype, uint64_t seed, uint32_t call_idx, const uint32_t* call_offset_dev,
+                            void* stream);
 /* d(loss)/d(domain) for the op above: grad_domain[d,0] = sum_r g*(1-u), grad_domain[d,1] = sum_r g*u,
  * uniforms regenerated from the counter.  grad_domain_f64 is double[dim*2] (device). */
 TQ_API int tq_mc_sample_backward(const void* grad_out, int64_t row_begin, int64_t row_end, int32_t dim,

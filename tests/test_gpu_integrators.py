@@ -430,3 +430,67 @@ def test_rng_surface(cuda):
     assert 0.0 <= float(big.min()) and float(big.max()) < 1.0 and abs(float(big.mean()) - 0.5) < 0.01
     with pytest.raises(ValueError):
         tq.RNG(backend="numpy")
+
+
+def test_compiled_integrate_replays_a_cuda_graph(cuda):
+    """get_jit_compiled_integrate (monte_carlo.py:108-225, grid_integrator.py:134-255): the whole call is captured
+    once per integrand and replayed; replays draw fresh Philox calls and follow the domain passed in."""
+    from torchquad_b200.integration.rng import RNG
+
+    torch.set_default_dtype(torch.float64)
+    dom = torch.tensor([[0.0, 1.0], [0.0, 2.0], [-1.0, 1.0]], dtype=torch.float64, device=cuda)
+
+    def fn(x):
+        return torch.exp(-(x * x).sum(dim=1)) + x[:, 1]
+
+    def exact(d):
+        import math
+        d = d.tolist()
+        vol = 1.0
+        g = 1.0
+        for a, b in d:
+            vol *= b - a
+            g *= math.sqrt(math.pi) / 2 * (math.erf(b) - math.erf(a))
+        lin = vol * (d[1][0] + d[1][1]) / 2
+        return g + lin
+
+    mc = tq.MonteCarlo()
+    compiled = mc.get_jit_compiled_integrate(dim=3, N=200_000, integration_domain=dom, seed=5)
+    r = [compiled(fn, dom) for _ in range(3)]
+    assert compiled.replays == 3
+    assert r[0].dtype == torch.float64 and r[0].is_cuda and r[0].dim() == 0
+    vals = [float(x) for x in r]
+    assert len(set(vals)) == 3  # fresh samples per replay
+    for v in vals:
+        assert abs(v - exact(dom)) < 0.02 * exact(dom)
+    # replay k runs Philox call 2 (baked at capture) + offset: the first one equals an eager run on call index 4
+    rng = RNG(seed=5)
+    rng._call = 4  # warm-up and dry run took calls 0 and 1 (+ offsets 0, 1); the capture baked call 2, offset is 2
+    assert float(tq.MonteCarlo().integrate(fn, 3, N=200_000, integration_domain=dom, rng=rng)) == vals[0]
+    dom2 = torch.tensor([[0.0, 0.5], [1.0, 2.0], [0.0, 1.0]], dtype=torch.float64, device=cuda)
+    assert abs(float(compiled(fn, dom2)) - exact(dom2)) < 0.02 * exact(dom2)
+    assert abs(float(compiled(fn, dom2.tolist())) - exact(dom2)) < 0.02 * exact(dom2)  # list domains work too
+
+    for rule, N in ((tq.Simpson(), 41**3), (tq.Boole(), 41**3), (tq.Trapezoid(), 101**3)):
+        c = rule.get_jit_compiled_integrate(dim=3, N=N, integration_domain=dom)
+        for d in (dom, dom2, dom):
+            got, want = float(c(fn, d)), float(rule.integrate(fn, 3, N=N, integration_domain=d))
+            assert abs(got - want) <= 1e-12 * abs(want)
+        assert c.replays == 3
+
+    # an integrand with a host read-back cannot be captured: the call still works (eagerly)
+    def syncing(x):
+        return torch.exp(-(x * x).sum(dim=1)) * float(x[0, 0] * 0 + 1)
+
+    c = tq.Simpson().get_jit_compiled_integrate(dim=3, N=21**3, integration_domain=dom)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = float(c(syncing, dom))
+        b = float(c(syncing, dom))
+    assert c.replays == 0 and a == b
+    torch.rand(4, device=cuda)  # torch's generator is usable after the refused capture
+    assert abs(a - float(tq.Simpson().integrate(lambda x: torch.exp(-(x * x).sum(dim=1)), 3, N=21**3, integration_domain=dom))) < 1e-12
+    # a built-in (fused) integrand is a single launch already and runs eagerly
+    unit = torch.tensor([[0.0, 1.0]] * 3, dtype=torch.float64, device=cuda)
+    c = tq.MonteCarlo().get_jit_compiled_integrate(dim=3, N=100_000, integration_domain=unit, seed=1)
+    assert abs(float(c(F.SumOfSines(3), unit)) - F.SumOfSines(3).exact()) < 0.02 and c.replays == 0

@@ -60,6 +60,7 @@ PROTOTYPES = {
     "tq_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
     "tq_philox_uniform": (ctypes.c_int, [c_p, c_i64, c_i64, c_i32, c_i32, c_u64, c_u32, c_p]),
     "tq_mc_sample": (ctypes.c_int, [c_p, c_p, c_i64, c_i64, c_i32, c_i32, c_u64, c_u32, c_p]),
+    "tq_mc_sample_replayable": (ctypes.c_int, [c_p, c_p, c_i64, c_i64, c_i32, c_i32, c_u64, c_u32, c_p, c_p]),
     "tq_mc_sample_backward": (ctypes.c_int, [c_p, c_i64, c_i64, c_i32, c_i32, c_u64, c_u32, c_p, c_p, c_sz, c_p]),
     "tq_sum_columns": (ctypes.c_int, [c_p, c_i64, c_i64, c_i32, c_p, c_p, c_p, c_sz, c_p]),
     "tq_vegas_map_forward": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),

@@ -33,8 +33,9 @@ template <> struct RawBits<double> {
 template <typename T, bool AFFINE>
 __global__ void __launch_bounds__(256)
 uniform_kernel(T* __restrict__ out, const T* __restrict__ domain, int64_t row_begin, int64_t nrows,
-               int dim, int nblk, uint64_t seed, uint32_t call) {
+               int dim, int nblk, uint64_t seed, uint32_t call, const uint32_t* __restrict__ call_offset) {
     constexpr int LANES = U01<T>::LANES;
+    if (call_offset) call += *call_offset;  // replayed launches (CUDA graphs) advance the stream on the device
     const int rows_per_pass = 256 / nblk;
     const int rloc = threadIdx.x / nblk;
     const int blk = threadIdx.x - rloc * nblk;
@@ -87,7 +88,7 @@ uniform_kernel(T* __restrict__ out, const T* __restrict__ domain, int64_t row_be
 
 template <typename T>
 static int launch_uniform(T* out, const T* domain, int64_t row_begin, int64_t row_end, int dim,
-                          uint64_t seed, uint32_t call, cudaStream_t st) {
+                          uint64_t seed, uint32_t call, cudaStream_t st, const uint32_t* call_offset = nullptr) {
     const int64_t nrows = row_end - row_begin;
     if (nrows <= 0) return TQ_OK;
     const int nblk = (dim + U01<T>::LANES - 1) / U01<T>::LANES;
@@ -96,9 +97,9 @@ static int launch_uniform(T* out, const T* domain, int64_t row_begin, int64_t ro
     const int64_t cap = (int64_t)num_sms() * 8;
     const int grid = (int)(passes < cap ? passes : cap);
     if (domain)
-        uniform_kernel<T, true><<<grid, 256, 0, st>>>(out, domain, row_begin, nrows, dim, nblk, seed, call);
+        uniform_kernel<T, true><<<grid, 256, 0, st>>>(out, domain, row_begin, nrows, dim, nblk, seed, call, call_offset);
     else
-        uniform_kernel<T, false><<<grid, 256, 0, st>>>(out, nullptr, row_begin, nrows, dim, nblk, seed, call);
+        uniform_kernel<T, false><<<grid, 256, 0, st>>>(out, nullptr, row_begin, nrows, dim, nblk, seed, call, call_offset);
     return check_launch("uniform_kernel");
 }
 
@@ -255,6 +256,19 @@ int tq_mc_sample(void* out, const void* domain, int64_t row_begin, int64_t row_e
     TQ_REQUIRE(domain != nullptr, "tq_mc_sample: domain is NULL");
     TQ_DISPATCH_DTYPE(dtype, {
         return launch_uniform<T>((T*)out, (const T*)domain, row_begin, row_end, dim, seed, call_idx, as_stream(stream));
+    });
+    return TQ_OK;
+}
+
+int tq_mc_sample_replayable(void* out, const void* domain, int64_t row_begin, int64_t row_end, int32_t dim,
+                            int32_t dtype, uint64_t seed, uint32_t call_idx, const uint32_t* call_offset_dev,
+                            void* stream) {
+    TQ_REQUIRE(dim >= 1 && dim <= 512, "tq_mc_sample_replayable: dim %d out of range (max 512)", dim);
+    TQ_REQUIRE(row_end >= row_begin && row_begin >= 0, "tq_mc_sample_replayable: bad row range");
+    TQ_REQUIRE(domain != nullptr && call_offset_dev != nullptr, "tq_mc_sample_replayable: NULL argument");
+    TQ_DISPATCH_DTYPE(dtype, {
+        return launch_uniform<T>((T*)out, (const T*)domain, row_begin, row_end, dim, seed, call_idx, as_stream(stream),
+                                 call_offset_dev);
     });
     return TQ_OK;
 }

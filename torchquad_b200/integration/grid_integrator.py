@@ -10,6 +10,7 @@ from .. import distributed as tqdist
 from .. import ops
 from ..integrands import BuiltinIntegrand
 from .base_integrator import BaseIntegrator
+from .compiled import GraphedIntegrate
 from .integration_grid import IntegrationGrid, grid_nodes
 from .utils import _linspace_with_grads, _setup_integration_domain, expand_func_values_and_squeeze_integral
 
@@ -30,6 +31,7 @@ class GridIntegrator(BaseIntegrator):
         def f(integration_domain, N, requires_grad=False, backend=None):
             return _linspace_with_grads(integration_domain[0], integration_domain[1], N, requires_grad=requires_grad)
 
+        f._equally_spaced = True
         return f
 
     def _weights(self, N, dim, backend, requires_grad=False):
@@ -43,9 +45,18 @@ class GridIntegrator(BaseIntegrator):
     def _adjust_N(dim, N):
         return N
 
+    _tables = {}  # (rule, n, dim, dtype, device) -> [dim, n] weight table; built once, treated as read-only
+
     def _weight_table(self, n, dim, dtype, device):
-        w = self._rule_weights_1d(n, dtype, device)
-        return w.reshape(1, n).repeat(dim, 1).contiguous()
+        key = (type(self).__name__, n, dim, dtype, str(device))
+        table = GridIntegrator._tables.get(key)
+        if table is None:
+            w = self._rule_weights_1d(n, dtype, device)
+            table = w.reshape(1, n).repeat(dim, 1).contiguous()
+            if len(GridIntegrator._tables) > 64:
+                GridIntegrator._tables.clear()
+            GridIntegrator._tables[key] = table
+        return table
 
     def _scale(self, hs, domain=None):
         """prod_d h_d / c, multiplied in the order the reference applies its passes."""
@@ -121,12 +132,16 @@ class GridIntegrator(BaseIntegrator):
         return grid.points, grid.h, grid._N
 
     def get_jit_compiled_integrate(self, dim, N=None, integration_domain=None, backend=None):
-        """API parity with grid_integrator.py:134-255; nothing to trace, returns a closure."""
+        """`compiled_integrate(fn, integration_domain)` with everything but the two arguments fixed
+        (grid_integrator.py:134-255).  The reference traces grid creation and the contraction with torch.jit; here
+        the whole call -- node/point kernels, the integrand's torch ops, the contraction -- is captured once per
+        integrand as a CUDA graph and replayed (integration/compiled.py)."""
         if N is None:
             N = self._get_minimal_N(dim)
         domain0 = _setup_integration_domain(dim, integration_domain, backend)
+        self._check_inputs(dim=dim, N=N, integration_domain=domain0)
 
-        def compiled_integrate(fn, integration_domain=None):
-            return self.integrate(fn, dim, N, domain0 if integration_domain is None else integration_domain, backend)
+        def run(fn, domain, _rng):
+            return self.integrate(fn, dim, N, domain)
 
-        return compiled_integrate
+        return GraphedIntegrate(run, domain0, None)

@@ -8,6 +8,7 @@ from .. import ops
 from ..integrands import BuiltinIntegrand
 from ..utils.set_log_level import logger
 from .base_integrator import BaseIntegrator
+from .compiled import GraphedIntegrate
 from .rng import RNG
 from .utils import _setup_integration_domain, expand_func_values_and_squeeze_integral
 
@@ -52,7 +53,7 @@ class MonteCarlo(BaseIntegrator):
             total, fevals = None, 0
             for r0 in range(begin, end, chunk_rows):
                 rows = min(chunk_rows, end - r0)
-                pts = ops.mc_sample(domain, rows, rng.seed, call, r0)
+                pts = ops.mc_sample(domain, rows, rng.seed, call, r0, call_offset=rng._call_offset)
                 vals, n = self.evaluate_integrand(fn, pts)
                 fevals += n
                 part = ops.reduce_sum_f64(vals)
@@ -115,7 +116,7 @@ class MonteCarlo(BaseIntegrator):
             raise ValueError("seed and rng cannot both be passed")
         dim = integration_domain.shape[0]
         if type(rng) is RNG:
-            return ops.mc_sample(integration_domain, N, rng.seed, rng.next_call(), 0)
+            return ops.mc_sample(integration_domain, N, rng.seed, rng.next_call(), 0, call_offset=rng._call_offset)
         # injected generator (reference semantics): scale and translate its numbers
         starts = integration_domain[:, 0]
         sizes = integration_domain[:, 1] - starts
@@ -123,13 +124,16 @@ class MonteCarlo(BaseIntegrator):
         return u.to(sizes.device) * sizes + starts
 
     def get_jit_compiled_integrate(self, dim, N=1000, integration_domain=None, seed=None, backend=None):
-        """API parity with monte_carlo.py:108-225: the kernels need no tracing, so this returns a closure."""
+        """`compiled_integrate(fn, integration_domain)` with everything but the two arguments fixed
+        (monte_carlo.py:108-225).  The reference traces its steps with torch.jit; here the whole call -- sampling
+        kernel, the integrand's torch ops, the fp64 reduction -- is captured once per integrand as a CUDA graph
+        and replayed (integration/compiled.py), which removes the per-call launch and Python overhead of small-N
+        repeated quadrature.  Every replay advances the Philox call index on the device: fresh samples per call."""
         self._check_inputs(dim=dim, N=N, integration_domain=integration_domain)
         domain0 = _setup_integration_domain(dim, integration_domain, backend)
         rng = RNG(backend="torch", seed=seed)
 
-        def compiled_integrate(fn, integration_domain=None):
-            domain = domain0 if integration_domain is None else integration_domain
-            return self.integrate(fn, dim, N, domain, rng=rng)
+        def run(fn, domain, graph_rng):
+            return self.integrate(fn, dim, N, domain, rng=graph_rng)
 
-        return compiled_integrate
+        return GraphedIntegrate(run, domain0, rng)

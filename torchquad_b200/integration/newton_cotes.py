@@ -26,8 +26,8 @@ class Trapezoid(NewtonCotes):
     @staticmethod
     def _rule_weights_1d(n, dtype, device):
         w = torch.full((n,), 2.0, dtype=dtype, device=device)
-        w[0] = 1.0
-        w[-1] = 1.0
+        w[:1] = 1.0  # slices: scalar fills on the device (w[0] = ... would be a host-to-device copy)
+        w[-1:] = 1.0
         return w
 
     @staticmethod
@@ -48,8 +48,8 @@ class Simpson(NewtonCotes):
     def _rule_weights_1d(n, dtype, device):
         w = torch.full((n,), 2.0, dtype=dtype, device=device)
         w[1::2] = 4.0
-        w[0] = 1.0
-        w[-1] = 1.0
+        w[:1] = 1.0
+        w[-1:] = 1.0
         return w
 
     @staticmethod
@@ -89,8 +89,8 @@ class Boole(NewtonCotes):
         w = torch.full((n,), 32.0, dtype=dtype, device=device)
         w[2::4] = 12.0
         w[0::4] = 14.0
-        w[0] = 7.0
-        w[-1] = 7.0
+        w[:1] = 7.0
+        w[-1:] = 7.0
         return w
 
     @staticmethod

@@ -29,6 +29,9 @@ class RNG:
         self._call = 0
         # The stream never touches torch's global generator, so `torch_save_state` has nothing to protect.
         self._save_state = bool(torch_save_state)
+        # Optional int32[1] device word added to the call index inside the sampling kernel: set by the CUDA-graph
+        # replay of get_jit_compiled_integrate so that every replay draws fresh samples (integration/compiled.py).
+        self._call_offset = None
 
     def next_call(self):
         """Reserve the next call index (used by the fused kernels, which draw inside the kernel)."""

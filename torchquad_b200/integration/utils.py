@@ -33,8 +33,10 @@ def _default_device():
 
 def _linspace_with_grads(start, stop, N, requires_grad):
     """Equally spaced 1-D grid that keeps gradients wrt start/stop (utils.py:24-58)."""
-    if requires_grad:
-        grid = torch.linspace(start.new_zeros(()), start.new_ones(()), N, dtype=start.dtype, device=start.device)
+    if requires_grad or _is_compiling(start):
+        # affine form: differentiable, and free of the host read-back of tensor bounds that torch.linspace makes
+        # (which a CUDA-graph capture cannot contain)
+        grid = torch.linspace(0.0, 1.0, N, dtype=start.dtype, device=start.device)
         return grid * (stop - start) + start
     return torch.linspace(start, stop, N, dtype=start.dtype, device=start.device)
 
@@ -139,6 +141,14 @@ def expand_func_values_and_squeeze_integral(f):
     return wrap
 
 
+_capture_probe = False  # set by integration/compiled.py while it dry-runs a call before capturing it
+
+
 def _is_compiling(x):
-    """True while torch.jit is tracing (utils.py:280-308)."""
-    return isinstance(x, torch.Tensor) and torch.jit.is_tracing()
+    """True while torch.jit is tracing (utils.py:280-308) or a CUDA graph is being captured: value-dependent
+    host checks (which would need a read-back) are skipped, as the reference does under tracing."""
+    if not isinstance(x, torch.Tensor):
+        return False
+    if torch.jit.is_tracing() or _capture_probe:
+        return True
+    return x.is_cuda and torch.cuda.is_current_stream_capturing()

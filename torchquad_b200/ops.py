@@ -58,9 +58,24 @@ class _MCSample(torch.autograd.Function):
         return gd.to(dtype), None, None, None, None
 
 
-def mc_sample(domain, rows, seed, call_idx, row_begin=0):
-    """points = u*(b-a)+a for the [dim,2] domain (monte_carlo.py:84-106); differentiable wrt domain."""
-    return _MCSample.apply(domain, rows, seed, call_idx, row_begin)
+def mc_sample(domain, rows, seed, call_idx, row_begin=0, call_offset=None):
+    """points = u*(b-a)+a for the [dim,2] domain (monte_carlo.py:84-106); differentiable wrt domain.
+
+    `call_offset` (uint32/int32 device tensor, 1 element) is added to `call_idx` ON THE DEVICE: launches replayed
+    from a CUDA graph draw fresh samples after the word is incremented (no autograd on that path)."""
+    if call_offset is None:
+        return _MCSample.apply(domain, rows, seed, call_idx, row_begin)
+    require_cuda(domain, call_offset)
+    if torch.is_grad_enabled() and domain.requires_grad:
+        raise RuntimeError("mc_sample: a device-side call offset is not differentiable; run without it")
+    dom = domain.detach().contiguous()
+    dim = dom.shape[0]
+    out = torch.empty((rows, dim), dtype=dom.dtype, device=dom.device)
+    if rows > 0:
+        with on_device(dom.device):
+            call("tq_mc_sample_replayable", ptr(out), ptr(dom), row_begin, row_begin + rows, dim, dtype_code(dom.dtype),
+                 seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, ptr(call_offset), stream_ptr(dom.device))
+    return out
 
 
 def sum_columns(f, want_sumsq=False):
