@@ -223,13 +223,28 @@ TQ_API int tq_vegas_map_pack_edges(const void* x_edges, const void* dx_edges, vo
  *     -row_end is then the caller's estimate of that count and only sizes the grid.
  *   warm-up (offsets == NULL): rows are plain samples y = u*0.999999 (vegas.py:236); out_f64 receives
  *     {sum jf, sum jf^2}.
- *   edges_packed: see tq_vegas_map_pack_edges.
+ *   edges_packed: see tq_vegas_map_pack_edges (edges_layout = TQ_EDGES_PAIRS) or the record layout below.
  *   weights/counts (map histogram, vegas_map.py:99-111) are accumulated unless weights == NULL. */
 TQ_API int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
                    int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_packed,
-                   int64_t n_intervals, void* weights, int64_t* counts, void* JF,
+                   int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* JF,
                    void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
                    size_t ws_bytes, void* stream);
+
+/* Record layout for LARGE maps (tables beyond L2, e.g. the reference's Ni = N_increment/10 of vegas.py:117 at
+ * N = 2.5e9: 8 x 1e7 bins).  One bin = one record {x_edge, dx_edge, weight, count}: 32 bytes {f64,f64,f64,u64}
+ * for TQ_F64, 16 bytes {f32,f32,f32,u32} for TQ_F32, [dim, Ni] records.  With edges_layout = TQ_EDGES_RECORDS
+ * tq_fused_vegas gathers the edges from the records and accumulates the histogram (vegas_map.py:99-111) INTO
+ * them (weights = counts = NULL): the three scattered accesses per sample and dimension fall into one DRAM
+ * sector.  tq_vegas_map_unpack_records then adds the record fields to weights/counts (the arrays
+ * tq_vegas_map_update reads) and zeroes them; tq_vegas_map_pack_records rewrites the records from new edges. */
+#define TQ_EDGES_PAIRS 0
+#define TQ_EDGES_RECORDS 1
+TQ_API size_t tq_vegas_map_records_bytes(int32_t dim, int64_t n_intervals, int32_t dtype);
+TQ_API int tq_vegas_map_pack_records(const void* x_edges, const void* dx_edges, void* records, int32_t dim,
+                              int64_t n_intervals, int32_t dtype, void* stream);
+TQ_API int tq_vegas_map_unpack_records(void* records, void* weights, int64_t* counts, int32_t dim,
+                                int64_t n_intervals, int32_t dtype, void* stream);
 
 /* ---- whole fused VEGAS run in one call (host loop in C++) ----------------------------------------
  * Runs VEGAS.integrate's warm-up, iterations and chi^2 / budget schedule (vegas.py:137-209,211-315) for a
@@ -240,7 +255,7 @@ TQ_API int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int6
 typedef struct tq_vegas_state {
     void* x_edges;      /* [dim, Ni+1] */
     void* dx_edges;     /* [dim, Ni] */
-    void* edges_packed; /* [dim, Ni, 2], already packed for the initial map */
+    void* edges_packed; /* initial map, already packed: pairs [dim, Ni, 2] or records (edges_layout) */
     void* weights;      /* [dim, Ni], zero */
     int64_t* counts;    /* [dim, Ni], zero */
     void* dh;           /* [n_cubes], initial 1/n_cubes */
@@ -248,12 +263,13 @@ typedef struct tq_vegas_state {
     int64_t* offsets;   /* [n_cubes + 1] */
     void* JF;           /* [2, n_cubes] */
     void* JF2;
-    double* records;    /* [TQ_VEGAS_MAX_PASSES * 4]: per iteration I, sigma^2, sum d^beta, unused */
+    double* records;    /* [TQ_VEGAS_MAX_PASSES * 4]: per iteration I, sigma^2, sum d^beta, sum nh */
     int32_t* status;    /* [TQ_VEGAS_MAX_PASSES * 4]: per map update, see tq_vegas_map_update */
     void* map_ws;       /* tq_vegas_map_workspace_bytes(dim, Ni, dtype) */
     size_t map_ws_bytes;
     void* ws;           /* tq_workspace_bytes(), zero-initialised */
     size_t ws_bytes;
+    int32_t edges_layout; /* TQ_EDGES_PAIRS or TQ_EDGES_RECORDS (large maps) */
 } tq_vegas_state;
 typedef struct tq_vegas_result {
     int32_t it;          /* iterations performed (VEGAS.it) */

@@ -494,3 +494,55 @@ def test_compiled_integrate_replays_a_cuda_graph(cuda):
     unit = torch.tensor([[0.0, 1.0]] * 3, dtype=torch.float64, device=cuda)
     c = tq.MonteCarlo().get_jit_compiled_integrate(dim=3, N=100_000, integration_domain=unit, seed=1)
     assert abs(float(c(F.SumOfSines(3), unit)) - F.SumOfSines(3).exact()) < 0.02 and c.replays == 0
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_vegas_record_layout_matches_pair_layout(cuda, monkeypatch, native):
+    """Large maps keep {x, dx, weight, count} records (TQ_EDGES_RECORDS); forcing that layout on a small problem
+    must reproduce the default layout's run: same samples, same histogram, same map."""
+    from torchquad_b200.integration.vegas_map import VEGASMap
+
+    fn = F.GenzGaussian(4, a=5.0, u=0.5)
+    dom = torch.tensor([[0.0, 1.0]] * 4, dtype=torch.float64, device=cuda)
+
+    def run():
+        v = tq.VEGAS()
+        v.native_loop = native
+        return v, v.integrate(fn, 4, N=400_000, integration_domain=dom, seed=3)
+
+    a, ra = run()
+    monkeypatch.setattr(VEGASMap, "records_min_bytes", 0)
+    b, rb = run()
+    assert b.map._records is not None and a.map._records is None
+    assert a.it == b.it and a._nr_of_fevals == b._nr_of_fevals
+    assert abs(float(ra) - float(rb)) <= 1e-9 * abs(float(ra))
+    assert float((a.map.x_edges - b.map.x_edges).abs().max()) <= 1e-9
+    assert torch.equal(a.map.counts, b.map.counts)
+    # kernel level: one stratified pass into records, unpacked, against the same pass into the arrays
+    from torchquad_b200 import ops
+
+    for dt in (torch.float64, torch.float32):
+        vm = VEGASMap(512, 3, "torch", dt, device=cuda)
+        vm.x_edges[:, 1:-1] += (torch.rand(3, 511, device=cuda, dtype=dt) - 0.5) * 1e-3
+        vm.dx_edges = (vm.x_edges[:, 1:] - vm.x_edges[:, :-1]).contiguous()
+        f3 = F.GenzOscillatory(3, a=0.7, u=0.2)
+        s = f3.to_struct([0.0] * 3, [1.0] * 3, 1.0)
+        nh = torch.randint(2, 9, (6**3,), device=cuda, dtype=torch.int64)
+        offsets = ops.strat_offsets(nh)
+        M = int(offsets[-1])
+        w1, c1 = torch.zeros_like(vm.weights), torch.zeros_like(vm.counts)
+        JF1 = torch.zeros((2, 6**3), dtype=dt, device=cuda)
+        ops.fused_vegas(s, ops.pack_edges(vm.x_edges, vm.dx_edges), w1, c1, 0, M, 1, 7, offsets=offsets, n_strat=6,
+                        JF=JF1[0], JF2=JF1[1])
+        rec = ops.pack_records(vm.x_edges, vm.dx_edges)
+        JF2 = torch.zeros((2, 6**3), dtype=dt, device=cuda)
+        ops.fused_vegas(s, None, None, None, 0, M, 1, 7, offsets=offsets, n_strat=6, JF=JF2[0], JF2=JF2[1], records=rec,
+                        dtype=dt, n_intervals=512)
+        w2, c2 = torch.zeros_like(vm.weights), torch.zeros_like(vm.counts)
+        ops.unpack_records(rec, w2, c2)
+        assert torch.equal(c1, c2) and int(c1.sum()) == 3 * M
+        assert torch.allclose(w1, w2, rtol=1e-5 if dt == torch.float32 else 1e-12, atol=0)
+        assert torch.allclose(JF1, JF2, rtol=1e-5 if dt == torch.float32 else 1e-12, atol=0)
+        w3, c3 = torch.zeros_like(vm.weights), torch.zeros_like(vm.counts)
+        ops.unpack_records(rec, w3, c3)  # the records were zeroed by the first unpack
+        assert int(c3.sum()) == 0 and float(w3.abs().sum()) == 0.0

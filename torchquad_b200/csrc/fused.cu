@@ -196,6 +196,13 @@ template <typename T> struct Pair2;
 template <> struct Pair2<float> { using type = float2; };
 template <> struct Pair2<double> { using type = double2; };
 
+// Record layout of a LARGE map (tables beyond L2): {x_edge, dx_edge, weight, count} of one bin in one 32-byte (fp64)
+// or 16-byte (fp32) record, so that the edge gather and both histogram updates of a sample touch ONE DRAM sector
+// instead of three scattered ones.
+template <typename T> struct MapRecord;
+template <> struct __align__(32) MapRecord<double> { double x, dx, w; unsigned long long c; };
+template <> struct __align__(16) MapRecord<float> { float x, dx, w; unsigned int c; };
+
 template <typename T>
 __device__ __forceinline__ void segmented_warp_sum2(unsigned key, T& a, T& b) {
     const int lane = threadIdx.x & 31;
@@ -212,7 +219,7 @@ template <int FAM, typename T, bool STRAT>
 __global__ void __launch_bounds__(FV_BLOCK, FV_MIN_CTAS)
 fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, int64_t n_cubes, int n_strat,
                    int64_t row_begin, int64_t row_end, bool rows_from_offsets, int64_t rows_per_cta,
-                   const typename Pair2<T>::type* __restrict__ edges, long long ni, T* __restrict__ weights,
+                   const void* __restrict__ edges_raw, bool records, long long ni, T* __restrict__ weights,
                    unsigned long long* __restrict__ counts, T* __restrict__ JF, T* __restrict__ JF2, uint64_t seed,
                    uint32_t call, bool hist_smem, double* partials, unsigned int* ticket, double* out) {
     constexpr int LANES = U01<T>::LANES;
@@ -227,7 +234,9 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
     int* s_ids = reinterpret_cast<int*>(smem_raw);                        // [dim][FV_BLOCK]
     T* s_w = reinterpret_cast<T*>(s_ids + dim * FV_BLOCK);                 // [dim*ni] when hist_smem
     unsigned int* s_c = reinterpret_cast<unsigned int*>(s_w + (hist_smem ? dim * ni : 0));
-    const bool do_hist = weights != nullptr;
+    const P2* __restrict__ edges = reinterpret_cast<const P2*>(edges_raw);
+    MapRecord<T>* recs = reinterpret_cast<MapRecord<T>*>(const_cast<void*>(edges_raw));
+    const bool do_hist = weights != nullptr || records;
     if (do_hist && hist_smem) {
         for (int i = threadIdx.x; i < dim * (int)ni; i += blockDim.x) { s_w[i] = (T)0; s_c[i] = 0u; }
     }
@@ -308,7 +317,8 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
                         long long k = (long long)fl;
                         k = k < 0 ? 0 : (k >= ni ? ni - 1 : k);
                         const T o = sub_rn(t, fl);
-                        const P2 e = __ldg(&edges[(int64_t)d * ni + k]);
+                        const int64_t bin = (int64_t)d * ni + k;
+                        const P2 e = records ? __ldg(reinterpret_cast<const P2*>(&recs[bin])) : __ldg(&edges[bin]);
                         const T x = add_rn(e.x, mul_rn(e.y, o));
                         jac = mul_rn(jac, mul_rn(nif, e.y));
                         s_ids[d * FV_BLOCK + threadIdx.x] = (int)k;
@@ -325,6 +335,12 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
                         const int b = d * (int)ni + s_ids[d * FV_BLOCK + threadIdx.x];
                         atomicAdd(&s_w[b], jf2);
                         atomicAdd(&s_c[b], 1u);
+                    }
+                } else if (records) {
+                    for (int d = 0; d < dim; ++d) {
+                        MapRecord<T>* r = &recs[(int64_t)d * ni + s_ids[d * FV_BLOCK + threadIdx.x]];
+                        atomicAdd(&r->w, jf2);
+                        atomicAdd(&r->c, 1);
                     }
                 } else {
                     for (int d = 0; d < dim; ++d) {
@@ -375,6 +391,39 @@ pack_edges_kernel(const T* __restrict__ xe, const T* __restrict__ dxe, typename 
         e.x = xe[d * (ni + 1) + k];
         e.y = dxe[i];
         out[i] = e;
+    }
+}
+
+// records[d,k] = {x_edges[d,k], dx_edges[d,k], 0, 0}
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_records_kernel(const T* __restrict__ xe, const T* __restrict__ dxe, MapRecord<T>* __restrict__ out, int dim, long long ni) {
+    const int64_t total = (int64_t)dim * ni;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = i / ni, k = i - d * ni;
+        MapRecord<T> r;
+        r.x = xe[d * (ni + 1) + k];
+        r.dx = dxe[i];
+        r.w = (T)0;
+        r.c = 0;
+        out[i] = r;
+    }
+}
+
+// weights += records.w, counts += records.c, and the record fields go back to zero
+template <typename T>
+__global__ void __launch_bounds__(256)
+unpack_records_kernel(MapRecord<T>* __restrict__ recs, T* __restrict__ weights, long long* __restrict__ counts, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const MapRecord<T> r = recs[i];
+        if (r.c != 0) {
+            weights[i] = add_rn(weights[i], r.w);
+            counts[i] += (long long)r.c;
+            MapRecord<T> z = r;
+            z.w = (T)0;
+            z.c = 0;
+            recs[i] = z;
+        }
     }
 }
 
@@ -466,9 +515,35 @@ int tq_vegas_map_pack_edges(const void* x_edges, const void* dx_edges, void* edg
     return check_launch("pack_edges_kernel");
 }
 
+size_t tq_vegas_map_records_bytes(int32_t dim, int64_t n_intervals, int32_t dtype) {
+    return (size_t)dim * (size_t)n_intervals * (dtype == TQ_F64 ? sizeof(MapRecord<double>) : sizeof(MapRecord<float>));
+}
+
+int tq_vegas_map_pack_records(const void* x_edges, const void* dx_edges, void* records, int32_t dim,
+                              int64_t n_intervals, int32_t dtype, void* stream) {
+    TQ_REQUIRE(dim >= 1 && n_intervals >= 1, "tq_vegas_map_pack_records: bad shape");
+    const int grid = grid_for((int64_t)dim * n_intervals, 256, 8);
+    TQ_DISPATCH_DTYPE(dtype, {
+        pack_records_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x_edges, (const T*)dx_edges,
+                                                                   (MapRecord<T>*)records, dim, n_intervals);
+    });
+    return check_launch("pack_records_kernel");
+}
+
+int tq_vegas_map_unpack_records(void* records, void* weights, int64_t* counts, int32_t dim, int64_t n_intervals,
+                                int32_t dtype, void* stream) {
+    TQ_REQUIRE(dim >= 1 && n_intervals >= 1, "tq_vegas_map_unpack_records: bad shape");
+    const int64_t total = (int64_t)dim * n_intervals;
+    const int grid = grid_for(total, 256, 8);
+    TQ_DISPATCH_DTYPE(dtype, {
+        unpack_records_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((MapRecord<T>*)records, (T*)weights, (long long*)counts, total);
+    });
+    return check_launch("unpack_records_kernel");
+}
+
 int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
                    int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_packed,
-                   int64_t n_intervals, void* weights, int64_t* counts, void* JF,
+                   int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* JF,
                    void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
                    size_t ws_bytes, void* stream) {
     int rc = check_integrand("tq_fused_vegas", fn_host);
@@ -484,6 +559,10 @@ int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* of
     TQ_REQUIRE(!strat || (n_cubes >= 1 && n_cubes < (1LL << 31) && n_strat >= 1 && JF && JF2),
                "tq_fused_vegas: stratified pass needs n_cubes, n_strat, JF, JF2");
     TQ_REQUIRE(strat || out_f64 != nullptr, "tq_fused_vegas: warm-up pass needs out_f64");
+    TQ_REQUIRE(edges_layout == TQ_EDGES_PAIRS || edges_layout == TQ_EDGES_RECORDS, "tq_fused_vegas: unknown edges layout %d", edges_layout);
+    const bool records = edges_layout == TQ_EDGES_RECORDS;
+    TQ_REQUIRE(!records || (weights == nullptr && counts == nullptr),
+               "tq_fused_vegas: with TQ_EDGES_RECORDS the histogram lives in the records; pass weights = counts = NULL");
     const int64_t nrows = row_end - row_begin;
     if (nrows == 0 && strat) return TQ_OK;
     Workspace w(ws, ws_bytes);
@@ -501,8 +580,12 @@ int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* of
     // Mid-size maps stay L2-resident and take plain L2 reductions: measured on B200 (8-D fp64) 6.4e9 evals/s
     // with Ni=4096 through L2 vs 2.9e9 with a 98 KB privatised copy that limits the SM to one CTA.
     const int64_t bins = (int64_t)dim * n_intervals;
-    bool hist_smem = weights != nullptr && bins <= 4096 && nrows >= 64 * bins;
-    int64_t ctas = tiles < (int64_t)sms * 6 ? tiles : (int64_t)sms * 6;
+    bool hist_smem = weights != nullptr && !records && bins <= 4096 && nrows >= 64 * bins;
+    // Record layout = tables beyond L2: a sample's histogram reductions find its record still in L2 only if few
+    // samples are in flight between the gather and the reduction.  Measured (8-D fp64, Ni=1e7): 6 CTAs/SM refetch
+    // every record from HBM for the reductions (5 DRAM sectors read per gather, 1.7e9 evals/s); 2 CTAs/SM: 2.07e9.
+    const int per_sm = records ? 2 : 6;
+    int64_t ctas = tiles < (int64_t)sms * per_sm ? tiles : (int64_t)sms * per_sm;
     if (hist_smem) {
         const int64_t cap = nrows / (16 * bins) > 0 ? nrows / (16 * bins) : 1;
         if (ctas > cap) ctas = cap;
@@ -510,6 +593,9 @@ int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* of
     int64_t rows_per_cta = (nrows + ctas - 1) / ctas;
     rows_per_cta = ((rows_per_cta + FV_BLOCK - 1) / FV_BLOCK) * FV_BLOCK;
     if (rows_per_cta < FV_BLOCK) rows_per_cta = FV_BLOCK;
+    // (Interleaving small row chunks across CTAs so that concurrent CTAs share the high dimensions' map blocks
+    // was measured on the reference-size 8-D map: no change, 1.08e9 evals/s either way -- the five fastest-varying
+    // dimensions still cover their whole tables.)
     ctas = nrows > 0 ? (nrows + rows_per_cta - 1) / rows_per_cta : 1;
     double* partials = w.take<double>((size_t)ctas * 2);
     if (!ticket || !partials) { set_error("tq_fused_vegas: workspace too small"); return TQ_ERR_WORKSPACE; }
@@ -521,12 +607,12 @@ int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* of
                 if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, true><<<(unsigned)ctas, FV_BLOCK, smem, st>>>(
                     *fn_host, (const long long*)offsets, n_cubes, n_strat, row_begin, row_end, rows_from_offsets, rows_per_cta,
-                    (const typename Pair2<T>::type*)edges_packed, n_intervals, (T*)weights, (unsigned long long*)counts,
+                    edges_packed, records, n_intervals, (T*)weights, (unsigned long long*)counts,
                     (T*)JF, (T*)JF2, seed, call_idx, hist_smem, partials, ticket, out_f64);
             } else {
                 if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, false><<<(unsigned)ctas, FV_BLOCK, smem, st>>>(
-                    *fn_host, nullptr, 0, 1, row_begin, row_end, false, rows_per_cta, (const typename Pair2<T>::type*)edges_packed,
+                    *fn_host, nullptr, 0, 1, row_begin, row_end, false, rows_per_cta, edges_packed, records,
                     n_intervals, (T*)weights, (unsigned long long*)counts, nullptr, nullptr, seed, call_idx, hist_smem,
                     partials, ticket, out_f64);
             }

@@ -63,18 +63,27 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
     int64_t fevals = 0;
     int passes = 0;
     const int max_passes = TQ_VEGAS_MAX_PASSES;
+    // Large maps keep {x, dx, weight, count} records (tq_fused_vegas, TQ_EDGES_RECORDS): the histogram is moved to
+    // the weights/counts arrays before an update and the records are rewritten from the new edges after it.
+    const bool recs = s->edges_layout == TQ_EDGES_RECORDS;
+    const int layout = recs ? TQ_EDGES_RECORDS : TQ_EDGES_PAIRS;
+    void* hist_w = recs ? nullptr : s->weights;
+    int64_t* hist_c = recs ? nullptr : s->counts;
     auto update_map = [&]() -> int {
         if (passes >= max_passes) { set_error("tq_vegas_run_fused: more than %d passes", max_passes); return TQ_ERR_UNSUPPORTED; }
-        int rc = map_update_launch(s->x_edges, s->dx_edges, s->weights, s->counts, s->edges_packed, dim, ni, alpha, dtype,
-                                   s->status + 4 * passes, false, s->map_ws, s->map_ws_bytes, stream);
+        int rc = TQ_OK;
+        if (recs && (rc = tq_vegas_map_unpack_records(s->edges_packed, s->weights, s->counts, dim, ni, dtype, stream))) return rc;
+        rc = map_update_launch(s->x_edges, s->dx_edges, s->weights, s->counts, recs ? nullptr : s->edges_packed, dim, ni, alpha,
+                               dtype, s->status + 4 * passes, false, s->map_ws, s->map_ws_bytes, stream);
         ++passes;
+        if (!rc && recs) rc = tq_vegas_map_pack_records(s->x_edges, s->dx_edges, s->edges_packed, dim, ni, dtype, stream);
         return rc;
     };
     cudaMemsetAsync(s->status, 0, 4 * (size_t)max_passes * sizeof(int32_t), st);
     if (warmup) {  // vegas.py:211-266: 5 unstratified passes of starting//5 samples, results discarded
         const int64_t ns = starting / 5;
         for (int w = 0; w < 5; ++w) {
-            int rc = tq_fused_vegas(fn, dtype, nullptr, 0, 1, 0, ns, s->edges_packed, ni, s->weights, s->counts, nullptr, nullptr,
+            int rc = tq_fused_vegas(fn, dtype, nullptr, 0, 1, 0, ns, s->edges_packed, layout, ni, hist_w, hist_c, nullptr, nullptr,
                                     seed, call++, s->records, s->ws, s->ws_bytes, stream);
             if (rc) return rc;
             fevals += ns;
@@ -83,7 +92,7 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
     }
     // Small problems: the stratification update, every dimension's map update and the NEXT pass's get_NH share one
     // launch (vegas_small.cu); get_NH runs on its own only after the schedule may have changed the sample budget.
-    const bool small = small_strat_ok(n_cubes) && (!grid_improve || small_map_ok(dim, ni));
+    const bool small = !recs && small_strat_ok(n_cubes) && (!grid_improve || small_map_ok(dim, ni));
     MapScratch scratch = {};
     if (small && grid_improve && !map_scratch_carve(s->map_ws, s->map_ws_bytes, dim, ni, dtype, true, scratch)) {
         set_error("tq_vegas_run_fused: map workspace too small");
@@ -104,8 +113,10 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
         }
         // sum nh <= starting * sum(dh) + 2 * n_cubes; the estimate only sizes the grid
         const int64_t m_est = starting + 2 * n_cubes + 1024;
-        rc = tq_fused_vegas(fn, dtype, s->offsets, n_cubes, n_strat, 0, -m_est, s->edges_packed, ni, grid_improve ? s->weights : nullptr,
-                            s->counts, s->JF, s->JF2, seed, call++, nullptr, s->ws, s->ws_bytes, stream);
+        // without grid improvement nothing is accumulated: the pass only needs the {x, dx} gather
+        rc = tq_fused_vegas(fn, dtype, s->offsets, n_cubes, n_strat, 0, -m_est, s->edges_packed, layout, ni,
+                            grid_improve ? hist_w : nullptr, grid_improve ? hist_c : nullptr, s->JF, s->JF2, seed, call++, nullptr,
+                            s->ws, s->ws_bytes, stream);
         if (rc) return rc;
         if (it > TQ_VEGAS_MAX_PASSES) { set_error("tq_vegas_run_fused: too many iterations"); return TQ_ERR_UNSUPPORTED; }
         double* record = s->records + 4 * (it - 1);

@@ -201,13 +201,24 @@ class VEGAS(BaseIntegrator):
         for w in words:
             self.map.check_status(w)
 
+    def _fused_pass(self, begin, end, hist, **strat_args):
+        """One fused pass over rows [begin, end).  Large maps go through the record layout: the histogram lands in
+        the records and is moved to `weights` / `counts` (what the all-reduce and `update_map` read) right after."""
+        vmap = self.map
+        if hist and vmap.wants_records():
+            ops.fused_vegas(self._fn_struct, None, None, None, begin, end, self.rng.seed, self.rng.next_call(),
+                            records=vmap.records(), dtype=self.dtype, n_intervals=vmap.N_intervals, **strat_args)
+            vmap.unpack_records()
+        else:
+            ops.fused_vegas(self._fn_struct, vmap.packed_edges(), vmap.weights if hist else None, vmap.counts, begin, end,
+                            self.rng.seed, self.rng.next_call(), **strat_args)
+
     def _warmup_grid(self, warmup_N_it=5, N_samples=1000):
         """Adapt the map with unstratified passes whose results are discarded (vegas.py:211-266)."""
         for _ in range(warmup_N_it):
             begin, end = self._rank_rows(N_samples)
             if self._fused:
-                ops.fused_vegas(self._fn_struct, self.map.packed_edges(), self.map.weights, self.map.counts,
-                                begin, end, self.rng.seed, self.rng.next_call())
+                self._fused_pass(begin, end, hist=True)
                 self._nr_of_fevals += N_samples
             else:
                 if type(self.rng) is RNG:
@@ -246,9 +257,8 @@ class VEGAS(BaseIntegrator):
                 JFs = self._stats_jf.zero_()
             else:
                 JFs = torch.zeros((2, strat.N_cubes), dtype=self.dtype, device=self.device)
-            ops.fused_vegas(self._fn_struct, vmap.packed_edges(),
-                            vmap.weights if self.use_grid_improve else None, vmap.counts, begin, end, self.rng.seed,
-                            self.rng.next_call(), offsets=offsets, n_strat=strat.N_strat, JF=JFs[0], JF2=JFs[1])
+            self._fused_pass(begin, end, hist=self.use_grid_improve, offsets=offsets, n_strat=strat.N_strat, JF=JFs[0],
+                             JF2=JFs[1])
             self._nr_of_fevals += M
             self._reduce_stats(with_cubes=True)
             strat.JF, strat.JF2 = JFs[0], JFs[1]

@@ -33,6 +33,7 @@ class VEGASMap:
         self.x_edges = edges.reshape(1, -1).repeat(dim, 1).contiguous()
         self._status_word = None
         self._edges2, self._edges2_stale = None, True
+        self._records, self._records_stale = None, True
         self._scratch = None
         self._reset_weight()
 
@@ -101,6 +102,7 @@ class VEGASMap:
         ops.map_update(self.x_edges, self.dx_edges, self.weights, self.counts, self.alpha, st,
                        edges_packed=self._edges2 if keep_packed else None, scratch=self._scratch)
         self._edges2_stale = not keep_packed
+        self._records_stale = True
         if check:
             self.check_status(st)
 
@@ -114,6 +116,27 @@ class VEGASMap:
 
     def invalidate_packed(self):
         self._edges2_stale = True
+        self._records_stale = True
+
+    # Large maps (tables beyond L2): one {x_edge, dx_edge, weight, count} record per bin, so that the gather and
+    # both histogram updates of a sample fall into one DRAM sector (include/tqb200.h, TQ_EDGES_RECORDS).
+    records_min_bytes = 48 << 20  # use records when they would occupy at least this much (None: never)
+
+    def wants_records(self):
+        if self.records_min_bytes is None:
+            return False
+        return ops.map_records_bytes(self.dim, self.N_intervals, self.dtype) >= self.records_min_bytes
+
+    def records(self):
+        """The record table of the current edges with zeroed histogram fields (opaque uint8 tensor), cached."""
+        if self._records is None or self._records_stale:
+            self._records = ops.pack_records(self.x_edges, self.dx_edges, self._records)
+            self._records_stale = False
+        return self._records
+
+    def unpack_records(self):
+        """Move the histogram a fused pass left in the records into `weights` / `counts`."""
+        ops.unpack_records(self._records, self.weights, self.counts)
 
     def check_status(self, status=None):
         """Raise / warn like vegas_map.py:188-196,240-257 from a status word (device read-back)."""

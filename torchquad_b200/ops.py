@@ -461,18 +461,48 @@ def pack_edges(x_edges, dx_edges, out=None):
     return out
 
 
+def map_records_bytes(dim, ni, dtype):
+    return _lib.load().tq_vegas_map_records_bytes(dim, ni, dtype_code(dtype))
+
+
+def pack_records(x_edges, dx_edges, out=None):
+    """{x_edge, dx_edge, 0, 0} records of a large map (see tq_vegas_map_pack_records): opaque uint8 [dim*Ni*rec]."""
+    require_cuda(x_edges, dx_edges)
+    dim, ni = dx_edges.shape
+    if out is None:
+        out = torch.empty(map_records_bytes(dim, ni, dx_edges.dtype), dtype=torch.uint8, device=dx_edges.device)
+    with on_device(dx_edges.device):
+        call("tq_vegas_map_pack_records", ptr(x_edges), ptr(dx_edges), ptr(out), dim, ni, dtype_code(dx_edges.dtype),
+             stream_ptr(dx_edges.device))
+    return out
+
+
+def unpack_records(records, weights, counts):
+    """weights += records.weight, counts += records.count, record fields back to zero."""
+    require_cuda(records, weights, counts)
+    dim, ni = weights.shape
+    with on_device(weights.device):
+        call("tq_vegas_map_unpack_records", ptr(records), ptr(weights), ptr(counts), dim, ni, dtype_code(weights.dtype),
+             stream_ptr(weights.device))
+
+
 def fused_vegas(fn_struct, edges_packed, weights, counts, row_begin, row_end, seed, call_idx,
-                offsets=None, n_strat=1, JF=None, JF2=None):
-    """One fused VEGAS pass (warm-up when offsets is None).  Returns fp64 [2] = {sum jf, sum jf^2} (warm-up only)."""
-    require_cuda(edges_packed, weights, counts, offsets, JF, JF2)
+                offsets=None, n_strat=1, JF=None, JF2=None, records=None, dtype=None, n_intervals=None):
+    """One fused VEGAS pass (warm-up when offsets is None).  Returns fp64 [2] = {sum jf, sum jf^2} (warm-up only).
+    With `records` (large maps) the histogram goes into the records and weights/counts are not touched."""
+    require_cuda(edges_packed, weights, counts, offsets, JF, JF2, records)
+    table = records if records is not None else edges_packed
+    dt = dtype if records is not None else edges_packed.dtype
+    ni = n_intervals if records is not None else edges_packed.shape[1]
     # only the warm-up pass reduces {sum jf, sum jf^2}; the stratified pass writes JF/JF2
-    out = torch.empty(2, dtype=torch.float64, device=edges_packed.device) if offsets is None else None
+    out = torch.empty(2, dtype=torch.float64, device=table.device) if offsets is None else None
     n_cubes = 0 if offsets is None else offsets.shape[0] - 1
-    with on_device(edges_packed.device):
-        wsp, wsn = _ws(edges_packed.device)
-        call("tq_fused_vegas", fn_struct, dtype_code(edges_packed.dtype), ptr(offsets), n_cubes, n_strat, row_begin, row_end,
-             ptr(edges_packed), edges_packed.shape[1], ptr(weights), ptr(counts), ptr(JF), ptr(JF2),
-             seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, ptr(out), wsp, wsn, stream_ptr(edges_packed.device))
+    with on_device(table.device):
+        wsp, wsn = _ws(table.device)
+        call("tq_fused_vegas", fn_struct, dtype_code(dt), ptr(offsets), n_cubes, n_strat, row_begin, row_end,
+             ptr(table), _lib.TQ_EDGES_RECORDS if records is not None else _lib.TQ_EDGES_PAIRS, ni,
+             None if records is not None else ptr(weights), None if records is not None else ptr(counts), ptr(JF), ptr(JF2),
+             seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, ptr(out), wsp, wsn, stream_ptr(table.device))
     return out
 
 
@@ -495,17 +525,22 @@ def vegas_run_fused(fn_struct, vmap, strat, N, max_iterations, eps_rel, eps_abs,
     status = torch.empty(_lib.TQ_VEGAS_MAX_PASSES * 4, dtype=torch.int32, device=dev)
     scratch = _map_scratch(vmap.dim, vmap.N_intervals, dt, dev)
     ws = workspace(dev)
-    packed = vmap.packed_edges()
+    use_records = bool(use_grid_improve) and vmap.wants_records()
+    packed = vmap.records() if use_records else vmap.packed_edges()
     state = _lib.tq_vegas_state(
         ptr(vmap.x_edges), ptr(vmap.dx_edges), ptr(packed), ptr(vmap.weights), ptr(vmap.counts), ptr(strat.dh), ptr(nh),
         ptr(offsets), ptr(JFs[0]), ptr(JFs[1]), ptr(records), ptr(status), ptr(scratch), scratch.numel(), ws.data_ptr(),
-        ws.numel())
+        ws.numel(), _lib.TQ_EDGES_RECORDS if use_records else _lib.TQ_EDGES_PAIRS)
     result = _lib.tq_vegas_result()
     with on_device(dev):
         call("tq_vegas_run_fused", fn_struct, dtype_code(dt), N, max_iterations, float(eps_rel), float(eps_abs),
              int(bool(use_grid_improve)), int(bool(use_warmup)), vmap.N_intervals, strat.N_strat, n_cubes,
              float(strat.V_cubes), float(vmap.alpha), float(strat.beta), seed & 0xFFFFFFFFFFFFFFFF, first_call & 0xFFFFFFFF,
              state, result, stream_ptr(dev))
+    if use_records:
+        vmap._edges2_stale = True   # the pair table was not maintained; the records were
+    else:
+        vmap._records_stale = True
     strat._nh, strat._offsets = nh, offsets
     strat._counts_stale = True  # strat_counts = float(nh) is materialised on first access
     return result
