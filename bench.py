@@ -138,8 +138,12 @@ def l2_flush(buf):
 
 def timed_steps(step, steps, warmup, flush_buf, barrier):
     """Per-step CUDA-event times (seconds) on the current stream; L2 flushed between iterations."""
-    for _ in range(warmup):
+    # W warm-up steps, and at least 0.3 s of them: the GPU drops its clocks while the host sets things up (e.g. waits
+    # for nvidia-smi), and a millisecond-scale step would otherwise be timed on the ramp
+    t0, done = time.time(), 0
+    while done < warmup or time.time() - t0 < 0.3:
         step()
+        done += 1
     torch.cuda.synchronize()
     times = []
     from torchquad_b200 import _lib as _tq_lib
@@ -150,12 +154,12 @@ def timed_steps(step, steps, warmup, flush_buf, barrier):
         barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = _tq_lib.launch_count
+        n0 = _tq_lib.kernel_launches()
         a.record()
         step()
         b.record()
         torch.cuda.synchronize()
-        timed_steps.launches += _tq_lib.launch_count - n0
+        timed_steps.launches += _tq_lib.kernel_launches() - n0
         times.append(a.elapsed_time(b) * 1e-3)
     return times
 
@@ -435,7 +439,7 @@ def run_ours(args, wl):
     if rank == 0:
         sampler.start()
     times = timed_steps(fused, args.steps, args.warmup, flush, barrier)
-    launches = timed_steps.launches  # C-ABI calls of libtqb200 inside the timed region (each launches >= 1 kernel)
+    launches = timed_steps.launches  # kernels libtqb200 launched inside the timed region (tq_kernel_launches)
     clocks = sampler.stop() if rank == 0 else None
     t_fused = max_over_ranks(sum(times), device, world)
     n_evals = evals()

@@ -85,6 +85,8 @@ typedef struct tq_integrand {
 /* ---- library ---------------------------------------------------------------------------------- */
 TQ_API const char* tq_last_error(void);
 TQ_API int tq_version(void);
+/* Kernels launched by this library in this process so far (bench.py reports the difference as gpu_launches). */
+TQ_API uint64_t tq_kernel_launches(void);
 TQ_API size_t tq_workspace_bytes(void);
 /* sm count / compute capability of the current device */
 TQ_API int tq_device_info(int* sm_count, int* cc_major, int* cc_minor);

@@ -57,6 +57,7 @@ class tq_vegas_result(ctypes.Structure):
 PROTOTYPES = {
     "tq_last_error": (ctypes.c_char_p, []),
     "tq_version": (ctypes.c_int, []),
+    "tq_kernel_launches": (ctypes.c_uint64, []),
     "tq_workspace_bytes": (c_sz, []),
     "tq_device_info": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3),
     "tq_philox_uniform": (ctypes.c_int, [c_p, c_i64, c_i64, c_i32, c_i32, c_u64, c_u32, c_p]),
@@ -204,6 +205,11 @@ def call(name, *args):
         raise RuntimeError(f"{name} failed ({rc}): {_cdll.tq_last_error().decode()}")
     launch_count += 1
     return rc
+
+
+def kernel_launches():
+    """Kernels launched by libtqb200 in this process so far (counted at every launch site of the library)."""
+    return int(load().tq_kernel_launches())
 
 
 def l2_fetch_granularity(device, nbytes=0):

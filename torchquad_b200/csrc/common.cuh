@@ -25,6 +25,11 @@ int check_launch(const char* what);
 
 int num_sms();
 
+// Every kernel launch of the library writes its grid as TQ_GRID(...): the wrapper counts the launch
+// (tq_kernel_launches, reported by bench.py as gpu_launches) and evaluates to the grid.
+unsigned long long count_launch();
+#define TQ_GRID(...) (tq::count_launch(), (__VA_ARGS__))
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Persistent-style grid: enough CTAs to fill every SM `per_sm` times, never more than needed.

@@ -474,7 +474,7 @@ int tq_fused_mc(const tq_integrand* fn_host, int32_t dtype, int64_t row_begin, i
     cudaStream_t st = as_stream(stream);
     TQ_DISPATCH_DTYPE(dtype, {
         TQ_DISPATCH_FAMILY(fn_host->family, {
-            fused_mc_kernel<FAM, T><<<grid, 256, 0, st>>>(*fn_host, row_begin, nrows, seed, call_idx, partials, ticket, out_f64);
+            fused_mc_kernel<FAM, T><<<TQ_GRID(grid), 256, 0, st>>>(*fn_host, row_begin, nrows, seed, call_idx, partials, ticket, out_f64);
         });
     });
     return check_launch("fused_mc_kernel");
@@ -497,7 +497,7 @@ int tq_fused_nc(const tq_integrand* fn_host, const void* nodes, const void* w, i
         const bool use_smem = table <= 96 * 1024;
         TQ_DISPATCH_FAMILY(fn_host->family, {
             cudaFuncSetAttribute(fused_nc_kernel<FAM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            fused_nc_kernel<FAM, T><<<grid, 256, use_smem ? table : 0, st>>>(*fn_host, (const T*)nodes, (const T*)w, (uint32_t)n,
+            fused_nc_kernel<FAM, T><<<TQ_GRID(grid), 256, use_smem ? table : 0, st>>>(*fn_host, (const T*)nodes, (const T*)w, (uint32_t)n,
                                                                            p_begin, p_end, partials, ticket, out_f64, use_smem);
         });
     });
@@ -509,7 +509,7 @@ int tq_vegas_map_pack_edges(const void* x_edges, const void* dx_edges, void* edg
     TQ_REQUIRE(dim >= 1 && n_intervals >= 1, "tq_vegas_map_pack_edges: bad shape");
     const int grid = grid_for((int64_t)dim * n_intervals, 256, 8);
     TQ_DISPATCH_DTYPE(dtype, {
-        pack_edges_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x_edges, (const T*)dx_edges,
+        pack_edges_kernel<T><<<TQ_GRID(grid), 256, 0, as_stream(stream)>>>((const T*)x_edges, (const T*)dx_edges,
                                                                  (typename Pair2<T>::type*)edges_packed, dim, n_intervals);
     });
     return check_launch("pack_edges_kernel");
@@ -524,7 +524,7 @@ int tq_vegas_map_pack_records(const void* x_edges, const void* dx_edges, void* r
     TQ_REQUIRE(dim >= 1 && n_intervals >= 1, "tq_vegas_map_pack_records: bad shape");
     const int grid = grid_for((int64_t)dim * n_intervals, 256, 8);
     TQ_DISPATCH_DTYPE(dtype, {
-        pack_records_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x_edges, (const T*)dx_edges,
+        pack_records_kernel<T><<<TQ_GRID(grid), 256, 0, as_stream(stream)>>>((const T*)x_edges, (const T*)dx_edges,
                                                                    (MapRecord<T>*)records, dim, n_intervals);
     });
     return check_launch("pack_records_kernel");
@@ -536,7 +536,7 @@ int tq_vegas_map_unpack_records(void* records, void* weights, int64_t* counts, i
     const int64_t total = (int64_t)dim * n_intervals;
     const int grid = grid_for(total, 256, 8);
     TQ_DISPATCH_DTYPE(dtype, {
-        unpack_records_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((MapRecord<T>*)records, (T*)weights, (long long*)counts, total);
+        unpack_records_kernel<T><<<TQ_GRID(grid), 256, 0, as_stream(stream)>>>((MapRecord<T>*)records, (T*)weights, (long long*)counts, total);
     });
     return check_launch("unpack_records_kernel");
 }
@@ -605,13 +605,13 @@ int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* of
         TQ_DISPATCH_FAMILY(fn_host->family, {
             if (strat) {
                 if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
-                fused_vegas_kernel<FAM, T, true><<<(unsigned)ctas, FV_BLOCK, smem, st>>>(
+                fused_vegas_kernel<FAM, T, true><<<TQ_GRID((unsigned)ctas), FV_BLOCK, smem, st>>>(
                     *fn_host, (const long long*)offsets, n_cubes, n_strat, row_begin, row_end, rows_from_offsets, rows_per_cta,
                     edges_packed, records, n_intervals, (T*)weights, (unsigned long long*)counts,
                     (T*)JF, (T*)JF2, seed, call_idx, hist_smem, partials, ticket, out_f64);
             } else {
                 if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
-                fused_vegas_kernel<FAM, T, false><<<(unsigned)ctas, FV_BLOCK, smem, st>>>(
+                fused_vegas_kernel<FAM, T, false><<<TQ_GRID((unsigned)ctas), FV_BLOCK, smem, st>>>(
                     *fn_host, nullptr, 0, 1, row_begin, row_end, false, rows_per_cta, edges_packed, records,
                     n_intervals, (T*)weights, (unsigned long long*)counts, nullptr, nullptr, seed, call_idx, hist_smem,
                     partials, ticket, out_f64);

@@ -299,7 +299,7 @@ int tq_nc_grid_points(const void* nodes, int32_t n, int32_t dim, int64_t p_begin
         const int64_t cap = (int64_t)num_sms() * 8;
         const int grid = (int)(passes < cap ? passes : cap);
         const bool vec_ok = (dim % V) == 0 && (reinterpret_cast<uintptr_t>(points) & 15) == 0;
-        grid_points_kernel<T, V><<<grid, 256, 0, as_stream(stream)>>>((const T*)nodes, (uint32_t)n, dim, nvb, p_begin, p_end,
+        grid_points_kernel<T, V><<<TQ_GRID(grid), 256, 0, as_stream(stream)>>>((const T*)nodes, (uint32_t)n, dim, nvb, p_begin, p_end,
                                                                      (T*)points, vec_ok);
     });
     return check_launch("grid_points_kernel");
@@ -317,7 +317,7 @@ int tq_nc_grid_points_backward(const void* grad_points, int32_t n, int32_t dim, 
     const size_t smem = use_smem ? (size_t)dim * n * sizeof(double) : 0;
     TQ_DISPATCH_DTYPE(dtype, {
         cudaFuncSetAttribute(grid_points_backward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NC_TABLE_SMEM);
-        grid_points_backward_kernel<T><<<grid, 256, smem, st>>>((const T*)grad_points, (uint32_t)n, dim, p_begin, p_end, grad_nodes_f64, use_smem);
+        grid_points_backward_kernel<T><<<TQ_GRID(grid), 256, smem, st>>>((const T*)grad_points, (uint32_t)n, dim, p_begin, p_end, grad_nodes_f64, use_smem);
     });
     return check_launch("grid_points_backward_kernel");
 }
@@ -332,7 +332,7 @@ int tq_nc_point_weights(const void* w, int32_t n, int32_t dim, int64_t p_begin, 
         const bool use_smem = (size_t)dim * n * sizeof(T) <= NC_TABLE_SMEM;
         const size_t smem = use_smem ? (size_t)dim * n * sizeof(T) : 0;
         cudaFuncSetAttribute(point_weights_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NC_TABLE_SMEM);
-        point_weights_kernel<T><<<grid, 256, smem, as_stream(stream)>>>((const T*)w, (uint32_t)n, dim, p_begin, p_end, (T*)out, use_smem);
+        point_weights_kernel<T><<<TQ_GRID(grid), 256, smem, as_stream(stream)>>>((const T*)w, (uint32_t)n, dim, p_begin, p_end, (T*)out, use_smem);
     });
     return check_launch("point_weights_kernel");
 }
@@ -359,10 +359,10 @@ int tq_nc_contract(const void* f, const void* w, int32_t n, int32_t dim, int64_t
             fd.set((uint32_t)n);
             if (aligned) {
                 cudaFuncSetAttribute(contract1_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NC_TABLE_SMEM);
-                contract1_kernel<T, V><<<grid, 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, fd, partials, ticket, out_f64, use_smem);
+                contract1_kernel<T, V><<<TQ_GRID(grid), 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, fd, partials, ticket, out_f64, use_smem);
             } else {
                 cudaFuncSetAttribute(contract1_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NC_TABLE_SMEM);
-                contract1_kernel<T, 1><<<grid, 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, fd, partials, ticket, out_f64, use_smem);
+                contract1_kernel<T, 1><<<TQ_GRID(grid), 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, fd, partials, ticket, out_f64, use_smem);
             }
         });
         return check_launch("contract1_kernel");
@@ -377,7 +377,7 @@ int tq_nc_contract(const void* f, const void* w, int32_t n, int32_t dim, int64_t
         const bool use_smem = (size_t)dim * n * sizeof(T) <= NC_TABLE_SMEM;
         const size_t smem = (size_t)cols * sizeof(double) + (use_smem ? (size_t)dim * n * sizeof(T) : 0);
         cudaFuncSetAttribute(contractk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NC_TABLE_SMEM + 2048 * sizeof(double)));
-        contractk_kernel<T><<<grid, 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, cols, S, partials, ticket, out_f64, use_smem);
+        contractk_kernel<T><<<TQ_GRID(grid), 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, cols, S, partials, ticket, out_f64, use_smem);
     });
     return check_launch("contractk_kernel");
 }

@@ -97,9 +97,9 @@ static int launch_uniform(T* out, const T* domain, int64_t row_begin, int64_t ro
     const int64_t cap = (int64_t)num_sms() * 8;
     const int grid = (int)(passes < cap ? passes : cap);
     if (domain)
-        uniform_kernel<T, true><<<grid, 256, 0, st>>>(out, domain, row_begin, nrows, dim, nblk, seed, call, call_offset);
+        uniform_kernel<T, true><<<TQ_GRID(grid), 256, 0, st>>>(out, domain, row_begin, nrows, dim, nblk, seed, call, call_offset);
     else
-        uniform_kernel<T, false><<<grid, 256, 0, st>>>(out, nullptr, row_begin, nrows, dim, nblk, seed, call, call_offset);
+        uniform_kernel<T, false><<<TQ_GRID(grid), 256, 0, st>>>(out, nullptr, row_begin, nrows, dim, nblk, seed, call, call_offset);
     return check_launch("uniform_kernel");
 }
 
@@ -285,7 +285,7 @@ int tq_mc_sample_backward(const void* grad_out, int64_t row_begin, int64_t row_e
     double* partials = w.take<double>((size_t)grid * dim * 2);
     if (!ticket || !partials) { set_error("tq_mc_sample_backward: workspace too small"); return TQ_ERR_WORKSPACE; }
     TQ_DISPATCH_DTYPE(dtype, {
-        mc_sample_backward_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)grad_out, row_begin, nrows, dim, seed,
+        mc_sample_backward_kernel<T><<<TQ_GRID(grid), 256, 0, as_stream(stream)>>>((const T*)grad_out, row_begin, nrows, dim, seed,
                                                                          call_idx, partials, ticket, grad_domain_f64);
     });
     return check_launch("mc_sample_backward_kernel");
@@ -303,8 +303,8 @@ int tq_sum_columns(const void* f, int64_t rows, int64_t cols, int32_t dtype, dou
         double* out = w.take<double>(2);
         if (!ticket || !partials || !out) { set_error("tq_sum_columns: workspace too small"); return TQ_ERR_WORKSPACE; }
         TQ_DISPATCH_DTYPE(dtype, {
-            if (sumsq_f64) sum1_kernel<T, true><<<grid, 256, 0, st>>>((const T*)f, rows, partials, ticket, out);
-            else sum1_kernel<T, false><<<grid, 256, 0, st>>>((const T*)f, rows, partials, ticket, out);
+            if (sumsq_f64) sum1_kernel<T, true><<<TQ_GRID(grid), 256, 0, st>>>((const T*)f, rows, partials, ticket, out);
+            else sum1_kernel<T, false><<<TQ_GRID(grid), 256, 0, st>>>((const T*)f, rows, partials, ticket, out);
         });
         int rc = check_launch("sum1_kernel");
         if (rc) return rc;
@@ -322,8 +322,8 @@ int tq_sum_columns(const void* f, int64_t rows, int64_t cols, int32_t dtype, dou
     if (!ticket || !partials) { set_error("tq_sum_columns: workspace too small"); return TQ_ERR_WORKSPACE; }
     const size_t smem = (size_t)cols * 2 * sizeof(double);
     TQ_DISPATCH_DTYPE(dtype, {
-        if (sumsq_f64) sumk_kernel<T, true><<<grid, 256, smem, st>>>((const T*)f, rows, cols, S, partials, ticket, sum_f64, sumsq_f64);
-        else sumk_kernel<T, false><<<grid, 256, smem, st>>>((const T*)f, rows, cols, S, partials, ticket, sum_f64, nullptr);
+        if (sumsq_f64) sumk_kernel<T, true><<<TQ_GRID(grid), 256, smem, st>>>((const T*)f, rows, cols, S, partials, ticket, sum_f64, sumsq_f64);
+        else sumk_kernel<T, false><<<TQ_GRID(grid), 256, smem, st>>>((const T*)f, rows, cols, S, partials, ticket, sum_f64, nullptr);
     });
     return check_launch("sumk_kernel");
 }

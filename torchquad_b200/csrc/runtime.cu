@@ -14,6 +14,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;  // host-side statistic; the library is driven from one thread per process
+
+unsigned long long count_launch() { return ++g_launches; }
+
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -67,6 +71,8 @@ const char* tq_last_error(void) { return tq::g_err; }
 
 int tq_version(void) { return 100; }
 
+uint64_t tq_kernel_launches(void) { return tq::g_launches; }
+
 size_t tq_workspace_bytes(void) { return (size_t)8 << 20; }
 
 int tq_device_info(int* sm_count, int* cc_major, int* cc_minor) {
@@ -99,13 +105,13 @@ int tq_peak_microbench(int32_t kind, int64_t iters, double* sink, double* ops_ou
     const int grid = tq::num_sms() * 8;
     const double threads = (double)grid * block;
     if (kind == 0) {
-        tq::fma_chain_kernel<float><<<grid, block, 0, tq::as_stream(stream)>>>(iters, sink);
+        tq::fma_chain_kernel<float><<<TQ_GRID(grid), block, 0, tq::as_stream(stream)>>>(iters, sink);
         *ops_out_host = threads * (double)iters * 8.0;  // FMA instructions (2 flop each)
     } else if (kind == 1) {
-        tq::fma_chain_kernel<double><<<grid, block, 0, tq::as_stream(stream)>>>(iters, sink);
+        tq::fma_chain_kernel<double><<<TQ_GRID(grid), block, 0, tq::as_stream(stream)>>>(iters, sink);
         *ops_out_host = threads * (double)iters * 8.0;
     } else if (kind == 2) {
-        tq::philox_chain_kernel<<<grid, block, 0, tq::as_stream(stream)>>>(iters, sink);
+        tq::philox_chain_kernel<<<TQ_GRID(grid), block, 0, tq::as_stream(stream)>>>(iters, sink);
         *ops_out_host = threads * (double)iters;  // Philox4x32-10 blocks
     } else {
         tq::set_error("tq_peak_microbench: unknown kind %d", kind);

@@ -421,11 +421,11 @@ template <typename T>
 static int run_smooth(const T* weights, const long long* counts, T* smoothed_out, MapScratch& s, int dim,
                       long long ni, double alpha, int32_t* status, cudaStream_t st) {
     dim3 grid(s.ntiles, dim);
-    map_average_kernel<T><<<grid, 256, 0, st>>>(weights, counts, (T*)s.avg, s.tile_sums, ni, s.ntiles, status);
-    map_tile_scan_kernel<<<dim, 256, 0, st>>>(s.tile_sums, s.totals, s.ntiles);
-    map_smooth_kernel<T><<<grid, 256, 0, st>>>((const T*)s.avg, s.totals, smoothed_out, s.tile_sums, ni, s.ntiles, dim,
+    map_average_kernel<T><<<TQ_GRID(grid), 256, 0, st>>>(weights, counts, (T*)s.avg, s.tile_sums, ni, s.ntiles, status);
+    map_tile_scan_kernel<<<TQ_GRID(dim), 256, 0, st>>>(s.tile_sums, s.totals, s.ntiles);
+    map_smooth_kernel<T><<<TQ_GRID(grid), 256, 0, st>>>((const T*)s.avg, s.totals, smoothed_out, s.tile_sums, ni, s.ntiles, dim,
                                                (T)alpha, status);
-    map_tile_scan_kernel<<<dim, 256, 0, st>>>(s.tile_sums, s.totals2, s.ntiles);
+    map_tile_scan_kernel<<<TQ_GRID(dim), 256, 0, st>>>(s.tile_sums, s.totals2, s.ntiles);
     return check_launch("map smoothing");
 }
 
@@ -450,11 +450,11 @@ static int launch_map_forward(const void* y, const void* xe, const void* dxe, co
         const size_t smem = ((size_t)tile_rows * (dim | 1) + 2 * (size_t)dim) * sizeof(T);
         constexpr int VW = 16 / sizeof(T);
         if (aligned)
-            map_forward_kernel<T, VW, PACKED><<<grid, 256, smem, as_stream(stream)>>>(
+            map_forward_kernel<T, VW, PACKED><<<TQ_GRID(grid), 256, smem, as_stream(stream)>>>(
                 (const T*)y, (const T*)xe, (const T*)dxe, (const T*)domain, (T*)x, (T*)jac, ids, (T*)offset, rows, dim,
                 n_intervals, tile_rows, magic);
         else
-            map_forward_kernel<T, 1, PACKED><<<grid, 256, smem, as_stream(stream)>>>(
+            map_forward_kernel<T, 1, PACKED><<<TQ_GRID(grid), 256, smem, as_stream(stream)>>>(
                 (const T*)y, (const T*)xe, (const T*)dxe, (const T*)domain, (T*)x, (T*)jac, ids, (T*)offset, rows, dim,
                 n_intervals, tile_rows, magic);
     });
@@ -477,11 +477,11 @@ static int launch_accumulate_global(const void* y, const void* a, const void* ja
     TQ_DISPATCH_DTYPE(dtype, {
         constexpr int VW = 16 / sizeof(T);
         if (aligned)
-            map_accumulate_global_kernel<T, VW, FUSED><<<grid, 256, 0, st>>>((const T*)y, (const T*)a, (const T*)jac, (T)volume,
+            map_accumulate_global_kernel<T, VW, FUSED><<<TQ_GRID(grid), 256, 0, st>>>((const T*)y, (const T*)a, (const T*)jac, (T)volume,
                                                                             (T*)jf_out, (T*)weights, (unsigned long long*)counts,
                                                                             rows, dim, n_intervals, tile_rows, magic);
         else
-            map_accumulate_global_kernel<T, 1, FUSED><<<grid, 256, 0, st>>>((const T*)y, (const T*)a, (const T*)jac, (T)volume,
+            map_accumulate_global_kernel<T, 1, FUSED><<<TQ_GRID(grid), 256, 0, st>>>((const T*)y, (const T*)a, (const T*)jac, (T)volume,
                                                                            (T*)jf_out, (T*)weights, (unsigned long long*)counts,
                                                                            rows, dim, n_intervals, tile_rows, magic);
     });
@@ -509,12 +509,12 @@ int map_update_launch(void* x_edges, void* dx_edges, void* weights, int64_t* cou
         int rc = run_smooth<T>((const T*)weights, (const long long*)counts, (T*)s.smoothed, s, dim, ni, alpha, status, st);
         if (rc) return rc;
         dim3 grid(s.ntiles, dim);
-        map_prefix_kernel<T><<<grid, 256, 0, st>>>((const T*)s.smoothed, s.tile_sums, s.S, ni, s.ntiles, status);
+        map_prefix_kernel<T><<<TQ_GRID(grid), 256, 0, st>>>((const T*)s.smoothed, s.tile_sums, s.S, ni, s.ntiles, status);
         dim3 grid_e((unsigned)((ni + 255) / 256), dim);
-        map_edges_kernel<T><<<grid_e, 256, 0, st>>>((const T*)s.smoothed, s.S, s.totals2, (const T*)x_edges,
+        map_edges_kernel<T><<<TQ_GRID(grid_e), 256, 0, st>>>((const T*)s.smoothed, s.S, s.totals2, (const T*)x_edges,
                                                    (const T*)dx_edges, (T*)s.x_new, ni, status);
         dim3 grid_f((unsigned)((ni + 1 + 255) / 256), dim);
-        map_finalize_kernel<T><<<grid_f, 256, 0, st>>>((const T*)s.x_new, (T*)x_edges, (T*)dx_edges, (T*)weights,
+        map_finalize_kernel<T><<<TQ_GRID(grid_f), 256, 0, st>>>((const T*)s.x_new, (T*)x_edges, (T*)dx_edges, (T*)weights,
                                                       (long long*)counts, (P2*)edges_packed, ni, status);
     });
     return check_launch("map update");
@@ -555,7 +555,7 @@ int tq_vegas_map_accumulate(const void* y, const void* jf2, void* weights, int64
         const int64_t rows_per_cta = (rows + ctas - 1) / ctas;
         TQ_DISPATCH_DTYPE(dtype, {
             cudaFuncSetAttribute(map_accumulate_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            map_accumulate_smem_kernel<T><<<(int)ctas, 512, smem, st>>>((const T*)y, (const T*)jf2, (T*)weights,
+            map_accumulate_smem_kernel<T><<<TQ_GRID((int)ctas), 512, smem, st>>>((const T*)y, (const T*)jf2, (T*)weights,
                                                                        (unsigned long long*)counts, rows, dim,
                                                                        n_intervals, rows_per_cta);
         });

@@ -386,7 +386,7 @@ int small_nh_launch(const void* dh, int64_t n_cubes, double nevals_exp, int32_t 
                     void* clear, size_t clear_bytes, void* stream) {
     TQ_REQUIRE(small_strat_ok(n_cubes), "small_nh_launch: %lld cubes out of range", (long long)n_cubes);
     TQ_DISPATCH_DTYPE(dtype, {
-        nh_small_kernel<T><<<SM_CL, SM_THREADS, 0, as_stream(stream)>>>((const T*)dh, n_cubes, (T)nevals_exp, (long long*)nh,
+        nh_small_kernel<T><<<TQ_GRID(SM_CL), SM_THREADS, 0, as_stream(stream)>>>((const T*)dh, n_cubes, (T)nevals_exp, (long long*)nh,
                                                                        (long long*)offsets, (uint32_t*)clear,
                                                                        (int64_t)(clear ? clear_bytes / 4 : 0));
     });
@@ -432,9 +432,9 @@ int small_update_launch(const SmallStrat* st, const SmallMap* mp, int32_t dtype,
             ma.status = mp->status;
             ma.do_edges = mp->do_edges;
         }
-        if (st && mp) vegas_update_small_kernel<T, true, true><<<(1 + mp->dim) * SM_CL, SM_THREADS, 0, s>>>(sa, ma);
-        else if (st) vegas_update_small_kernel<T, true, false><<<SM_CL, SM_THREADS, 0, s>>>(sa, ma);
-        else vegas_update_small_kernel<T, false, true><<<mp->dim * SM_CL, SM_THREADS, 0, s>>>(sa, ma);
+        if (st && mp) vegas_update_small_kernel<T, true, true><<<TQ_GRID((1 + mp->dim) * SM_CL), SM_THREADS, 0, s>>>(sa, ma);
+        else if (st) vegas_update_small_kernel<T, true, false><<<TQ_GRID(SM_CL), SM_THREADS, 0, s>>>(sa, ma);
+        else vegas_update_small_kernel<T, false, true><<<TQ_GRID(mp->dim * SM_CL), SM_THREADS, 0, s>>>(sa, ma);
     });
     return check_launch("vegas_update_small_kernel");
 }

@@ -338,9 +338,9 @@ int strat_nh_launch(const void* dh, int64_t n_cubes, double nevals_exp, int32_t 
     if (small_strat_ok(n_cubes)) return small_nh_launch(dh, n_cubes, nevals_exp, dtype, nh, offsets, clear, clear_bytes, stream);
     if (clear && clear_bytes) cudaMemsetAsync(clear, 0, clear_bytes, st);
     TQ_DISPATCH_DTYPE(dtype, {
-        nh_tile_sum_kernel<T><<<(unsigned)ntiles, 256, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, tile_sums);
-        i64_tile_scan_kernel<<<1, 256, 0, st>>>(tile_sums, ntiles, (long long*)offsets + n_cubes);
-        nh_scan_kernel<T><<<(unsigned)ntiles, 256, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, tile_sums,
+        nh_tile_sum_kernel<T><<<TQ_GRID((unsigned)ntiles), 256, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, tile_sums);
+        i64_tile_scan_kernel<<<TQ_GRID(1), 256, 0, st>>>(tile_sums, ntiles, (long long*)offsets + n_cubes);
+        nh_scan_kernel<T><<<TQ_GRID((unsigned)ntiles), 256, 0, st>>>((const T*)dh, n_cubes, (T)nevals_exp, tile_sums,
                                                            (long long*)nh, (long long*)offsets);
     });
     return check_launch("tq_vegas_strat_nh");
@@ -366,9 +366,9 @@ int tq_vegas_strat_offsets(const int64_t* nh, int64_t n_cubes, int64_t* offsets,
     long long* tile_sums = w.take<long long>((size_t)ntiles);
     if (!tile_sums) { set_error("tq_vegas_strat_offsets: workspace too small for %lld cubes", (long long)n_cubes); return TQ_ERR_WORKSPACE; }
     cudaStream_t st = as_stream(stream);
-    i64_tile_sum_kernel<<<(unsigned)ntiles, 256, 0, st>>>((const long long*)nh, n_cubes, tile_sums);
-    i64_tile_scan_kernel<<<1, 256, 0, st>>>(tile_sums, ntiles, (long long*)offsets + n_cubes);
-    i64_scan_kernel<<<(unsigned)ntiles, 256, 0, st>>>((const long long*)nh, n_cubes, tile_sums, (long long*)offsets);
+    i64_tile_sum_kernel<<<TQ_GRID((unsigned)ntiles), 256, 0, st>>>((const long long*)nh, n_cubes, tile_sums);
+    i64_tile_scan_kernel<<<TQ_GRID(1), 256, 0, st>>>(tile_sums, ntiles, (long long*)offsets + n_cubes);
+    i64_scan_kernel<<<TQ_GRID((unsigned)ntiles), 256, 0, st>>>((const long long*)nh, n_cubes, tile_sums, (long long*)offsets);
     return check_launch("tq_vegas_strat_offsets");
 }
 
@@ -390,7 +390,7 @@ int tq_vegas_strat_sample(const int64_t* offsets, int64_t n_cubes, int32_t n_str
         TQ_REQUIRE(nblk <= 128, "tq_vegas_strat_sample: dim %d too large", dim);
         FastDiv fdn;
         fdn.set((uint32_t)n_strat);
-        strat_sample_kernel<T><<<(unsigned)ctas, 256, 0, as_stream(stream)>>>((const long long*)offsets, n_cubes, n_strat, dim, nblk,
+        strat_sample_kernel<T><<<TQ_GRID((unsigned)ctas), 256, 0, as_stream(stream)>>>((const long long*)offsets, n_cubes, n_strat, dim, nblk,
                                                                              (const T*)u_in, seed, call_idx, row_begin, row_end,
                                                                              rows_per_cta, fdn, (T*)y);
     });
@@ -404,7 +404,7 @@ int tq_vegas_strat_accumulate(const void* jf, int64_t row_base, const int64_t* o
     if (cube_end == cube_begin) return TQ_OK;
     const int grid = grid_for(cube_end - cube_begin, 256, 8);
     TQ_DISPATCH_DTYPE(dtype, {
-        strat_accumulate_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)jf, row_base, (const long long*)offsets,
+        strat_accumulate_kernel<T><<<TQ_GRID(grid), 256, 0, as_stream(stream)>>>((const T*)jf, row_base, (const long long*)offsets,
                                                                        cube_begin, cube_end, (T*)JF, (T*)JF2);
     });
     return check_launch("strat_accumulate_kernel");
@@ -417,7 +417,7 @@ int tq_vegas_strat_accumulate_backward(const void* grad_JF, const int64_t* offse
     if (row_end == row_begin) return TQ_OK;
     const int grid = grid_for(row_end - row_begin, ST_TILE, 8);
     TQ_DISPATCH_DTYPE(dtype, {
-        strat_accumulate_backward_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(
+        strat_accumulate_backward_kernel<T><<<TQ_GRID(grid), 256, 0, as_stream(stream)>>>(
             (const T*)grad_JF, (const long long*)offsets, n_cubes, row_begin, row_end, (T*)grad_jf);
     });
     return check_launch("strat_accumulate_backward_kernel");
@@ -438,10 +438,10 @@ int tq_vegas_strat_update(const void* JF, const void* JF2, const int64_t* nh, in
         return small_update_launch(&a, nullptr, dtype, stream);
     }
     TQ_DISPATCH_DTYPE(dtype, {
-        strat_update_kernel<T><<<grid, 256, 0, st>>>((const T*)JF, (const T*)JF2, (const long long*)nh, n_cubes,
+        strat_update_kernel<T><<<TQ_GRID(grid), 256, 0, st>>>((const T*)JF, (const T*)JF2, (const long long*)nh, n_cubes,
                                                     (T)v_cubes, (T)(v_cubes * v_cubes), (T)beta, (T*)dh, partials, ticket,
                                                     scalars_f64);
-        strat_normalise_kernel<T><<<grid, 256, 0, st>>>((T*)dh, n_cubes, scalars_f64);
+        strat_normalise_kernel<T><<<TQ_GRID(grid), 256, 0, st>>>((T*)dh, n_cubes, scalars_f64);
     });
     return check_launch("tq_vegas_strat_update");
 }

@@ -123,18 +123,17 @@ class VEGAS(BaseIntegrator):
         self._host_block = None
         self._status_used = 0
 
-        if (self._fused and self.native_loop and not tqdist.is_enabled()
-                and max_iterations + 5 <= _lib.TQ_VEGAS_MAX_PASSES):
-            return self._integrate_native_loop(N, use_warmup)
-        # one status word per map update, written by the kernels, read back in one go at the sync points
-        self._status_buf = torch.zeros((max_iterations + 16, 4), dtype=torch.int32, device=self.device)
-
-        # random-access regime: shrink the L2 fetch granularity while the big tables are in flight
+        # random-access regime: optionally change the L2 fetch granularity while the big tables are in flight
         restore_l2 = None
         if (self.l2_fetch_bytes and self.device.type == "cuda"
                 and dim * N_intervals * (2 * domain.element_size() + 8) > self._large_map_bytes):
             restore_l2 = _lib.l2_fetch_granularity(self.device, int(self.l2_fetch_bytes))
         try:
+            if (self._fused and self.native_loop and not tqdist.is_enabled()
+                    and max_iterations + 5 <= _lib.TQ_VEGAS_MAX_PASSES):
+                return self._integrate_native_loop(N, use_warmup)
+            # one status word per map update, written by the kernels, read back in one go at the sync points
+            self._status_buf = torch.zeros((max_iterations + 16, 4), dtype=torch.int32, device=self.device)
             if use_warmup:
                 self._warmup_grid(5, self._starting_N // 5)
             while True:
