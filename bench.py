@@ -328,6 +328,10 @@ NCU_TRAFFIC = {
 }
 
 
+# smsp__inst_executed.sum / evaluations from the same captures (10-D sum-of-sines, fp32: 1.772e10 / 1e9)
+NCU_WARP_INST_PER_EVAL = {"fused_mc_kernel": 17.72}
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -493,6 +497,19 @@ def run_ours(args, wl):
                             "achieved": ach / 1e9, "peak": micro["philox_blocks_per_s"] / 1e9, "unit": "G Philox blocks/s",
                             "frac": ach / micro["philox_blocks_per_s"], "traffic": NCU_TRAFFIC.get("fused_mc_kernel"),
                             "note": "peak = Philox-only microbenchmark on this GPU; the kernel also evaluates dim sin() per eval"}
+        # Second view of the same kernel: instruction issue.  Warp instructions per eval come from the ncu capture
+        # of this kernel (profiles/r1/prof_fused_mc.txt: smsp__inst_executed.sum / evals); the denominator is
+        # 4 schedulers x SMs x the SM clock sampled during the timed region.
+        if elt == 4 and wl["dim"] == 10 and clocks and clocks.get("sm_mhz"):
+            import ctypes as _ct
+
+            sm, maj, mnr = _ct.c_int(), _ct.c_int(), _ct.c_int()
+            _lib.call("tq_device_info", _ct.byref(sm), _ct.byref(maj), _ct.byref(mnr))
+            winst = NCU_WARP_INST_PER_EVAL["fused_mc_kernel"] * n_evals * args.steps / t_fused
+            peak_issue = 4.0 * sm.value * clocks["sm_mhz"] * 1e6
+            line["roofline"]["issue"] = {"warp_inst_per_eval": NCU_WARP_INST_PER_EVAL["fused_mc_kernel"],
+                                         "achieved_gwarp_inst_s": winst / 1e9, "peak_gwarp_inst_s": peak_issue / 1e9,
+                                         "frac": winst / peak_issue}
     if wl["kind"] == "vegas":
         line["config"]["map_intervals"] = info["integrator"].map.N_intervals
         line["config"]["n_cubes"] = info["integrator"].strat.N_cubes
