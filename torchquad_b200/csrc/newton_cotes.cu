@@ -159,18 +159,66 @@ point_weights_kernel(const T* __restrict__ w, uint32_t n, int dim, int64_t p_beg
         out[r] = point_weight<T>(sw, gi, (uint64_t)(p_begin + r));
 }
 
+// 128-bit register <-> element helpers (keep the prefetched vector in registers, not in a local array)
+template <typename T> __device__ __forceinline__ T vec_elem(const uint4& q, int j);
+template <> __device__ __forceinline__ float vec_elem<float>(const uint4& q, int j) {
+    return __uint_as_float(j == 0 ? q.x : j == 1 ? q.y : j == 2 ? q.z : q.w);
+}
+template <> __device__ __forceinline__ double vec_elem<double>(const uint4& q, int j) {
+    return j == 0 ? __hiloint2double((int)q.y, (int)q.x) : __hiloint2double((int)q.w, (int)q.z);
+}
+template <typename T> __device__ __forceinline__ uint4 pack_vec(const T* v, int count);
+template <> __device__ __forceinline__ uint4 pack_vec<float>(const float* v, int count) {
+    return make_uint4(__float_as_uint(v[0]), count > 1 ? __float_as_uint(v[1]) : 0u, count > 2 ? __float_as_uint(v[2]) : 0u,
+                      count > 3 ? __float_as_uint(v[3]) : 0u);
+}
+template <> __device__ __forceinline__ uint4 pack_vec<double>(const double* v, int count) {
+    const double b = count > 1 ? v[1] : 0.0;
+    return make_uint4((unsigned)__double2loint(v[0]), (unsigned)__double2hiint(v[0]), (unsigned)__double2loint(b),
+                      (unsigned)__double2hiint(b));
+}
+
+// Weight of the leading dim-1 digits of row h = p / n (fastest leading digit first).  Out of line: the hot loop
+// of contract1_kernel only needs it when a carry ripples past the fastest digit.
+template <typename T>
+__device__ __noinline__ T row_prefix(const T* sw, uint32_t n, int dim, FastDiv fd, uint64_t h) {
+    T pr = (T)1;
+    if (h <= 0xffffffffull) {
+        uint32_t q = (uint32_t)h;
+        for (int d = dim - 2; d >= 0; --d) {
+            const uint32_t t = fd.div(q);
+            pr *= sw[d * n + (q - t * n)];
+            q = t;
+        }
+    } else {
+        for (int d = dim - 2; d >= 0; --d) {
+            const uint64_t t = h / n;
+            pr *= sw[d * n + (uint32_t)(h - t * n)];
+            h = t;
+        }
+    }
+    return pr;
+}
+
 // cols == 1 contraction: fp64 accumulation of f[p]*W[p], deterministic two-stage reduction.
 // Each thread handles vectors of V consecutive points (32 bytes: two 128-bit loads of f) advancing by a constant step.
 // The point index is carried as (hi, last) = (p / n, p % n) without division; the weight of the leading
 // dim-1 digits (the digits of hi, extracted with multiply-shift divisions) is formed once per vector and the
 // last digit steps through the vector, with a carry when the vector crosses a row of the last dimension.
-template <typename T, int V>
-__global__ void __launch_bounds__(256)
+template <typename T, int V, bool SMEM>
+__global__ void __launch_bounds__(256, 4)
 contract1_kernel(const T* __restrict__ f, const T* __restrict__ w, uint32_t n, int dim, int64_t p_begin,
-                 int64_t p_end, FastDiv fd, double* partials, unsigned int* ticket, double* out, bool use_smem) {
+                 int64_t p_end, FastDiv fd, double* partials, unsigned int* ticket, double* out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double sh[32];
-    const T* sw = stage_weights<T>(w, reinterpret_cast<T*>(smem_raw), dim, n, use_smem);
+    // SMEM is a template parameter so that the table reads compile to shared-memory loads, not generic ones
+    const T* sw = w;
+    if (SMEM) {
+        T* st = reinterpret_cast<T*>(smem_raw);
+        for (int i = threadIdx.x; i < dim * (int)n; i += blockDim.x) st[i] = w[i];
+        __syncthreads();
+        sw = st;
+    }
     const T* wl = sw + (dim - 1) * n;
     const int64_t npts = p_end - p_begin;
     const int64_t nvec = (npts + V - 1) / V;
@@ -184,47 +232,79 @@ contract1_kernel(const T* __restrict__ f, const T* __restrict__ w, uint32_t n, i
         const uint64_t sp = (uint64_t)step * V;
         const uint64_t step_hi = sp / n;
         const uint32_t step_last = (uint32_t)(sp - step_hi * n);
-        auto prefix_of = [&](uint64_t h) {
-            T pr = (T)1;
-            if (h <= 0xffffffffull) {
-                uint32_t q = (uint32_t)h;
-                for (int d = dim - 2; d >= 0; --d) {
-                    const uint32_t t = fd.div(q);
-                    pr *= sw[d * n + (q - t * n)];
-                    q = t;
-                }
-            } else {
-                for (int d = dim - 2; d >= 0; --d) {
-                    const uint64_t t = h / n;
-                    pr *= sw[d * n + (uint32_t)(h - t * n)];
-                    h = t;
-                }
+        auto prefix_of = [&](uint64_t h) { return row_prefix<T>(sw, n, dim, fd, h); };
+        // prefixes of rows h and h + 1 (same multiplication order as prefix_of: fastest leading digit first)
+        auto prefix_pair = [&](uint64_t h, T& p0, T& p1) {
+            if (dim < 2) { p0 = p1 = (T)1; return; }
+            if (h >= 0xffffffffull) { p0 = prefix_of(h); p1 = prefix_of(h + 1); return; }
+            uint32_t q = (uint32_t)h;
+            const uint32_t t0 = fd.div(q);
+            const uint32_t d0 = q - t0 * n;  // fastest leading digit
+            const T* w0 = sw + (dim - 2) * n;
+            p0 = w0[d0];
+            const bool carry = d0 + 1 >= n;
+            p1 = carry ? (T)0 : w0[d0 + 1];
+            q = t0;
+            for (int d = dim - 3; d >= 0; --d) {
+                const uint32_t t = fd.div(q);
+                const T wd = sw[d * n + (q - t * n)];
+                p0 *= wd;
+                p1 *= wd;
+                q = t;
             }
-            return pr;
+            if (carry) p1 = prefix_of(h + 1);  // one row in n: the carry ripples into slower digits
         };
-        for (; vi < nvec; vi += step) {
-            const int64_t r = vi * V;
-            alignas(16) T fv[V];
+        // The loads of the NEXT vector are issued before the (long, dependent) index arithmetic of the current
+        // one: without that a thread has less than one 32-byte request in flight and the kernel sits at a
+        // quarter of the HBM rate.
+        constexpr int NQ = V > 1 ? (int)(V * sizeof(T) / 16) : 1;  // 128-bit registers per vector
+        auto load_vec = [&](int64_t v, uint4 (&q)[NQ]) {
+            const int64_t r = v * V;
             if (V > 1 && r + V <= npts) {
 #pragma unroll
-                for (int q = 0; q < (int)(V * sizeof(T) / 16); ++q)
-                    reinterpret_cast<uint4*>(fv)[q] = __ldcs(reinterpret_cast<const uint4*>(f + r) + q);
+                for (int k = 0; k < NQ; ++k) q[k] = __ldcs(reinterpret_cast<const uint4*>(f + r) + k);
             } else {
+                T tmp[V];
 #pragma unroll
-                for (int j = 0; j < V; ++j) fv[j] = r + j < npts ? f[r + j] : (T)0;
+                for (int j = 0; j < V; ++j) tmp[j] = r + j < npts ? f[r + j] : (T)0;
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) q[k] = pack_vec<T>(tmp + k * (16 / sizeof(T)), V);
             }
-            T prefix = prefix_of(hi);
-            uint32_t l = last;
-            uint64_t h = hi;
+        };
+        uint4 nxt[NQ];
+        load_vec(vi, nxt);
+        for (; vi < nvec; vi += step) {
+            T fv[V];
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                if (l >= n) {  // crossed into the next row of the last dimension
-                    l = 0;
-                    ++h;
-                    prefix = prefix_of(h);
+            for (int j = 0; j < V; ++j) fv[j] = vec_elem<T>(nxt[j / (16 / (int)sizeof(T))], j % (16 / (int)sizeof(T)));
+            if (vi + step < nvec) load_vec(vi + step, nxt);
+            if (n >= (uint32_t)V) {
+                // A vector crosses at most one row of the last dimension.  Both rows' prefixes come from ONE digit
+                // walk (they differ in the fastest leading digit only) and each element selects: a branch on the
+                // crossing would diverge in every warp (32 x V consecutive points span several rows) and execute
+                // the whole digit walk once per element.
+                T p0, p1;
+                prefix_pair(hi, p0, p1);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const uint32_t lj = last + j;
+                    const bool next_row = lj >= n;
+                    acc[0] += (double)fv[j] * (double)((next_row ? p1 : p0) * wl[next_row ? lj - n : lj]);
                 }
-                acc[0] += (double)fv[j] * (double)(prefix * wl[l]);
-                ++l;
+            } else {  // rows shorter than a vector (tiny grids): generic walk
+                T prefix = prefix_of(hi);
+                uint32_t l = last;
+                uint64_t h = hi;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    if (l >= n) {
+                        l = 0;
+                        ++h;
+                        prefix = prefix_of(h);
+                    }
+                    acc[0] += (double)fv[j] * (double)(prefix * wl[l]);
+                    ++l;
+                }
             }
             hi += step_hi;
             last += step_last;
@@ -357,13 +437,15 @@ int tq_nc_contract(const void* f, const void* w, int32_t n, int32_t dim, int64_t
             const size_t smem = use_smem ? (size_t)dim * n * sizeof(T) : 0;
             FastDiv fd;
             fd.set((uint32_t)n);
-            if (aligned) {
-                cudaFuncSetAttribute(contract1_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NC_TABLE_SMEM);
-                contract1_kernel<T, V><<<TQ_GRID(grid), 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, fd, partials, ticket, out_f64, use_smem);
-            } else {
-                cudaFuncSetAttribute(contract1_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NC_TABLE_SMEM);
-                contract1_kernel<T, 1><<<TQ_GRID(grid), 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, fd, partials, ticket, out_f64, use_smem);
-            }
+            auto launch = [&](auto kernel) {
+                if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NC_TABLE_SMEM);
+                kernel<<<TQ_GRID(grid), 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, fd, partials,
+                                                       ticket, out_f64);
+            };
+            if (aligned && use_smem) launch(contract1_kernel<T, V, true>);
+            else if (aligned) launch(contract1_kernel<T, V, false>);
+            else if (use_smem) launch(contract1_kernel<T, 1, true>);
+            else launch(contract1_kernel<T, 1, false>);
         });
         return check_launch("contract1_kernel");
     }
