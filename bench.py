@@ -18,6 +18,7 @@ N per GPU fixed); time is the max over ranks of CUDA-event time.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -136,14 +137,30 @@ def l2_flush(buf):
     buf.add_(1)  # 512 MiB read+write: evicts the 126 MB L2 between timed iterations
 
 
+def agree_max(x):
+    """max over ranks of a host float (identity in a single-process run)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
 def timed_steps(step, steps, warmup, flush_buf, barrier):
     """Per-step CUDA-event times (seconds) on the current stream; L2 flushed between iterations."""
     # W warm-up steps, and at least 0.3 s of them: the GPU drops its clocks while the host sets things up (e.g. waits
     # for nvidia-smi), and a millisecond-scale step would otherwise be timed on the ramp
-    t0, done = time.time(), 0
-    while done < warmup or time.time() - t0 < 0.3:
+    # The number of extra steps is derived from a rank-agreed time (steps contain collectives under torchrun).
+    t0 = time.time()
+    for _ in range(warmup):
         step()
-        done += 1
+    torch.cuda.synchronize()
+    spent = agree_max(time.time() - t0)
+    if spent < 0.3:
+        for _ in range(min(200, int(math.ceil((0.3 - spent) / max(spent / max(warmup, 1), 1e-4))))):
+            step()
     torch.cuda.synchronize()
     times = []
     from torchquad_b200 import _lib as _tq_lib

@@ -40,6 +40,16 @@ for dt, tol in [(torch.float64, 1e-9), (torch.float32, 2e-4)]:
         checks.append((f"VEGAS {label} {dt}", a, b, tol * (1 if dt == torch.float64 else 20)))
         a, b, integ = both(tq.Boole, fn, 4, dict(N=21**4), dt)
         checks.append((f"Boole {label} {dt}", a, b, tol))
+# large-map record layout ({x, dx, weight, count} per bin), forced on this small problem: the histogram is
+# unpacked into weights/counts before the all-reduce, so sharded == single still holds
+from torchquad_b200.integration.vegas_map import VEGASMap
+
+default_threshold = VEGASMap.records_min_bytes
+VEGASMap.records_min_bytes = 0
+a, b, integ = both(tq.VEGAS, g, 4, dict(N=400_000, seed=3), torch.float64)
+checks.append(("VEGAS fused records float64", a, b, 1e-9))
+assert integ.map._records is not None
+VEGASMap.records_min_bytes = default_threshold
 ok = True
 for name, a, b, tol in checks:
     good = abs(a - b) <= tol * abs(a)
