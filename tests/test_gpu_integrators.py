@@ -546,3 +546,34 @@ def test_vegas_record_layout_matches_pair_layout(cuda, monkeypatch, native):
         w3, c3 = torch.zeros_like(vm.weights), torch.zeros_like(vm.counts)
         ops.unpack_records(rec, w3, c3)  # the records were zeroed by the first unpack
         assert int(c3.sum()) == 0 and float(w3.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_vegas_adaptation_state_round_trip(cuda, fused, tmp_path):
+    """`adaptation_state()` / `initial_adaptation`: a run that starts from a saved map and stratification skips the
+    warm-up, begins with exactly the saved tables and is at least as accurate as a cold run."""
+    g = F.GenzGaussian(4, a=6.0, u=0.4)
+    fn = g if fused else (lambda x: g(x))
+    dom = torch.tensor([[0.0, 1.0]] * 4, dtype=torch.float64, device=cuda)
+    cold = tq.VEGAS()
+    r0 = cold.integrate(fn, 4, N=400_000, integration_domain=dom, seed=1)
+    state = cold.adaptation_state()
+    torch.save(state, tmp_path / "vegas_state.pt")
+    state = torch.load(tmp_path / "vegas_state.pt")
+    assert torch.equal(state["x_edges"], cold.map.x_edges.cpu()) and torch.equal(state["dh"], cold.strat.dh.cpu())
+
+    warm = tq.VEGAS()
+    warm.initial_adaptation = state
+    r1 = warm.integrate(fn, 4, N=400_000, integration_domain=dom, seed=2, use_grid_improve=False)
+    # no warm-up evaluations, and without grid improvement the map is still the saved one
+    assert torch.equal(warm.map.x_edges.cpu(), state["x_edges"])
+    assert abs(float(r1) - g.exact()) <= 5 * float(warm._get_error())
+    fresh = tq.VEGAS()
+    fresh.integrate(fn, 4, N=400_000, integration_domain=dom, seed=2, use_grid_improve=False, use_warmup=False)
+    assert float(warm._get_error()) < float(fresh._get_error())  # the saved adaptation pays from the first iteration
+    assert abs(float(r0) - g.exact()) <= 5 * float(cold._get_error())
+
+    other = tq.VEGAS()
+    other.initial_adaptation = state
+    with pytest.raises(ValueError):
+        other.integrate(fn, 4, N=100_000, integration_domain=dom, seed=2)  # different table shapes

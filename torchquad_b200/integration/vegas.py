@@ -36,12 +36,17 @@ class VEGAS(BaseIntegrator):
                          (vegas.py:117), i.e. 1e7 .. 4e7 bins per dimension for N = 2.5e9 .. 1e10: tables far
                          larger than L2 that turn every bin lookup and histogram update into a random HBM
                          access (and collapse numerically in fp32).  None keeps the formula.
+      initial_adaptation dict returned by `adaptation_state()` of an earlier run with the same dim / N / dtype
+                         (so that the table shapes agree): the run starts from that map and those hypercube
+                         probabilities and skips the warm-up.  The reference keeps this state on the integrator
+                         (`vegas.py:118-133`) but offers no way to carry it over.
       l2_fetch_bytes     L2 fetch granularity hint used while a large map is in flight (None: leave as is;
                          measured on B200: 32 vs the default 64 makes no difference, profiles/README.md).
     """
 
     max_map_intervals = None
     l2_fetch_bytes = None
+    initial_adaptation = None  # adaptation_state() of an earlier run: start from its map and stratification
     native_loop = True  # fused single-GPU runs: drive all passes from C++ (tq_vegas_run_fused)
     _large_map_bytes = 64 << 20
 
@@ -117,6 +122,9 @@ class VEGAS(BaseIntegrator):
             self.map.weights = self._stats[:n_w].view(dim, N_intervals)
             self._stats_w = self._stats[:n_w]
             self._stats_jf = self._stats[n_w:].view(2, self.strat.N_cubes)
+        if self.initial_adaptation is not None:
+            self._load_adaptation(self.initial_adaptation)
+            use_warmup = False
         self.results = []  # per-iteration integral estimates (0-dim tensors)
         self.sigma2 = []   # per-iteration variances (0-dim tensors, detached)
         self.it = 0
@@ -149,6 +157,25 @@ class VEGAS(BaseIntegrator):
         self._flush_map_status()
         logger.debug("VEGAS finished")
         return self._get_result()
+
+    # ------------------------------------------------------------------ save / resume of the adaptation
+    def adaptation_state(self):
+        """The adapted map and stratification of the last run as a dict of CPU tensors (torch.save-able)."""
+        vmap, strat = self.map, self.strat
+        return {"dim": vmap.dim, "N_intervals": vmap.N_intervals, "N_strat": strat.N_strat, "dtype": str(vmap.dtype),
+                "x_edges": vmap.x_edges.detach().cpu().clone(), "dx_edges": vmap.dx_edges.detach().cpu().clone(),
+                "dh": strat.dh.detach().cpu().clone()}
+
+    def _load_adaptation(self, state):
+        vmap, strat = self.map, self.strat
+        want = (vmap.dim, vmap.N_intervals, strat.N_strat, str(vmap.dtype))
+        got = (state["dim"], state["N_intervals"], state["N_strat"], state["dtype"])
+        if want != got:
+            raise ValueError(f"initial_adaptation was made for (dim, N_intervals, N_strat, dtype) = {got}, this run needs {want}")
+        vmap.x_edges.copy_(state["x_edges"])
+        vmap.dx_edges.copy_(state["dx_edges"])
+        vmap.invalidate_packed()
+        strat.dh.copy_(state["dh"])
 
     def _integrate_native_loop(self, N, use_warmup):
         """Fused single-GPU run with the pass loop and schedule in C++ (csrc/vegas_driver.cu): same kernels, same
