@@ -82,6 +82,10 @@ typedef struct tq_integrand {
     double scale;
 } tq_integrand;
 
+/* layouts of the packed VEGAS map tables (tq_vegas_map_pack_edges / tq_vegas_map_pack_records) */
+#define TQ_EDGES_PAIRS 0
+#define TQ_EDGES_RECORDS 1
+
 /* ---- library ---------------------------------------------------------------------------------- */
 TQ_API const char* tq_last_error(void);
 TQ_API int tq_version(void);
@@ -130,18 +134,20 @@ TQ_API int tq_vegas_map_forward(const void* y, const void* x_edges, const void* 
                          int32_t dtype, void* stream);
 /* Same pass with the edges packed as {x_edge, dx_edge} pairs (tq_vegas_map_pack_edges; one gather per element)
  * and, when `domain` ([dim,2], nullable) is given, the unit-cube -> domain transform x*size + start of
- * vegas.py:109-110 applied in the same kernel. */
-TQ_API int tq_vegas_map_forward_packed(const void* y, const void* edges_packed, const void* domain, void* x, void* jac,
-                                int32_t* ids, int64_t rows, int32_t dim, int64_t n_intervals, int32_t dtype,
-                                void* stream);
+ * vegas.py:109-110 applied in the same kernel.  edges_layout = TQ_EDGES_RECORDS reads the pairs out of the
+ * large-map record table (see tq_vegas_map_pack_records below). */
+TQ_API int tq_vegas_map_forward_packed(const void* y, const void* edges_packed, int32_t edges_layout, const void* domain,
+                                void* x, void* jac, int32_t* ids, int64_t rows, int32_t dim, int64_t n_intervals,
+                                int32_t dtype, void* stream);
 /* accumulate_weight (:99-111): weights[d,k] += jf2[r], counts[d,k] += 1 (int64, bit-exact). */
 TQ_API int tq_vegas_map_accumulate(const void* y, const void* jf2, void* weights, int64_t* counts, int64_t rows,
                             int32_t dim, int64_t n_intervals, int32_t dtype, void* stream);
 /* The tail of an unfused VEGAS pass in one kernel (vegas.py:104-112,284-290): jf = (f*volume)*jac,
- * weights[d,k] += jf^2, counts[d,k] += 1, and jf written to jf_out (nullable) for tq_vegas_strat_accumulate. */
+ * weights[d,k] += jf^2, counts[d,k] += 1, and jf written to jf_out (nullable) for tq_vegas_strat_accumulate.
+ * Large maps: pass `records` (and weights = counts = NULL) to accumulate into the record table instead. */
 TQ_API int tq_vegas_accumulate_fused(const void* y, const void* f, const void* jac, double volume, void* jf_out, void* weights,
-                              int64_t* counts, int64_t rows, int32_t dim, int64_t n_intervals, int32_t dtype,
-                              void* stream);
+                              int64_t* counts, void* records, int64_t rows, int32_t dim, int64_t n_intervals,
+                              int32_t dtype, void* stream);
 /* Scratch bytes tq_vegas_map_smooth / tq_vegas_map_update need for a [dim, Ni] map (pass as ws). */
 TQ_API size_t tq_vegas_map_workspace_bytes(int32_t dim, int64_t n_intervals, int32_t dtype);
 /* _smooth_map (:113-172) written to `smoothed[dim, Ni]`; status[0] = 1 when a dimension sums to zero
@@ -240,8 +246,6 @@ TQ_API int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int6
  * them (weights = counts = NULL): the three scattered accesses per sample and dimension fall into one DRAM
  * sector.  tq_vegas_map_unpack_records then adds the record fields to weights/counts (the arrays
  * tq_vegas_map_update reads) and zeroes them; tq_vegas_map_pack_records rewrites the records from new edges. */
-#define TQ_EDGES_PAIRS 0
-#define TQ_EDGES_RECORDS 1
 TQ_API size_t tq_vegas_map_records_bytes(int32_t dim, int64_t n_intervals, int32_t dtype);
 TQ_API int tq_vegas_map_pack_records(const void* x_edges, const void* dx_edges, void* records, int32_t dim,
                               int64_t n_intervals, int32_t dtype, void* stream);

@@ -577,3 +577,30 @@ def test_vegas_adaptation_state_round_trip(cuda, fused, tmp_path):
     other.initial_adaptation = state
     with pytest.raises(ValueError):
         other.integrate(fn, 4, N=100_000, integration_domain=dom, seed=2)  # different table shapes
+
+
+def test_vegas_unfused_record_layout_matches_pair_layout(cuda, monkeypatch):
+    """Torch-callable integrand on a (forced) large-map record table: the gather reads the pairs out of the records,
+    the fused tail accumulates into them; the run must reproduce the default layout."""
+    from torchquad_b200.integration.vegas_map import VEGASMap
+
+    g = F.GenzGaussian(4, a=5.0, u=0.5)
+    for dt, tol in ((torch.float64, 1e-9), (torch.float32, None)):
+        dom = torch.tensor([[0.0, 1.0]] * 4, dtype=dt, device=cuda)
+
+        def run():
+            v = tq.VEGAS()
+            return v, v.integrate(lambda x: g(x), 4, N=300_000, integration_domain=dom, seed=3)
+
+        monkeypatch.setattr(VEGASMap, "records_min_bytes", 48 << 20)
+        a, ra = run()
+        monkeypatch.setattr(VEGASMap, "records_min_bytes", 0)
+        b, rb = run()
+        assert b.map._records is not None and a.map._records is None
+        assert a.it == b.it
+        if tol is not None:
+            assert a._nr_of_fevals == b._nr_of_fevals
+            assert abs(float(ra) - float(rb)) <= tol * abs(float(ra))
+            assert float((a.map.x_edges - b.map.x_edges).abs().max()) <= 1e-9
+        else:  # fp32 runs agree statistically (see test_vegas_native_loop_equals_python_loop)
+            assert abs(float(ra) - float(rb)) <= 2.5 * float(a._get_error())

@@ -66,8 +66,8 @@ PROTOTYPES = {
     "tq_mc_sample_backward": (ctypes.c_int, [c_p, c_i64, c_i64, c_i32, c_i32, c_u64, c_u32, c_p, c_p, c_sz, c_p]),
     "tq_sum_columns": (ctypes.c_int, [c_p, c_i64, c_i64, c_i32, c_p, c_p, c_p, c_sz, c_p]),
     "tq_vegas_map_forward": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
-    "tq_vegas_map_forward_packed": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
-    "tq_vegas_accumulate_fused": (ctypes.c_int, [c_p, c_p, c_p, c_f64, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
+    "tq_vegas_map_forward_packed": (ctypes.c_int, [c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
+    "tq_vegas_accumulate_fused": (ctypes.c_int, [c_p, c_p, c_p, c_f64, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
     "tq_vegas_map_accumulate": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
     "tq_vegas_map_workspace_bytes": (c_sz, [c_i32, c_i64, c_i32]),
     "tq_vegas_map_smooth": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_f64, c_i32, c_p, c_p, c_sz, c_p]),

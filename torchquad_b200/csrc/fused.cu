@@ -3,6 +3,7 @@
 // reference's test integrands (tests/integration_test_functions.py:146-325), all of which factor as
 // finish(combine_d step(x_d)), so a thread streams over the dimensions without holding the point.
 #include "common.cuh"
+#include "vegas_dev.cuh"
 
 namespace tq {
 
@@ -195,13 +196,6 @@ constexpr int FV_SLICE = FV_BLOCK / 2 + 4;
 template <typename T> struct Pair2;
 template <> struct Pair2<float> { using type = float2; };
 template <> struct Pair2<double> { using type = double2; };
-
-// Record layout of a LARGE map (tables beyond L2): {x_edge, dx_edge, weight, count} of one bin in one 32-byte (fp64)
-// or 16-byte (fp32) record, so that the edge gather and both histogram updates of a sample touch ONE DRAM sector
-// instead of three scattered ones.
-template <typename T> struct MapRecord;
-template <> struct __align__(32) MapRecord<double> { double x, dx, w; unsigned long long c; };
-template <> struct __align__(16) MapRecord<float> { float x, dx, w; unsigned int c; };
 
 template <typename T>
 __device__ __forceinline__ void segmented_warp_sum2(unsigned key, T& a, T& b) {

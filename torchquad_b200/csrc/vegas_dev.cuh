@@ -8,6 +8,13 @@ template <typename T> struct EdgePair;
 template <> struct EdgePair<float> { using type = float2; };
 template <> struct EdgePair<double> { using type = double2; };
 
+// Record layout of a LARGE map (tables beyond L2): {x_edge, dx_edge, weight, count} of one bin in one 32-byte (fp64)
+// or 16-byte (fp32) record, so that the edge gather and both histogram updates of a sample touch ONE DRAM sector
+// instead of three scattered ones.
+template <typename T> struct MapRecord;
+template <> struct __align__(32) MapRecord<double> { double x, dx, w; unsigned long long c; };
+template <> struct __align__(16) MapRecord<float> { float x, dx, w; unsigned int c; };
+
 // get_NH for one cube: max(2, floor(dh * nevals_exp)) (vegas_stratification.py:92-103)
 template <typename T>
 __device__ __forceinline__ long long nh_of(T dh, T nev) {

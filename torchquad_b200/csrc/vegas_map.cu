@@ -34,7 +34,7 @@ template <typename T, int V, bool PACKED>
 __global__ void __launch_bounds__(256)
 map_forward_kernel(const T* __restrict__ y, const T* __restrict__ xe, const T* __restrict__ dxe,
                    const T* __restrict__ domain, T* __restrict__ x, T* __restrict__ jac, int32_t* __restrict__ ids,
-                   T* __restrict__ off, int64_t rows, int dim, long long ni, int tile_rows, uint32_t magic) {
+                   T* __restrict__ off, int64_t rows, int dim, long long ni, int tile_rows, uint32_t magic, int ep_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_fac = reinterpret_cast<T*>(smem_raw);  // [tile_rows][dimp]
     const int dimp = dim | 1;
@@ -74,7 +74,8 @@ map_forward_kernel(const T* __restrict__ y, const T* __restrict__ xe, const T* _
                 if (v + j < n_el) {
                     T xev, dxv;
                     if (PACKED) {
-                        const typename EdgePair<T>::type e2 = __ldg(&ep[(int64_t)d * ni + k]);
+                        // ep_stride 1: pair table; 2: {x, dx, weight, count} records (the pair is a record's first half)
+                        const typename EdgePair<T>::type e2 = __ldg(&ep[((int64_t)d * ni + k) * ep_stride]);
                         xev = e2.x;
                         dxv = e2.y;
                     } else {
@@ -130,8 +131,8 @@ template <typename T, int V, bool FUSED>
 __global__ void __launch_bounds__(256)
 map_accumulate_global_kernel(const T* __restrict__ y, const T* __restrict__ jf2_or_f, const T* __restrict__ jacp,
                              T volume, T* __restrict__ jf_out, T* __restrict__ weights,
-                             unsigned long long* __restrict__ counts, int64_t rows, int dim, long long ni,
-                             int tile_rows, uint32_t magic) {
+                             unsigned long long* __restrict__ counts, MapRecord<T>* __restrict__ recs, int64_t rows, int dim,
+                             long long ni, int tile_rows, uint32_t magic) {
     const T nif = (T)ni;
     const int64_t ntiles = (rows + tile_rows - 1) / tile_rows;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -163,8 +164,14 @@ map_accumulate_global_kernel(const T* __restrict__ y, const T* __restrict__ jf2_
                     } else {
                         wgt = __ldg(&jf2_or_f[r0 + r]);
                     }
-                    atomicAdd(&weights[(int64_t)d * ni + k], wgt);
-                    atomicAdd(&counts[(int64_t)d * ni + k], 1ull);
+                    if (recs) {  // large maps: both reductions in the bin's record (one DRAM sector)
+                        MapRecord<T>* rc = &recs[(int64_t)d * ni + k];
+                        atomicAdd(&rc->w, wgt);
+                        atomicAdd(&rc->c, 1);
+                    } else {
+                        atomicAdd(&weights[(int64_t)d * ni + k], wgt);
+                        atomicAdd(&counts[(int64_t)d * ni + k], 1ull);
+                    }
                 }
             }
         }
@@ -432,7 +439,7 @@ static int run_smooth(const T* weights, const long long* counts, T* smoothed_out
 template <bool PACKED>
 static int launch_map_forward(const void* y, const void* xe, const void* dxe, const void* domain, void* x, void* jac,
                               int32_t* ids, void* offset, int64_t rows, int32_t dim, int64_t n_intervals, int32_t dtype,
-                              void* stream) {
+                              void* stream, int ep_stride = 1) {
     TQ_REQUIRE(dim >= 1 && n_intervals >= 1 && rows >= 0, "tq_vegas_map_forward: bad shape");
     TQ_REQUIRE(ids == nullptr || n_intervals <= 0x7fffffffLL, "tq_vegas_map_forward: ids need Ni < 2^31");
     if (rows == 0) return TQ_OK;
@@ -452,11 +459,11 @@ static int launch_map_forward(const void* y, const void* xe, const void* dxe, co
         if (aligned)
             map_forward_kernel<T, VW, PACKED><<<TQ_GRID(grid), 256, smem, as_stream(stream)>>>(
                 (const T*)y, (const T*)xe, (const T*)dxe, (const T*)domain, (T*)x, (T*)jac, ids, (T*)offset, rows, dim,
-                n_intervals, tile_rows, magic);
+                n_intervals, tile_rows, magic, ep_stride);
         else
             map_forward_kernel<T, 1, PACKED><<<TQ_GRID(grid), 256, smem, as_stream(stream)>>>(
                 (const T*)y, (const T*)xe, (const T*)dxe, (const T*)domain, (T*)x, (T*)jac, ids, (T*)offset, rows, dim,
-                n_intervals, tile_rows, magic);
+                n_intervals, tile_rows, magic, ep_stride);
     });
     return check_launch("map_forward_kernel");
 }
@@ -464,7 +471,7 @@ static int launch_map_forward(const void* y, const void* xe, const void* dxe, co
 template <bool FUSED>
 static int launch_accumulate_global(const void* y, const void* a, const void* jac, double volume, void* jf_out,
                                     void* weights, int64_t* counts, int64_t rows, int32_t dim, int64_t n_intervals,
-                                    int32_t dtype, cudaStream_t st) {
+                                    int32_t dtype, cudaStream_t st, void* records = nullptr) {
     TQ_REQUIRE(dim <= 255, "tq_vegas_map_accumulate: dim %d too large (max 255)", dim);
     int tile_rows = MF_TILE_ELEMS / dim;
     if (tile_rows < 4) tile_rows = 4;
@@ -479,11 +486,11 @@ static int launch_accumulate_global(const void* y, const void* a, const void* ja
         if (aligned)
             map_accumulate_global_kernel<T, VW, FUSED><<<TQ_GRID(grid), 256, 0, st>>>((const T*)y, (const T*)a, (const T*)jac, (T)volume,
                                                                             (T*)jf_out, (T*)weights, (unsigned long long*)counts,
-                                                                            rows, dim, n_intervals, tile_rows, magic);
+                                                                            (MapRecord<T>*)records, rows, dim, n_intervals, tile_rows, magic);
         else
             map_accumulate_global_kernel<T, 1, FUSED><<<TQ_GRID(grid), 256, 0, st>>>((const T*)y, (const T*)a, (const T*)jac, (T)volume,
                                                                            (T*)jf_out, (T*)weights, (unsigned long long*)counts,
-                                                                           rows, dim, n_intervals, tile_rows, magic);
+                                                                           (MapRecord<T>*)records, rows, dim, n_intervals, tile_rows, magic);
     });
     return check_launch("map_accumulate_global_kernel");
 }
@@ -533,10 +540,12 @@ int tq_vegas_map_forward(const void* y, const void* x_edges, const void* dx_edge
     return launch_map_forward<false>(y, x_edges, dx_edges, nullptr, x, jac, ids, offset, rows, dim, n_intervals, dtype, stream);
 }
 
-int tq_vegas_map_forward_packed(const void* y, const void* edges_packed, const void* domain, void* x, void* jac,
-                                int32_t* ids, int64_t rows, int32_t dim, int64_t n_intervals, int32_t dtype,
+int tq_vegas_map_forward_packed(const void* y, const void* edges_packed, int32_t edges_layout, const void* domain, void* x,
+                                void* jac, int32_t* ids, int64_t rows, int32_t dim, int64_t n_intervals, int32_t dtype,
                                 void* stream) {
-    return launch_map_forward<true>(y, edges_packed, nullptr, domain, x, jac, ids, nullptr, rows, dim, n_intervals, dtype, stream);
+    TQ_REQUIRE(edges_layout == TQ_EDGES_PAIRS || edges_layout == TQ_EDGES_RECORDS, "tq_vegas_map_forward_packed: unknown edges layout %d", edges_layout);
+    return launch_map_forward<true>(y, edges_packed, nullptr, domain, x, jac, ids, nullptr, rows, dim, n_intervals, dtype, stream,
+                                    edges_layout == TQ_EDGES_RECORDS ? 2 : 1);
 }
 
 int tq_vegas_map_accumulate(const void* y, const void* jf2, void* weights, int64_t* counts, int64_t rows,
@@ -565,12 +574,14 @@ int tq_vegas_map_accumulate(const void* y, const void* jf2, void* weights, int64
 }
 
 int tq_vegas_accumulate_fused(const void* y, const void* f, const void* jac, double volume, void* jf_out, void* weights,
-                              int64_t* counts, int64_t rows, int32_t dim, int64_t n_intervals, int32_t dtype,
-                              void* stream) {
+                              int64_t* counts, void* records, int64_t rows, int32_t dim, int64_t n_intervals,
+                              int32_t dtype, void* stream) {
     TQ_REQUIRE(dim >= 1 && n_intervals >= 1 && rows >= 0, "tq_vegas_accumulate_fused: bad shape");
+    TQ_REQUIRE((records != nullptr) != (weights != nullptr && counts != nullptr),
+               "tq_vegas_accumulate_fused: pass either weights + counts or records");
     if (rows == 0) return TQ_OK;
     return launch_accumulate_global<true>(y, f, jac, volume, jf_out, weights, counts, rows, dim, n_intervals, dtype,
-                                          as_stream(stream));
+                                          as_stream(stream), records);
 }
 
 size_t tq_vegas_map_workspace_bytes(int32_t dim, int64_t n_intervals, int32_t dtype) {

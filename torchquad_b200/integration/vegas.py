@@ -257,8 +257,7 @@ class VEGAS(BaseIntegrator):
                 if tqdist.is_enabled():
                     self._nr_of_fevals += N_samples - (end - begin)
                 if f_raw is not None and not (torch.is_grad_enabled() and f_raw.requires_grad):
-                    ops.accumulate_fused(yrnd, f_raw, jac, self._volume_host, self.map.weights, self.map.counts,
-                                         want_jf=False)
+                    self._accumulate_tail(yrnd, f_raw, jac, want_jf=False)
                 else:
                     f_eval = self._last_f_eval
                     jf_vec2 = ((f_eval * jac) ** 2).detach()
@@ -301,7 +300,7 @@ class VEGAS(BaseIntegrator):
                 self._nr_of_fevals += M - (end - begin)
             if f_raw is not None and not (torch.is_grad_enabled() and f_raw.requires_grad):
                 if self.use_grid_improve:
-                    jf_vec = ops.accumulate_fused(y, f_raw, jac, self._volume_host, vmap.weights, vmap.counts)
+                    jf_vec = self._accumulate_tail(y, f_raw, jac, want_jf=True)
                 else:
                     jf_vec = (f_raw * self._volume.detach()) * jac
             else:
@@ -334,13 +333,28 @@ class VEGAS(BaseIntegrator):
         if self.use_grid_improve:
             self._update_map()
 
+    def _accumulate_tail(self, y, f_raw, jac, want_jf):
+        """jf = f*V*jac and the map histogram in one kernel; large maps accumulate into their record table and the
+        histogram is moved to `weights` / `counts` (what the all-reduce and `update_map` read) right after."""
+        vmap = self.map
+        if vmap.wants_records():
+            jf = ops.accumulate_fused(y, f_raw, jac, self._volume_host, None, None, want_jf=want_jf, records=vmap.records(),
+                                      n_intervals=vmap.N_intervals)
+            vmap.unpack_records()
+            return jf
+        return ops.accumulate_fused(y, f_raw, jac, self._volume_host, vmap.weights, vmap.counts, want_jf=want_jf)
+
     def _map_and_eval(self, y):
         """y -> (raw integrand values, jac).  Fused tail: x comes out of the map kernel already in domain
         coordinates and the raw values are returned for `accumulate_fused`; otherwise (gradient through the
         domain) the reference's torch expressions are used and (None, jac) is returned with the scaled values
         left in `self._last_f_eval`."""
         if self._fuse_tail:
-            x, jac, _ = ops.map_forward_packed(y, self.map.packed_edges(), self._domain.detach())
+            if self.map.wants_records():  # large map: gather the edge pairs out of the record table
+                x, jac, _ = ops.map_forward_packed(y, None, self._domain.detach(), records=self.map.records(),
+                                                   n_intervals=self.map.N_intervals)
+            else:
+                x, jac, _ = ops.map_forward_packed(y, self.map.packed_edges(), self._domain.detach())
             f_raw, n = self.evaluate_integrand(self._user_fn, x)
             self._nr_of_fevals += n
             f_raw = f_raw.reshape(-1) if f_raw.numel() == n else f_raw.squeeze()

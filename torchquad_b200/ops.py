@@ -168,24 +168,29 @@ def map_forward(y, x_edges, dx_edges, want_x=True, want_jac=True, want_ids=False
     return x, jac, ids
 
 
-def map_forward_packed(y, edges_packed, domain=None, want_ids=False):
-    """(x, jac, ids) from packed edges; with `domain` ([dim, 2]) x is already x*size + start (vegas.py:109-110)."""
-    require_cuda(y, edges_packed, domain)
+def map_forward_packed(y, edges_packed, domain=None, want_ids=False, records=None, n_intervals=None):
+    """(x, jac, ids) from packed edges; with `domain` ([dim, 2]) x is already x*size + start (vegas.py:109-110).
+    `records` (large maps, see pack_records) replaces `edges_packed`; `n_intervals` is then required."""
+    table = records if records is not None else edges_packed
+    require_cuda(y, table, domain)
     y = y.contiguous()
     rows, dim = y.shape
     x = torch.empty_like(y)
     jac = torch.empty(rows, dtype=y.dtype, device=y.device)
     ids = torch.empty((rows, dim), dtype=torch.int32, device=y.device) if want_ids else None
     if rows > 0:
+        ni = n_intervals if records is not None else edges_packed.shape[1]
         with on_device(y.device):
-            call("tq_vegas_map_forward_packed", ptr(y), ptr(edges_packed), ptr(domain), ptr(x), ptr(jac), ptr(ids), rows,
-                 dim, edges_packed.shape[1], dtype_code(y.dtype), stream_ptr(y.device))
+            call("tq_vegas_map_forward_packed", ptr(y), ptr(table),
+                 _lib.TQ_EDGES_RECORDS if records is not None else _lib.TQ_EDGES_PAIRS, ptr(domain), ptr(x), ptr(jac), ptr(ids),
+                 rows, dim, ni, dtype_code(y.dtype), stream_ptr(y.device))
     return x, jac, ids
 
 
-def accumulate_fused(y, f, jac, volume, weights, counts, want_jf=True):
-    """jf = (f*volume)*jac, weights[d,k] += jf^2, counts[d,k] += 1 in one pass; returns jf (or None)."""
-    require_cuda(y, f, jac, weights, counts)
+def accumulate_fused(y, f, jac, volume, weights, counts, want_jf=True, records=None, n_intervals=None):
+    """jf = (f*volume)*jac, weights[d,k] += jf^2, counts[d,k] += 1 in one pass; returns jf (or None).
+    With `records` the histogram goes into the record table instead (weights / counts untouched)."""
+    require_cuda(y, f, jac, weights, counts, records)
     y = y.contiguous()
     f = f.detach().contiguous()
     rows, dim = y.shape
@@ -193,9 +198,11 @@ def accumulate_fused(y, f, jac, volume, weights, counts, want_jf=True):
         raise ValueError(f"integrand values must have shape ({rows},) and dtype {y.dtype}, got {tuple(f.shape)} / {f.dtype}")
     jf = torch.empty(rows, dtype=y.dtype, device=y.device) if want_jf else None
     if rows > 0:
+        ni = n_intervals if records is not None else weights.shape[1]
         with on_device(y.device):
-            call("tq_vegas_accumulate_fused", ptr(y), ptr(f), ptr(jac), float(volume), ptr(jf), ptr(weights), ptr(counts),
-                 rows, dim, weights.shape[1], dtype_code(y.dtype), stream_ptr(y.device))
+            call("tq_vegas_accumulate_fused", ptr(y), ptr(f), ptr(jac), float(volume), ptr(jf),
+                 None if records is not None else ptr(weights), None if records is not None else ptr(counts), ptr(records),
+                 rows, dim, ni, dtype_code(y.dtype), stream_ptr(y.device))
     return jf
 
 
