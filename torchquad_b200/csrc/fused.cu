@@ -244,121 +244,121 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
     // complete when the device-side count exceeds it.
     for (int64_t r_lo = row_begin + (int64_t)blockIdx.x * rows_per_cta; r_lo < row_end;
          r_lo += (int64_t)gridDim.x * rows_per_cta) {
-    const int64_t r_hi = r_lo + rows_per_cta < row_end ? r_lo + rows_per_cta : row_end;
-    long long c_lo = 0;
-    if (STRAT) {
-        // largest c with offsets[c] <= r_lo, by a CTA-wide FV_BLOCK-ary search: every round all threads probe
-        // one point each, so 10^4 cubes take two load latencies instead of fourteen dependent ones.
-        long long hi = n_cubes;  // offsets[c_lo] <= r_lo < offsets[hi]
-        while (hi - c_lo > 1) {
-            const long long step = (hi - c_lo + FV_BLOCK - 1) / FV_BLOCK;
-            const long long p = c_lo + (long long)(threadIdx.x + 1) * step;
-            const int below = __syncthreads_count(p < hi && __ldg(&offsets[p]) <= r_lo);
-            c_lo += below * step;
-            if (c_lo + step < hi) hi = c_lo + step;
-        }
-    }
-    for (int64_t rb = r_lo; rb < r_hi; rb += FV_BLOCK, buf ^= 1) {
-        const int64_t re = rb + FV_BLOCK < r_hi ? rb + FV_BLOCK : r_hi;
-        const int64_t row = rb + threadIdx.x;
-        const bool active = row < re;
+        const int64_t r_hi = r_lo + rows_per_cta < row_end ? r_lo + rows_per_cta : row_end;
+        long long c_lo = 0;
         if (STRAT) {
-            if (threadIdx.x < FV_SLICE) {
-                const long long c = c_lo + threadIdx.x;
-                const long long lo = __ldg(&offsets[c < n_cubes ? c : n_cubes]);
-                const long long hi = __ldg(&offsets[c + 1 < n_cubes ? c + 1 : n_cubes]);
-                s_off[buf][threadIdx.x] = lo;
-                const long long a = lo > rb ? lo : rb, b = hi < re ? hi : re;
-                for (long long r = a; r < b; ++r) s_cube[buf][r - rb] = (unsigned char)threadIdx.x;
+            // largest c with offsets[c] <= r_lo, by a CTA-wide FV_BLOCK-ary search: every round all threads probe
+            // one point each, so 10^4 cubes take two load latencies instead of fourteen dependent ones.
+            long long hi = n_cubes;  // offsets[c_lo] <= r_lo < offsets[hi]
+            while (hi - c_lo > 1) {
+                const long long step = (hi - c_lo + FV_BLOCK - 1) / FV_BLOCK;
+                const long long p = c_lo + (long long)(threadIdx.x + 1) * step;
+                const int below = __syncthreads_count(p < hi && __ldg(&offsets[p]) <= r_lo);
+                c_lo += below * step;
+                if (c_lo + step < hi) hi = c_lo + step;
             }
-            __syncthreads();
         }
-        T jf = (T)0, jf2 = (T)0;
-        unsigned key = 0xffffu;
-        if (active) {
-            uint32_t i0, i1, c = 0;
+        for (int64_t rb = r_lo; rb < r_hi; rb += FV_BLOCK, buf ^= 1) {
+            const int64_t re = rb + FV_BLOCK < r_hi ? rb + FV_BLOCK : r_hi;
+            const int64_t row = rb + threadIdx.x;
+            const bool active = row < re;
             if (STRAT) {
-                key = s_cube[buf][threadIdx.x];
-                i0 = (uint32_t)(c_lo + key);
-                i1 = (uint32_t)(row - s_off[buf][key]);
-                c = i0;
-            } else {
-                i0 = (uint32_t)(uint64_t)row;
-                i1 = (uint32_t)((uint64_t)row >> 32);
-            }
-            Integrand<FAM, T> fn;
-            fn.init();
-            T jac = (T)1;
-            for (int d0 = 0; d0 < dim; d0 += LANES) {
-                T u[LANES];
-                philox_block<T>(seed, call, i0, i1, (uint32_t)(d0 / LANES), u);
-#pragma unroll
-                for (int j = 0; j < LANES; ++j) {
-                    const int d = d0 + j;
-                    if (d < dim) {
-                        T y;
-                        if (STRAT) {
-                            const uint32_t q = c / (uint32_t)n_strat;
-                            const uint32_t p = c - q * (uint32_t)n_strat;
-                            c = q;
-                            y = div_rn(add_rn((T)p, u[j]), nsf);
-                            if (y >= (T)1) y = (T)0.999999;
-                        } else {
-                            y = mul_rn(u[j], (T)0.999999);
-                        }
-                        const T t = mul_rn(y, nif);
-                        const T fl = floor(t);
-                        long long k = (long long)fl;
-                        k = k < 0 ? 0 : (k >= ni ? ni - 1 : k);
-                        const T o = sub_rn(t, fl);
-                        const int64_t bin = (int64_t)d * ni + k;
-                        const P2 e = records ? __ldg(reinterpret_cast<const P2*>(&recs[bin])) : __ldg(&edges[bin]);
-                        const T x = add_rn(e.x, mul_rn(e.y, o));
-                        jac = mul_rn(jac, mul_rn(nif, e.y));
-                        s_ids[d * FV_BLOCK + threadIdx.x] = (int)k;
-                        fn.step(add_rn(mul_rn(x, S.size[d]), S.start[d]), d, S);
-                    }
+                if (threadIdx.x < FV_SLICE) {
+                    const long long c = c_lo + threadIdx.x;
+                    const long long lo = __ldg(&offsets[c < n_cubes ? c : n_cubes]);
+                    const long long hi = __ldg(&offsets[c + 1 < n_cubes ? c + 1 : n_cubes]);
+                    s_off[buf][threadIdx.x] = lo;
+                    const long long a = lo > rb ? lo : rb, b = hi < re ? hi : re;
+                    for (long long r = a; r < b; ++r) s_cube[buf][r - rb] = (unsigned char)threadIdx.x;
                 }
+                __syncthreads();
             }
-            const T f = mul_rn(fn.finish(S), S.scale);
-            jf = mul_rn(f, jac);
-            jf2 = mul_rn(jf, jf);
-            if (do_hist) {
-                if (hist_smem) {
-                    for (int d = 0; d < dim; ++d) {
-                        const int b = d * (int)ni + s_ids[d * FV_BLOCK + threadIdx.x];
-                        atomicAdd(&s_w[b], jf2);
-                        atomicAdd(&s_c[b], 1u);
-                    }
-                } else if (records) {
-                    for (int d = 0; d < dim; ++d) {
-                        MapRecord<T>* r = &recs[(int64_t)d * ni + s_ids[d * FV_BLOCK + threadIdx.x]];
-                        atomicAdd(&r->w, jf2);
-                        atomicAdd(&r->c, 1);
-                    }
+            T jf = (T)0, jf2 = (T)0;
+            unsigned key = 0xffffu;
+            if (active) {
+                uint32_t i0, i1, c = 0;
+                if (STRAT) {
+                    key = s_cube[buf][threadIdx.x];
+                    i0 = (uint32_t)(c_lo + key);
+                    i1 = (uint32_t)(row - s_off[buf][key]);
+                    c = i0;
                 } else {
-                    for (int d = 0; d < dim; ++d) {
-                        const int64_t b = (int64_t)d * ni + s_ids[d * FV_BLOCK + threadIdx.x];
-                        atomicAdd(&weights[b], jf2);
-                        atomicAdd(&counts[b], 1ull);
+                    i0 = (uint32_t)(uint64_t)row;
+                    i1 = (uint32_t)((uint64_t)row >> 32);
+                }
+                Integrand<FAM, T> fn;
+                fn.init();
+                T jac = (T)1;
+                for (int d0 = 0; d0 < dim; d0 += LANES) {
+                    T u[LANES];
+                    philox_block<T>(seed, call, i0, i1, (uint32_t)(d0 / LANES), u);
+    #pragma unroll
+                    for (int j = 0; j < LANES; ++j) {
+                        const int d = d0 + j;
+                        if (d < dim) {
+                            T y;
+                            if (STRAT) {
+                                const uint32_t q = c / (uint32_t)n_strat;
+                                const uint32_t p = c - q * (uint32_t)n_strat;
+                                c = q;
+                                y = div_rn(add_rn((T)p, u[j]), nsf);
+                                if (y >= (T)1) y = (T)0.999999;
+                            } else {
+                                y = mul_rn(u[j], (T)0.999999);
+                            }
+                            const T t = mul_rn(y, nif);
+                            const T fl = floor(t);
+                            long long k = (long long)fl;
+                            k = k < 0 ? 0 : (k >= ni ? ni - 1 : k);
+                            const T o = sub_rn(t, fl);
+                            const int64_t bin = (int64_t)d * ni + k;
+                            const P2 e = records ? __ldg(reinterpret_cast<const P2*>(&recs[bin])) : __ldg(&edges[bin]);
+                            const T x = add_rn(e.x, mul_rn(e.y, o));
+                            jac = mul_rn(jac, mul_rn(nif, e.y));
+                            s_ids[d * FV_BLOCK + threadIdx.x] = (int)k;
+                            fn.step(add_rn(mul_rn(x, S.size[d]), S.start[d]), d, S);
+                        }
+                    }
+                }
+                const T f = mul_rn(fn.finish(S), S.scale);
+                jf = mul_rn(f, jac);
+                jf2 = mul_rn(jf, jf);
+                if (do_hist) {
+                    if (hist_smem) {
+                        for (int d = 0; d < dim; ++d) {
+                            const int b = d * (int)ni + s_ids[d * FV_BLOCK + threadIdx.x];
+                            atomicAdd(&s_w[b], jf2);
+                            atomicAdd(&s_c[b], 1u);
+                        }
+                    } else if (records) {
+                        for (int d = 0; d < dim; ++d) {
+                            MapRecord<T>* r = &recs[(int64_t)d * ni + s_ids[d * FV_BLOCK + threadIdx.x]];
+                            atomicAdd(&r->w, jf2);
+                            atomicAdd(&r->c, 1);
+                        }
+                    } else {
+                        for (int d = 0; d < dim; ++d) {
+                            const int64_t b = (int64_t)d * ni + s_ids[d * FV_BLOCK + threadIdx.x];
+                            atomicAdd(&weights[b], jf2);
+                            atomicAdd(&counts[b], 1ull);
+                        }
                     }
                 }
             }
-        }
-        if (STRAT) {
-            const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
-            T a = jf, b = jf2;
-            segmented_warp_sum2<T>(key, a, b);
-            if (active && ((threadIdx.x & 31) == 0 || prev != key)) {
-                atomicAdd(&JF[c_lo + key], a);
-                atomicAdd(&JF2[c_lo + key], b);
+            if (STRAT) {
+                const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+                T a = jf, b = jf2;
+                segmented_warp_sum2<T>(key, a, b);
+                if (active && ((threadIdx.x & 31) == 0 || prev != key)) {
+                    atomicAdd(&JF[c_lo + key], a);
+                    atomicAdd(&JF2[c_lo + key], b);
+                }
+                c_lo += s_cube[buf][(int)(re - rb) - 1];  // cube of the tile's last row: where the next tile starts
+            } else {
+                acc[0] += (double)jf;
+                acc[1] += (double)jf2;
             }
-            c_lo += s_cube[buf][(int)(re - rb) - 1];  // cube of the tile's last row: where the next tile starts
-        } else {
-            acc[0] += (double)jf;
-            acc[1] += (double)jf2;
         }
-    }
     }
     if (do_hist && hist_smem) {
         __syncthreads();
