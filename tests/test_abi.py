@@ -78,3 +78,22 @@ def test_cpu_tensors_fail_loudly():
         tq.MonteCarlo().integrate(lambda x: x.sum(1), 2, 100, torch.tensor([[0.0, 1.0]] * 2), seed=0)
     with pytest.raises(RuntimeError, match="CUDA only"):
         tq.VEGASMap(10, 2, "torch", torch.float64, device="cpu").get_X(torch.rand(4, 2, dtype=torch.float64))
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/tqb200.h must compile as C (it is the FFI contract) and the ctypes mirrors must have the C layout."""
+    from torchquad_b200 import _lib
+
+    src = tmp_path / "sizes.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "tqb200.h"\n'
+        "int main(void) {\n"
+        '  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(tq_integrand), sizeof(tq_vegas_state), sizeof(tq_vegas_result),\n'
+        "         offsetof(tq_vegas_state, edges_layout), offsetof(tq_vegas_result, results), offsetof(tq_vegas_result, status));\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_lib.tq_integrand), ctypes.sizeof(_lib.tq_vegas_state), ctypes.sizeof(_lib.tq_vegas_result),
+            _lib.tq_vegas_state.edges_layout.offset, _lib.tq_vegas_result.results.offset, _lib.tq_vegas_result.status.offset]
+    assert got == want
