@@ -294,6 +294,15 @@ TQ_API int tq_vegas_run_fused(const tq_integrand* fn_host, int32_t dtype, int64_
                        double beta, uint64_t seed, uint32_t first_call, const tq_vegas_state* state,
                        tq_vegas_result* result_host, void* stream);
 
+/* The schedule decision tq_vegas_run_fused takes after every fifth iteration, as a host-only function (no GPU
+ * work; tested against the reference's tensor arithmetic): VEGAS._check_abort_conditions + the weighted mean /
+ * error / chi^2 of vegas.py:161-209,318-362 on a block of n_block <= 5 (result, sigma^2) pairs, evaluated in the
+ * working precision `dtype`.  *stop_out = 1 to stop; otherwise *starting_N_inout holds the next per-iteration
+ * budget.  *mean_out = the block's weighted mean (VEGAS._get_result). */
+TQ_API int tq_vegas_schedule(const double* results_host, const double* sigma2_host, int32_t n_block, int32_t dtype,
+                      double eps_rel, double eps_abs, int64_t N, int64_t fevals, int32_t it, int32_t max_iterations,
+                      int64_t increment, int64_t* starting_N_inout, double* mean_out, int32_t* stop_out);
+
 /* Get (and, when bytes > 0, set) the device's L2 fetch granularity hint (cudaLimitMaxL2FetchGranularity:
  * 32, 64 or 128).  The VEGAS kernels gather map edges and update histogram bins at random positions of
  * tables that exceed L2 when the reference's map size formula is used (Ni = N/250 per dimension); with

@@ -119,6 +119,18 @@ def test_vegas_schedule_matches_oracle_decisions():
             stop_ref = run.check_abort()
             stop = v._check_abort_conditions()
             assert stop == stop_ref and v._starting_N == run.starting_N, (trial, dt)
+            # the same checkpoint as taken by the C++ loop of tq_vegas_run_fused (host-only entry point)
+            import ctypes
+
+            from torchquad_b200 import _lib
+
+            arr = ctypes.c_double * 5
+            start, mean, flag = ctypes.c_int64(100_000 // 25), ctypes.c_double(), ctypes.c_int32()
+            _lib.call("tq_vegas_schedule", arr(*[float(npdt(r)) for r in res]), arr(*[float(npdt(s)) for s in sig]), 5,
+                      _lib.dtype_code(dt), 0.0, 0.0, 100_000, run.fevals, 5, 20, 100_000 // 25, ctypes.byref(start),
+                      ctypes.byref(mean), ctypes.byref(flag))
+            assert bool(flag.value) == stop_ref and (stop_ref or start.value == run.starting_N), (trial, dt)
+            assert mean.value == float(want_mean)
 
 
 def test_shard_ranges_partition_exactly():

@@ -90,6 +90,7 @@ PROTOTYPES = {
     "tq_vegas_map_records_bytes": (c_sz, [c_i32, c_i64, c_i32]),
     "tq_vegas_map_pack_records": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
     "tq_vegas_map_unpack_records": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
+    "tq_vegas_schedule": (ctypes.c_int, [c_p, c_p, c_i32, c_i32, c_f64, c_f64, c_i64, c_i64, c_i32, c_i32, c_i64, c_p, c_p, c_p]),
     "tq_vegas_run_fused": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_i64, c_i32, c_f64, c_f64, c_i32, c_i32, c_i64, c_i32, c_i64,
                                           c_f64, c_f64, c_f64, c_u64, c_u32, ctypes.POINTER(tq_vegas_state),
                                           ctypes.POINTER(tq_vegas_result), c_p]),

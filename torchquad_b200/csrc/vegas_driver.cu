@@ -50,6 +50,31 @@ struct Block {
     }
 };
 
+// vegas.py:161-209 at an iteration with it % 5 == 0: true = stop; otherwise `starting` holds the next budget.
+template <typename T>
+static bool schedule_checkpoint(const Block<T>& blk, double eps_rel, double eps_abs, int64_t N, int64_t fevals, int it,
+                                int max_it, int64_t increment, int64_t& starting) {
+    const T mean = blk.mean();
+    const T res_abs = (T)fabs((double)mean);
+    const T err = blk.error();
+    const T chi2 = blk.chisq(mean);
+    if ((err <= (T)eps_rel * res_abs || err <= (T)eps_abs) && chi2 / (T)5 < (T)1) return true;
+    if (chi2 / (T)5 < (T)1) {
+        if (res_abs == (T)0) {
+            starting += increment;
+        } else {
+            const T acc = err / res_abs;
+            const T scaled = (T)starting * tsqrt((T)(acc / (T)(eps_rel + 1e-8)));
+            const int64_t alt = isfinite((double)scaled) && (double)scaled < 9.0e18 ? (int64_t)scaled : INT64_MAX;
+            starting = starting + increment < alt ? starting + increment : alt;
+        }
+    } else if (chi2 / (T)5 > (T)1) {
+        starting += increment;
+    }
+    if (fevals + starting * 5 > N) return true;
+    return it + 5 > max_it;
+}
+
 template <typename T>
 static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t max_it, double eps_rel, double eps_abs,
                      bool grid_improve, bool warmup, int64_t ni, int32_t n_strat, int64_t n_cubes, double v_cubes,
@@ -154,28 +179,7 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
             blk.sig.push_back((T)rec[4 * k + 1]);
             fevals += (int64_t)rec[4 * k + 3];  // sum nh of the pass (vegas.py:291)
         }
-        const T mean = blk.mean();
-        const T res_abs = (T)fabs((double)mean);
-        const T err = blk.error();
-        const T chi2 = blk.chisq(mean);
-        bool stop = false;
-        if ((err <= (T)eps_rel * res_abs || err <= (T)eps_abs) && chi2 / (T)5 < (T)1) stop = true;
-        if (!stop) {
-            if (chi2 / (T)5 < (T)1) {
-                if (res_abs == (T)0) {
-                    starting += increment;
-                } else {
-                    const T acc = err / res_abs;
-                    const T scaled = (T)starting * tsqrt((T)(acc / (T)(eps_rel + 1e-8)));
-                    const int64_t alt = isfinite((double)scaled) && (double)scaled < 9.0e18 ? (int64_t)scaled : INT64_MAX;
-                    starting = starting + increment < alt ? starting + increment : alt;
-                }
-            } else if (chi2 / (T)5 > (T)1) {
-                starting += increment;
-            }
-            if (fevals + starting * 5 > N) stop = true;
-            else if (it + 5 > max_it) stop = true;
-        }
+        const bool stop = schedule_checkpoint<T>(blk, eps_rel, eps_abs, N, fevals, it, max_it, increment, starting);
         if (stop) break;
         first_rec = it;
     }
@@ -193,6 +197,36 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
 }
 
 }  // namespace tq
+
+template <typename T>
+static int schedule_entry(const double* results, const double* sigma2, int n_block, double eps_rel, double eps_abs, int64_t N,
+                          int64_t fevals, int it, int max_it, int64_t increment, int64_t* starting, double* mean_out,
+                          int32_t* stop_out) {
+    tq::Block<T> blk;
+    for (int k = 0; k < n_block; ++k) {
+        blk.res.push_back((T)results[k]);
+        blk.sig.push_back((T)sigma2[k]);
+    }
+    *mean_out = (double)blk.mean();
+    *stop_out = tq::schedule_checkpoint<T>(blk, eps_rel, eps_abs, N, fevals, it, max_it, increment, *starting) ? 1 : 0;
+    return TQ_OK;
+}
+
+extern "C" int tq_vegas_schedule(const double* results_host, const double* sigma2_host, int32_t n_block, int32_t dtype,
+                                 double eps_rel, double eps_abs, int64_t N, int64_t fevals, int32_t it,
+                                 int32_t max_iterations, int64_t increment, int64_t* starting_N_inout, double* mean_out,
+                                 int32_t* stop_out) {
+    TQ_REQUIRE(results_host && sigma2_host && starting_N_inout && mean_out && stop_out && n_block >= 1,
+               "tq_vegas_schedule: NULL argument or empty block");
+    if (dtype == TQ_F32)
+        return schedule_entry<float>(results_host, sigma2_host, n_block, eps_rel, eps_abs, N, fevals, it, max_iterations, increment,
+                                     starting_N_inout, mean_out, stop_out);
+    if (dtype == TQ_F64)
+        return schedule_entry<double>(results_host, sigma2_host, n_block, eps_rel, eps_abs, N, fevals, it, max_iterations, increment,
+                                      starting_N_inout, mean_out, stop_out);
+    tq::set_error("tq_vegas_schedule: unsupported dtype %d", dtype);
+    return TQ_ERR_INVALID_ARGUMENT;
+}
 
 extern "C" int tq_vegas_run_fused(const tq_integrand* fn_host, int32_t dtype, int64_t N, int32_t max_iterations,
                                   double eps_rel, double eps_abs, int32_t use_grid_improve, int32_t use_warmup,
