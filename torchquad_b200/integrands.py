@@ -46,9 +46,14 @@ class BuiltinIntegrand:
             raise ValueError("at most 8 polynomial coefficients")
 
     def _params(self, x):
-        a = torch.tensor(self.a, dtype=x.dtype, device=x.device)
-        u = torch.tensor(self.u, dtype=x.dtype, device=x.device)
-        return a, u
+        """(a, u) as tensors like x; cached per (dtype, device): two host-to-device copies per CALL otherwise."""
+        key = (x.dtype, x.device, tuple(self.a), tuple(self.u))
+        cached = getattr(self, "_param_cache", None)
+        if cached is None or cached[0] != key:
+            a = torch.tensor(self.a, dtype=x.dtype, device=x.device)
+            u = torch.tensor(self.u, dtype=x.dtype, device=x.device)
+            self._param_cache = cached = (key, a, u)
+        return cached[1], cached[2]
 
     def __call__(self, x):
         raise NotImplementedError

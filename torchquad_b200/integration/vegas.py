@@ -318,7 +318,7 @@ class VEGAS(BaseIntegrator):
                 JF = JF + (both[0] - JF.detach()) if grad_path else both[0]
                 JF2 = both[1]
             strat.JF, strat.JF2 = JF, JF2
-            strat.strat_counts = neval.to(self.dtype)
+            strat._counts_stale = True  # strat_counts = float(nh) is materialised on first access
 
         # estimator + damped-variance update in one kernel (vegas.py:293-303, vegas_stratification.py:72-90)
         strat.update_DH()

@@ -125,7 +125,8 @@ class VEGASMap:
     def wants_records(self):
         if self.records_min_bytes is None:
             return False
-        return ops.map_records_bytes(self.dim, self.N_intervals, self.dtype) >= self.records_min_bytes
+        elt = 4 if self.dtype == torch.float32 else 8
+        return self.dim * self.N_intervals * 4 * elt >= self.records_min_bytes  # = tq_vegas_map_records_bytes
 
     def records(self):
         """The record table of the current edges with zeroed histogram fields (opaque uint8 tensor), cached."""
