@@ -35,6 +35,7 @@ extern "C" {
 #define TQ_ERR_INVALID_ARGUMENT (-1)
 #define TQ_ERR_WORKSPACE (-2)
 #define TQ_ERR_UNSUPPORTED (-3)
+#define TQ_ERR_CALLBACK (-4) /* an integrand callback returned non-zero */
 
 #define TQ_F32 0
 #define TQ_F64 1
@@ -144,7 +145,8 @@ TQ_API int tq_vegas_map_accumulate(const void* y, const void* jf2, void* weights
                             int32_t dim, int64_t n_intervals, int32_t dtype, void* stream);
 /* The tail of an unfused VEGAS pass in one kernel (vegas.py:104-112,284-290): jf = (f*volume)*jac,
  * weights[d,k] += jf^2, counts[d,k] += 1, and jf written to jf_out (nullable) for tq_vegas_strat_accumulate.
- * Large maps: pass `records` (and weights = counts = NULL) to accumulate into the record table instead. */
+ * Large maps: pass `records` (and weights = counts = NULL) to accumulate into the record table instead;
+ * weights = counts = records = NULL computes jf only (no grid improvement). */
 TQ_API int tq_vegas_accumulate_fused(const void* y, const void* f, const void* jac, double volume, void* jf_out, void* weights,
                               int64_t* counts, void* records, int64_t rows, int32_t dim, int64_t n_intervals,
                               int32_t dtype, void* stream);
@@ -293,6 +295,31 @@ TQ_API int tq_vegas_run_fused(const tq_integrand* fn_host, int32_t dtype, int64_
                        int64_t n_intervals, int32_t n_strat, int64_t n_cubes, double v_cubes, double alpha,
                        double beta, uint64_t seed, uint32_t first_call, const tq_vegas_state* state,
                        tq_vegas_result* result_host, void* stream);
+
+/* ---- whole VEGAS run with a CALLBACK integrand (the drop-in path for arbitrary Python callables) -------
+ * Same loop and schedule as tq_vegas_run_fused, but every pass materialises its samples: stratified y
+ * (tq_vegas_strat_sample) -> x, jac (tq_vegas_map_forward_packed, with the unit-cube -> domain transform) ->
+ * `eval(user, rows, &f)` -> jf, histogram (tq_vegas_accumulate_fused) -> per-cube sums
+ * (tq_vegas_strat_accumulate) -> updates.  The callback evaluates the integrand on the first `rows` rows of
+ * buffers->x on the SAME stream and stores the device pointer of its `rows` values (working dtype) in *f;
+ * non-zero return aborts the run with TQ_ERR_CALLBACK.  One 8-byte read-back per pass (rows sizes the
+ * callback's view).  Buffers hold `cap_rows` rows; a pass that needs more fails with TQ_ERR_WORKSPACE. */
+typedef int (*tq_eval_callback)(void* user, int64_t rows, const void** f);
+typedef struct tq_vegas_unfused_buffers {
+    void* y;            /* [cap_rows, dim] */
+    void* x;            /* [cap_rows, dim] */
+    void* jac;          /* [cap_rows] */
+    void* jf;           /* [cap_rows] */
+    const void* domain; /* [dim, 2] integration domain (device) */
+    const void* warm_domain; /* [dim, 2] rows {0, 0.999999}: the warm-up's y = u * 0.999999 (vegas.py:236) */
+    int64_t cap_rows;
+    double volume;      /* prod(domain sizes) in the working precision */
+} tq_vegas_unfused_buffers;
+TQ_API int tq_vegas_run_unfused(tq_eval_callback eval, void* user, int32_t dim, int32_t dtype, int64_t N,
+                         int32_t max_iterations, double eps_rel, double eps_abs, int32_t use_grid_improve,
+                         int32_t use_warmup, int64_t n_intervals, int32_t n_strat, int64_t n_cubes, double v_cubes,
+                         double alpha, double beta, uint64_t seed, uint32_t first_call, const tq_vegas_state* state,
+                         const tq_vegas_unfused_buffers* buffers, tq_vegas_result* result_host, void* stream);
 
 /* The schedule decision tq_vegas_run_fused takes after every fifth iteration, as a host-only function (no GPU
  * work; tested against the reference's tensor arithmetic): VEGAS._check_abort_conditions + the weighted mean /

@@ -604,3 +604,58 @@ def test_vegas_unfused_record_layout_matches_pair_layout(cuda, monkeypatch):
             assert float((a.map.x_edges - b.map.x_edges).abs().max()) <= 1e-9
         else:  # fp32 runs agree statistically (see test_vegas_native_loop_equals_python_loop)
             assert abs(float(ra) - float(rb)) <= 2.5 * float(a._get_error())
+
+
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_vegas_native_unfused_loop_equals_python_loop(cuda, tag):
+    """Python-callable integrand: the C++-driven loop (tq_vegas_run_unfused, integrand evaluated through a callback)
+    against the Python-driven loop on the same seed -- same samples, same schedule."""
+    dt = DT[tag]
+    g = F.GenzGaussian(4, a=5.0, u=0.5)
+    calls = []
+
+    def fn(x):
+        calls.append(x.shape[0])
+        return g(x)
+
+    dom = torch.tensor([[0.0, 1.0], [0.0, 1.0], [-0.5, 1.0], [0.0, 2.0]], dtype=dt, device=cuda)
+    runs = {}
+    for native in (True, False):
+        calls.clear()
+        v = tq.VEGAS()
+        v.native_loop = native
+        r = v.integrate(fn, 4, N=300_000, integration_domain=dom, seed=11)
+        runs[native] = (v, r, list(calls))
+    (a, ra, ca), (b, rb, cb_) = runs[True], runs[False]
+    assert a.it == b.it and a.rng._call == b.rng._call and len(ca) == len(cb_) == 5 + a.it
+    assert ra.dtype == rb.dtype == dt and ra.is_cuda
+    if tag == "f64":
+        assert ca == cb_ and a._nr_of_fevals == b._nr_of_fevals == sum(ca)
+        assert abs(float(ra) - float(rb)) <= 1e-9 * abs(float(rb))
+        assert float((a.map.x_edges - b.map.x_edges).abs().max()) <= 1e-9
+        assert torch.equal(a.strat._nh, b.strat._nh)
+    else:  # fp32: see test_vegas_native_loop_equals_python_loop
+        assert abs(a._nr_of_fevals - b._nr_of_fevals) <= 2e-3 * b._nr_of_fevals
+        assert abs(float(ra) - float(rb)) <= 2.5 * float(b._get_error())
+
+    # exceptions raised by the integrand propagate out of the C++ loop
+    class Boom(Exception):
+        pass
+
+    def bad(x):
+        if len(calls) >= 3:
+            raise Boom("third pass")
+        calls.append(0)
+        return g(x)
+
+    calls.clear()
+    with pytest.raises(Boom):
+        tq.VEGAS().integrate(bad, 4, N=300_000, integration_domain=dom, seed=1)
+    # wrong output shape -> the reference's ValueError
+    with pytest.raises(ValueError):
+        tq.VEGAS().integrate(lambda x: g(x)[:-1], 4, N=300_000, integration_domain=dom, seed=1)
+    # an integrand whose values require grad falls back to the differentiable loop
+    w = torch.tensor(1.5, dtype=dt, device=cuda, requires_grad=True)
+    r = tq.VEGAS().integrate(lambda x: w * g(x), 4, N=300_000, integration_domain=dom, seed=11)
+    r.backward()
+    assert r.requires_grad and abs(float(w.grad) - float(r) / 1.5) <= 1e-3 * abs(float(r))

@@ -45,6 +45,19 @@ class tq_vegas_state(ctypes.Structure):
     ]
 
 
+class tq_vegas_unfused_buffers(ctypes.Structure):
+    """Mirror of `struct tq_vegas_unfused_buffers`: sample buffers of a callback-integrand VEGAS run."""
+
+    _fields_ = [
+        ("y", c_p), ("x", c_p), ("jac", c_p), ("jf", c_p), ("domain", c_p), ("warm_domain", c_p), ("cap_rows", c_i64),
+        ("volume", c_f64),
+    ]
+
+
+# int eval(void* user, int64_t rows, const void** f)
+tq_eval_callback = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p))
+
+
 class tq_vegas_result(ctypes.Structure):
     """Mirror of `struct tq_vegas_result` (host memory)."""
 
@@ -90,6 +103,9 @@ PROTOTYPES = {
     "tq_vegas_map_records_bytes": (c_sz, [c_i32, c_i64, c_i32]),
     "tq_vegas_map_pack_records": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
     "tq_vegas_map_unpack_records": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
+    "tq_vegas_run_unfused": (ctypes.c_int, [tq_eval_callback, c_p, c_i32, c_i32, c_i64, c_i32, c_f64, c_f64, c_i32, c_i32, c_i64,
+                                            c_i32, c_i64, c_f64, c_f64, c_f64, c_u64, c_u32, ctypes.POINTER(tq_vegas_state),
+                                            ctypes.POINTER(tq_vegas_unfused_buffers), ctypes.POINTER(tq_vegas_result), c_p]),
     "tq_vegas_schedule": (ctypes.c_int, [c_p, c_p, c_i32, c_i32, c_f64, c_f64, c_i64, c_i64, c_i32, c_i32, c_i64, c_p, c_p, c_p]),
     "tq_vegas_run_fused": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_i64, c_i32, c_f64, c_f64, c_i32, c_i32, c_i64, c_i32, c_i64,
                                           c_f64, c_f64, c_f64, c_u64, c_u32, ctypes.POINTER(tq_vegas_state),

@@ -196,6 +196,141 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
     return TQ_OK;
 }
 
+// The same loop with materialised samples and a callback integrand (tq_vegas_run_unfused).
+template <typename T>
+static int run_unfused(tq_eval_callback eval, void* user, int dim, int32_t dtype, int64_t N, int32_t max_it, double eps_rel,
+                       double eps_abs, bool grid_improve, bool warmup, int64_t ni, int32_t n_strat, int64_t n_cubes,
+                       double v_cubes, double alpha, double beta, uint64_t seed, uint32_t call, const tq_vegas_state* s,
+                       const tq_vegas_unfused_buffers* b, tq_vegas_result* out, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    const size_t elt = sizeof(T);
+    const int64_t increment = N / (max_it + 5);
+    int64_t starting = increment;
+    int64_t fevals = 0;
+    int passes = 0;
+    const int max_passes = TQ_VEGAS_MAX_PASSES;
+    const bool recs = s->edges_layout == TQ_EDGES_RECORDS;
+    const int layout = recs ? TQ_EDGES_RECORDS : TQ_EDGES_PAIRS;
+    const bool small = !recs && small_strat_ok(n_cubes) && (!grid_improve || small_map_ok(dim, ni));
+    MapScratch scratch = {};
+    if (small && grid_improve && !map_scratch_carve(s->map_ws, s->map_ws_bytes, dim, ni, dtype, true, scratch)) {
+        set_error("tq_vegas_run_unfused: map workspace too small");
+        return TQ_ERR_WORKSPACE;
+    }
+    auto update_map = [&]() -> int {
+        if (passes >= max_passes) { set_error("tq_vegas_run_unfused: more than %d passes", max_passes); return TQ_ERR_UNSUPPORTED; }
+        int rc = TQ_OK;
+        if (recs && (rc = tq_vegas_map_unpack_records(s->edges_packed, s->weights, s->counts, dim, ni, dtype, stream))) return rc;
+        rc = map_update_launch(s->x_edges, s->dx_edges, s->weights, s->counts, recs ? nullptr : s->edges_packed, dim, ni, alpha,
+                               dtype, s->status + 4 * passes, false, s->map_ws, s->map_ws_bytes, stream);
+        ++passes;
+        if (!rc && recs) rc = tq_vegas_map_pack_records(s->x_edges, s->dx_edges, s->edges_packed, dim, ni, dtype, stream);
+        return rc;
+    };
+    // y -> x, jac -> f = eval(x) -> jf (+ histogram): everything between sampling and the per-cube sums
+    auto evaluate = [&](int64_t rows, bool hist, void* jf_out) -> int {
+        if (rows > b->cap_rows) {
+            set_error("tq_vegas_run_unfused: a pass of %lld rows exceeds the buffers (%lld)", (long long)rows, (long long)b->cap_rows);
+            return TQ_ERR_WORKSPACE;
+        }
+        int rc = tq_vegas_map_forward_packed(b->y, s->edges_packed, layout, b->domain, b->x, b->jac, nullptr, rows, dim, ni, dtype, stream);
+        if (rc) return rc;
+        const void* f = nullptr;
+        if (eval(user, rows, &f) != 0 || f == nullptr) {
+            set_error("tq_vegas_run_unfused: the integrand callback failed");
+            return TQ_ERR_CALLBACK;
+        }
+        fevals += rows;
+        const bool to_arrays = hist && !recs;
+        return tq_vegas_accumulate_fused(b->y, f, b->jac, b->volume, jf_out, to_arrays ? s->weights : nullptr,
+                                         to_arrays ? s->counts : nullptr, hist && recs ? s->edges_packed : nullptr, rows, dim, ni,
+                                         dtype, stream);
+    };
+    cudaMemsetAsync(s->status, 0, 4 * (size_t)max_passes * sizeof(int32_t), st);
+    if (warmup) {  // vegas.py:211-266
+        const int64_t ns = starting / 5;
+        for (int w = 0; w < 5; ++w) {
+            int rc = tq_mc_sample(b->y, b->warm_domain, 0, ns, dim, dtype, seed, call++, stream);
+            if (rc) return rc;
+            if ((rc = evaluate(ns, true, nullptr))) return rc;
+            if ((rc = update_map())) return rc;
+        }
+    }
+    Block<T> blk;
+    int it = 0;
+    int first_rec = 0;
+    bool have_nh = false;
+    while (true) {
+        ++it;
+        int rc = TQ_OK;
+        if (!have_nh) {
+            rc = strat_nh_launch(s->dh, n_cubes, (double)starting, dtype, s->nh, s->offsets, nullptr, 0, s->ws, s->ws_bytes, stream);
+            if (rc) return rc;
+        }
+        long long M = 0;
+        cudaMemcpyAsync(&M, s->offsets + n_cubes, sizeof(long long), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);  // the callback's view of x needs the row count
+        if (e != cudaSuccess) { set_error("tq_vegas_run_unfused: %s", cudaGetErrorString(e)); return (int)e; }
+        if (M > b->cap_rows) {
+            set_error("tq_vegas_run_unfused: a pass of %lld rows exceeds the buffers (%lld)", M, (long long)b->cap_rows);
+            return TQ_ERR_WORKSPACE;
+        }
+        rc = tq_vegas_strat_sample(s->offsets, n_cubes, n_strat, dim, dtype, nullptr, seed, call++, 0, M, b->y, stream);
+        if (rc) return rc;
+        if ((rc = evaluate(M, grid_improve, b->jf))) return rc;
+        rc = tq_vegas_strat_accumulate(b->jf, 0, s->offsets, 0, n_cubes, s->JF, s->JF2, dtype, stream);
+        if (rc) return rc;
+        if (it > TQ_VEGAS_MAX_PASSES) { set_error("tq_vegas_run_unfused: too many iterations"); return TQ_ERR_UNSUPPORTED; }
+        double* record = s->records + 4 * (it - 1);
+        if (small) {
+            have_nh = it % 5 > 0;
+            SmallStrat sa = {s->JF, s->JF2, s->nh, n_cubes, v_cubes, beta, s->dh, record, have_nh ? (double)starting : 0.0,
+                             s->offsets, nullptr, 0};
+            if (grid_improve) {
+                if (passes >= max_passes) { set_error("tq_vegas_run_unfused: more than %d passes", max_passes); return TQ_ERR_UNSUPPORTED; }
+                SmallMap ma = {s->x_edges, s->dx_edges, s->weights, s->counts, s->edges_packed, scratch, dim, ni, alpha,
+                               s->status + 4 * passes, true};
+                ++passes;
+                rc = small_update_launch(&sa, &ma, dtype, stream);
+            } else {
+                rc = small_update_launch(&sa, nullptr, dtype, stream);
+            }
+            if (rc) return rc;
+        } else {
+            rc = tq_vegas_strat_update(s->JF, s->JF2, s->nh, n_cubes, v_cubes, beta, dtype, s->dh, record, s->ws, s->ws_bytes, stream);
+            if (rc) return rc;
+            if (grid_improve && (rc = update_map())) return rc;
+        }
+        if (it % 5 > 0) continue;
+        const int nrec = it - first_rec;
+        std::vector<double> rec(4 * nrec);
+        cudaMemcpyAsync(rec.data(), s->records + 4 * first_rec, rec.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+        if (passes > 0) cudaMemcpyAsync(out->status, s->status, 4 * (size_t)passes * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("tq_vegas_run_unfused: %s", cudaGetErrorString(e)); return (int)e; }
+        blk.res.clear();
+        blk.sig.clear();
+        for (int k = 0; k < nrec; ++k) {
+            blk.res.push_back((T)rec[4 * k]);
+            blk.sig.push_back((T)rec[4 * k + 1]);
+        }
+        if (schedule_checkpoint<T>(blk, eps_rel, eps_abs, N, fevals, it, max_it, increment, starting)) break;
+        first_rec = it;
+    }
+    out->it = it;
+    out->n_block = (int32_t)blk.res.size();
+    out->fevals = fevals;
+    out->starting_N = starting;
+    out->calls_used = (int32_t)(call);
+    out->n_passes = passes;
+    for (size_t k = 0; k < blk.res.size() && k < 8; ++k) {
+        out->results[k] = (double)blk.res[k];
+        out->sigma2[k] = (double)blk.sig[k];
+    }
+    (void)elt;
+    return TQ_OK;
+}
+
 }  // namespace tq
 
 template <typename T>
@@ -225,6 +360,28 @@ extern "C" int tq_vegas_schedule(const double* results_host, const double* sigma
         return schedule_entry<double>(results_host, sigma2_host, n_block, eps_rel, eps_abs, N, fevals, it, max_iterations, increment,
                                       starting_N_inout, mean_out, stop_out);
     tq::set_error("tq_vegas_schedule: unsupported dtype %d", dtype);
+    return TQ_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int tq_vegas_run_unfused(tq_eval_callback eval, void* user, int32_t dim, int32_t dtype, int64_t N,
+                                    int32_t max_iterations, double eps_rel, double eps_abs, int32_t use_grid_improve,
+                                    int32_t use_warmup, int64_t n_intervals, int32_t n_strat, int64_t n_cubes, double v_cubes,
+                                    double alpha, double beta, uint64_t seed, uint32_t first_call, const tq_vegas_state* state,
+                                    const tq_vegas_unfused_buffers* buffers, tq_vegas_result* result_host, void* stream) {
+    TQ_REQUIRE(eval && state && buffers && result_host, "tq_vegas_run_unfused: NULL argument");
+    TQ_REQUIRE(dim >= 1 && dim <= 255, "tq_vegas_run_unfused: dim %d out of range", dim);
+    TQ_REQUIRE(N >= 1 && max_iterations >= 1 && max_iterations + 5 <= TQ_VEGAS_MAX_PASSES,
+               "tq_vegas_run_unfused: max_iterations must be in [1, %d]", TQ_VEGAS_MAX_PASSES - 5);
+    TQ_REQUIRE(n_cubes >= 1 && n_strat >= 1 && n_intervals >= 2, "tq_vegas_run_unfused: bad map / stratification sizes");
+    if (dtype == TQ_F32)
+        return tq::run_unfused<float>(eval, user, dim, dtype, N, max_iterations, eps_rel, eps_abs, use_grid_improve != 0,
+                                      use_warmup != 0, n_intervals, n_strat, n_cubes, v_cubes, alpha, beta, seed, first_call, state,
+                                      buffers, result_host, stream);
+    if (dtype == TQ_F64)
+        return tq::run_unfused<double>(eval, user, dim, dtype, N, max_iterations, eps_rel, eps_abs, use_grid_improve != 0,
+                                       use_warmup != 0, n_intervals, n_strat, n_cubes, v_cubes, alpha, beta, seed, first_call, state,
+                                       buffers, result_host, stream);
+    tq::set_error("tq_vegas_run_unfused: unsupported dtype %d", dtype);
     return TQ_ERR_INVALID_ARGUMENT;
 }
 

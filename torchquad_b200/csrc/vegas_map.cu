@@ -164,6 +164,7 @@ map_accumulate_global_kernel(const T* __restrict__ y, const T* __restrict__ jf2_
                     } else {
                         wgt = __ldg(&jf2_or_f[r0 + r]);
                     }
+                    if (!recs && !weights) continue;  // jf only
                     if (recs) {  // large maps: both reductions in the bin's record (one DRAM sector)
                         MapRecord<T>* rc = &recs[(int64_t)d * ni + k];
                         atomicAdd(&rc->w, wgt);
@@ -577,8 +578,8 @@ int tq_vegas_accumulate_fused(const void* y, const void* f, const void* jac, dou
                               int64_t* counts, void* records, int64_t rows, int32_t dim, int64_t n_intervals,
                               int32_t dtype, void* stream) {
     TQ_REQUIRE(dim >= 1 && n_intervals >= 1 && rows >= 0, "tq_vegas_accumulate_fused: bad shape");
-    TQ_REQUIRE((records != nullptr) != (weights != nullptr && counts != nullptr),
-               "tq_vegas_accumulate_fused: pass either weights + counts or records");
+    TQ_REQUIRE(!(records != nullptr && (weights != nullptr || counts != nullptr)) && ((weights != nullptr) == (counts != nullptr)),
+               "tq_vegas_accumulate_fused: pass weights + counts, or records, or neither (jf only)");
     if (rows == 0) return TQ_OK;
     return launch_accumulate_global<true>(y, f, jac, volume, jf_out, weights, counts, rows, dim, n_intervals, dtype,
                                           as_stream(stream), records);

@@ -28,6 +28,10 @@ from .vegas_map import VEGASMap
 from .vegas_stratification import VEGASStratification
 
 
+class _NeedsAutograd(Exception):
+    """Raised by the callback of the C++-driven loop when the integrand's values require grad."""
+
+
 class VEGAS(BaseIntegrator):
     """VEGAS Enhanced, arXiv:2009.05112.  Same surface as the reference class.
 
@@ -47,7 +51,8 @@ class VEGAS(BaseIntegrator):
     max_map_intervals = None
     l2_fetch_bytes = None
     initial_adaptation = None  # adaptation_state() of an earlier run: start from its map and stratification
-    native_loop = True  # fused single-GPU runs: drive all passes from C++ (tq_vegas_run_fused)
+    native_loop = True  # single-GPU runs: drive all passes from C++ (tq_vegas_run_fused / tq_vegas_run_unfused)
+    native_unfused_max_bytes = 1 << 30  # sample buffers (y, x) the callback-integrand loop may allocate up front
     _large_map_bytes = 64 << 20
 
     def __init__(self):
@@ -137,9 +142,24 @@ class VEGAS(BaseIntegrator):
                 and dim * N_intervals * (2 * domain.element_size() + 8) > self._large_map_bytes):
             restore_l2 = _lib.l2_fetch_granularity(self.device, int(self.l2_fetch_bytes))
         try:
-            if (self._fused and self.native_loop and not tqdist.is_enabled()
-                    and max_iterations + 5 <= _lib.TQ_VEGAS_MAX_PASSES):
+            native = self.native_loop and not tqdist.is_enabled() and max_iterations + 5 <= _lib.TQ_VEGAS_MAX_PASSES
+            if native and self._fused:
                 return self._integrate_native_loop(N, use_warmup)
+            if native and self._fuse_tail and type(rng) is RNG:
+                # a pass has at most starting_N * sum(dh) + 2 * N_cubes rows and the schedule keeps 5 * starting_N <= N
+                cap_rows = N // 5 + N // 500 + 2 * self.strat.N_cubes + 4096
+                if 2 * cap_rows * dim * domain.element_size() <= self.native_unfused_max_bytes:
+                    try:
+                        return self._integrate_native_unfused(N, use_warmup, cap_rows)
+                    except _NeedsAutograd:
+                        # the integrand's values carry a graph: start over with the differentiable Python loop
+                        self._nr_of_fevals = 0
+                        self.rng._call = self._first_call
+                        self.map = VEGASMap(N_intervals, dim, "torch", self.dtype, device=self.device)
+                        self.strat = VEGASStratification(self._N_increment, dim=dim, rng=self.rng, backend="torch",
+                                                         dtype=self.dtype, device=self.device)
+                        if self.initial_adaptation is not None:
+                            self._load_adaptation(self.initial_adaptation)
             # one status word per map update, written by the kernels, read back in one go at the sync points
             self._status_buf = torch.zeros((max_iterations + 16, 4), dtype=torch.int32, device=self.device)
             if use_warmup:
@@ -177,12 +197,34 @@ class VEGAS(BaseIntegrator):
         vmap.invalidate_packed()
         strat.dh.copy_(state["dh"])
 
+    def _integrate_native_unfused(self, N, use_warmup, cap_rows):
+        """Single-GPU run with an arbitrary Python integrand and the pass loop in C++ (tq_vegas_run_unfused): per
+        pass Python only evaluates the integrand on a view of the sample buffer.  Same kernels and Philox call
+        indices as the Python-driven loop below; gradients need that loop (`_NeedsAutograd`)."""
+        self._first_call = self.rng._call
+
+        def evaluate(x):
+            f_raw, n = self.evaluate_integrand(self._user_fn, x)
+            f_raw = f_raw.reshape(-1) if f_raw.numel() == n else f_raw.squeeze()
+            if torch.is_grad_enabled() and f_raw.requires_grad:
+                raise _NeedsAutograd()
+            return f_raw if f_raw.dtype == self.dtype else f_raw.to(self.dtype)
+
+        res = ops.vegas_run_unfused(evaluate, self.map, self.strat, self._domain, self._volume_host, cap_rows, N,
+                                    self._max_iterations, self._eps_rel, self._eps_abs, self.use_grid_improve, use_warmup,
+                                    self.rng.seed, self._first_call)
+        return self._finish_native(res)
+
     def _integrate_native_loop(self, N, use_warmup):
         """Fused single-GPU run with the pass loop and schedule in C++ (csrc/vegas_driver.cu): same kernels, same
         Philox call indices and therefore the same samples as the Python-driven loop below."""
         first_call = self.rng._call
         res = ops.vegas_run_fused(self._fn_struct, self.map, self.strat, N, self._max_iterations, self._eps_rel,
                                   self._eps_abs, self.use_grid_improve, use_warmup, self.rng.seed, first_call)
+        return self._finish_native(res)
+
+    def _finish_native(self, res):
+        """Adopt the outcome of a C++-driven run (tq_vegas_result) as the integrator's state."""
         self.rng._call = res.calls_used
         self.it = res.it
         self._nr_of_fevals = res.fevals

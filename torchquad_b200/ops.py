@@ -513,18 +513,14 @@ def fused_vegas(fn_struct, edges_packed, weights, counts, row_begin, row_end, se
     return out
 
 
-def vegas_run_fused(fn_struct, vmap, strat, N, max_iterations, eps_rel, eps_abs, use_grid_improve, use_warmup, seed,
-                    first_call):
-    """Whole fused VEGAS run through `tq_vegas_run_fused` (host loop in C++).  `vmap` / `strat` are the
-    VEGASMap / VEGASStratification objects whose tensors hold the state (mutated in place).
-    Returns the filled `tq_vegas_result`; synchronises (the schedule needs the per-block estimates)."""
+def _vegas_state(vmap, strat, use_records):
+    """(tq_vegas_state, keep-alive tensors) over the map / stratification tensors of a native-loop run."""
     dev, dt = vmap.device, vmap.dtype
     n_cubes = strat.N_cubes
     # JF and JF2 must be adjacent ([2, n_cubes]); the constructor's layout is, a user-replaced pair may not be
     if strat.JF.data_ptr() + n_cubes * strat.JF.element_size() != strat.JF2.data_ptr() or strat.JF.dtype != dt:
         pair = torch.empty((2, n_cubes), dtype=dt, device=dev)
         strat.JF, strat.JF2 = pair[0], pair[1]
-    JFs = (strat.JF, strat.JF2)
     # every buffer below is fully written on the device before it is read (the driver clears what it needs)
     ints = torch.empty(2 * n_cubes + 1, dtype=torch.int64, device=dev)
     nh, offsets = ints[:n_cubes], ints[n_cubes:]
@@ -532,22 +528,87 @@ def vegas_run_fused(fn_struct, vmap, strat, N, max_iterations, eps_rel, eps_abs,
     status = torch.empty(_lib.TQ_VEGAS_MAX_PASSES * 4, dtype=torch.int32, device=dev)
     scratch = _map_scratch(vmap.dim, vmap.N_intervals, dt, dev)
     ws = workspace(dev)
-    use_records = bool(use_grid_improve) and vmap.wants_records()
     packed = vmap.records() if use_records else vmap.packed_edges()
     state = _lib.tq_vegas_state(
         ptr(vmap.x_edges), ptr(vmap.dx_edges), ptr(packed), ptr(vmap.weights), ptr(vmap.counts), ptr(strat.dh), ptr(nh),
-        ptr(offsets), ptr(JFs[0]), ptr(JFs[1]), ptr(records), ptr(status), ptr(scratch), scratch.numel(), ws.data_ptr(),
+        ptr(offsets), ptr(strat.JF), ptr(strat.JF2), ptr(records), ptr(status), ptr(scratch), scratch.numel(), ws.data_ptr(),
         ws.numel(), _lib.TQ_EDGES_RECORDS if use_records else _lib.TQ_EDGES_PAIRS)
-    result = _lib.tq_vegas_result()
-    with on_device(dev):
-        call("tq_vegas_run_fused", fn_struct, dtype_code(dt), N, max_iterations, float(eps_rel), float(eps_abs),
-             int(bool(use_grid_improve)), int(bool(use_warmup)), vmap.N_intervals, strat.N_strat, n_cubes,
-             float(strat.V_cubes), float(vmap.alpha), float(strat.beta), seed & 0xFFFFFFFFFFFFFFFF, first_call & 0xFFFFFFFF,
-             state, result, stream_ptr(dev))
+    return state, (ints, records, status, scratch, packed), nh, offsets
+
+
+def _vegas_finish(vmap, strat, use_records, nh, offsets):
     if use_records:
         vmap._edges2_stale = True   # the pair table was not maintained; the records were
     else:
         vmap._records_stale = True
     strat._nh, strat._offsets = nh, offsets
     strat._counts_stale = True  # strat_counts = float(nh) is materialised on first access
+
+
+def vegas_run_fused(fn_struct, vmap, strat, N, max_iterations, eps_rel, eps_abs, use_grid_improve, use_warmup, seed,
+                    first_call):
+    """Whole fused VEGAS run through `tq_vegas_run_fused` (host loop in C++).  `vmap` / `strat` are the
+    VEGASMap / VEGASStratification objects whose tensors hold the state (mutated in place).
+    Returns the filled `tq_vegas_result`; synchronises (the schedule needs the per-block estimates)."""
+    dev, dt = vmap.device, vmap.dtype
+    use_records = bool(use_grid_improve) and vmap.wants_records()
+    state, keep, nh, offsets = _vegas_state(vmap, strat, use_records)
+    result = _lib.tq_vegas_result()
+    with on_device(dev):
+        call("tq_vegas_run_fused", fn_struct, dtype_code(dt), N, max_iterations, float(eps_rel), float(eps_abs),
+             int(bool(use_grid_improve)), int(bool(use_warmup)), vmap.N_intervals, strat.N_strat, strat.N_cubes,
+             float(strat.V_cubes), float(vmap.alpha), float(strat.beta), seed & 0xFFFFFFFFFFFFFFFF, first_call & 0xFFFFFFFF,
+             state, result, stream_ptr(dev))
+    _vegas_finish(vmap, strat, use_records, nh, offsets)
+    del keep
+    return result
+
+
+def vegas_run_unfused(evaluate, vmap, strat, domain, volume, cap_rows, N, max_iterations, eps_rel, eps_abs, use_grid_improve,
+                      use_warmup, seed, first_call):
+    """Whole VEGAS run with a callback integrand through `tq_vegas_run_unfused` (host loop in C++).
+    `evaluate(x)` receives the [rows, dim] view of the sample buffer and returns the `rows` integrand values as a
+    contiguous tensor of the working dtype on the same device (it runs on the current stream).  Exceptions raised
+    by `evaluate` abort the run and propagate.  Returns the filled `tq_vegas_result`."""
+    dev, dt = vmap.device, vmap.dtype
+    dim = vmap.dim
+    use_records = bool(use_grid_improve) and vmap.wants_records()
+    state, keep, nh, offsets = _vegas_state(vmap, strat, use_records)
+    y = torch.empty((cap_rows, dim), dtype=dt, device=dev)
+    x = torch.empty((cap_rows, dim), dtype=dt, device=dev)
+    jac = torch.empty(cap_rows, dtype=dt, device=dev)
+    jf = torch.empty(cap_rows, dtype=dt, device=dev)
+    warm = torch.tensor([[0.0, 0.999999]] * dim, dtype=dt, device=dev)
+    dom = domain.detach().contiguous()
+    buffers = _lib.tq_vegas_unfused_buffers(ptr(y), ptr(x), ptr(jac), ptr(jf), ptr(dom), ptr(warm), cap_rows, float(volume))
+    failure = []
+    last = [None]  # keeps the latest value tensor alive until the kernels that read it are queued behind it
+
+    def _cb(_user, rows, f_out):
+        try:
+            f = evaluate(x[:rows])
+            if f.dtype != dt or f.device != dev or f.numel() != rows:
+                raise ValueError(f"integrand values must be {rows} values of dtype {dt} on {dev}, "
+                                 f"got {tuple(f.shape)} / {f.dtype} / {f.device}")
+            last[0] = f = f.contiguous()
+            f_out[0] = f.data_ptr()
+            return 0
+        except BaseException as exc:  # noqa: BLE001 - re-raised by the caller below
+            failure.append(exc)
+            return 1
+
+    callback = _lib.tq_eval_callback(_cb)
+    result = _lib.tq_vegas_result()
+    try:
+        with on_device(dev):
+            call("tq_vegas_run_unfused", callback, None, dim, dtype_code(dt), N, max_iterations, float(eps_rel), float(eps_abs),
+                 int(bool(use_grid_improve)), int(bool(use_warmup)), vmap.N_intervals, strat.N_strat, strat.N_cubes,
+                 float(strat.V_cubes), float(vmap.alpha), float(strat.beta), seed & 0xFFFFFFFFFFFFFFFF,
+                 first_call & 0xFFFFFFFF, state, buffers, result, stream_ptr(dev))
+    except RuntimeError:
+        if failure:
+            raise failure[0]
+        raise
+    _vegas_finish(vmap, strat, use_records, nh, offsets)
+    del keep
     return result
