@@ -102,3 +102,30 @@ def test_results_do_not_depend_on_launch_geometry(cuda):
     f = torch.rand(13**3, dtype=torch.float64, device=cuda)
     both = float(ops.nc_contract_f64(f[:777].contiguous(), table, 0, 777) + ops.nc_contract_f64(f[777:].contiguous(), table, 777, 13**3))
     assert abs(float(ops.nc_contract(f, table)) - both) <= 1e-14 * abs(both)
+
+
+@pytest.mark.parametrize("cols", [2, 3, 16, 200, 256, 257, 1000, 2048])
+def test_vector_valued_reductions_every_column_count(cuda, cols):
+    """Vector-valued integrands (base_integrator.py:77-89, grid_integrator.py:70-82): column sums and the weighted
+    contraction for narrow (a thread keeps one column) and wide (a thread keeps several) outputs, tile remainders."""
+    g = torch.Generator().manual_seed(cols)
+    for dt, rtol in ((torch.float64, 1e-12), (torch.float32, 2e-6)):
+        rows = 3000 if cols > 256 else 70_001
+        f = (torch.rand(rows, cols, generator=g, dtype=torch.float64) - 0.3).to(dt)
+        s, q = ops.sum_columns(f.to(cuda), want_sumsq=True)
+        assert torch.allclose(s.cpu(), f.double().sum(0), rtol=1e-11, atol=1e-9)
+        assert torch.allclose(q.cpu(), (f.double() ** 2).sum(0), rtol=1e-11, atol=1e-9)
+        n, dim = 11, 3
+        w = (torch.rand(dim, n, generator=g, dtype=torch.float64) + 0.5).to(dt)
+        fv = (torch.rand(n**dim, cols, generator=g, dtype=torch.float64) - 0.3).to(dt)
+        W = torch.einsum("i,j,k->ijk", w[0].double(), w[1].double(), w[2].double()).reshape(-1, 1)
+        want = (fv.double() * W).sum(0)
+        got = ops.nc_contract(fv.to(cuda), w.to(cuda))
+        assert got.shape == (cols,) and got.dtype == dt
+        assert torch.allclose(got.double().cpu(), want, rtol=rtol * 50, atol=rtol * 50 * float(want.abs().max()))
+        # a sub-range of points, as the chunked / multi-GPU paths use it
+        part = ops.nc_contract_f64(fv[100:900].contiguous().to(cuda), w.to(cuda), 100, 900)
+        assert torch.allclose(part.cpu(), (fv[100:900].double() * W[100:900]).sum(0), rtol=rtol * 50,
+                              atol=rtol * 50 * float(want.abs().max()))
+        # deterministic: the same launch twice gives the same bits
+        assert torch.equal(ops.nc_contract(fv.to(cuda), w.to(cuda)), got)

@@ -314,30 +314,87 @@ contract1_kernel(const T* __restrict__ f, const T* __restrict__ w, uint32_t n, i
     grid_sum_finish<1>(acc, sh, partials, ticket, out);
 }
 
-// cols > 1: each thread owns one column (flat stride a multiple of cols), shared accumulators per CTA.
+// cols > 1 (vector-valued integrands, grid_integrator.py:70-82): a CTA walks tiles of CK_ROWS grid points.  Per tile
+// the point weights are formed ONCE per row (one thread each) into shared memory, then the tile's rows x cols values
+// are read coalesced by threads that keep a FIXED column (stride a multiple of cols), so a thread accumulates in
+// registers and touches the per-CTA column accumulators once, at the end.  Up to CK_COLS_PER_THREAD * 256 columns.
+constexpr int CK_ROWS = 1024;
+constexpr int CK_COLS_PER_THREAD = 8;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 contractk_kernel(const T* __restrict__ f, const T* __restrict__ w, uint32_t n, int dim, int64_t p_begin,
-                 int64_t p_end, int64_t cols, int64_t S, double* partials, unsigned int* ticket, double* out,
-                 bool use_smem) {
+                 int64_t p_end, int cols, double* partials, unsigned int* ticket, double* out, bool use_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ bool is_last;
+    __shared__ T s_pw[CK_ROWS];
     double* sacc = reinterpret_cast<double*>(smem_raw);  // [cols]
-    for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) sacc[c] = 0.0;
-    const T* sw = stage_weights<T>(w, reinterpret_cast<T*>(sacc + cols), dim, n, use_smem);  // [dim*n]
+    for (int c = threadIdx.x; c < cols; c += 256) sacc[c] = 0.0;
+    const T* sw = stage_weights<T>(w, reinterpret_cast<T*>(sacc + cols), dim, n, use_smem);  // [dim*n]; syncs when staged
     const GridIndex gi{n, dim};
-    const int64_t total = (p_end - p_begin) * cols;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid < S) {
-        double acc = 0.0;
-        for (int64_t e = tid; e < total; e += S) {
-            const int64_t r = e / cols;
-            acc += (double)f[e] * (double)point_weight<T>(sw, gi, (uint64_t)(p_begin + r));
+    const int64_t rows = p_end - p_begin;
+    const int64_t ntiles = (rows + CK_ROWS - 1) / CK_ROWS;
+    double acc[CK_COLS_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < CK_COLS_PER_THREAD; ++k) acc[k] = 0.0;
+    // narrow: threads [0, span) own column t % cols and rows t / cols, t / cols + rstep, ...
+    const int span = cols <= 256 ? (256 / cols) * cols : 0;
+    const int rstep = cols <= 256 ? 256 / cols : 1;
+    const int my_col = cols <= 256 ? (int)threadIdx.x % cols : 0;
+    const int my_row0 = cols <= 256 ? (int)threadIdx.x / cols : 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t r0 = t * CK_ROWS;
+        const int rows_here = (int)(rows - r0 < CK_ROWS ? rows - r0 : CK_ROWS);
+        __syncthreads();  // previous tile's weights are no longer read
+        for (int r = threadIdx.x; r < rows_here; r += 256) s_pw[r] = point_weight<T>(sw, gi, (uint64_t)(p_begin + r0 + r));
+        __syncthreads();
+        const T* ft = f + r0 * cols;
+        if (cols <= 256) {
+            if ((int)threadIdx.x < span) {
+                int r = my_row0;
+                for (; r + 3 * rstep < rows_here; r += 4 * rstep) {  // four independent loads in flight
+                    const T v0 = __ldcs(ft + (int64_t)r * cols + my_col);
+                    const T v1 = __ldcs(ft + (int64_t)(r + rstep) * cols + my_col);
+                    const T v2 = __ldcs(ft + (int64_t)(r + 2 * rstep) * cols + my_col);
+                    const T v3 = __ldcs(ft + (int64_t)(r + 3 * rstep) * cols + my_col);
+                    acc[0] += (double)v0 * (double)s_pw[r];
+                    acc[0] += (double)v1 * (double)s_pw[r + rstep];
+                    acc[0] += (double)v2 * (double)s_pw[r + 2 * rstep];
+                    acc[0] += (double)v3 * (double)s_pw[r + 3 * rstep];
+                }
+                for (; r < rows_here; r += rstep) acc[0] += (double)__ldcs(ft + (int64_t)r * cols + my_col) * (double)s_pw[r];
+            }
+        } else {  // wide: thread owns columns threadIdx.x + 256 k
+            for (int r = 0; r < rows_here; ++r) {
+                const double pw = (double)s_pw[r];
+                const T* fr = ft + (int64_t)r * cols;
+#pragma unroll
+                for (int k = 0; k < CK_COLS_PER_THREAD; ++k) {
+                    const int c = (int)threadIdx.x + 256 * k;
+                    if (c < cols) acc[k] += (double)__ldcs(fr + c) * pw;
+                }
+            }
         }
-        atomicAdd(&sacc[tid % cols], acc);
     }
     __syncthreads();
-    for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) partials[(size_t)blockIdx.x * cols + c] = sacc[c];
+    if (cols <= 256) {  // fixed-order sum of the rstep threads that share a column (deterministic)
+        __shared__ double s_thr[256];
+        s_thr[threadIdx.x] = acc[0];
+        __syncthreads();
+        if ((int)threadIdx.x < cols) {
+            double a = 0.0;
+            for (int j = 0; j < rstep; ++j) a += s_thr[threadIdx.x + j * cols];
+            sacc[threadIdx.x] = a;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CK_COLS_PER_THREAD; ++k) {
+            const int c = (int)threadIdx.x + 256 * k;
+            if (c < cols) sacc[c] = acc[k];  // one owner per column
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cols; c += 256) partials[(size_t)blockIdx.x * cols + c] = sacc[c];
     if (threadIdx.x == 0) {
         __threadfence();
         is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
@@ -345,7 +402,7 @@ contractk_kernel(const T* __restrict__ f, const T* __restrict__ w, uint32_t n, i
     __syncthreads();
     if (is_last) {
         __threadfence();
-        for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
+        for (int c = threadIdx.x; c < cols; c += 256) {
             double a = 0.0;
             for (unsigned int b = 0; b < gridDim.x; ++b) a += __ldcg(&partials[(size_t)b * cols + c]);
             out[c] = a;
@@ -449,17 +506,22 @@ int tq_nc_contract(const void* f, const void* w, int32_t n, int32_t dim, int64_t
         });
         return check_launch("contract1_kernel");
     }
-    int grid = grid_for(rows * cols, 256, 2);
-    int64_t threads = (int64_t)grid * 256;
-    if (threads < cols) { grid = (int)((cols + 255) / 256); threads = (int64_t)grid * 256; }
-    const int64_t S = (threads / cols) * cols;
+    const int64_t ntiles = (rows + CK_ROWS - 1) / CK_ROWS;
+    int64_t grid = ntiles < (int64_t)num_sms() * 4 ? ntiles : (int64_t)num_sms() * 4;
+    if (grid < 1) grid = 1;
+    // the per-CTA partials (cols doubles each) must fit the caller's workspace
+    const size_t ws_left = ws_bytes > (size_t)(64 << 10) ? ws_bytes - (size_t)(64 << 10) : 0;
+    const int64_t grid_cap = (int64_t)(ws_left / ((size_t)cols * sizeof(double)));
+    if (grid > grid_cap) grid = grid_cap > 0 ? grid_cap : 1;
     double* partials = wk.take<double>((size_t)grid * cols);
     if (!ticket || !partials) { set_error("tq_nc_contract: workspace too small"); return TQ_ERR_WORKSPACE; }
     TQ_DISPATCH_DTYPE(dtype, {
         const bool use_smem = (size_t)dim * n * sizeof(T) <= NC_TABLE_SMEM;
         const size_t smem = (size_t)cols * sizeof(double) + (use_smem ? (size_t)dim * n * sizeof(T) : 0);
-        cudaFuncSetAttribute(contractk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NC_TABLE_SMEM + 2048 * sizeof(double)));
-        contractk_kernel<T><<<TQ_GRID(grid), 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, cols, S, partials, ticket, out_f64, use_smem);
+        if (smem > 40 * 1024)
+            cudaFuncSetAttribute(contractk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NC_TABLE_SMEM + 2048 * sizeof(double)));
+        contractk_kernel<T><<<TQ_GRID((int)grid), 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, (int)cols,
+                                                                  partials, ticket, out_f64, use_smem);
     });
     return check_launch("contractk_kernel");
 }

@@ -203,8 +203,21 @@ sumk_kernel(const T* __restrict__ f, int64_t rows, int64_t cols, int64_t S, doub
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid < S) {
         double s = 0.0, q = 0.0;
-        for (int64_t i = tid; i < n; i += S) {
-            double x = (double)f[i];
+        constexpr int U = 8;  // independent loads in flight per thread (HBM latency x bandwidth needs ~5 MB in flight)
+        int64_t i = tid;
+        for (; i + (U - 1) * S < n; i += U * S) {
+            T v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = __ldcs(f + i + u * S);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double x = (double)v[u];
+                s += x;
+                if (SQ) q += x * x;
+            }
+        }
+        for (; i < n; i += S) {
+            const double x = (double)f[i];
             s += x;
             if (SQ) q += x * x;
         }
@@ -313,7 +326,11 @@ int tq_sum_columns(const void* f, int64_t rows, int64_t cols, int32_t dtype, dou
         return check_launch("tq_sum_columns copy");
     }
     TQ_REQUIRE(cols <= 2048, "tq_sum_columns: at most 2048 integrand components (got %lld)", (long long)cols);
-    int grid = grid_for(rows * cols, 256, 2);
+    int grid = grid_for((rows * cols + 7) / 8, 256, 8);
+    // the per-CTA partials (cols * 2 doubles each) must fit the caller's workspace
+    const size_t ws_left = ws_bytes > (size_t)(64 << 10) ? ws_bytes - (size_t)(64 << 10) : 0;
+    const int64_t grid_cap = (int64_t)(ws_left / ((size_t)cols * 2 * sizeof(double)));
+    if (grid > grid_cap) grid = (int)(grid_cap > 0 ? grid_cap : 1);
     // stride S: largest multiple of cols not exceeding the thread count (at least cols)
     int64_t threads = (int64_t)grid * 256;
     if (threads < cols) { grid = (int)((cols + 255) / 256); threads = (int64_t)grid * 256; }
