@@ -73,7 +73,7 @@ int tq_version(void) { return 100; }
 
 uint64_t tq_kernel_launches(void) { return tq::g_launches; }
 
-size_t tq_workspace_bytes(void) { return (size_t)8 << 20; }
+size_t tq_workspace_bytes(void) { return (size_t)32 << 20; }  // scan tile sums of 2^31 cubes need 16 MiB
 
 int tq_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;
