@@ -12,7 +12,8 @@ from ..integrands import BuiltinIntegrand
 from .base_integrator import BaseIntegrator
 from .compiled import GraphedIntegrate
 from .integration_grid import IntegrationGrid, grid_nodes
-from .utils import _linspace_with_grads, _setup_integration_domain, expand_func_values_and_squeeze_integral
+from .utils import (_check_integration_domain, _is_compiling, _linspace_with_grads, _setup_integration_domain,
+                    expand_func_values_and_squeeze_integral)
 
 
 class GridIntegrator(BaseIntegrator):
@@ -60,9 +61,10 @@ class GridIntegrator(BaseIntegrator):
 
     def _scale(self, hs, domain=None):
         """prod_d h_d / c, multiplied in the order the reference applies its passes."""
-        s = hs[0] / self._rule_denominator
-        for d in range(1, hs.shape[0]):
-            s = s * (hs[d] / self._rule_denominator)
+        q = (hs / self._rule_denominator).unbind()  # one division kernel, then views
+        s = q[0]
+        for d in range(1, len(q)):
+            s = s * q[d]
         return s
 
     def integrate(self, fn, dim, N, integration_domain, backend):
@@ -70,7 +72,15 @@ class GridIntegrator(BaseIntegrator):
         if N is None:
             N = self._get_minimal_N(dim)
         domain = _setup_integration_domain(dim, integration_domain, backend)
-        self._check_inputs(dim=dim, N=N, integration_domain=domain)
+        # One read-back of the domain serves the reference's value check (utils.py:196-205) and the node vectors.
+        self._check_inputs(dim=dim, N=N)
+        if _check_integration_domain(domain, check_values=False) != dim:
+            raise ValueError("The dimension of the integration domain must match the passed function dimensionality dim.")
+        host_bounds = None
+        if not domain.requires_grad and not _is_compiling(domain):
+            host_bounds = domain.detach().tolist()
+            if any(hi < lo for lo, hi in host_bounds):
+                raise ValueError("integration_domain has invalid boundary values")
         N = self._adjust_N(dim=dim, N=N)
         rank, world = tqdist.rank_and_world()
         fused = isinstance(fn, BuiltinIntegrand) and fn.dim == dim and not domain.requires_grad
@@ -78,7 +88,13 @@ class GridIntegrator(BaseIntegrator):
         total_points = n**dim
         chunk_rows = max(1, self.max_points_bytes // (dim * domain.element_size()))
         if not fused and world == 1 and total_points <= chunk_rows:
-            grid_points, hs, n_per_dim = self.calculate_grid(N, domain)
+            grid_func = self._grid_func
+            if host_bounds is not None and getattr(grid_func, "_equally_spaced", False):
+                IntegrationGrid._check_inputs(None, N, domain, True)
+                nodes, hs, n_per_dim = grid_nodes(N, domain, grid_func, host_bounds=host_bounds)
+                grid_points = ops.nc_grid_points(nodes)
+            else:
+                grid_points, hs, n_per_dim = self.calculate_grid(N, domain, disable_integration_domain_check=True)
             function_values, num_points = self.evaluate_integrand(fn, grid_points)
             self._nr_of_fevals = num_points
             if hasattr(self, "integrate_values"):  # Gaussian rules: weights go into the contraction kernel
@@ -86,8 +102,8 @@ class GridIntegrator(BaseIntegrator):
             return self.calculate_result(function_values, dim, n_per_dim, hs, domain)
 
         # sharded / chunked / fused: contiguous point ranges of the same grid
-        IntegrationGrid._check_inputs(None, N, domain, False)
-        nodes, hs, n = grid_nodes(N, domain, self._grid_func)
+        IntegrationGrid._check_inputs(None, N, domain, True)  # values already validated above
+        nodes, hs, n = grid_nodes(N, domain, self._grid_func, host_bounds=host_bounds)
         table = self._weight_table(n, dim, domain.dtype, domain.device)
         begin, end = tqdist.shard_range(total_points, rank, world)
         if fused:

@@ -21,21 +21,23 @@ def grid_func(integration_domain, N, requires_grad=False, backend=None):
 grid_func._equally_spaced = True  # lets grid_nodes read all bounds back at once instead of two scalars per dim
 
 
-def grid_nodes(N, integration_domain, grid_func=grid_func):
-    """(nodes [dim, n], h [dim], n): per-dimension nodes and mesh widths (integration_grid.py:64-93)."""
+def grid_nodes(N, integration_domain, grid_func=grid_func, host_bounds=None):
+    """(nodes [dim, n], h [dim], n): per-dimension nodes and mesh widths (integration_grid.py:64-93).
+    `host_bounds` = integration_domain.tolist() when the caller has already read it back."""
     dim = integration_domain.shape[0]
     n = int(N ** (1.0 / dim) + 1e-8)
     requires_grad = bool(getattr(integration_domain, "requires_grad", False))
     if getattr(grid_func, "_equally_spaced", False) and not requires_grad and not _is_compiling(integration_domain):
         # torch.linspace reads tensor bounds back one scalar at a time; one copy of the whole domain gives the
         # same numbers with a single synchronisation
-        bounds = integration_domain.detach().tolist()
+        bounds = host_bounds if host_bounds is not None else integration_domain.detach().tolist()
         grid_1d = [torch.linspace(lo, hi, n, dtype=integration_domain.dtype, device=integration_domain.device)
                    for lo, hi in bounds]
     else:
         grid_1d = [grid_func(integration_domain[d], n, requires_grad=requires_grad, backend="torch") for d in range(dim)]
-    h = torch.stack([g[1] - g[0] for g in grid_1d])
-    return torch.stack(grid_1d), h, n
+    nodes = torch.stack(grid_1d)
+    h = nodes[:, 1] - nodes[:, 0]  # g[1] - g[0] per dimension (integration_grid.py:91), one kernel for all of them
+    return nodes, h, n
 
 
 class IntegrationGrid:
