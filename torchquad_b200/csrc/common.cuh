@@ -68,6 +68,11 @@ struct FastDiv {
         const uint32_t t = __umulhi(m, x);
         return (t + ((x - t) >> 1)) >> (s - 1);
     }
+    // same for callers that know d >= 2 (no test, no branch)
+    __device__ __forceinline__ uint32_t div_ge2(uint32_t x) const {
+        const uint32_t t = __umulhi(m, x);
+        return (t + ((x - t) >> 1)) >> (s - 1);
+    }
 };
 
 

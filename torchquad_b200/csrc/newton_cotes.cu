@@ -238,7 +238,7 @@ contract1_kernel(const T* __restrict__ f, const T* __restrict__ w, uint32_t n, i
             if (dim < 2) { p0 = p1 = (T)1; return; }
             if (h >= 0xffffffffull) { p0 = prefix_of(h); p1 = prefix_of(h + 1); return; }
             uint32_t q = (uint32_t)h;
-            const uint32_t t0 = fd.div(q);
+            const uint32_t t0 = fd.div_ge2(q);
             const uint32_t d0 = q - t0 * n;  // fastest leading digit
             const T* w0 = sw + (dim - 2) * n;
             p0 = w0[d0];
@@ -246,7 +246,7 @@ contract1_kernel(const T* __restrict__ f, const T* __restrict__ w, uint32_t n, i
             p1 = carry ? (T)0 : w0[d0 + 1];
             q = t0;
             for (int d = dim - 3; d >= 0; --d) {
-                const uint32_t t = fd.div(q);
+                const uint32_t t = fd.div_ge2(q);
                 const T wd = sw[d * n + (q - t * n)];
                 p0 *= wd;
                 p1 *= wd;
@@ -278,7 +278,7 @@ contract1_kernel(const T* __restrict__ f, const T* __restrict__ w, uint32_t n, i
 #pragma unroll
             for (int j = 0; j < V; ++j) fv[j] = vec_elem<T>(nxt[j / (16 / (int)sizeof(T))], j % (16 / (int)sizeof(T)));
             if (vi + step < nvec) load_vec(vi + step, nxt);
-            if (n >= (uint32_t)V) {
+            if (n >= (uint32_t)V && n >= 2) {
                 // A vector crosses at most one row of the last dimension.  Both rows' prefixes come from ONE digit
                 // walk (they differ in the fastest leading digit only) and each element selects: a branch on the
                 // crossing would diverge in every warp (32 x V consecutive points span several rows) and execute
