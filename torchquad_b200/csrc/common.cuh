@@ -193,6 +193,34 @@ __device__ __forceinline__ void grid_sum_finish(double (&v)[NV], double* sh, dou
     }
 }
 
+// The same reduction of two values with separate destinations (out1 may be NULL).
+__device__ __forceinline__ void grid_sum_finish_split(double (&v)[2], double* sh, double* partials, unsigned int* ticket,
+                                                      double* out0, double* out1) {
+    block_sum<2>(v, sh);
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        partials[(size_t)blockIdx.x * 2] = v[0];
+        partials[(size_t)blockIdx.x * 2 + 1] = v[1];
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double acc[2] = {0.0, 0.0};
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            acc[0] += __ldcg(&partials[(size_t)b * 2]);
+            acc[1] += __ldcg(&partials[(size_t)b * 2 + 1]);
+        }
+        block_sum<2>(acc, sh);
+        if (threadIdx.x == 0) {
+            *out0 = acc[0];
+            if (out1) *out1 = acc[1];
+            *ticket = 0u;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- scans
 template <typename V>
 __device__ __forceinline__ V warp_incl_scan(V v) {

@@ -163,7 +163,7 @@ mc_sample_backward_kernel(const T* __restrict__ g, int64_t row_begin, int64_t nr
 // Column sums of f[rows, cols] in fp64.  cols == 1: vectorised grid-stride loads, deterministic tree.
 template <typename T, bool SQ>
 __global__ void __launch_bounds__(256)
-sum1_kernel(const T* __restrict__ f, int64_t n, double* partials, unsigned int* ticket, double* out) {
+sum1_kernel(const T* __restrict__ f, int64_t n, double* partials, unsigned int* ticket, double* out_s, double* out_q) {
     constexpr int V = 16 / sizeof(T);
     __shared__ double sh[32 * 2];
     double s = 0.0, q = 0.0;
@@ -186,7 +186,7 @@ sum1_kernel(const T* __restrict__ f, int64_t n, double* partials, unsigned int* 
         if (SQ) q += x * x;
     }
     double v[2] = {s, q};
-    grid_sum_finish<2>(v, sh, partials, ticket, out);
+    grid_sum_finish_split(v, sh, partials, ticket, out_s, SQ ? out_q : nullptr);  // straight into the caller's tensors
 }
 
 // cols > 1: thread t of the grid owns flat elements t, t+S, ... with S a multiple of cols, so its
@@ -313,17 +313,12 @@ int tq_sum_columns(const void* f, int64_t rows, int64_t cols, int32_t dtype, dou
     if (cols == 1) {
         const int grid = grid_for((rows + 3) / 4, 256, 4);
         double* partials = w.take<double>((size_t)grid * 2);
-        double* out = w.take<double>(2);
-        if (!ticket || !partials || !out) { set_error("tq_sum_columns: workspace too small"); return TQ_ERR_WORKSPACE; }
+        if (!ticket || !partials) { set_error("tq_sum_columns: workspace too small"); return TQ_ERR_WORKSPACE; }
         TQ_DISPATCH_DTYPE(dtype, {
-            if (sumsq_f64) sum1_kernel<T, true><<<TQ_GRID(grid), 256, 0, st>>>((const T*)f, rows, partials, ticket, out);
-            else sum1_kernel<T, false><<<TQ_GRID(grid), 256, 0, st>>>((const T*)f, rows, partials, ticket, out);
+            if (sumsq_f64) sum1_kernel<T, true><<<TQ_GRID(grid), 256, 0, st>>>((const T*)f, rows, partials, ticket, sum_f64, sumsq_f64);
+            else sum1_kernel<T, false><<<TQ_GRID(grid), 256, 0, st>>>((const T*)f, rows, partials, ticket, sum_f64, nullptr);
         });
-        int rc = check_launch("sum1_kernel");
-        if (rc) return rc;
-        cudaMemcpyAsync(sum_f64, out, sizeof(double), cudaMemcpyDeviceToDevice, st);
-        if (sumsq_f64) cudaMemcpyAsync(sumsq_f64, out + 1, sizeof(double), cudaMemcpyDeviceToDevice, st);
-        return check_launch("tq_sum_columns copy");
+        return check_launch("sum1_kernel");
     }
     TQ_REQUIRE(cols <= 2048, "tq_sum_columns: at most 2048 integrand components (got %lld)", (long long)cols);
     int grid = grid_for((rows * cols + 7) / 8, 256, 8);

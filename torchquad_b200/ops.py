@@ -84,8 +84,9 @@ def sum_columns(f, want_sumsq=False):
     f2 = f.detach().contiguous()
     rows = f2.shape[0]
     cols = 1 if f2.dim() == 1 else int(f2[0].numel()) if rows > 0 else int(torch.Size(f2.shape[1:]).numel())
-    s = torch.zeros(cols, dtype=torch.float64, device=f2.device)
-    q = torch.zeros(cols, dtype=torch.float64, device=f2.device) if want_sumsq else None
+    make = torch.empty if rows > 0 else torch.zeros  # the kernels write every output element
+    s = make(cols, dtype=torch.float64, device=f2.device)
+    q = make(cols, dtype=torch.float64, device=f2.device) if want_sumsq else None
     if rows > 0:
         with on_device(f2.device):
             wsp, wsn = _ws(f2.device)
