@@ -494,8 +494,11 @@ def run_ours(args, wl):
     line = {
         "metric": "integrand evals/s", "value": n_evals * args.steps / t_fused, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_fused / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if wl["dtype"] == "float32" else "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "kind": wl["kind"], "dim": wl["dim"], "N_per_gpu": wl["N"],
+        # MC / VEGAS: N per GPU fixed (weak); the Newton-Cotes grid is one fixed grid sharded over the ranks (strong)
+        "scaling": "strong" if wl["kind"] == "boole" else "weak", "vs_baseline": None,
+        "dtype": "f32" if wl["dtype"] == "float32" else "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "kind": wl["kind"], "dim": wl["dim"],
+                   ("N_total" if wl["kind"] == "boole" else "N_per_gpu"): wl["N"],
                    "integrand": wl["integrand"], "path": "fused functor (generate+evaluate+accumulate in one kernel)",
                    "l2": "512 MiB buffer rewritten between timed iterations", "rng": "Philox4x32-10, fresh seed per step"},
         "clocks": clocks,
