@@ -253,9 +253,10 @@ def run_reference(args, wl):
     line = {
         "impl": "reference", "metric": "integrand evals/s", "value": base["value"], "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base.pop("ms_per_step"),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if wl["dtype"] == "float32" else "f64",
-        "data": "synthetic",
-        "config": {"workload": args.workload, "kind": wl["kind"], "dim": wl["dim"], "N_per_gpu": wl["N"],
+        "higher_is_better": True, "scaling": "strong" if wl["kind"] == "boole" else "weak", "vs_baseline": None,
+        "dtype": "f32" if wl["dtype"] == "float32" else "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "kind": wl["kind"], "dim": wl["dim"],
+                   ("N_total" if wl["kind"] == "boole" else "N_per_gpu"): wl["N"],
                    "integrand": wl["integrand"], "path": "reference algorithm on the host cores, bounded sample per step"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
