@@ -42,6 +42,26 @@ __device__ __forceinline__ T filled_average(const T* __restrict__ w, const long 
     return w[j];
 }
 
+// Rebinning predicate of update_map (vegas_map.py:214-229): trunc(S_j / delta) > m.  With q = m + 1 this is
+// RN(S_j / delta) >= q, and because the rounded quotient is monotone in S_j it equals S_j >= t for the smallest
+// double t with RN(t / delta) >= q.  division_threshold finds t with two or three divisions ONCE per new edge,
+// so every probe of the search is a load and a compare instead of an fp64 division and a 64-bit conversion
+// (those made map_edges_kernel issue-bound: 1190 instructions per edge at Ni = 1e7).  Returns a negative value
+// when q * delta is not a normal positive number; callers then keep the division.
+__device__ __forceinline__ double division_threshold(double q, double delta) {
+    double x = __dmul_rn(q, delta);
+    if (!(x >= 2.2250738585072014e-308) || isinf(x)) return -1.0;
+    for (int i = 0; i < 64; ++i) {  // walk down while the predecessor still reaches q
+        const double p = __longlong_as_double(__double_as_longlong(x) - 1);
+        if (p >= 2.2250738585072014e-308 && __ddiv_rn(p, delta) >= q) x = p; else break;
+    }
+    for (int i = 0; i < 64; ++i) {  // walk up until x reaches q
+        if (__ddiv_rn(x, delta) >= q) return x;
+        x = __longlong_as_double(__double_as_longlong(x) + 1);
+    }
+    return -1.0;
+}
+
 // Non-finite repair of one new edge (vegas_map.py:240-257): the mean of its two neighbours.
 template <typename T>
 __device__ __forceinline__ T repaired_edge(const T* __restrict__ xn, long long e, long long ni, bool& was_bad,

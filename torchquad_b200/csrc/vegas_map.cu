@@ -345,12 +345,20 @@ map_edges_kernel(const T* __restrict__ smoothed, const double* __restrict__ S, c
     const double* Sd = S + (int64_t)d * ni;
     const T delta_t = div_rn((T)row_totals[d], (T)ni);
     const double delta = (double)delta_t;
-    // smallest j in [0, Ni-2] with trunc(S_j/delta) > m; Ni-1 when there is none
+    // smallest j in [0, Ni-2] with trunc(S_j/delta) > m; Ni-1 when there is none: bisection on S_j >= t
+    // (division_threshold, vegas_dev.cuh)
+    const double thr = division_threshold((double)(m + 1), delta);
     long long lo = 0, hi = ni - 1;
-    while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        const long long k = (long long)(__ddiv_rn(Sd[mid], delta));
-        if (k > m) hi = mid; else lo = mid + 1;
+    if (thr >= 0.0) {
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (Sd[mid] >= thr) hi = mid; else lo = mid + 1;
+        }
+    } else {
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if ((long long)(__ddiv_rn(Sd[mid], delta)) > m) hi = mid; else lo = mid + 1;
+        }
     }
     const long long idx = lo;
     const double below = idx > 0 ? Sd[idx - 1] : 0.0;

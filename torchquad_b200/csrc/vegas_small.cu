@@ -320,11 +320,14 @@ __device__ __forceinline__ void map_update_body(cg::cluster_group& cluster, cons
     if (rank == 0 && tid == 0) { xn[0] = x_old[0]; xn[ni] = x_old[ni]; }
     __syncthreads();
     for (long long m = j_lo + tid; m < j_hi && m <= last; m += SM_THREADS) {
-        // smallest j in [0, last] with trunc(S_j / delta) > m; ni - 1 when there is none
+        // smallest j in [0, last] with trunc(S_j / delta) > m; ni - 1 when there is none.  The predicate is
+        // S_j >= thr (division_threshold, vegas_dev.cuh); thr < 0 keeps the division for degenerate delta.
+        const double thr = division_threshold((double)(m + 1), delta);
+        auto reached = [&](double sj) { return thr >= 0.0 ? sj >= thr : (long long)__ddiv_rn(sj, delta) > m; };
         int lo = 0, hi = nblk;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if ((long long)__ddiv_rn(s_coarse[mid], delta) > m) hi = mid; else lo = mid + 1;
+            if (reached(s_coarse[mid])) hi = mid; else lo = mid + 1;
         }
         long long idx = ni - 1;
         if (lo < nblk) {
@@ -332,7 +335,7 @@ __device__ __forceinline__ void map_update_body(cg::cluster_group& cluster, cons
             if (fhi > last) fhi = last;
             while (flo < fhi) {
                 const long long mid = (flo + fhi) >> 1;
-                if ((long long)__ddiv_rn(Sd[mid], delta) > m) fhi = mid; else flo = mid + 1;
+                if (reached(Sd[mid])) fhi = mid; else flo = mid + 1;
             }
             idx = flo;
         }
