@@ -1,11 +1,15 @@
-// Host-side VEGAS+ loop for the fused path: one C-ABI call runs warm-up, all iterations and the
-// chi^2 / budget schedule of torchquad/integration/vegas.py:137-209,211-315 without returning to Python
-// between passes.  Small problems (the reference's own N = 1e6 configuration is ~0.5 ms of GPU work) are
-// bound by per-launch host overhead; from C++ a pass costs a handful of launches and one 8-byte read-back.
+// Host-side VEGAS+ loops: one C-ABI call runs warm-up, all iterations and the chi^2 / budget schedule of
+// torchquad/integration/vegas.py:137-209,211-315 without returning to Python between passes.  Small problems
+// (the reference's own N = 1e6 configuration is ~0.4 ms of GPU work) are bound by per-launch host overhead.
 // The kernels are exactly those of the step-by-step API, so a run draws the same samples as the Python-driven
-// loop (tests/test_gpu_integrators.py).  Nothing is read back inside a block of five iterations: the fused
-// pass takes its sample count from get_NH's offsets on the device, the stratification update records it next
-// to the iteration estimate, and the schedule reads the block's records in one copy.
+// loop (tests/test_gpu_integrators.py).
+//   tq_vegas_run_fused    built-in integrands: nothing is read back inside a block of five iterations -- the
+//                         fused pass takes its sample count from get_NH's offsets on the device, the
+//                         stratification update records it next to the iteration estimate, and the schedule
+//                         reads the block's records in one copy.
+//   tq_vegas_run_unfused  any integrand through a per-pass callback: samples are materialised, the callback
+//                         evaluates them, one 8-byte read-back per pass sizes its view.
+//   tq_vegas_schedule     the checkpoint decision alone (host only; tested against the oracle on CPU).
 #include <math.h>
 #include <vector>
 
