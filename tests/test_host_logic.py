@@ -172,3 +172,23 @@ def test_stratification_configuration_matches_reference_formula():
         s = tq.VEGASStratification.__new__(tq.VEGASStratification)
         n_strat = int((inc / 4.0) ** (1.0 / dim))
         assert n_strat == ns
+
+
+def test_record_layout_selection_is_by_table_size():
+    """Large maps switch to {x, dx, weight, count} records (include/tqb200.h, TQ_EDGES_RECORDS): the choice is a pure
+    function of the table size, 32 B (fp64) / 16 B (fp32) per bin against `records_min_bytes`."""
+    from torchquad_b200.integration.vegas_map import VEGASMap
+
+    class Probe(VEGASMap):
+        def __init__(self, dim, ni, dtype):  # no device tensors: only the fields wants_records reads
+            self.dim, self.N_intervals, self.dtype = dim, ni, dtype
+
+    assert VEGASMap.records_min_bytes == 48 << 20
+    assert not Probe(4, 4000, torch.float64).wants_records()           # configs[0]: 512 KB
+    assert not Probe(8, 4096, torch.float64).wants_records()           # capped maps stay on pair tables
+    assert Probe(8, 10_000_000, torch.float64).wants_records()         # configs[3] at the reference's size: 2.56 GB
+    assert Probe(16, 4_194_304, torch.float32).wants_records()         # 1 GiB
+    assert Probe(8, 196_608, torch.float64).wants_records() and not Probe(8, 196_607, torch.float64).wants_records()
+    p = Probe(8, 10_000_000, torch.float64)
+    p.records_min_bytes = None
+    assert not p.wants_records()
