@@ -148,3 +148,8 @@ def test_vegas_options(cuda):
     e.max_map_intervals = 64
     re = e.integrate(fn, 3, N=100_000, integration_domain=dom, seed=2)
     assert e.map.N_intervals == 64 and abs(float(re) - exact) < 6 * float(e._get_error())
+
+
+def test_deployment_self_check(cuda):
+    """torchquad._deployment_test (utils/deployment_test.py of the reference): the package's self-check passes."""
+    assert tq._deployment_test() is True

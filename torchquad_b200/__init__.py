@@ -19,6 +19,7 @@ from .integration.vegas import VEGAS
 from .integration.vegas_map import VEGASMap
 from .integration.vegas_stratification import VEGASStratification
 from .utils.config import enable_cuda, set_precision, set_up_backend
+from .utils.deployment_test import _deployment_test
 from .utils.set_log_level import set_log_level
 
 import os as _os
@@ -26,6 +27,7 @@ import os as _os
 set_log_level(_os.environ.get("TORCHQUAD_LOG_LEVEL", "WARNING"))
 
 __all__ = [
+    "_deployment_test",
     "__version__", "GridIntegrator", "BaseIntegrator", "IntegrationGrid", "MonteCarlo", "Trapezoid", "Simpson",
     "Boole", "NewtonCotes", "GaussLegendre", "Gaussian", "VEGAS", "VEGASMap", "VEGASStratification", "RNG", "enable_cuda", "set_precision",
     "set_log_level", "set_up_backend", "integrands", "distributed",
