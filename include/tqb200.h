@@ -234,16 +234,24 @@ TQ_API int tq_vegas_map_pack_edges(const void* x_edges, const void* dx_edges, vo
  *   warm-up (offsets == NULL): rows are plain samples y = u*0.999999 (vegas.py:236); out_f64 receives
  *     {sum jf, sum jf^2}.
  *   edges_packed: see tq_vegas_map_pack_edges (edges_layout = TQ_EDGES_PAIRS) or the record layout below.
- *   weights/counts (map histogram, vegas_map.py:99-111) are accumulated unless weights == NULL. */
+ *   Map histogram (vegas_map.py:99-111), one of:
+ *     weights/counts != NULL   accumulated directly (two L2 reductions per sample and dimension; small passes);
+ *     hist_pairs != NULL       fp64 [dim, Ni, 2] = {sum jf^2, count} per bin (both dtypes; the count is an exact fp64
+ *                              integer): ONE reduction sector per sample and dimension.  Zero it once; fold it into
+ *                              weights/counts with tq_vegas_map_unpack_hist before tq_vegas_map_update;
+ *     all NULL                 no grid improvement (or TQ_EDGES_RECORDS: the histogram lives in the records). */
 TQ_API int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
                    int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_packed,
-                   int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* JF,
-                   void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
+                   int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* hist_pairs,
+                   void* JF, void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
                    size_t ws_bytes, void* stream);
+/* weights += hist.sum (rounded once to the working dtype), counts += hist.count, hist = 0 (vegas_map.py:99-111). */
+TQ_API int tq_vegas_map_unpack_hist(void* hist_pairs, void* weights, int64_t* counts, int32_t dim, int64_t n_intervals,
+                             int32_t dtype, void* stream);
 
 /* Record layout for LARGE maps (tables beyond L2, e.g. the reference's Ni = N_increment/10 of vegas.py:117 at
- * N = 2.5e9: 8 x 1e7 bins).  One bin = one record {x_edge, dx_edge, weight, count}: 32 bytes {f64,f64,f64,u64}
- * for TQ_F64, 16 bytes {f32,f32,f32,u32} for TQ_F32, [dim, Ni] records.  With edges_layout = TQ_EDGES_RECORDS
+ * N = 2.5e9: 8 x 1e7 bins).  One bin = one record {x_edge, dx_edge, weight, count}: 32 bytes {f64,f64,f64,f64}
+ * for TQ_F64 (the count is an exact fp64 integer), 16 bytes {f32,f32,f32,u32} for TQ_F32, [dim, Ni] records.  With edges_layout = TQ_EDGES_RECORDS
  * tq_fused_vegas gathers the edges from the records and accumulates the histogram (vegas_map.py:99-111) INTO
  * them (weights = counts = NULL): the three scattered accesses per sample and dimension fall into one DRAM
  * sector.  tq_vegas_map_unpack_records then adds the record fields to weights/counts (the arrays
@@ -266,6 +274,7 @@ typedef struct tq_vegas_state {
     void* edges_packed; /* initial map, already packed: pairs [dim, Ni, 2] or records (edges_layout) */
     void* weights;      /* [dim, Ni], zero */
     int64_t* counts;    /* [dim, Ni], zero */
+    void* hist_pairs;   /* fp64 [dim, Ni, 2], zero, or NULL: see tq_fused_vegas (used for passes of >= 2^20 rows) */
     void* dh;           /* [n_cubes], initial 1/n_cubes */
     int64_t* nh;        /* [n_cubes] */
     int64_t* offsets;   /* [n_cubes + 1] */

@@ -39,7 +39,7 @@ class tq_vegas_state(ctypes.Structure):
     """Mirror of `struct tq_vegas_state`: caller-owned device buffers of a fused VEGAS run."""
 
     _fields_ = [
-        ("x_edges", c_p), ("dx_edges", c_p), ("edges_packed", c_p), ("weights", c_p), ("counts", c_p),
+        ("x_edges", c_p), ("dx_edges", c_p), ("edges_packed", c_p), ("weights", c_p), ("counts", c_p), ("hist_pairs", c_p),
         ("dh", c_p), ("nh", c_p), ("offsets", c_p), ("JF", c_p), ("JF2", c_p), ("records", c_p), ("status", c_p),
         ("map_ws", c_p), ("map_ws_bytes", c_sz), ("ws", c_p), ("ws_bytes", c_sz), ("edges_layout", c_i32),
     ]
@@ -98,8 +98,9 @@ PROTOTYPES = {
     "tq_fused_mc": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_i64, c_i64, c_u64, c_u32, c_p, c_p, c_sz, c_p]),
     "tq_fused_nc": (ctypes.c_int, [_P_INTEGRAND, c_p, c_p, c_i32, c_i32, c_i64, c_i64, c_p, c_p, c_sz, c_p]),
     "tq_vegas_map_pack_edges": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
-    "tq_fused_vegas": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_p, c_i64, c_i32, c_i64, c_i64, c_p, c_i32, c_i64, c_p, c_p,
+    "tq_fused_vegas": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_p, c_i64, c_i32, c_i64, c_i64, c_p, c_i32, c_i64, c_p, c_p, c_p,
                                       c_p, c_p, c_u64, c_u32, c_p, c_p, c_sz, c_p]),
+    "tq_vegas_map_unpack_hist": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
     "tq_vegas_map_records_bytes": (c_sz, [c_i32, c_i64, c_i32]),
     "tq_vegas_map_pack_records": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
     "tq_vegas_map_unpack_records": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),

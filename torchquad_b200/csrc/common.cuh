@@ -52,6 +52,20 @@ __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(
 __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
 
+// a / b for a divisor b that is constant over the launch, given inv = RN(1/b): q0 = RN(a*inv), r = a - q0*b (exact, FMA),
+// q = RN(q0 + r*inv) is the CORRECTLY ROUNDED quotient (Markstein 1990: inv correctly rounded, q0 faithful), i.e. bit-identical
+// to __fdiv_rn/__ddiv_rn for the operands of the stratified sampling (a = digit + u in [0, N_strat), b = N_strat <= 1000;
+// checked exhaustively in u for fp32 and on 4e8 random operands for fp64, tests/test_host_logic.py).  Three pipelined
+// operations instead of the ~30-instruction fp64 division sequence.
+__device__ __forceinline__ float div_by_const(float a, float b, float inv) {
+    const float q0 = __fmul_rn(a, inv);
+    return __fmaf_rn(__fmaf_rn(-q0, b, a), inv, q0);
+}
+__device__ __forceinline__ double div_by_const(double a, double b, double inv) {
+    const double q0 = __dmul_rn(a, inv);
+    return __fma_rn(__fma_rn(-q0, b, a), inv, q0);
+}
+
 // Exact 32-bit division by a runtime constant (Granlund-Montgomery round-up form): q = x / d for all x.
 struct FastDiv {
     uint32_t d, m, s;

@@ -209,13 +209,28 @@ __device__ __forceinline__ void segmented_warp_sum2(unsigned key, T& a, T& b) {
     }
 }
 
+// Where the f^2 histogram of a pass goes (vegas_map.py:99-111).
+enum HistMode {
+    HIST_NONE = 0,     // no grid improvement
+    HIST_ARRAYS = 1,   // weights[T] / counts[u64]: two L2 reductions per (sample, dim); small passes
+    HIST_SMEM = 2,     // whole map privatised in shared memory (tiny maps), flushed to weights / counts
+    HIST_PAIRS = 3,    // {sum jf^2, count} as an fp64 pair per bin: ONE reduction sector per (sample, dim), see below
+    HIST_RECORDS = 4,  // the {weight, count} words of the bin's record (large maps)
+};
+
+// Sector-paired reductions.  L2 executes a reduction per 32-byte SECTOR, not per lane (measured on B200,
+// scripts/microbench/lsu_rates.cu: RED.F64 to 32 scattered sectors 1.82 cyc/lane/SM; RED.F64 + RED.U64 to adjacent words
+// of the same bins 3.65; ONE RED.F64 whose lane pairs hit the two words of 16 bins 1.82 per bin).  So the count lives
+// next to the weight as an fp64 (exact below 2^53) and lanes 2i / 2i+1 of one instruction add {jf^2, 1.0} of sample i.
+// Bin ids and jf^2 of the warp's 32 samples are parked in shared memory; two rounds of 16 samples cover the warp.
 template <int FAM, typename T, bool STRAT>
 __global__ void __launch_bounds__(FV_BLOCK, FV_MIN_CTAS)
-fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, int64_t n_cubes, int n_strat,
+fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, int64_t n_cubes, FastDiv ns_div, T inv_ns,
                    int64_t row_begin, int64_t row_end, bool rows_from_offsets, int64_t rows_per_cta,
                    const void* __restrict__ edges_raw, bool records, long long ni, T* __restrict__ weights,
-                   unsigned long long* __restrict__ counts, T* __restrict__ JF, T* __restrict__ JF2, uint64_t seed,
-                   uint32_t call, bool hist_smem, double* partials, unsigned int* ticket, double* out) {
+                   unsigned long long* __restrict__ counts, double* __restrict__ hist_pairs, T* __restrict__ JF,
+                   T* __restrict__ JF2, uint64_t seed, uint32_t call, int hist_mode, double* partials, unsigned int* ticket,
+                   double* out) {
     constexpr int LANES = U01<T>::LANES;
     using P2 = typename Pair2<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -225,19 +240,25 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
     __shared__ unsigned char s_cube[2][FV_BLOCK];
     stage_integrand<T>(P, S);
     const int dim = S.dim;
-    int* s_ids = reinterpret_cast<int*>(smem_raw);                        // [dim][FV_BLOCK]
+    double* s_jf2 = reinterpret_cast<double*>(smem_raw);                   // [FV_BLOCK] (paired reductions)
+    int* s_ids = reinterpret_cast<int*>(s_jf2 + FV_BLOCK);                 // [dim][FV_BLOCK]
     T* s_w = reinterpret_cast<T*>(s_ids + dim * FV_BLOCK);                 // [dim*ni] when hist_smem
+    const bool hist_smem = hist_mode == HIST_SMEM;
     unsigned int* s_c = reinterpret_cast<unsigned int*>(s_w + (hist_smem ? dim * ni : 0));
     const P2* __restrict__ edges = reinterpret_cast<const P2*>(edges_raw);
     MapRecord<T>* recs = reinterpret_cast<MapRecord<T>*>(const_cast<void*>(edges_raw));
-    const bool do_hist = weights != nullptr || records;
+    const bool do_hist = hist_mode != HIST_NONE;
+    // fp64 records keep their count as an fp64 next to the weight: the same sector-paired reduction applies
+    const bool paired = hist_mode == HIST_PAIRS || (hist_mode == HIST_RECORDS && sizeof(T) == 8);
+    double* pair_base = hist_mode == HIST_PAIRS ? hist_pairs : reinterpret_cast<double*>(recs) + 2;
+    const int pair_stride = hist_mode == HIST_PAIRS ? 2 : 4;
     if (do_hist && hist_smem) {
         for (int i = threadIdx.x; i < dim * (int)ni; i += blockDim.x) { s_w[i] = (T)0; s_c[i] = 0u; }
     }
     __syncthreads();
     if (STRAT && rows_from_offsets) row_end = __ldg(&offsets[n_cubes]);  // sample count of the pass, never read back
     const T nif = (T)ni;
-    const T nsf = (T)n_strat;
+    const T nsf = (T)ns_div.d;
     double acc[2] = {0.0, 0.0};
     int buf = 0;
     // The host sizes the grid so that one chunk per CTA covers its row estimate; the stride loop keeps the pass
@@ -298,10 +319,10 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
                         if (d < dim) {
                             T y;
                             if (STRAT) {
-                                const uint32_t q = c / (uint32_t)n_strat;
-                                const uint32_t p = c - q * (uint32_t)n_strat;
+                                const uint32_t q = ns_div.div(c);
+                                const uint32_t p = c - q * ns_div.d;
                                 c = q;
-                                y = div_rn(add_rn((T)p, u[j]), nsf);
+                                y = div_by_const(add_rn((T)p, u[j]), nsf, inv_ns);
                                 if (y >= (T)1) y = (T)0.999999;
                             } else {
                                 y = mul_rn(u[j], (T)0.999999);
@@ -323,7 +344,7 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
                 const T f = mul_rn(fn.finish(S), S.scale);
                 jf = mul_rn(f, jac);
                 jf2 = mul_rn(jf, jf);
-                if (do_hist) {
+                if (do_hist && !paired) {
                     if (hist_smem) {
                         for (int d = 0; d < dim; ++d) {
                             const int b = d * (int)ni + s_ids[d * FV_BLOCK + threadIdx.x];
@@ -334,7 +355,7 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
                         for (int d = 0; d < dim; ++d) {
                             MapRecord<T>* r = &recs[(int64_t)d * ni + s_ids[d * FV_BLOCK + threadIdx.x]];
                             atomicAdd(&r->w, jf2);
-                            atomicAdd(&r->c, 1);
+                            atomicAdd(&r->c, (decltype(r->c))1);
                         }
                     } else {
                         for (int d = 0; d < dim; ++d) {
@@ -344,6 +365,24 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
                         }
                     }
                 }
+            }
+            if (paired) {  // warp-convergent: every lane serves half a sample of its warp
+                s_jf2[threadIdx.x] = (double)jf2;
+                if (!active) s_ids[threadIdx.x] = -1;  // dimension 0 marks the row: inactive rows have no bins at all
+                __syncwarp();
+                {
+                    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31, word = lane & 1;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int src = wbase + (lane >> 1) + 16 * h;
+                        if (s_ids[src] >= 0) {
+                            const double v = word ? 1.0 : s_jf2[src];
+                            for (int d = 0; d < dim; ++d)
+                                atomicAdd(pair_base + ((int64_t)d * ni + s_ids[d * FV_BLOCK + src]) * pair_stride + word, v);
+                        }
+                    }
+                }
+                __syncwarp();
             }
             if (STRAT) {
                 const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
@@ -417,6 +456,20 @@ unpack_records_kernel(MapRecord<T>* __restrict__ recs, T* __restrict__ weights, 
             z.w = (T)0;
             z.c = 0;
             recs[i] = z;
+        }
+    }
+}
+
+// weights += (T)hist.w, counts += (int64)hist.c, and the pair goes back to zero (fp64 pair table of HIST_PAIRS)
+template <typename T>
+__global__ void __launch_bounds__(256)
+unpack_hist_kernel(double2* __restrict__ hist, T* __restrict__ weights, long long* __restrict__ counts, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 h = hist[i];
+        if (h.y != 0.0) {
+            weights[i] = (T)((double)weights[i] + h.x);
+            counts[i] += (long long)h.y;
+            hist[i] = make_double2(0.0, 0.0);
         }
     }
 }
@@ -535,10 +588,21 @@ int tq_vegas_map_unpack_records(void* records, void* weights, int64_t* counts, i
     return check_launch("unpack_records_kernel");
 }
 
+int tq_vegas_map_unpack_hist(void* hist_pairs, void* weights, int64_t* counts, int32_t dim, int64_t n_intervals,
+                             int32_t dtype, void* stream) {
+    TQ_REQUIRE(dim >= 1 && n_intervals >= 1 && hist_pairs && weights && counts, "tq_vegas_map_unpack_hist: bad arguments");
+    const int64_t total = (int64_t)dim * n_intervals;
+    const int grid = grid_for(total, 256, 8);
+    TQ_DISPATCH_DTYPE(dtype, {
+        unpack_hist_kernel<T><<<TQ_GRID(grid), 256, 0, as_stream(stream)>>>((double2*)hist_pairs, (T*)weights, (long long*)counts, total);
+    });
+    return check_launch("unpack_hist_kernel");
+}
+
 int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
                    int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_packed,
-                   int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* JF,
-                   void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
+                   int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* hist_pairs,
+                   void* JF, void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
                    size_t ws_bytes, void* stream) {
     int rc = check_integrand("tq_fused_vegas", fn_host);
     if (rc) return rc;
@@ -555,15 +619,17 @@ int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* of
     TQ_REQUIRE(strat || out_f64 != nullptr, "tq_fused_vegas: warm-up pass needs out_f64");
     TQ_REQUIRE(edges_layout == TQ_EDGES_PAIRS || edges_layout == TQ_EDGES_RECORDS, "tq_fused_vegas: unknown edges layout %d", edges_layout);
     const bool records = edges_layout == TQ_EDGES_RECORDS;
-    TQ_REQUIRE(!records || (weights == nullptr && counts == nullptr),
-               "tq_fused_vegas: with TQ_EDGES_RECORDS the histogram lives in the records; pass weights = counts = NULL");
+    TQ_REQUIRE(!records || (weights == nullptr && counts == nullptr && hist_pairs == nullptr),
+               "tq_fused_vegas: with TQ_EDGES_RECORDS the histogram lives in the records; pass weights = counts = hist_pairs = NULL");
+    TQ_REQUIRE(!(weights && hist_pairs), "tq_fused_vegas: pass either weights/counts or hist_pairs, not both");
+    TQ_REQUIRE((weights == nullptr) == (counts == nullptr) || records, "tq_fused_vegas: weights and counts go together");
     const int64_t nrows = row_end - row_begin;
     if (nrows == 0 && strat) return TQ_OK;
     Workspace w(ws, ws_bytes);
     unsigned int* ticket = w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
     const int dim = fn_host->dim;
     const size_t elt = dtype == TQ_F64 ? 8 : 4;
-    const size_t ids_bytes = (size_t)dim * FV_BLOCK * sizeof(int);
+    const size_t ids_bytes = (size_t)FV_BLOCK * sizeof(double) + (size_t)dim * FV_BLOCK * sizeof(int);
     const size_t hist_bytes = (size_t)dim * n_intervals * (elt + 4);
     // CTAs: persistent, each with a contiguous chunk of rows; fewer CTAs when the problem is small.
     const int sms = num_sms();
@@ -571,44 +637,43 @@ int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* of
     if (tiles < 1) tiles = 1;
     // Shared-memory privatised histogram only for SMALL maps (<= 4096 bins, where same-address contention on
     // L2 atomics would serialise) and only when every CTA sees enough rows to amortise zero + flush.
-    // Mid-size maps stay L2-resident and take plain L2 reductions: measured on B200 (8-D fp64) 6.4e9 evals/s
-    // with Ni=4096 through L2 vs 2.9e9 with a 98 KB privatised copy that limits the SM to one CTA.
     const int64_t bins = (int64_t)dim * n_intervals;
-    bool hist_smem = weights != nullptr && !records && bins <= 4096 && nrows >= 64 * bins;
+    int hist_mode = records ? HIST_RECORDS : hist_pairs ? HIST_PAIRS : weights ? HIST_ARRAYS : HIST_NONE;
+    if (hist_mode == HIST_ARRAYS && bins <= 4096 && nrows >= 64 * bins) hist_mode = HIST_SMEM;
     // Record layout = tables beyond L2: a sample's histogram reductions find its record still in L2 only if few
     // samples are in flight between the gather and the reduction.  Measured (8-D fp64, Ni=1e7): 6 CTAs/SM refetch
     // every record from HBM for the reductions (5 DRAM sectors read per gather, 1.7e9 evals/s); 2 CTAs/SM: 2.07e9.
     const int per_sm = records ? 2 : 6;
     int64_t ctas = tiles < (int64_t)sms * per_sm ? tiles : (int64_t)sms * per_sm;
-    if (hist_smem) {
+    if (hist_mode == HIST_SMEM) {
         const int64_t cap = nrows / (16 * bins) > 0 ? nrows / (16 * bins) : 1;
         if (ctas > cap) ctas = cap;
     }
     int64_t rows_per_cta = (nrows + ctas - 1) / ctas;
     rows_per_cta = ((rows_per_cta + FV_BLOCK - 1) / FV_BLOCK) * FV_BLOCK;
     if (rows_per_cta < FV_BLOCK) rows_per_cta = FV_BLOCK;
-    // (Interleaving small row chunks across CTAs so that concurrent CTAs share the high dimensions' map blocks
-    // was measured on the reference-size 8-D map: no change, 1.08e9 evals/s either way -- the five fastest-varying
-    // dimensions still cover their whole tables.)
     ctas = nrows > 0 ? (nrows + rows_per_cta - 1) / rows_per_cta : 1;
     double* partials = w.take<double>((size_t)ctas * 2);
     if (!ticket || !partials) { set_error("tq_fused_vegas: workspace too small"); return TQ_ERR_WORKSPACE; }
-    const size_t smem = ids_bytes + (hist_smem ? hist_bytes : 0);
+    const size_t smem = ids_bytes + (hist_mode == HIST_SMEM ? hist_bytes : 0);
     cudaStream_t st = as_stream(stream);
+    FastDiv ns_div;
+    ns_div.set((uint32_t)(strat ? n_strat : 1));
     TQ_DISPATCH_DTYPE(dtype, {
+        const T inv_ns = (T)1 / (T)(strat ? n_strat : 1);  // RN(1 / N_strat) in the working precision (div_by_const)
         TQ_DISPATCH_FAMILY(fn_host->family, {
             if (strat) {
                 if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, true><<<TQ_GRID((unsigned)ctas), FV_BLOCK, smem, st>>>(
-                    *fn_host, (const long long*)offsets, n_cubes, n_strat, row_begin, row_end, rows_from_offsets, rows_per_cta,
-                    edges_packed, records, n_intervals, (T*)weights, (unsigned long long*)counts,
-                    (T*)JF, (T*)JF2, seed, call_idx, hist_smem, partials, ticket, out_f64);
+                    *fn_host, (const long long*)offsets, n_cubes, ns_div, inv_ns, row_begin, row_end, rows_from_offsets, rows_per_cta,
+                    edges_packed, records, n_intervals, (T*)weights, (unsigned long long*)counts, (double*)hist_pairs,
+                    (T*)JF, (T*)JF2, seed, call_idx, hist_mode, partials, ticket, out_f64);
             } else {
                 if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, false><<<TQ_GRID((unsigned)ctas), FV_BLOCK, smem, st>>>(
-                    *fn_host, nullptr, 0, 1, row_begin, row_end, false, rows_per_cta, edges_packed, records,
-                    n_intervals, (T*)weights, (unsigned long long*)counts, nullptr, nullptr, seed, call_idx, hist_smem,
-                    partials, ticket, out_f64);
+                    *fn_host, nullptr, 0, ns_div, inv_ns, row_begin, row_end, false, rows_per_cta, edges_packed, records,
+                    n_intervals, (T*)weights, (unsigned long long*)counts, (double*)hist_pairs, nullptr, nullptr, seed, call_idx,
+                    hist_mode, partials, ticket, out_f64);
             }
         });
     });

@@ -12,7 +12,9 @@ template <> struct EdgePair<double> { using type = double2; };
 // or 16-byte (fp32) record, so that the edge gather and both histogram updates of a sample touch ONE DRAM sector
 // instead of three scattered ones.
 template <typename T> struct MapRecord;
-template <> struct __align__(32) MapRecord<double> { double x, dx, w; unsigned long long c; };
+// The fp64 record keeps its count as an fp64 (exact below 2^53) so that ONE reduction instruction whose lane pairs
+// address {w, c} updates both words of the sector (fused.cu, "sector-paired reductions").
+template <> struct __align__(32) MapRecord<double> { double x, dx, w, c; };
 template <> struct __align__(16) MapRecord<float> { float x, dx, w; unsigned int c; };
 
 // get_NH for one cube: max(2, floor(dh * nevals_exp)) (vegas_stratification.py:92-103)

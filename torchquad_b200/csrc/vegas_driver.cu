@@ -98,10 +98,26 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
     const int layout = recs ? TQ_EDGES_RECORDS : TQ_EDGES_PAIRS;
     void* hist_w = recs ? nullptr : s->weights;
     int64_t* hist_c = recs ? nullptr : s->counts;
+    // Small problems: the stratification update, every dimension's map update and the NEXT pass's get_NH share one
+    // launch (vegas_small.cu); get_NH runs on its own only after the schedule may have changed the sample budget.
+    const bool small = !recs && small_strat_ok(n_cubes) && (!grid_improve || small_map_ok(dim, ni));
+    // Passes of >= 2^20 rows accumulate the histogram as fp64 {sum, count} pairs (one reduction sector per sample and
+    // dimension instead of two, tq_fused_vegas); it is folded into weights / counts right before the map update.
+    const bool pairs_ok = !recs && !small && s->hist_pairs != nullptr;
+    bool pairs_dirty = false;
+    auto hist_args = [&](int64_t rows, void*& w, int64_t*& c, void*& h) {
+        const bool use_pairs = pairs_ok && rows >= (1 << 20);
+        w = use_pairs ? nullptr : hist_w;
+        c = use_pairs ? nullptr : hist_c;
+        h = use_pairs ? s->hist_pairs : nullptr;
+        pairs_dirty |= use_pairs;
+    };
     auto update_map = [&]() -> int {
         if (passes >= max_passes) { set_error("tq_vegas_run_fused: more than %d passes", max_passes); return TQ_ERR_UNSUPPORTED; }
         int rc = TQ_OK;
         if (recs && (rc = tq_vegas_map_unpack_records(s->edges_packed, s->weights, s->counts, dim, ni, dtype, stream))) return rc;
+        if (pairs_dirty && (rc = tq_vegas_map_unpack_hist(s->hist_pairs, s->weights, s->counts, dim, ni, dtype, stream))) return rc;
+        pairs_dirty = false;
         rc = map_update_launch(s->x_edges, s->dx_edges, s->weights, s->counts, recs ? nullptr : s->edges_packed, dim, ni, alpha,
                                dtype, s->status + 4 * passes, false, s->map_ws, s->map_ws_bytes, stream);
         ++passes;
@@ -112,16 +128,16 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
     if (warmup) {  // vegas.py:211-266: 5 unstratified passes of starting//5 samples, results discarded
         const int64_t ns = starting / 5;
         for (int w = 0; w < 5; ++w) {
-            int rc = tq_fused_vegas(fn, dtype, nullptr, 0, 1, 0, ns, s->edges_packed, layout, ni, hist_w, hist_c, nullptr, nullptr,
+            void *hw, *hp;
+            int64_t* hc;
+            hist_args(ns, hw, hc, hp);
+            int rc = tq_fused_vegas(fn, dtype, nullptr, 0, 1, 0, ns, s->edges_packed, layout, ni, hw, hc, hp, nullptr, nullptr,
                                     seed, call++, s->records, s->ws, s->ws_bytes, stream);
             if (rc) return rc;
             fevals += ns;
             if ((rc = update_map())) return rc;
         }
     }
-    // Small problems: the stratification update, every dimension's map update and the NEXT pass's get_NH share one
-    // launch (vegas_small.cu); get_NH runs on its own only after the schedule may have changed the sample budget.
-    const bool small = !recs && small_strat_ok(n_cubes) && (!grid_improve || small_map_ok(dim, ni));
     MapScratch scratch = {};
     if (small && grid_improve && !map_scratch_carve(s->map_ws, s->map_ws_bytes, dim, ni, dtype, true, scratch)) {
         set_error("tq_vegas_run_fused: map workspace too small");
@@ -143,9 +159,11 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
         // sum nh <= starting * sum(dh) + 2 * n_cubes; the estimate only sizes the grid
         const int64_t m_est = starting + 2 * n_cubes + 1024;
         // without grid improvement nothing is accumulated: the pass only needs the {x, dx} gather
-        rc = tq_fused_vegas(fn, dtype, s->offsets, n_cubes, n_strat, 0, -m_est, s->edges_packed, layout, ni,
-                            grid_improve ? hist_w : nullptr, grid_improve ? hist_c : nullptr, s->JF, s->JF2, seed, call++, nullptr,
-                            s->ws, s->ws_bytes, stream);
+        void *hw = nullptr, *hp = nullptr;
+        int64_t* hc = nullptr;
+        if (grid_improve) hist_args(starting, hw, hc, hp);
+        rc = tq_fused_vegas(fn, dtype, s->offsets, n_cubes, n_strat, 0, -m_est, s->edges_packed, layout, ni, hw, hc, hp, s->JF,
+                            s->JF2, seed, call++, nullptr, s->ws, s->ws_bytes, stream);
         if (rc) return rc;
         if (it > TQ_VEGAS_MAX_PASSES) { set_error("tq_vegas_run_fused: too many iterations"); return TQ_ERR_UNSUPPORTED; }
         double* record = s->records + 4 * (it - 1);

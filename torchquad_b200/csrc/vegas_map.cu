@@ -168,7 +168,7 @@ map_accumulate_global_kernel(const T* __restrict__ y, const T* __restrict__ jf2_
                     if (recs) {  // large maps: both reductions in the bin's record (one DRAM sector)
                         MapRecord<T>* rc = &recs[(int64_t)d * ni + k];
                         atomicAdd(&rc->w, wgt);
-                        atomicAdd(&rc->c, 1);
+                        atomicAdd(&rc->c, (decltype(rc->c))1);
                     } else {
                         atomicAdd(&weights[(int64_t)d * ni + k], wgt);
                         atomicAdd(&counts[(int64_t)d * ni + k], 1ull);

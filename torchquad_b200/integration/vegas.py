@@ -54,6 +54,7 @@ class VEGAS(BaseIntegrator):
     native_loop = True  # single-GPU runs: drive all passes from C++ (tq_vegas_run_fused / tq_vegas_run_unfused)
     native_unfused_max_bytes = 1 << 30  # sample buffers (y, x) the callback-integrand loop may allocate up front
     _large_map_bytes = 64 << 20
+    _pairs_min_rows = 1 << 20  # fused passes at least this long accumulate the histogram as fp64 pairs
 
     def __init__(self):
         super().__init__()
@@ -277,6 +278,11 @@ class VEGAS(BaseIntegrator):
             ops.fused_vegas(self._fn_struct, None, None, None, begin, end, self.rng.seed, self.rng.next_call(),
                             records=vmap.records(), dtype=self.dtype, n_intervals=vmap.N_intervals, **strat_args)
             vmap.unpack_records()
+        elif hist and end - begin >= self._pairs_min_rows:
+            # big passes: {sum jf^2, count} fp64 pairs, one reduction sector per sample and dimension (ops.fused_vegas)
+            ops.fused_vegas(self._fn_struct, vmap.packed_edges(), None, None, begin, end, self.rng.seed, self.rng.next_call(),
+                            hist_pairs=vmap.hist_pairs(), **strat_args)
+            vmap.unpack_hist()
         else:
             ops.fused_vegas(self._fn_struct, vmap.packed_edges(), vmap.weights if hist else None, vmap.counts, begin, end,
                             self.rng.seed, self.rng.next_call(), **strat_args)

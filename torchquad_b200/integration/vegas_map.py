@@ -35,6 +35,7 @@ class VEGASMap:
         self._edges2, self._edges2_stale = None, True
         self._records, self._records_stale = None, True
         self._scratch = None
+        self._hist = None
         self._reset_weight()
 
     @property
@@ -113,6 +114,17 @@ class VEGASMap:
             self._edges2 = ops.pack_edges(self.x_edges, self.dx_edges, self._edges2)
             self._edges2_stale = False
         return self._edges2
+
+    def hist_pairs(self):
+        """fp64 [dim, Ni, 2] = {sum jf^2, count} accumulator of the fused passes (zero between passes), see
+        `ops.fused_vegas` / `ops.unpack_hist`."""
+        if self._hist is None:
+            self._hist = torch.zeros((self.dim, self.N_intervals, 2), dtype=torch.float64, device=self.device)
+        return self._hist
+
+    def unpack_hist(self):
+        """Fold the pair accumulator into `weights` / `counts` (and zero it)."""
+        ops.unpack_hist(self._hist, self.weights, self.counts)
 
     def invalidate_packed(self):
         self._edges2_stale = True

@@ -494,11 +494,23 @@ def unpack_records(records, weights, counts):
              stream_ptr(weights.device))
 
 
+def unpack_hist(hist_pairs, weights, counts):
+    """weights += hist[..., 0] (rounded once), counts += hist[..., 1], hist = 0 (fp64 pair table of fused_vegas)."""
+    require_cuda(hist_pairs, weights, counts)
+    dim, ni = weights.shape
+    with on_device(weights.device):
+        call("tq_vegas_map_unpack_hist", ptr(hist_pairs), ptr(weights), ptr(counts), dim, ni, dtype_code(weights.dtype),
+             stream_ptr(weights.device))
+
+
 def fused_vegas(fn_struct, edges_packed, weights, counts, row_begin, row_end, seed, call_idx,
-                offsets=None, n_strat=1, JF=None, JF2=None, records=None, dtype=None, n_intervals=None):
+                offsets=None, n_strat=1, JF=None, JF2=None, records=None, dtype=None, n_intervals=None, hist_pairs=None):
     """One fused VEGAS pass (warm-up when offsets is None).  Returns fp64 [2] = {sum jf, sum jf^2} (warm-up only).
-    With `records` (large maps) the histogram goes into the records and weights/counts are not touched."""
-    require_cuda(edges_packed, weights, counts, offsets, JF, JF2, records)
+    With `records` (large maps) the histogram goes into the records and weights/counts are not touched; with
+    `hist_pairs` (fp64 [dim, Ni, 2], see `unpack_hist`) it goes there instead of weights/counts."""
+    require_cuda(edges_packed, weights, counts, offsets, JF, JF2, records, hist_pairs)
+    if hist_pairs is not None:
+        weights = counts = None
     table = records if records is not None else edges_packed
     dt = dtype if records is not None else edges_packed.dtype
     ni = n_intervals if records is not None else edges_packed.shape[1]
@@ -509,7 +521,8 @@ def fused_vegas(fn_struct, edges_packed, weights, counts, row_begin, row_end, se
         wsp, wsn = _ws(table.device)
         call("tq_fused_vegas", fn_struct, dtype_code(dt), ptr(offsets), n_cubes, n_strat, row_begin, row_end,
              ptr(table), _lib.TQ_EDGES_RECORDS if records is not None else _lib.TQ_EDGES_PAIRS, ni,
-             None if records is not None else ptr(weights), None if records is not None else ptr(counts), ptr(JF), ptr(JF2),
+             None if records is not None or weights is None else ptr(weights),
+             None if records is not None or weights is None else ptr(counts), ptr(hist_pairs), ptr(JF), ptr(JF2),
              seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, ptr(out), wsp, wsn, stream_ptr(table.device))
     return out
 
@@ -530,11 +543,12 @@ def _vegas_state(vmap, strat, use_records):
     scratch = _map_scratch(vmap.dim, vmap.N_intervals, dt, dev)
     ws = workspace(dev)
     packed = vmap.records() if use_records else vmap.packed_edges()
+    hist = None if use_records else vmap.hist_pairs()
     state = _lib.tq_vegas_state(
-        ptr(vmap.x_edges), ptr(vmap.dx_edges), ptr(packed), ptr(vmap.weights), ptr(vmap.counts), ptr(strat.dh), ptr(nh),
+        ptr(vmap.x_edges), ptr(vmap.dx_edges), ptr(packed), ptr(vmap.weights), ptr(vmap.counts), ptr(hist), ptr(strat.dh), ptr(nh),
         ptr(offsets), ptr(strat.JF), ptr(strat.JF2), ptr(records), ptr(status), ptr(scratch), scratch.numel(), ws.data_ptr(),
         ws.numel(), _lib.TQ_EDGES_RECORDS if use_records else _lib.TQ_EDGES_PAIRS)
-    return state, (ints, records, status, scratch, packed), nh, offsets
+    return state, (ints, records, status, scratch, packed, hist), nh, offsets
 
 
 def _vegas_finish(vmap, strat, use_records, nh, offsets):
