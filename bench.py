@@ -1,25 +1,30 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path on BASELINE.json's metric: integrand evaluations per second.
+"""Benchmark of the hot path on BASELINE.json's metric: integrand evaluations per second (VEGAS, MC, Boole).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME|all]
 
 Workloads (BASELINE.json `configs`):
-  mc10      configs[1]  MonteCarlo, 10-D sum-of-sines, N=1e9 evals per GPU, fp32   (default; the metric config)
-  vegas4    configs[0]  VEGAS 4-D Genz Gaussian N=1e6 fp64 (the reference's CPU-runnable case)
-  boole6    configs[2]  Boole 6-D product-of-cosines, 33^6 points, fp64
-  vegas8    configs[3]  VEGAS 8-D Genz oscillatory, fp64, 1e8-sample iterations
-  vegas16   configs[4]  VEGAS 16-D Genz product-peak, fp32 fused, N=1e10 total
-A "step" is one complete integration of the workload.  `value` times the fused functor path (inputs: none
-beyond the 80-byte domain, resident in HBM); `e2e` times the same call through the public drop-in API with
-the domain in host memory and the result read back to the host every step; `unfused` reports the
-torch-callable path (points materialised in HBM) with its own HBM roofline.
-Under torchrun each rank owns one GPU and a disjoint row range of the same Philox stream (weak scaling:
-N per GPU fixed); time is the max over ranks of CUDA-event time.
+  mc10             configs[1]  MonteCarlo, 10-D sum-of-sines, N=1e9 evals per GPU, fp32       (HEADLINE: the metric config)
+  vegas4           configs[0]  VEGAS 4-D Genz Gaussian N=1e6 fp64 (the reference's CPU-runnable case)
+  boole6           configs[2]  Boole 6-D product-of-cosines, 33^6 points, fp64, grid sharded over the ranks
+  vegas8_cap4096   configs[3]  VEGAS 8-D Genz oscillatory fp64, N=2.5e9 (1e8-sample iterations), map capped at 4096
+                               intervals per dimension (L2-resident); fixed N at every GPU count (strong scaling)
+  vegas8           configs[3]  the same at the reference's own map size Ni = N/250 = 1e7 per dimension (2.6 GB of records)
+  vegas16_cap4096  configs[4]  VEGAS 16-D Genz product-peak fp32, N=1e10, fused path, map capped at 4096 (the reference
+                               itself raises "Could not replace all infinite edges" for its fp32 map with Ni=4e7)
+The default run (`--workload all`) prints ONE JSON line: the headline record (mc10) at top level, plus `workloads`:
+one sub-record per other workload, each with its own value / e2e / roofline (and cpu_baseline at N=1).
+A "step" is one complete integration of the workload.  `value` times the fused functor path (inputs: the [dim, 2]
+domain, resident in HBM); `e2e` times the same call through the public drop-in API with the domain in host memory and
+the result read back to the host every step; `unfused` reports the torch-callable path (points materialised in HBM).
+Under torchrun each rank owns one GPU; time is the max over ranks of CUDA-event time.
+`--impl reference` times the UNMODIFIED reference (baseline/_ref, staged by baseline/stage_ref.sh) on the host cores.
 """
 import argparse
 import json
 import math
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -32,12 +37,20 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 WORKLOADS = {
-    "mc10": dict(kind="mc", dim=10, N=10**9, dtype="float32", integrand="sum_sin"),
-    "vegas4": dict(kind="vegas", dim=4, N=10**6, dtype="float64", integrand="genz_gaussian"),
-    "boole6": dict(kind="boole", dim=6, N=33**6, dtype="float64", integrand="prod_cos"),
-    "vegas8": dict(kind="vegas", dim=8, N=2_500_000_000, dtype="float64", integrand="genz_oscillatory"),
-    "vegas16": dict(kind="vegas", dim=16, N=10**10, dtype="float32", integrand="genz_product_peak"),
+    "mc10": dict(kind="mc", dim=10, N=10**9, dtype="float32", integrand="sum_sin", scaling="weak", config_index=1),
+    "vegas4": dict(kind="vegas", dim=4, N=10**6, dtype="float64", integrand="genz_gaussian", scaling="strong", config_index=0),
+    "boole6": dict(kind="boole", dim=6, N=33**6, dtype="float64", integrand="prod_cos", scaling="strong", config_index=2),
+    "vegas8_cap4096": dict(kind="vegas", dim=8, N=2_500_000_000, dtype="float64", integrand="genz_oscillatory", map_cap=4096,
+                           scaling="strong", config_index=3),
+    "vegas8": dict(kind="vegas", dim=8, N=2_500_000_000, dtype="float64", integrand="genz_oscillatory", map_cap=None,
+                   scaling="strong", config_index=3),
+    "vegas16_cap4096": dict(kind="vegas", dim=16, N=10**10, dtype="float32", integrand="genz_product_peak", map_cap=4096,
+                            scaling="strong", config_index=4,
+                            note="map capped: the unmodified reference raises 'Could not replace all infinite edges' for an fp32 "
+                                 "map with Ni = N/250 = 4e7 (only 2.6e7 of its initial edges are distinct)"),
 }
+HEADLINE = "mc10"
+SUB_WORKLOADS = ["vegas8_cap4096", "vegas8", "vegas16_cap4096", "vegas4", "boole6"]
 
 
 def parse():
@@ -46,12 +59,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mc10", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="all", choices=sorted(WORKLOADS) + ["all"])
     ap.add_argument("--no-unfused", action="store_true", help="skip the unfused torch-callable arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--map-cap", type=int, default=None,
-                    help="VEGAS workloads: cap the map at this many intervals per dimension (VEGAS.max_map_intervals); "
-                         "default keeps the reference's Ni = N/250")
+                    help="VEGAS workloads: override the cap on map intervals per dimension (VEGAS.max_map_intervals)")
     return ap.parse_args()
 
 
@@ -119,17 +131,25 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        return len(self.rows)
+
+    def summary(self, first=0, last=None):
+        rows = self.rows[first:last]
+        sm = [float(r[1]) for r in rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in rows if len(r) > 8 and r[3].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return self.summary()
 
 
 # ------------------------------------------------------------------------------------ timing helpers
@@ -148,7 +168,7 @@ def agree_max(x):
     return float(t[0])
 
 
-def timed_steps(step, steps, warmup, flush_buf, barrier):
+def timed_steps(step, steps, warmup, flush_buf, barrier, min_warm_s=0.3):
     """Per-step CUDA-event times (seconds) on the current stream; L2 flushed between iterations."""
     # W warm-up steps, and at least 0.3 s of them: the GPU drops its clocks while the host sets things up (e.g. waits
     # for nvidia-smi), and a millisecond-scale step would otherwise be timed on the ramp
@@ -158,8 +178,8 @@ def timed_steps(step, steps, warmup, flush_buf, barrier):
         step()
     torch.cuda.synchronize()
     spent = agree_max(time.time() - t0)
-    if spent < 0.3:
-        for _ in range(min(200, int(math.ceil((0.3 - spent) / max(spent / max(warmup, 1), 1e-4))))):
+    if spent < min_warm_s:
+        for _ in range(min(200, int(math.ceil((min_warm_s - spent) / max(spent / max(warmup, 1), 1e-4))))):
             step()
     torch.cuda.synchronize()
     times = []
@@ -191,35 +211,92 @@ def max_over_ranks(x, device, world):
     return float(t[0])
 
 
+def time_call(fn, reps=5):
+    """Mean CUDA-event time (s) of fn() alone on the current stream after one warm-up call."""
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e-3)
+    return statistics.mean(ts)
+
+
 # ------------------------------------------------------------------------------------ reference / CPU arm
-def cpu_reference_runner(wl):
-    """(run, sample description): one bounded repetition of the reference algorithm on the host cores
-    (oracle port: torch CPU ops = the reference's own arithmetic).  run() returns the evaluations it did."""
-    from oracle import ref_oracle as O
+CPU_SAMPLE = {  # bounded samples of each workload for the host-core baseline (BASELINE.md "CPU-baseline plan")
+    "mc10": dict(N=10**7), "boole6": dict(n_per_dim=17), "vegas4": dict(N=10**6), "vegas8": dict(N=2_500_000),
+    "vegas8_cap4096": dict(N=2_500_000), "vegas16_cap4096": dict(N=2_000_000),
+}
+
+
+def cpu_reference_runner(name, wl):
+    """(run, sample description, kind): one bounded repetition of the workload on the host cores through the UNMODIFIED
+    reference (baseline/_ref, kind "reference"); the oracle port (same ATen CPU kernels, kind "port") only when the
+    staged copy is missing.  run() returns the evaluations it did."""
+    from baseline import ref as ref_loader
 
     torch.set_num_threads(os.cpu_count() or 1)
     dt = getattr(torch, wl["dtype"])
     fn = torch_callable(wl["integrand"])
     dim = wl["dim"]
-    dom = torch.tensor([[0.0, 1.0]] * dim, dtype=dt)
+    sample = CPU_SAMPLE[name]
+    torch.set_default_dtype(dt)  # the reference builds list domains in torch's default dtype
+    dom_list = [[0.0, 1.0]] * dim
+    if ref_loader.available():
+        tqr = ref_loader.import_reference()
+        where = f"unmodified esa/torchquad {getattr(tqr, '__version__', '0.5.0')} from baseline/_ref, torch CPU backend"
+        if wl["kind"] == "mc":
+            n = sample["N"]
+            integ = tqr.MonteCarlo()
+
+            def run():
+                integ.integrate(fn, dim, N=n, integration_domain=dom_list, seed=0, backend="torch")
+                return n
+
+            return run, f"MonteCarlo {dim}-D N={n:,} per repetition; {where}", "reference"
+        if wl["kind"] == "boole":
+            npd = sample["n_per_dim"]
+            integ = tqr.Boole()
+
+            def run():
+                integ.integrate(fn, dim, N=npd**dim, integration_domain=dom_list, backend="torch")
+                return npd**dim
+
+            return run, f"Boole {dim}-D n={npd} per dim per repetition; {where}", "reference"
+        n = min(wl["N"], sample["N"])
+        integ = tqr.VEGAS()
+
+        def run():
+            integ.integrate(fn, dim, N=n, integration_domain=dom_list, seed=0, backend="torch")
+            return integ._nr_of_fevals
+
+        return run, f"VEGAS {dim}-D N={n:,} per repetition (the reference's own map size Ni = N/250); {where}", "reference"
+    from oracle import ref_oracle as O
+
+    where = "oracle/ref_oracle.py (restates the reference over the same ATen CPU kernels; baseline/_ref is not staged here)"
+    dom = torch.tensor(dom_list, dtype=dt)
     if wl["kind"] == "mc":
-        n = 10**7
+        n = sample["N"]
 
         def run():
             O.mc_integrate(fn, dim, n, dom, seed=0)
             return n
 
-        return run, f"MonteCarlo {dim}-D N={n:.0e} per repetition"
+        return run, f"MonteCarlo {dim}-D N={n:,} per repetition; {where}", "port"
     if wl["kind"] == "boole":
-        npd = 17
+        npd = sample["n_per_dim"]
 
         def run():
             pts, hs, n_ = O.nc_grid("boole", npd**dim, dom)
             O.nc_result("boole", fn(pts), dim, n_, hs)
             return npd**dim
 
-        return run, f"Boole {dim}-D n={npd} per dim per repetition"
-    n = min(wl["N"], 2 * 10**6 if dim > 4 else 10**6)
+        return run, f"Boole {dim}-D n={npd} per dim per repetition; {where}", "port"
+    n = min(wl["N"], sample["N"])
 
     def run():
         g = torch.Generator().manual_seed(0)
@@ -227,12 +304,12 @@ def cpu_reference_runner(wl):
         r.run()
         return r.fevals
 
-    return run, f"VEGAS {dim}-D N={n:.0e} per repetition"
+    return run, f"VEGAS {dim}-D N={n:,} per repetition; {where}", "port"
 
 
-def cpu_reference_rate(wl, budget_s=12.0, steps=None, warmup=1):
-    """Time the reference algorithm on the host: `steps` repetitions when given, else a time budget."""
-    run, sample = cpu_reference_runner(wl)
+def cpu_reference_rate(name, wl, budget_s=8.0, steps=None, warmup=1):
+    """Time the reference on the host: `steps` repetitions when given, else a time budget."""
+    run, sample, kind = cpu_reference_runner(name, wl)
     for _ in range(max(1, warmup)):
         run()  # warm-up (thread pool, allocator)
     evals, reps, t0 = 0, 0, time.perf_counter()
@@ -240,34 +317,48 @@ def cpu_reference_rate(wl, budget_s=12.0, steps=None, warmup=1):
         evals += run()
         reps += 1
     dt_s = time.perf_counter() - t0
-    return {"value": evals / dt_s, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{sample} x {reps} repetitions ({dt_s:.1f} s); oracle/ref_oracle.py restates the reference over the same ATen CPU kernels",
-            "ms_per_step": dt_s / reps * 1e3}
+    return {"value": evals / dt_s, "unit": "evals/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": kind,
+            "sample": f"{sample} x {reps} repetitions ({dt_s:.1f} s)", "ms_per_step": dt_s / reps * 1e3}
 
 
-def run_reference(args, wl):
+def workload_config(name, wl, path):
+    cfg = {"workload": name, "baseline_config": f"configs[{wl['config_index']}]", "kind": wl["kind"], "dim": wl["dim"],
+           ("N_per_gpu" if wl["scaling"] == "weak" else "N_total"): wl["N"], "integrand": wl["integrand"], "path": path}
+    if wl["kind"] == "vegas":
+        cfg["map_cap"] = wl.get("map_cap")
+    if wl.get("note"):
+        cfg["note"] = wl["note"]
+    return cfg
+
+
+def run_reference(args, names):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    base = cpu_reference_rate(wl, steps=args.steps, warmup=args.warmup)
-    line = {
-        "impl": "reference", "metric": "integrand evals/s", "value": base["value"], "unit": "evals/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base.pop("ms_per_step"),
-        "higher_is_better": True, "scaling": "strong" if wl["kind"] == "boole" else "weak", "vs_baseline": None,
-        "dtype": "f32" if wl["dtype"] == "float32" else "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "kind": wl["kind"], "dim": wl["dim"],
-                   ("N_total" if wl["kind"] == "boole" else "N_per_gpu"): wl["N"],
-                   "integrand": wl["integrand"], "path": "reference algorithm on the host cores, bounded sample per step"},
-        "cpu_baseline": base,
-        "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
+    records = {}
+    for name in names:
+        wl = WORKLOADS[name]
+        head = name == names[0]
+        base = cpu_reference_rate(name, wl, steps=args.steps if head else 2, warmup=args.warmup if head else 1)
+        ms = base.pop("ms_per_step")
+        records[name] = {
+            "metric": "integrand evals/s", "value": base["value"], "unit": "evals/s", "ms_per_step": ms,
+            "higher_is_better": True, "scaling": wl["scaling"], "dtype": "f32" if wl["dtype"] == "float32" else "f64",
+            "config": workload_config(name, wl, "reference implementation on the host cores, bounded sample per step"),
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+    head = records[names[0]]
+    line = {"impl": "reference", **head, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "vs_baseline": None,
+            "data": "synthetic", "gpu_launches": 0}
+    if len(names) > 1:
+        line["workloads"] = {n: records[n] for n in names[1:]}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------ our arm
-def build_steps(wl, device, world, map_cap=None):
-    """Returns (fused_step, e2e_step, unfused_step, evals_per_step_per_job, info)."""
+def build_steps(name, wl, device, world, map_cap):
+    """Returns (fused_step, e2e_step, unfused_step, evals(), info)."""
     import torchquad_b200 as tq
 
     dt = getattr(torch, wl["dtype"])
@@ -276,8 +367,8 @@ def build_steps(wl, device, world, map_cap=None):
     call = torch_callable(wl["integrand"])
     dom_host = [[0.0, 1.0]] * dim
     dom_dev = torch.tensor(dom_host, dtype=dt, device=device)
-    N = wl["N"] * world  # weak scaling: per-GPU work fixed
-    state = {"evals": N, "seed": 0}
+    N = wl["N"] * (world if wl["scaling"] == "weak" else 1)
+    state = {"seed": 0}
     torch.set_default_dtype(dt)  # list domains take torch's default dtype, like in the reference
     if wl["kind"] == "mc":
         integ = tq.MonteCarlo()
@@ -299,13 +390,13 @@ def build_steps(wl, device, world, map_cap=None):
         integ = tq.Boole()
 
         def fused():
-            return integ.integrate(fn, dim, N=wl["N"], integration_domain=dom_dev)
+            return integ.integrate(fn, dim, N=N, integration_domain=dom_dev)
 
         def e2e():
-            return float(integ.integrate(fn, dim, N=wl["N"], integration_domain=dom_host, backend="torch"))
+            return float(integ.integrate(fn, dim, N=N, integration_domain=dom_host, backend="torch"))
 
         def unfused():
-            return float(integ.integrate(call, dim, N=wl["N"], integration_domain=dom_host, backend="torch"))
+            return float(integ.integrate(call, dim, N=N, integration_domain=dom_host, backend="torch"))
 
         evals = lambda: integ._nr_of_fevals  # noqa: E731
     else:
@@ -325,7 +416,7 @@ def build_steps(wl, device, world, map_cap=None):
             return float(integ.integrate(call, dim, N=N, integration_domain=dom_host, seed=state["seed"], backend="torch"))
 
         evals = lambda: integ._nr_of_fevals  # noqa: E731
-    info = {"dtype": dt, "dim": dim, "exact": fn.exact(), "integrator": integ}
+    info = {"dtype": dt, "dim": dim, "exact": fn.exact(), "integrator": integ, "fn": fn, "N": N}
     if wl["kind"] == "mc":
         fast_fn = make_integrand(wl["integrand"], dim, fast_math=True)
 
@@ -337,19 +428,6 @@ def build_steps(wl, device, world, map_cap=None):
     return fused, e2e, unfused, evals, info
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised in
-# profiles/r1 (same launch shapes as kernel_rooflines below / the default workload).
-NCU_TRAFFIC = {
-    "fused_mc_kernel": 28_160,            # profiles/r1/prof_fused_mc.txt (1e9 evals: no sample traffic)
-    "sum1_kernel": 865_042_944,           # profiles/r1/prof_sum1.txt (2e8 fp32 values = 800 MB algorithmic)
-    "uniform_kernel": 8_028_438_320,      # profiles/r1/prof_uniform_f32_d10.txt (2e8 x 10 fp32 = 8.0 GB algorithmic)
-}
-
-
-# smsp__inst_executed.sum / evaluations from the same captures (10-D sum-of-sines, fp32: 1.772e10 / 1e9)
-NCU_WARP_INST_PER_EVAL = {"fused_mc_kernel": 17.72}
-
-
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -358,8 +436,38 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def kernel_rooflines(wl, device, clocks_mhz):
-    """Live CUDA-event timings of the dominant kernels alone + measured issue-rate denominators."""
+def ncu_metrics():
+    """Per-kernel figures taken from the `ncu --set full` captures of this round (written by scripts/ncu_summary.py --json
+    into profiles/r2/ncu_metrics.json): dram bytes and warp instructions per launch + the launch's work units."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2", "ncu_metrics.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
+def ncu_entry(key):
+    return ncu_metrics().get(key) or {}
+
+
+def issue_roofline(kernel, ncu_key, evals_per_s, sm_count, sm_mhz):
+    """Fused kernels move no sample data: they are bound by instruction issue.  achieved = warp instructions per eval
+    (ncu smsp__inst_executed.sum / evals of the captured launch) x evals/s; peak = 4 schedulers x SMs x the SM clock
+    sampled during the timed region."""
+    e = ncu_entry(ncu_key)
+    if not e.get("warp_inst_per_unit") or not sm_mhz:
+        return {"kernel": kernel, "bound": "instruction issue (no tensor, no sample traffic)", "achieved": None, "peak": None,
+                "unit": "G warp-inst/s", "frac": None, "traffic": e.get("dram_bytes"), "note": f"no ncu capture for {ncu_key}"}
+    winst = e["warp_inst_per_unit"] * evals_per_s
+    peak = 4.0 * sm_count * sm_mhz * 1e6
+    return {"kernel": kernel, "bound": "instruction issue (no tensor, no sample traffic)", "achieved": winst / 1e9,
+            "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": winst / peak, "traffic": e.get("dram_bytes"),
+            "warp_inst_per_eval": e["warp_inst_per_unit"], "ncu_issue_active_pct": e.get("issue_active_pct"),
+            "source": f"profiles/r2/ncu_metrics.json[{ncu_key}]", "peak_source": "4 issue slots x SMs x sampled SM clock"}
+
+
+def mc_kernel_rooflines(wl, device):
+    """Live CUDA-event timings of the unfused path's own kernels alone (HBM-bound) + FP issue microbenchmarks."""
     import ctypes
 
     from torchquad_b200 import _lib, ops
@@ -368,21 +476,6 @@ def kernel_rooflines(wl, device, clocks_mhz):
     peaks, peak_src = measured_peaks()
     dt = getattr(torch, wl["dtype"])
     dim = wl["dim"]
-
-    def time_call(fn, reps=5):
-        fn()
-        torch.cuda.synchronize()
-        ts = []
-        for _ in range(reps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn()
-            b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b) * 1e-3)
-        return statistics.mean(ts)
-
-    # measured instruction-issue denominators (FP32 FMA chains, FP64 FMA chains, Philox blocks)
     sink = torch.zeros(1, dtype=torch.float64, device=device)
     micro = {}
     for kind, name in [(0, "fp32_fma_per_s"), (1, "fp64_fma_per_s"), (2, "philox_blocks_per_s")]:
@@ -391,41 +484,181 @@ def kernel_rooflines(wl, device, clocks_mhz):
                                         ctypes.byref(ops_out), _lib.stream_ptr(device)))
         micro[name] = ops_out.value / t
     out["microbench"] = micro
-    if wl["kind"] == "mc":
-        rows = 2 * 10**8
-        dom = torch.tensor([[0.0, 1.0]] * dim, dtype=dt, device=device)
-        buf = torch.empty((rows, dim), dtype=dt, device=device)
+    rows = 2 * 10**8
+    dom = torch.tensor([[0.0, 1.0]] * dim, dtype=dt, device=device)
+    buf = torch.empty((rows, dim), dtype=dt, device=device)
 
-        def gen():
-            _lib.call("tq_mc_sample", buf.data_ptr(), dom.data_ptr(), 0, rows, dim, _lib.dtype_code(dt), 1, 0,
-                      _lib.stream_ptr(device))
+    def gen():
+        _lib.call("tq_mc_sample", buf.data_ptr(), dom.data_ptr(), 0, rows, dim, _lib.dtype_code(dt), 1, 0,
+                  _lib.stream_ptr(device))
 
-        t = time_call(gen)
-        bytes_alg = rows * dim * buf.element_size()  # algorithmic: every sample coordinate written once
-        out["roofline_unfused"] = {
-            "kernel": "uniform_kernel<T,true> (tq_mc_sample: Philox + affine map, points written to HBM)",
-            "bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": bytes_alg / t / 1e9 / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get("uniform_kernel"),
-            "peak_source": peak_src, "launch_ms": t * 1e3, "algorithmic_bytes_per_launch": bytes_alg,
-        }
-        del buf
-        f = torch.rand(rows, dtype=dt, device=device)
-        t = time_call(lambda: ops.sum_columns(f))
-        out["roofline_reduce"] = {
-            "kernel": "sum1_kernel<T> (tq_sum_columns: fp64-accumulated reduction of f)", "bound": "hbm",
-            "achieved": rows * f.element_size() / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": rows * f.element_size() / t / 1e9 / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get("sum1_kernel"),
-            "peak_source": peak_src,
-            "launch_ms": t * 1e3,
-        }
+    t = time_call(gen)
+    bytes_alg = rows * dim * buf.element_size()  # algorithmic: every sample coordinate written once
+    out["roofline_unfused"] = {
+        "kernel": "uniform_kernel<T,true> (tq_mc_sample: Philox + affine map, points written to HBM)",
+        "bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": bytes_alg / t / 1e9 / peaks["hbm_gbs"], "traffic": ncu_entry("uniform_kernel_f32_d10").get("dram_bytes"),
+        "peak_source": peak_src, "launch_ms": t * 1e3, "algorithmic_bytes_per_launch": bytes_alg,
+    }
+    del buf
+    f = torch.rand(rows, dtype=dt, device=device)
+    t = time_call(lambda: ops.sum_columns(f))
+    out["roofline_reduce"] = {
+        "kernel": "sum1_kernel<T> (tq_sum_columns: fp64-accumulated reduction of f)", "bound": "hbm",
+        "achieved": rows * f.element_size() / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": rows * f.element_size() / t / 1e9 / peaks["hbm_gbs"], "traffic": ncu_entry("sum1_kernel_f32").get("dram_bytes"),
+        "peak_source": peak_src, "launch_ms": t * 1e3,
+    }
     return out
 
 
-def run_ours(args, wl):
+def vegas_kernel_roofline(name, wl, info, device):
+    """The dominant kernel of a fused VEGAS run -- one stratified pass of fused_vegas_kernel over the run's final map and
+    sample allocation -- timed alone with CUDA events, against the roofline that bounds it:
+      map in L2 (capped):   the L2 reduction rate.  Algorithmic work per sample = dim reduction sectors ({sum jf^2, count} of
+                            one bin each); peak = the same paired RED.F64 pattern alone on a table of the same size, measured
+                            live (tq_red_microbench).
+      map beyond L2:        HBM.  Algorithmic bytes per sample = dim x 64 (one 32-byte record sector read, one written back)."""
+    import ctypes
+
+    from torchquad_b200 import _lib, ops
+
+    v = info["integrator"]
+    vmap, strat = v.map, v.strat
+    dim, dt = info["dim"], info["dtype"]
+    offsets = strat._offsets
+    rows = int(offsets[-1].item())
+    s = v._fn_struct
+    JF = torch.zeros((2, strat.N_cubes), dtype=dt, device=device)
+    peaks, peak_src = measured_peaks()
+    if vmap.wants_records():
+        rec = vmap.records()
+        run = lambda: ops.fused_vegas(s, None, None, None, 0, rows, 1, 7, offsets=offsets, n_strat=strat.N_strat, JF=JF[0],  # noqa: E731
+                                      JF2=JF[1], records=rec, dtype=dt, n_intervals=vmap.N_intervals)
+        t = time_call(run)
+        bytes_alg = rows * dim * 64
+        e = ncu_entry(name + ":fused_vegas_kernel")
+        traffic = e.get("dram_bytes_per_unit")
+        return {"kernel": "fused_vegas_kernel<STRAT> (record layout, one pass)", "bound": "hbm", "achieved": bytes_alg / t / 1e9,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bytes_alg / t / 1e9 / peaks["hbm_gbs"],
+                "traffic": traffic * rows if traffic else None, "peak_source": peak_src, "launch_ms": t * 1e3,
+                "rows_per_launch": rows, "samples_per_s": rows / t, "algorithmic_bytes_per_sample": dim * 64,
+                "ncu_dram_bytes_per_sample": traffic,
+                "note": "random 32-byte sector accesses: HBM delivers 64-byte bursts, so 0.5 is the ceiling of this fraction"}
+    h = vmap.hist_pairs()
+    h.zero_()
+    run = lambda: ops.fused_vegas(s, vmap.packed_edges(), None, None, 0, rows, 1, 7, offsets=offsets, n_strat=strat.N_strat,  # noqa: E731
+                                  JF=JF[0], JF2=JF[1], hist_pairs=h)
+    t = time_call(run)
+    h.zero_()
+    bins = dim * vmap.N_intervals
+    table = torch.zeros((bins, 2), dtype=torch.float64, device=device)
+    ops_out = ctypes.c_double()
+    t_red = time_call(lambda: _lib.call("tq_red_microbench", table.data_ptr(), bins, 2000, ctypes.byref(ops_out),
+                                        _lib.stream_ptr(device)))
+    peak = ops_out.value / t_red
+    ach = rows * dim / t
+    e = ncu_entry(name + ":fused_vegas_kernel")
+    return {"kernel": "fused_vegas_kernel<STRAT> (pair layout, one pass)", "bound": "l2 reduction sectors (map resident in L2)",
+            "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G reduction sectors/s", "frac": ach / peak,
+            "traffic": e.get("dram_bytes"), "launch_ms": t * 1e3, "rows_per_launch": rows, "samples_per_s": rows / t,
+            "algorithmic_sectors_per_sample": dim, "ncu_issue_active_pct": e.get("issue_active_pct"),
+            "ncu_lts_throughput_pct": e.get("lts_throughput_pct"),
+            "peak_source": f"tq_red_microbench: paired RED.F64 alone on a {bins}-bin fp64 pair table, measured in this run"}
+
+
+def measure(name, wl, args, ctx, headline):
+    """One workload on this rank: fused value, e2e, (N=1) kernel roofline + unfused arm.  Returns the record on rank 0."""
+    device, world, rank = ctx["device"], ctx["world"], ctx["rank"]
+    flush, barrier, sampler = ctx["flush"], ctx["barrier"], ctx["sampler"]
+    map_cap = args.map_cap if (args.map_cap is not None and wl["kind"] == "vegas") else wl.get("map_cap")
+    fused, e2e, unfused, evals, info = build_steps(name, wl, device, world, map_cap)
+    steps = args.steps if headline else max(2, min(args.steps, 4))
+    warmup = max(3, args.warmup) if headline else 3
+    mark0 = sampler.mark() if sampler else 0
+    times = timed_steps(fused, steps, warmup, flush, barrier)
+    launches = timed_steps.launches
+    mark1 = sampler.mark() if sampler else 0
+    t_fused = max_over_ranks(sum(times), device, world)
+    n_evals = evals()
+    result_check = float(fused())
+    e2e_steps = max(2, steps // 2)
+    t_e2e = max_over_ranks(sum(timed_steps(e2e, e2e_steps, 1, flush, barrier, min_warm_s=0.0)), device, world)
+    n_evals_e2e = evals()
+    fast = unf = None
+    if "fused_fast" in info and headline:
+        f_steps = max(2, steps // 2)
+        t_fast = max_over_ranks(sum(timed_steps(info["fused_fast"], f_steps, 1, flush, barrier)), device, world)
+        fast = {"value": evals() * f_steps / t_fast, "unit": "evals/s", "ms_per_step": t_fast / f_steps * 1e3,
+                "last_integral": float(info["fused_fast"]()),
+                "note": "same fused kernel with sin() evaluated by the SFU (__sinf, abs error ~5e-7): opt-in "
+                        "SumOfSines(dim, fast_math=True); not used for `value`"}
+    if not args.no_unfused and world == 1 and (headline or name in ("boole6", "vegas4")):
+        u_steps = 2
+        t_unf = sum(timed_steps(unfused, u_steps, 1, flush, barrier, min_warm_s=0.0))
+        unf = {"value": evals() * u_steps / t_unf, "unit": "evals/s", "ms_per_step": t_unf / u_steps * 1e3,
+               "path": "torch-callable integrand, points materialised in HBM (chunked), e2e through the public API"}
+    if rank != 0:
+        return None
+    elt = 4 if wl["dtype"] == "float32" else 8
+    value = n_evals * steps / t_fused
+    rec = {
+        "metric": "integrand evals/s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": t_fused / steps * 1e3, "higher_is_better": True, "scaling": wl["scaling"],
+        "dtype": "f32" if wl["dtype"] == "float32" else "f64", "data": "synthetic",
+        "config": {**workload_config(name, wl, "fused functor (generate+map+evaluate+accumulate in one kernel)"),
+                   "l2": "512 MiB buffer rewritten between timed iterations", "rng": "Philox4x32-10, fresh seed per step"},
+        "e2e": {"value": n_evals_e2e * e2e_steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": wl["dim"] * 2 * elt,
+                "d2h_bytes_per_step": elt, "steps": e2e_steps,
+                "call": f"torchquad_b200.{'MonteCarlo' if wl['kind']=='mc' else 'Boole' if wl['kind']=='boole' else 'VEGAS'}()"
+                        ".integrate(fn, dim, N, integration_domain=<host list>, backend='torch') -> float"},
+        "gpu_launches": launches, "evals_per_step": n_evals,
+        "result": {"last_integral": result_check, "exact": info["exact"]},
+    }
+    if wl["kind"] == "vegas":
+        v = info["integrator"]
+        rec["config"].update(map_intervals=v.map.N_intervals, n_cubes=v.strat.N_cubes, iterations=v.it, map_cap=map_cap,
+                             map_layout="records" if v.map.wants_records() else "pairs",
+                             sharding=("block-cyclic cubes, one fp64 all-reduce per pass" if v._shard is not None
+                                       else "replicas" if world > 1 else "single GPU"))
+        rec["result"]["error_estimate"] = float(v._get_error())
+    clocks = sampler.summary(mark0, mark1) if sampler else None
+    rec["clocks"] = clocks
+    if world == 1:
+        from torchquad_b200 import _lib
+
+        sm_count = _lib.device_info()[0]
+        sm_mhz = (clocks or {}).get("sm_mhz")
+        if wl["kind"] == "mc":
+            rec["roofline"] = issue_roofline("fused_mc_kernel<SUM_SIN,float>", "mc10:fused_mc_kernel", value, sm_count, sm_mhz)
+            rec.update(mc_kernel_rooflines(wl, device))
+        elif wl["kind"] == "boole":
+            rec["roofline"] = issue_roofline("fused_nc_kernel<PROD_COS,double>", "boole6:fused_nc_kernel", value, sm_count, sm_mhz)
+        else:
+            if wl["N"] >= 10**8:
+                rec["roofline"] = vegas_kernel_roofline(name, wl, info, device)
+            else:
+                rec["roofline"] = {"kernel": "fused_vegas_kernel + vegas_update_small_kernel (15 passes of ~6e4 samples)",
+                                   "bound": "launch latency (a chain of ~30 dependent launches of 5-15 us)", "achieved": None,
+                                   "peak": None, "unit": None, "frac": None, "traffic": None,
+                                   "note": "no throughput roofline applies at this size; see profiles/r1/launches_vegas4.txt"}
+    if fast:
+        rec["fast_math"] = fast
+    if unf:
+        rec["unfused"] = unf
+    return rec
+
+
+def run_ours(args, names):
     rank, local_rank, world = dist_env()
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
+    # stdout carries exactly ONE JSON line: everything else that reaches fd 1 (NCCL_DEBUG=INFO banners and channel
+    # reports, whenever NCCL chooses to print them) goes to stderr, where the rank / transport evidence stays visible
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     import torchquad_b200 as tq
@@ -437,126 +670,46 @@ def run_ours(args, wl):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO; stdout must carry ONE JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("TQ_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        # ... and whatever still reaches fd 1 during communicator set-up goes to stderr instead
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=device)
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
+        dist.init_process_group("nccl", device_id=device)
+        dist.barrier()
+        torch.cuda.synchronize()
         tq.distributed.enable()
         barrier = dist.barrier
     flush = torch.zeros(128 << 20, dtype=torch.float32, device=device)
-    fused, e2e, unfused, evals, info = build_steps(wl, device, world, args.map_cap)
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
         sampler.start()
-    times = timed_steps(fused, args.steps, args.warmup, flush, barrier)
-    launches = timed_steps.launches  # kernels libtqb200 launched inside the timed region (tq_kernel_launches)
-    clocks = sampler.stop() if rank == 0 else None
-    t_fused = max_over_ranks(sum(times), device, world)
-    n_evals = evals()
-    result_check = float(fused())
-
-    t_e2e = max_over_ranks(sum(timed_steps(e2e, max(2, args.steps // 2), 1, flush, barrier)), device, world)
-    e2e_steps = max(2, args.steps // 2)
-    n_evals_e2e = evals()
-
-    fast = None
-    if "fused_fast" in info:
-        f_steps = max(2, args.steps // 2)
-        t_fast = max_over_ranks(sum(timed_steps(info["fused_fast"], f_steps, 1, flush, barrier)), device, world)
-        fast = {"value": evals() * f_steps / t_fast, "unit": "evals/s", "ms_per_step": t_fast / f_steps * 1e3,
-                "last_integral": float(info["fused_fast"]()),
-                "note": "same fused kernel with sin() evaluated by the SFU (__sinf, abs error ~5e-7): opt-in "
-                        "SumOfSines(dim, fast_math=True); not used for `value`"}
-    unf = None
-    if not args.no_unfused and wl["kind"] in ("mc", "boole", "vegas") and wl["N"] <= 3 * 10**9:
-        u_steps = 2
-        t_unf = max_over_ranks(sum(timed_steps(unfused, u_steps, 1, flush, barrier)), device, world)
-        unf = {"value": evals() * u_steps / t_unf, "unit": "evals/s", "ms_per_step": t_unf / u_steps * 1e3,
-               "path": "torch-callable integrand, points materialised in HBM (chunked), e2e through the public API"}
-    if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
-        return
-    roof = kernel_rooflines(wl, device, clocks) if world == 1 else {}
-    micro = roof.get("microbench", {})
-    elt = 4 if wl["dtype"] == "float32" else 8
-    line = {
-        "metric": "integrand evals/s", "value": n_evals * args.steps / t_fused, "unit": "evals/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_fused / args.steps * 1e3, "higher_is_better": True,
-        # MC / VEGAS: N per GPU fixed (weak); the Newton-Cotes grid is one fixed grid sharded over the ranks (strong)
-        "scaling": "strong" if wl["kind"] == "boole" else "weak", "vs_baseline": None,
-        "dtype": "f32" if wl["dtype"] == "float32" else "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "kind": wl["kind"], "dim": wl["dim"],
-                   ("N_total" if wl["kind"] == "boole" else "N_per_gpu"): wl["N"],
-                   "integrand": wl["integrand"], "path": "fused functor (generate+evaluate+accumulate in one kernel)",
-                   "l2": "512 MiB buffer rewritten between timed iterations", "rng": "Philox4x32-10, fresh seed per step"},
-        "clocks": clocks,
-        "e2e": {"value": n_evals_e2e * e2e_steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": wl["dim"] * 2 * elt,
-                "d2h_bytes_per_step": elt, "steps": e2e_steps,
-                "call": f"torchquad_b200.{'MonteCarlo' if wl['kind']=='mc' else 'Boole' if wl['kind']=='boole' else 'VEGAS'}().integrate(fn, dim, N, integration_domain=<host list>, backend='torch') -> float"},
-        "gpu_launches": launches,
-        "result": {"last_integral": result_check, "exact": info["exact"]},
-    }
-    if wl["kind"] == "mc" and micro:
-        # Fused kernel: no sample traffic, bound by instruction issue (INT32 Philox + FP32 sin).  Work model per
-        # eval: ceil(dim/4) Philox blocks; denominator: measured Philox-block rate of this GPU.
-        blocks_per_eval = -(-wl["dim"] // (4 if elt == 4 else 2))
-        ach = n_evals * args.steps / t_fused * blocks_per_eval
-        line["roofline"] = {"kernel": "fused_mc_kernel<SUM_SIN,float>", "bound": "int32/fp32 issue (no tensor, no HBM traffic)",
-                            "achieved": ach / 1e9, "peak": micro["philox_blocks_per_s"] / 1e9, "unit": "G Philox blocks/s",
-                            "frac": ach / micro["philox_blocks_per_s"], "traffic": NCU_TRAFFIC.get("fused_mc_kernel"),
-                            "note": "peak = Philox-only microbenchmark on this GPU; the kernel also evaluates dim sin() per eval"}
-        # Second view of the same kernel: instruction issue.  Warp instructions per eval come from the ncu capture
-        # of this kernel (profiles/r1/prof_fused_mc.txt: smsp__inst_executed.sum / evals); the denominator is
-        # 4 schedulers x SMs x the SM clock sampled during the timed region.
-        if elt == 4 and wl["dim"] == 10 and clocks and clocks.get("sm_mhz"):
-            import ctypes as _ct
-
-            sm, maj, mnr = _ct.c_int(), _ct.c_int(), _ct.c_int()
-            _lib.call("tq_device_info", _ct.byref(sm), _ct.byref(maj), _ct.byref(mnr))
-            winst = NCU_WARP_INST_PER_EVAL["fused_mc_kernel"] * n_evals * args.steps / t_fused
-            peak_issue = 4.0 * sm.value * clocks["sm_mhz"] * 1e6
-            line["roofline"]["issue"] = {"warp_inst_per_eval": NCU_WARP_INST_PER_EVAL["fused_mc_kernel"],
-                                         "achieved_gwarp_inst_s": winst / 1e9, "peak_gwarp_inst_s": peak_issue / 1e9,
-                                         "frac": winst / peak_issue}
-    if wl["kind"] == "vegas":
-        line["config"]["map_intervals"] = info["integrator"].map.N_intervals
-        line["config"]["n_cubes"] = info["integrator"].strat.N_cubes
-        line["config"]["iterations"] = info["integrator"].it
-    if roof:
-        line.update({k: v for k, v in roof.items()})
-    if fast:
-        line["fast_math"] = fast
-    if unf:
-        line["unfused"] = unf
-    if not args.no_cpu_baseline and world == 1:
-        base = cpu_reference_rate(wl)
-        base.pop("ms_per_step", None)
-        line["cpu_baseline"] = base
-    print(json.dumps(line))
+    ctx = {"device": device, "world": world, "rank": rank, "flush": flush, "barrier": barrier, "sampler": sampler}
+    records = {}
+    for i, name in enumerate(names):
+        records[name] = measure(name, WORKLOADS[name], args, ctx, headline=(i == 0))
+        torch.cuda.empty_cache()
+    all_clocks = sampler.stop() if sampler else None
     if world > 1:
         torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
+    if world == 1 and not args.no_cpu_baseline:
+        for i, name in enumerate(names):
+            base = cpu_reference_rate(name, WORKLOADS[name], budget_s=10.0 if i == 0 else 3.0)
+            base.pop("ms_per_step", None)
+            records[name]["cpu_baseline"] = base
+    head = records[names[0]]
+    line = {**head, "vs_baseline": None}
+    line["clocks"] = head.get("clocks") or all_clocks
+    line["clocks_whole_run"] = all_clocks
+    if len(names) > 1:
+        line["workloads"] = {n: records[n] for n in names[1:]}
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 def main():
     args = parse()
-    wl = WORKLOADS[args.workload]
+    names = [HEADLINE] + SUB_WORKLOADS if args.workload == "all" else [args.workload]
     if args.impl == "reference":
-        run_reference(args, wl)
+        run_reference(args, names)
     else:
-        run_ours(args, wl)
+        run_ours(args, names)
 
 
 if __name__ == "__main__":

@@ -245,6 +245,16 @@ TQ_API int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int6
                    int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* hist_pairs,
                    void* JF, void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
                    size_t ws_bytes, void* stream);
+/* The same pass on one rank of a multi-GPU run.  Cubes are dealt to the ranks block-cyclically in blocks of
+ * 2^cube_block_log2 cubes; offsets/JF/JF2 index this rank's cubes only (n_cubes = how many it owns), local cube l being
+ * global cube l + (((l >> cube_block_log2) * (world - 1) + rank) << cube_block_log2), which keys its Philox stream and
+ * gives its position in the unit cube -- so every world size draws exactly the samples of the single-GPU run.
+ * Warm-up passes (offsets == NULL) are sharded by the caller through [row_begin, row_end). */
+TQ_API int tq_fused_vegas_sharded(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
+                           int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_packed,
+                           int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* hist_pairs,
+                           void* JF, void* JF2, uint64_t seed, uint32_t call_idx, int32_t cube_block_log2, int32_t rank,
+                           int32_t world, double* out_f64, void* ws, size_t ws_bytes, void* stream);
 /* weights += hist.sum (rounded once to the working dtype), counts += hist.count, hist = 0 (vegas_map.py:99-111). */
 TQ_API int tq_vegas_map_unpack_hist(void* hist_pairs, void* weights, int64_t* counts, int32_t dim, int64_t n_intervals,
                              int32_t dtype, void* stream);
@@ -305,6 +315,29 @@ TQ_API int tq_vegas_run_fused(const tq_integrand* fn_host, int32_t dtype, int64_
                        double beta, uint64_t seed, uint32_t first_call, const tq_vegas_state* state,
                        tq_vegas_result* result_host, void* stream);
 
+/* ---- the same run on one rank of a multi-GPU job (one process per GPU) -----------------------------------
+ * Hypercubes are dealt to the ranks block-cyclically (tq_fused_vegas_sharded): `state`'s dh / nh / offsets / JF / JF2 hold
+ * this rank's `n_cubes_local` cubes only (dh initialised to 1 / n_cubes, the GLOBAL count passed as n_cubes); the map is
+ * replicated.  Per pass the library calls `allreduce(user, offset, count)` ONCE: sum `comm[offset, offset + count)` (fp64,
+ * device memory) over all ranks, in place, stream-ordered on `stream` (NCCL all-reduce in the Python host,
+ * torchquad_b200/ops.py).  comm = [{sum jf^2, count} pairs of the map histogram, dim * Ni * 2 | 8 scalars]; it must be zero
+ * on entry.  Every rank receives the same summed statistics, takes the same schedule decisions and returns the same result. */
+typedef int (*tq_allreduce_callback)(void* user, int64_t offset, int64_t count);
+typedef struct tq_vegas_shard {
+    int32_t rank, world;
+    int32_t cube_block_log2;   /* cubes are dealt in blocks of 2^cube_block_log2 */
+    int32_t _pad;
+    int64_t n_cubes_local;     /* cubes this rank owns */
+    double* comm;              /* device fp64 [dim * Ni * 2 + 8], zero */
+    tq_allreduce_callback allreduce;
+    void* user;
+} tq_vegas_shard;
+TQ_API int tq_vegas_run_fused_sharded(const tq_integrand* fn_host, int32_t dtype, int64_t N, int32_t max_iterations,
+                               double eps_rel, double eps_abs, int32_t use_grid_improve, int32_t use_warmup,
+                               int64_t n_intervals, int32_t n_strat, int64_t n_cubes, double v_cubes, double alpha,
+                               double beta, uint64_t seed, uint32_t first_call, const tq_vegas_state* state,
+                               const tq_vegas_shard* shard, tq_vegas_result* result_host, void* stream);
+
 /* ---- whole VEGAS run with a CALLBACK integrand (the drop-in path for arbitrary Python callables) -------
  * Same loop and schedule as tq_vegas_run_fused, but every pass materialises its samples: stratified y
  * (tq_vegas_strat_sample) -> x, jac (tq_vegas_map_forward_packed, with the unit-cube -> domain transform) ->
@@ -349,6 +382,10 @@ TQ_API int tq_l2_fetch_granularity(int32_t bytes, int32_t* previous_host);
  * kind 0 = dependent-free FP32 FMA chains, 1 = FP64 FMA chains, 2 = Philox4x32-10 blocks.
  * Performs iters*threads*ops_per_iter operations; returns ops per launch through ops_out_host. */
 TQ_API int tq_peak_microbench(int32_t kind, int64_t iters, double* sink, double* ops_out_host, void* stream);
+/* The reduction pattern of the fused VEGAS pass alone: every thread adds {1.5, 1.0} to the two fp64 words of a random bin
+ * of table[bins][2] per iteration (lane pairs of one RED.F64 share a bin = one 32-byte sector).  ops_out_host = reduction
+ * sectors issued by the launch; bench.py times it for the L2-reduction roofline of the L2-resident VEGAS workloads. */
+TQ_API int tq_red_microbench(double* table, int64_t bins, int64_t iters, double* ops_out_host, void* stream);
 
 #ifdef __cplusplus
 }

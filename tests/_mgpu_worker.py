@@ -40,6 +40,21 @@ for dt, tol in [(torch.float64, 1e-9), (torch.float32, 2e-4)]:
         checks.append((f"VEGAS {label} {dt}", a, b, tol * (1 if dt == torch.float64 else 20)))
         a, b, integ = both(tq.Boole, fn, 4, dict(N=21**4), dt)
         checks.append((f"Boole {label} {dt}", a, b, tol))
+# bigger fused VEGAS runs: the block-cyclic cube shards of tq_vegas_run_fused_sharded (65536 / 6561 cubes), several
+# checkpoints of the schedule, both dtypes; the evaluation counts must agree too (same nh on every world size up to a
+# last-ulp flip of one floor())
+g8 = F.GenzOscillatory(8, a=0.5, u=0.3)
+a, b, integ = both(tq.VEGAS, g8, 8, dict(N=20_000_000, seed=5), torch.float64)
+checks.append(("VEGAS fused 8-D float64 N=2e7", a, b, 1e-9))
+assert integ._shard is not None and integ.strat.dh.shape[0] == integ._shard[1] < integ.strat.N_cubes
+tq.distributed.disable()
+ref = tq.VEGAS()
+ref.integrate(g8, 8, N=20_000_000, integration_domain=torch.tensor([[0.0, 1.0]] * 8, dtype=torch.float64, device=dev), seed=5)
+checks.append(("VEGAS fused 8-D fevals", float(ref._nr_of_fevals), float(integ._nr_of_fevals), 1e-6))
+checks.append(("VEGAS fused 8-D iterations", float(ref.it), float(integ.it), 0.0))
+g6 = F.GenzProductPeak(6, a=2.0, u=0.5)
+a, b, integ = both(tq.VEGAS, g6, 6, dict(N=3_000_000, seed=2, max_iterations=10), torch.float32)
+checks.append(("VEGAS fused 6-D float32", a, b, 5e-3))
 # large-map record layout ({x, dx, weight, count} per bin), forced on this small problem: the histogram is
 # unpacked into weights/counts before the all-reduce, so sharded == single still holds
 from torchquad_b200.integration.vegas_map import VEGASMap

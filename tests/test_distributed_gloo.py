@@ -69,6 +69,29 @@ def _worker(rank, world, port, ret):
         tqdist.all_reduce_sum_(c)
         assert torch.equal(c, c_full)
         assert torch.allclose(w, w_full, rtol=1e-13) and torch.equal(both[0], JF_full) and torch.equal(both[1], JF2_full)
+        # ---- fused VEGAS: block-cyclic cube ownership (tq_vegas_run_fused_sharded).  Every cube has exactly one owner, so
+        # the per-cube sums need no collective; one packed fp64 all-reduce [hist pairs | I, sigma2, sum d^beta, sum nh]
+        # reproduces the single-process statistics.
+        lb, n_local = tqdist.cube_shard(nc)
+        ids = tqdist.global_cube_ids(n_local, lb, rank, world)
+        owned = [None] * world
+        dist.all_gather_object(owned, ids.tolist())
+        assert sorted(i for part in owned for i in part) == list(range(nc))
+        cube_of_row = torch.repeat_interleave(torch.arange(nc), nh)
+        mine = torch.isin(cube_of_row, ids)
+        pairs = torch.zeros(3 * 64 * 2 + 8, dtype=dt)
+        w_l, c_l = O.map_reset(64, 3, dt)
+        O.map_accumulate(w_l, c_l, y_full[mine], jf_full[mine] ** 2)
+        pairs[: 3 * 64 * 2] = torch.stack([w_l, c_l.to(dt)], dim=-1).reshape(-1)
+        JF_l, JF2_l, nh_l = JF_full[ids], JF2_full[ids], nh[ids].to(dt)  # complete per-cube sums, owned cubes only
+        ih = JF_l * vc / nh_l
+        sig2 = torch.abs(JF2_l * vc * vc / nh_l - ih * ih)
+        pairs[-8:-4] = torch.stack([ih.sum(), (sig2 / nh_l).sum(), torch.zeros((), dtype=dt), nh_l.sum()])
+        tqdist.all_reduce_sum_(pairs)
+        summed = pairs[: 3 * 64 * 2].view(3, 64, 2)
+        assert torch.equal(summed[..., 1].to(torch.int64), c_full) and torch.allclose(summed[..., 0], w_full, rtol=1e-13)
+        ih_f = JF_full * vc / nh.to(dt)
+        assert abs(float(pairs[-8]) - float(ih_f.sum())) < 1e-12 * abs(float(ih_f.sum())) and float(pairs[-5]) == float(nh.sum())
         # ---- Newton-Cotes: point ranges of the flattened grid
         pts, hs, n = O.nc_grid("simpson", 9**3, torch.tensor([[0.0, 1.0]] * 3, dtype=dt))
         fvals = torch.prod(torch.cos(pts), dim=1)

@@ -54,6 +54,19 @@ class tq_vegas_unfused_buffers(ctypes.Structure):
     ]
 
 
+# int allreduce(void* user, int64_t offset, int64_t count): sum comm[offset:offset+count] over the ranks, in place
+tq_allreduce_callback = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64)
+
+
+class tq_vegas_shard(ctypes.Structure):
+    """Mirror of `struct tq_vegas_shard`: this rank's share of a multi-GPU fused VEGAS run."""
+
+    _fields_ = [
+        ("rank", c_i32), ("world", c_i32), ("cube_block_log2", c_i32), ("_pad", c_i32), ("n_cubes_local", c_i64),
+        ("comm", c_p), ("allreduce", tq_allreduce_callback), ("user", c_p),
+    ]
+
+
 # int eval(void* user, int64_t rows, const void** f)
 tq_eval_callback = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p))
 
@@ -100,7 +113,12 @@ PROTOTYPES = {
     "tq_vegas_map_pack_edges": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
     "tq_fused_vegas": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_p, c_i64, c_i32, c_i64, c_i64, c_p, c_i32, c_i64, c_p, c_p, c_p,
                                       c_p, c_p, c_u64, c_u32, c_p, c_p, c_sz, c_p]),
+    "tq_fused_vegas_sharded": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_p, c_i64, c_i32, c_i64, c_i64, c_p, c_i32, c_i64, c_p, c_p,
+                                              c_p, c_p, c_p, c_u64, c_u32, c_i32, c_i32, c_i32, c_p, c_p, c_sz, c_p]),
     "tq_vegas_map_unpack_hist": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
+    "tq_vegas_run_fused_sharded": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_i64, c_i32, c_f64, c_f64, c_i32, c_i32, c_i64, c_i32, c_i64,
+                                                  c_f64, c_f64, c_f64, c_u64, c_u32, ctypes.POINTER(tq_vegas_state),
+                                                  ctypes.POINTER(tq_vegas_shard), ctypes.POINTER(tq_vegas_result), c_p]),
     "tq_vegas_map_records_bytes": (c_sz, [c_i32, c_i64, c_i32]),
     "tq_vegas_map_pack_records": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
     "tq_vegas_map_unpack_records": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
@@ -113,6 +131,7 @@ PROTOTYPES = {
                                           ctypes.POINTER(tq_vegas_result), c_p]),
     "tq_l2_fetch_granularity": (ctypes.c_int, [c_i32, ctypes.POINTER(c_i32)]),
     "tq_peak_microbench": (ctypes.c_int, [c_i32, c_i64, c_p, ctypes.POINTER(c_f64), c_p]),
+    "tq_red_microbench": (ctypes.c_int, [c_p, c_i64, c_i64, ctypes.POINTER(c_f64), c_p]),
 }
 
 _cdll = None

@@ -4,6 +4,7 @@
 // finish(combine_d step(x_d)), so a thread streams over the dimensions without holding the point.
 #include "common.cuh"
 #include "vegas_dev.cuh"
+#include "internal.cuh"
 
 namespace tq {
 
@@ -188,6 +189,14 @@ fused_nc_kernel(const tq_integrand P, const T* __restrict__ nodes, const T* __re
 // JF/JF2 with one L2 reduction each -- no shared-memory atomics.
 // Map edges arrive packed as {x_edge[k], dx_edge[k]} pairs: one 8/16-byte gather per dimension.
 constexpr int FV_BLOCK = 256;
+
+// Multi-GPU: cubes are dealt to the ranks block-cyclically (blocks of 2^lb cubes), so that the hot regions VEGAS
+// concentrates its samples on are spread over all ranks.  A rank's state arrays (dh, nh, offsets, JF, JF2) hold only
+// its own cubes, numbered locally 0..n_local; local cube l is global cube l + (((l >> lb) * (world-1) + rank) << lb).
+struct CubeShard {
+    uint32_t lb, mul, add;  // log2(block), world - 1, rank
+    __device__ __forceinline__ uint32_t global_cube(uint32_t l) const { return l + ((((l >> lb) * mul) + add) << lb); }
+};
 #ifndef FV_MIN_CTAS
 #define FV_MIN_CTAS 6
 #endif
@@ -225,7 +234,7 @@ enum HistMode {
 // Bin ids and jf^2 of the warp's 32 samples are parked in shared memory; two rounds of 16 samples cover the warp.
 template <int FAM, typename T, bool STRAT>
 __global__ void __launch_bounds__(FV_BLOCK, FV_MIN_CTAS)
-fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, int64_t n_cubes, FastDiv ns_div, T inv_ns,
+fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, int64_t n_cubes, CubeShard shard, FastDiv ns_div, T inv_ns,
                    int64_t row_begin, int64_t row_end, bool rows_from_offsets, int64_t rows_per_cta,
                    const void* __restrict__ edges_raw, bool records, long long ni, T* __restrict__ weights,
                    unsigned long long* __restrict__ counts, double* __restrict__ hist_pairs, T* __restrict__ JF,
@@ -300,7 +309,7 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
                 uint32_t i0, i1, c = 0;
                 if (STRAT) {
                     key = s_cube[buf][threadIdx.x];
-                    i0 = (uint32_t)(c_lo + key);
+                    i0 = shard.global_cube((uint32_t)(c_lo + key));  // Philox key and digits come from the GLOBAL cube id
                     i1 = (uint32_t)(row - s_off[buf][key]);
                     c = i0;
                 } else {
@@ -474,6 +483,34 @@ unpack_hist_kernel(double2* __restrict__ hist, T* __restrict__ weights, long lon
     }
 }
 
+// pairs[i] += {record.w, record.c}; the record's histogram fields go back to zero
+template <typename T>
+__global__ void __launch_bounds__(256)
+records_to_pairs_kernel(MapRecord<T>* __restrict__ recs, double2* __restrict__ pairs, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const MapRecord<T> r = recs[i];
+        if (r.c != 0) {
+            double2 p = pairs[i];
+            p.x += (double)r.w;
+            p.y += (double)r.c;
+            pairs[i] = p;
+            MapRecord<T> z = r;
+            z.w = (T)0;
+            z.c = 0;
+            recs[i] = z;
+        }
+    }
+}
+
+int records_to_pairs_launch(void* records, double* pairs, int32_t dim, int64_t ni, int32_t dtype, void* stream) {
+    const int64_t total = (int64_t)dim * ni;
+    const int grid = grid_for(total, 256, 8);
+    TQ_DISPATCH_DTYPE(dtype, {
+        records_to_pairs_kernel<T><<<TQ_GRID(grid), 256, 0, as_stream(stream)>>>((MapRecord<T>*)records, (double2*)pairs, total);
+    });
+    return check_launch("records_to_pairs_kernel");
+}
+
 #define TQ_DISPATCH_FAMILY(fam, ...)                                                                  \
     switch (fam) {                                                                                    \
         case TQ_F_GENZ_OSCILLATORY: { constexpr int FAM = TQ_F_GENZ_OSCILLATORY; __VA_ARGS__; break; }      \
@@ -604,8 +641,21 @@ int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* of
                    int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* hist_pairs,
                    void* JF, void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
                    size_t ws_bytes, void* stream) {
+    return tq_fused_vegas_sharded(fn_host, dtype, offsets, n_cubes, n_strat, row_begin, row_end, edges_packed, edges_layout,
+                                  n_intervals, weights, counts, hist_pairs, JF, JF2, seed, call_idx, 0, 0, 1, out_f64, ws, ws_bytes,
+                                  stream);
+}
+
+int tq_fused_vegas_sharded(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
+                           int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_packed,
+                           int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* hist_pairs,
+                           void* JF, void* JF2, uint64_t seed, uint32_t call_idx, int32_t cube_block_log2, int32_t rank,
+                           int32_t world, double* out_f64, void* ws, size_t ws_bytes, void* stream) {
     int rc = check_integrand("tq_fused_vegas", fn_host);
     if (rc) return rc;
+    TQ_REQUIRE(world >= 1 && rank >= 0 && rank < world && cube_block_log2 >= 0 && cube_block_log2 < 31,
+               "tq_fused_vegas: bad cube shard (block 2^%d, rank %d of %d)", cube_block_log2, rank, world);
+    const CubeShard shard = {(uint32_t)cube_block_log2, (uint32_t)(world - 1), (uint32_t)rank};
     const bool strat = offsets != nullptr;
     const bool rows_from_offsets = row_end < 0;  // count stays on the device; -row_end is the sizing estimate
     if (rows_from_offsets) {
@@ -665,13 +715,13 @@ int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int64_t* of
             if (strat) {
                 if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, true><<<TQ_GRID((unsigned)ctas), FV_BLOCK, smem, st>>>(
-                    *fn_host, (const long long*)offsets, n_cubes, ns_div, inv_ns, row_begin, row_end, rows_from_offsets, rows_per_cta,
+                    *fn_host, (const long long*)offsets, n_cubes, shard, ns_div, inv_ns, row_begin, row_end, rows_from_offsets, rows_per_cta,
                     edges_packed, records, n_intervals, (T*)weights, (unsigned long long*)counts, (double*)hist_pairs,
                     (T*)JF, (T*)JF2, seed, call_idx, hist_mode, partials, ticket, out_f64);
             } else {
                 if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, false><<<TQ_GRID((unsigned)ctas), FV_BLOCK, smem, st>>>(
-                    *fn_host, nullptr, 0, ns_div, inv_ns, row_begin, row_end, false, rows_per_cta, edges_packed, records,
+                    *fn_host, nullptr, 0, shard, ns_div, inv_ns, row_begin, row_end, false, rows_per_cta, edges_packed, records,
                     n_intervals, (T*)weights, (unsigned long long*)counts, (double*)hist_pairs, nullptr, nullptr, seed, call_idx,
                     hist_mode, partials, ticket, out_f64);
             }

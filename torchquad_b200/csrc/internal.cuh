@@ -9,6 +9,14 @@ namespace tq {
 int strat_nh_launch(const void* dh, int64_t n_cubes, double nevals_exp, int32_t dtype, int64_t* nh, int64_t* offsets,
                     void* clear, size_t clear_bytes, void* ws, size_t ws_bytes, void* stream);
 
+// estimator partial sums + unnormalised d^beta (first half of tq_vegas_strat_update): scalars[0..4) = this rank's
+// {sum ih, sum sig2/n, sum d^beta, sum nh}; strat_normalise_launch divides dh by scalars[2] once those are global.
+int strat_update_partial_launch(const void* JF, const void* JF2, const int64_t* nh, int64_t n_cubes, double v_cubes, double beta,
+                                int32_t dtype, void* dh, double* scalars, void* ws, size_t ws_bytes, void* stream);
+int strat_normalise_launch(void* dh, int64_t n_cubes, const double* scalars, int32_t dtype, void* stream);
+// fused.cu: pairs += {record.w, record.c}, record fields back to zero (records -> the all-reduce buffer)
+int records_to_pairs_launch(void* records, double* pairs, int32_t dim, int64_t ni, int32_t dtype, void* stream);
+
 int map_update_launch(void* x_edges, void* dx_edges, void* weights, int64_t* counts, void* edges_packed, int32_t dim,
                       int64_t n_intervals, double alpha, int32_t dtype, int32_t* status, bool clear_status, void* ws,
                       size_t ws_bytes, void* stream);

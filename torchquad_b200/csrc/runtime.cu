@@ -63,6 +63,22 @@ __global__ void __launch_bounds__(256) philox_chain_kernel(int64_t iters, double
     if (acc == 0x9e3779b9u) sink[0] = (double)acc;
 }
 
+// Sector-paired RED.F64 (lanes 2i / 2i+1 -> the two words of one random bin) on a [bins, 2] fp64 table: the reduction
+// pattern of the fused VEGAS pass alone, i.e. the L2 reduction rate that bounds it (bench.py, roofline of vegas*_cap).
+__global__ void __launch_bounds__(256) red_pairs_kernel(double* table, uint32_t bins, int64_t iters) {
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    const int lane = threadIdx.x & 31;
+    for (int64_t it = 0; it < iters; ++it) {
+        s = s * 1664525u + 1013904223u;
+        const uint32_t idx = (uint32_t)(((uint64_t)(s >> 8) * bins) >> 24);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t b = __shfl_sync(0xffffffffu, idx, (lane >> 1) + 16 * h);
+            atomicAdd(table + 2 * (size_t)b + (lane & 1), (lane & 1) ? 1.0 : 1.5);
+        }
+    }
+}
+
 }  // namespace tq
 
 extern "C" {
@@ -98,6 +114,14 @@ int tq_l2_fetch_granularity(int32_t bytes, int32_t* previous_host) {
         if (e != cudaSuccess) { tq::set_error("cudaDeviceSetLimit: %s", cudaGetErrorString(e)); return (int)e; }
     }
     return TQ_OK;
+}
+
+int tq_red_microbench(double* table, int64_t bins, int64_t iters, double* ops_out_host, void* stream) {
+    TQ_REQUIRE(table && bins >= 1 && bins < (1LL << 31) && iters >= 1 && ops_out_host, "tq_red_microbench: bad arguments");
+    const int grid = tq::num_sms() * 8;
+    tq::red_pairs_kernel<<<TQ_GRID(grid), 256, 0, tq::as_stream(stream)>>>(table, (uint32_t)bins, iters);
+    *ops_out_host = (double)grid * 256.0 * (double)iters;  // one reduction sector ({sum, count} of one bin) per thread and iteration
+    return tq::check_launch("tq_red_microbench");
 }
 
 int tq_peak_microbench(int32_t kind, int64_t iters, double* sink, double* ops_out_host, void* stream) {

@@ -80,6 +80,12 @@ static bool schedule_checkpoint(const Block<T>& blk, double eps_rel, double eps_
 }
 
 template <typename T>
+static int run_fused_sharded(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t max_it, double eps_rel, double eps_abs,
+                             bool grid_improve, bool warmup, int64_t ni, int32_t n_strat, int64_t n_cubes, double v_cubes,
+                             double alpha, double beta, uint64_t seed, uint32_t call, const tq_vegas_state* s,
+                             const tq_vegas_shard* sh, tq_vegas_result* out, void* stream);
+
+template <typename T>
 static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t max_it, double eps_rel, double eps_abs,
                      bool grid_improve, bool warmup, int64_t ni, int32_t n_strat, int64_t n_cubes, double v_cubes,
                      double alpha, double beta, uint64_t seed, uint32_t call, const tq_vegas_state* s,
@@ -215,6 +221,120 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
         out->results[k] = (double)blk.res[k];
         out->sigma2[k] = (double)blk.sig[k];
     }
+    return TQ_OK;
+}
+
+// Multi-GPU fused run: every rank owns a block-cyclic share of the hypercubes -- its slice of dh / nh /
+// offsets / JF / JF2 never leaves the GPU -- and the map is replicated.  Per pass ONE collective: the fp64 buffer
+// [{sum jf^2, count} pairs of the map histogram | I, sigma^2, sum d^beta, sum nh] is summed over the ranks through the
+// caller's all-reduce (NCCL over NVLink in torch.distributed); nothing else crosses the links and nothing is read back
+// inside a block of five iterations.  The map update runs redundantly on every rank from the summed histogram (it is
+// O(dim * Ni), independent of the sample count), or -- `shard_map_update`, for maps beyond L2 -- each rank rebins
+// dim / world dimensions after a reduce-scatter and the new edges are all-gathered.
+template <typename T>
+static int run_fused_sharded(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t max_it, double eps_rel, double eps_abs,
+                             bool grid_improve, bool warmup, int64_t ni, int32_t n_strat, int64_t n_cubes, double v_cubes,
+                             double alpha, double beta, uint64_t seed, uint32_t call, const tq_vegas_state* s,
+                             const tq_vegas_shard* sh, tq_vegas_result* out, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    const int dim = fn->dim;
+    const size_t elt = sizeof(T);
+    const int64_t increment = N / (max_it + 5);
+    int64_t starting = increment;
+    int64_t fevals = 0;
+    int passes = 0;
+    const int max_passes = TQ_VEGAS_MAX_PASSES;
+    const int rank = sh->rank, world = sh->world, lb = sh->cube_block_log2;
+    const int64_t n_local = sh->n_cubes_local;
+    const bool recs = s->edges_layout == TQ_EDGES_RECORDS;
+    const int layout = recs ? TQ_EDGES_RECORDS : TQ_EDGES_PAIRS;
+    double* comm = sh->comm;                               // [hist_len + 8]
+    const int64_t hist_len = (int64_t)dim * ni * 2;
+    double* tail = comm + hist_len;                        // I, sigma^2, sum d^beta, sum nh of the pass
+    auto allreduce = [&](int64_t offset, int64_t count) -> int {
+        if (sh->allreduce(sh->user, offset, count) != 0) {
+            set_error("tq_vegas_run_fused_sharded: the all-reduce callback failed");
+            return TQ_ERR_CALLBACK;
+        }
+        return TQ_OK;
+    };
+    // summed histogram -> weights / counts -> new edges (replicated on every rank)
+    auto update_map = [&]() -> int {
+        if (passes >= max_passes) { set_error("tq_vegas_run_fused_sharded: more than %d passes", max_passes); return TQ_ERR_UNSUPPORTED; }
+        int rc = tq_vegas_map_unpack_hist(comm, s->weights, s->counts, dim, ni, dtype, stream);
+        if (rc) return rc;
+        rc = map_update_launch(s->x_edges, s->dx_edges, s->weights, s->counts, recs ? nullptr : s->edges_packed, dim, ni, alpha,
+                               dtype, s->status + 4 * passes, false, s->map_ws, s->map_ws_bytes, stream);
+        ++passes;
+        if (!rc && recs) rc = tq_vegas_map_pack_records(s->x_edges, s->dx_edges, s->edges_packed, dim, ni, dtype, stream);
+        return rc;
+    };
+    cudaMemsetAsync(s->status, 0, 4 * (size_t)max_passes * sizeof(int32_t), st);
+    cudaMemsetAsync(tail, 0, 8 * sizeof(double), st);
+    if (warmup) {  // vegas.py:211-266, rows split evenly over the ranks
+        const int64_t ns = starting / 5;
+        const int64_t r0 = ns * rank / world, r1 = ns * (rank + 1) / world;
+        for (int w = 0; w < 5; ++w) {
+            int rc = tq_fused_vegas(fn, dtype, nullptr, 0, 1, r0, r1, s->edges_packed, layout, ni, nullptr, nullptr,
+                                    recs ? nullptr : comm, nullptr, nullptr, seed, call++, s->records, s->ws, s->ws_bytes, stream);
+            if (rc) return rc;
+            if (recs && (rc = records_to_pairs_launch(s->edges_packed, comm, dim, ni, dtype, stream))) return rc;
+            fevals += ns;
+            if ((rc = allreduce(0, hist_len))) return rc;
+            if ((rc = update_map())) return rc;
+        }
+    }
+    const size_t jf_bytes = 2 * (size_t)n_local * elt;
+    Block<T> blk;
+    int it = 0;
+    int first_rec = 0;
+    while (true) {
+        ++it;
+        int rc = strat_nh_launch(s->dh, n_local, (double)starting, dtype, s->nh, s->offsets, s->JF, jf_bytes, s->ws, s->ws_bytes, stream);
+        if (rc) return rc;
+        const int64_t m_est = starting / world + 2 * n_local + 1024;
+        rc = tq_fused_vegas_sharded(fn, dtype, s->offsets, n_local, n_strat, 0, -m_est, s->edges_packed, layout, ni, nullptr, nullptr,
+                                    grid_improve && !recs ? comm : nullptr, s->JF, s->JF2, seed, call++, lb, rank, world, nullptr,
+                                    s->ws, s->ws_bytes, stream);
+        if (rc) return rc;
+        if (grid_improve && recs && (rc = records_to_pairs_launch(s->edges_packed, comm, dim, ni, dtype, stream))) return rc;
+        if (it > TQ_VEGAS_MAX_PASSES) { set_error("tq_vegas_run_fused_sharded: too many iterations"); return TQ_ERR_UNSUPPORTED; }
+        // local estimator sums + unnormalised d^beta, then the pass's one collective, then the normalisation
+        if ((rc = strat_update_partial_launch(s->JF, s->JF2, s->nh, n_local, v_cubes, beta, dtype, s->dh, tail, s->ws, s->ws_bytes, stream))) return rc;
+        if ((rc = grid_improve ? allreduce(0, hist_len + 4) : allreduce(hist_len, 4))) return rc;
+        double* record = s->records + 4 * (it - 1);
+        cudaMemcpyAsync(record, tail, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if ((rc = strat_normalise_launch(s->dh, n_local, record, dtype, stream))) return rc;
+        if (grid_improve && (rc = update_map())) return rc;
+        if (it % 5 > 0) continue;
+        const int nrec = it - first_rec;
+        std::vector<double> rec(4 * nrec);
+        cudaMemcpyAsync(rec.data(), s->records + 4 * first_rec, rec.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+        if (passes > 0) cudaMemcpyAsync(out->status, s->status, 4 * (size_t)passes * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("tq_vegas_run_fused_sharded: %s", cudaGetErrorString(e)); return (int)e; }
+        blk.res.clear();
+        blk.sig.clear();
+        for (int k = 0; k < nrec; ++k) {
+            blk.res.push_back((T)rec[4 * k]);
+            blk.sig.push_back((T)rec[4 * k + 1]);
+            fevals += (int64_t)rec[4 * k + 3];
+        }
+        // every rank holds the same summed records, so every rank takes the same decision
+        if (schedule_checkpoint<T>(blk, eps_rel, eps_abs, N, fevals, it, max_it, increment, starting)) break;
+        first_rec = it;
+    }
+    out->it = it;
+    out->n_block = (int32_t)blk.res.size();
+    out->fevals = fevals;
+    out->starting_N = starting;
+    out->calls_used = (int32_t)(call);
+    out->n_passes = passes;
+    for (size_t k = 0; k < blk.res.size() && k < 8; ++k) {
+        out->results[k] = (double)blk.res[k];
+        out->sigma2[k] = (double)blk.sig[k];
+    }
+    (void)n_cubes;
     return TQ_OK;
 }
 
@@ -404,6 +524,30 @@ extern "C" int tq_vegas_run_unfused(tq_eval_callback eval, void* user, int32_t d
                                        use_warmup != 0, n_intervals, n_strat, n_cubes, v_cubes, alpha, beta, seed, first_call, state,
                                        buffers, result_host, stream);
     tq::set_error("tq_vegas_run_unfused: unsupported dtype %d", dtype);
+    return TQ_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int tq_vegas_run_fused_sharded(const tq_integrand* fn_host, int32_t dtype, int64_t N, int32_t max_iterations,
+                                          double eps_rel, double eps_abs, int32_t use_grid_improve, int32_t use_warmup,
+                                          int64_t n_intervals, int32_t n_strat, int64_t n_cubes, double v_cubes, double alpha,
+                                          double beta, uint64_t seed, uint32_t first_call, const tq_vegas_state* state,
+                                          const tq_vegas_shard* shard, tq_vegas_result* result_host, void* stream) {
+    TQ_REQUIRE(fn_host && state && result_host && shard, "tq_vegas_run_fused_sharded: NULL argument");
+    TQ_REQUIRE(N >= 1 && max_iterations >= 1 && max_iterations + 5 <= TQ_VEGAS_MAX_PASSES,
+               "tq_vegas_run_fused_sharded: max_iterations must be in [1, %d]", TQ_VEGAS_MAX_PASSES - 5);
+    TQ_REQUIRE(n_cubes >= 1 && n_strat >= 1 && n_intervals >= 2, "tq_vegas_run_fused_sharded: bad map / stratification sizes");
+    TQ_REQUIRE(shard->world >= 1 && shard->rank >= 0 && shard->rank < shard->world && shard->n_cubes_local >= 1 &&
+                   shard->cube_block_log2 >= 0 && shard->cube_block_log2 < 31 && shard->comm && shard->allreduce,
+               "tq_vegas_run_fused_sharded: bad shard description");
+    if (dtype == TQ_F32)
+        return tq::run_fused_sharded<float>(fn_host, dtype, N, max_iterations, eps_rel, eps_abs, use_grid_improve != 0, use_warmup != 0,
+                                            n_intervals, n_strat, n_cubes, v_cubes, alpha, beta, seed, first_call, state, shard,
+                                            result_host, stream);
+    if (dtype == TQ_F64)
+        return tq::run_fused_sharded<double>(fn_host, dtype, N, max_iterations, eps_rel, eps_abs, use_grid_improve != 0, use_warmup != 0,
+                                             n_intervals, n_strat, n_cubes, v_cubes, alpha, beta, seed, first_call, state, shard,
+                                             result_host, stream);
+    tq::set_error("tq_vegas_run_fused_sharded: unsupported dtype %d", dtype);
     return TQ_ERR_INVALID_ARGUMENT;
 }
 

@@ -165,6 +165,7 @@ strat_sample_kernel(const long long* __restrict__ offsets, int64_t n_cubes, int 
     fd0.set(pw > 0xffffffffull ? 0xffffffffu : (uint32_t)pw);
     const uint32_t ns = (uint32_t)n_strat;
     const T nsf = (T)n_strat;
+    const T inv_ns = div_rn((T)1, nsf);
     const bool base16 = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(u_in)) & 15) == 0;
     const int mode = (nvalid == LANES && base16 && (dim % LANES) == 0) ? 2 : 0;
     const int64_t r_lo = row_begin + (int64_t)blockIdx.x * rows_per_cta;
@@ -201,7 +202,10 @@ strat_sample_kernel(const long long* __restrict__ offsets, int64_t n_cubes, int 
                     const uint32_t q = fdn.div(c);
                     const uint32_t p = c - q * ns;
                     c = q;
-                    T v = div_rn(add_rn((T)p, u[j]), nsf);
+                    // Philox uniforms are multiples of 2^-24 / 2^-53: the multiply-FMA-FMA quotient is the correctly rounded
+                    // one (div_by_const); injected uniforms may be anything (subnormals), they keep the IEEE division
+                    const T a = add_rn((T)p, u[j]);
+                    T v = u_in ? div_rn(a, nsf) : div_by_const(a, nsf, inv_ns);
                     if (v >= (T)1) v = (T)0.999999;
                     u[j] = v;
                 }
@@ -344,6 +348,29 @@ int strat_nh_launch(const void* dh, int64_t n_cubes, double nevals_exp, int32_t 
                                                            (long long*)nh, (long long*)offsets);
     });
     return check_launch("tq_vegas_strat_nh");
+}
+
+int strat_update_partial_launch(const void* JF, const void* JF2, const int64_t* nh, int64_t n_cubes, double v_cubes, double beta,
+                                int32_t dtype, void* dh, double* scalars, void* ws, size_t ws_bytes, void* stream) {
+    Workspace w(ws, ws_bytes);
+    unsigned int* ticket = w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
+    const int grid = grid_for(n_cubes, 256, 4);
+    double* partials = w.take<double>((size_t)grid * 4);
+    if (!ticket || !partials) { set_error("strat_update: workspace too small"); return TQ_ERR_WORKSPACE; }
+    TQ_DISPATCH_DTYPE(dtype, {
+        strat_update_kernel<T><<<TQ_GRID(grid), 256, 0, as_stream(stream)>>>((const T*)JF, (const T*)JF2, (const long long*)nh, n_cubes,
+                                                                   (T)v_cubes, (T)(v_cubes * v_cubes), (T)beta, (T*)dh, partials,
+                                                                   ticket, scalars);
+    });
+    return check_launch("strat_update_kernel");
+}
+
+int strat_normalise_launch(void* dh, int64_t n_cubes, const double* scalars, int32_t dtype, void* stream) {
+    const int grid = grid_for(n_cubes, 256, 4);
+    TQ_DISPATCH_DTYPE(dtype, {
+        strat_normalise_kernel<T><<<TQ_GRID(grid), 256, 0, as_stream(stream)>>>((T*)dh, n_cubes, scalars);
+    });
+    return check_launch("strat_normalise_kernel");
 }
 
 }  // namespace tq

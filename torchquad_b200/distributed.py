@@ -47,6 +47,29 @@ def shard_range(total, rank=None, world=None):
     return (total * rank) // world, (total * (rank + 1)) // world
 
 
+def cube_shard(n_cubes, rank=None, world=None):
+    """Block-cyclic deal of the VEGAS hypercubes: (log2 block, cubes owned by this rank), or None when there are too few
+    cubes to share (every rank then runs the whole problem redundantly, no collective).  Blocks of up to 4096 cubes
+    spread the regions VEGAS concentrates its samples on over all ranks; local cube l of rank r is global cube
+    l + (((l >> lb) * (world - 1) + r) << lb) (include/tqb200.h, tq_fused_vegas_sharded)."""
+    if rank is None or world is None:
+        rank, world = rank_and_world()
+    if world == 1 or n_cubes < 16 * world:
+        return None
+    lb = min(12, (n_cubes // (8 * world)).bit_length() - 1)
+    block = 1 << lb
+    full, rem = divmod(n_cubes, block)
+    owned = full // world + (1 if rank < full % world else 0)
+    n_local = owned * block + (rem if full % world == rank else 0)
+    return lb, n_local
+
+
+def global_cube_ids(n_local, lb, rank, world, device=None):
+    """Global ids of this rank's cubes in local order (int64 tensor), the mapping of `cube_shard`."""
+    l = torch.arange(n_local, dtype=torch.int64, device=device)
+    return l + ((((l >> lb) * (world - 1)) + rank) << lb)
+
+
 def all_reduce_sum_(*tensors):
     """In-place sum over ranks of every tensor (no-op when not enabled)."""
     if not _state["enabled"]:

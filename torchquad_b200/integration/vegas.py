@@ -117,12 +117,19 @@ class VEGAS(BaseIntegrator):
         if self.max_map_intervals is not None:
             N_intervals = max(2, min(N_intervals, int(self.max_map_intervals)))
         self.map = VEGASMap(N_intervals, dim, "torch", self.dtype, device=self.device)
+        # Multi-GPU, built-in integrand: the hypercubes are dealt to the ranks (block-cyclic), each rank keeps only its
+        # share of the stratification state and a pass needs ONE all-reduce (tq_vegas_run_fused_sharded).
+        self._shard = None
+        if (tqdist.is_enabled() and self._fused and self.native_loop and self.initial_adaptation is None
+                and max_iterations + 5 <= _lib.TQ_VEGAS_MAX_PASSES):
+            n_strat = min(1000, int((self._N_increment / 4.0) ** (1.0 / dim)))
+            self._shard = tqdist.cube_shard(n_strat**dim)
         self.strat = VEGASStratification(self._N_increment, dim=dim, rng=self.rng, backend="torch", dtype=self.dtype,
-                                         device=self.device)
-        # Multi-GPU: the float statistics of a pass live in ONE buffer [weights | JF | JF2] so that a pass needs
-        # one all-reduce for them plus one for the int64 counts.
+                                         device=self.device, shard=self._shard)
+        # Multi-GPU, arbitrary integrand: the float statistics of a pass live in ONE buffer [weights | JF | JF2] so that
+        # a pass needs one all-reduce for them plus one for the int64 counts.
         self._stats = None
-        if tqdist.is_enabled():
+        if tqdist.is_enabled() and self._shard is None:
             n_w = dim * N_intervals
             self._stats = torch.zeros(n_w + 2 * self.strat.N_cubes, dtype=self.dtype, device=self.device)
             self.map.weights = self._stats[:n_w].view(dim, N_intervals)
@@ -143,6 +150,8 @@ class VEGAS(BaseIntegrator):
                 and dim * N_intervals * (2 * domain.element_size() + 8) > self._large_map_bytes):
             restore_l2 = _lib.l2_fetch_granularity(self.device, int(self.l2_fetch_bytes))
         try:
+            if self._shard is not None:
+                return self._integrate_native_loop(N, use_warmup)
             native = self.native_loop and not tqdist.is_enabled() and max_iterations + 5 <= _lib.TQ_VEGAS_MAX_PASSES
             if native and self._fused:
                 return self._integrate_native_loop(N, use_warmup)
@@ -220,8 +229,12 @@ class VEGAS(BaseIntegrator):
         """Fused single-GPU run with the pass loop and schedule in C++ (csrc/vegas_driver.cu): same kernels, same
         Philox call indices and therefore the same samples as the Python-driven loop below."""
         first_call = self.rng._call
+        shard = None
+        if self._shard is not None:
+            rank, world = tqdist.rank_and_world()
+            shard = (rank, world, self._shard[0], tqdist.all_reduce_sum_)
         res = ops.vegas_run_fused(self._fn_struct, self.map, self.strat, N, self._max_iterations, self._eps_rel,
-                                  self._eps_abs, self.use_grid_improve, use_warmup, self.rng.seed, first_call)
+                                  self._eps_abs, self.use_grid_improve, use_warmup, self.rng.seed, first_call, shard=shard)
         return self._finish_native(res)
 
     def _finish_native(self, res):

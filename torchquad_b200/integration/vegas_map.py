@@ -35,7 +35,7 @@ class VEGASMap:
         self._edges2, self._edges2_stale = None, True
         self._records, self._records_stale = None, True
         self._scratch = None
-        self._hist = None
+        self._hist = self._hist_flat = None
         self._reset_weight()
 
     @property
@@ -119,7 +119,11 @@ class VEGASMap:
         """fp64 [dim, Ni, 2] = {sum jf^2, count} accumulator of the fused passes (zero between passes), see
         `ops.fused_vegas` / `ops.unpack_hist`."""
         if self._hist is None:
-            self._hist = torch.zeros((self.dim, self.N_intervals, 2), dtype=torch.float64, device=self.device)
+            # 8 spare words behind the table: the multi-GPU loop appends its per-pass scalars so that one all-reduce
+            # carries both (tq_vegas_run_fused_sharded)
+            n = self.dim * self.N_intervals * 2
+            self._hist_flat = torch.zeros(n + 8, dtype=torch.float64, device=self.device)
+            self._hist = self._hist_flat[:n].view(self.dim, self.N_intervals, 2)
         return self._hist
 
     def unpack_hist(self):

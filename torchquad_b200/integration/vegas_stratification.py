@@ -15,7 +15,9 @@ from .utils import _default_device, _require_torch_backend
 class VEGASStratification:
     """Hypercube stratification of VEGAS Enhanced (arXiv:2009.05112, section III)."""
 
-    def __init__(self, N_increment, dim, rng, backend="torch", dtype=torch.float32, beta=0.75, device=None):
+    def __init__(self, N_increment, dim, rng, backend="torch", dtype=torch.float32, beta=0.75, device=None, shard=None):
+        """`shard` = (log2 block, cubes owned) from `torchquad_b200.distributed.cube_shard`: a multi-GPU fused run keeps
+        only this rank's cubes in `dh`, `JF`, `JF2`, ... (block-cyclic deal); `N_cubes` / `V_cubes` stay global."""
         _require_torch_backend(backend)
         self.rng = rng
         self.dim = dim
@@ -30,12 +32,14 @@ class VEGASStratification:
         self.dtype = dtype
         self.backend = "torch"
         self.device = torch.device(device) if device is not None else _default_device()
-        zeros = torch.zeros((3, self.N_cubes), dtype=dtype, device=self.device)  # one fill; JF and JF2 stay adjacent
+        self.shard = shard
+        self.N_cubes_local = self.N_cubes if shard is None else shard[1]
+        zeros = torch.zeros((3, self.N_cubes_local), dtype=dtype, device=self.device)  # one fill; JF and JF2 stay adjacent
         self.JF, self.JF2, self._strat_counts = zeros[0], zeros[1], zeros[2]
         self._counts_stale = False  # set by the native loop: strat_counts = float(nh) is made on first access
         # dh = ones * 1.0 / N_cubes (vegas_stratification.py:43): the working-dtype quotient, computed on the host
         one = (np.float32 if dtype == torch.float32 else np.float64)(1.0)
-        self.dh = torch.full([self.N_cubes], float(one / type(one)(self.N_cubes)), dtype=dtype, device=self.device)
+        self.dh = torch.full([self.N_cubes_local], float(one / type(one)(self.N_cubes)), dtype=dtype, device=self.device)
         self._nh = None        # int64 counts of the current iteration
         self._offsets = None   # their exclusive scan, [N_cubes + 1]
         self.last_scalars = None  # fp64 [4]: I_it, sigma2_it, sum d^beta, sum nh of the last update_DH

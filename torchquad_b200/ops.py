@@ -530,7 +530,7 @@ def fused_vegas(fn_struct, edges_packed, weights, counts, row_begin, row_end, se
 def _vegas_state(vmap, strat, use_records):
     """(tq_vegas_state, keep-alive tensors) over the map / stratification tensors of a native-loop run."""
     dev, dt = vmap.device, vmap.dtype
-    n_cubes = strat.N_cubes
+    n_cubes = strat.N_cubes_local
     # JF and JF2 must be adjacent ([2, n_cubes]); the constructor's layout is, a user-replaced pair may not be
     if strat.JF.data_ptr() + n_cubes * strat.JF.element_size() != strat.JF2.data_ptr() or strat.JF.dtype != dt:
         pair = torch.empty((2, n_cubes), dtype=dt, device=dev)
@@ -561,19 +561,48 @@ def _vegas_finish(vmap, strat, use_records, nh, offsets):
 
 
 def vegas_run_fused(fn_struct, vmap, strat, N, max_iterations, eps_rel, eps_abs, use_grid_improve, use_warmup, seed,
-                    first_call):
+                    first_call, shard=None):
     """Whole fused VEGAS run through `tq_vegas_run_fused` (host loop in C++).  `vmap` / `strat` are the
     VEGASMap / VEGASStratification objects whose tensors hold the state (mutated in place).
-    Returns the filled `tq_vegas_result`; synchronises (the schedule needs the per-block estimates)."""
+    Returns the filled `tq_vegas_result`; synchronises (the schedule needs the per-block estimates).
+
+    `shard` = (rank, world, log2 block, all_reduce) runs this rank's share of a multi-GPU job through
+    `tq_vegas_run_fused_sharded`: `strat` then holds this rank's cubes only and `all_reduce(tensor)` must sum a fp64
+    device tensor over the ranks in place on the current stream (torch.distributed.all_reduce)."""
     dev, dt = vmap.device, vmap.dtype
     use_records = bool(use_grid_improve) and vmap.wants_records()
     state, keep, nh, offsets = _vegas_state(vmap, strat, use_records)
     result = _lib.tq_vegas_result()
-    with on_device(dev):
-        call("tq_vegas_run_fused", fn_struct, dtype_code(dt), N, max_iterations, float(eps_rel), float(eps_abs),
-             int(bool(use_grid_improve)), int(bool(use_warmup)), vmap.N_intervals, strat.N_strat, strat.N_cubes,
-             float(strat.V_cubes), float(vmap.alpha), float(strat.beta), seed & 0xFFFFFFFFFFFFFFFF, first_call & 0xFFFFFFFF,
-             state, result, stream_ptr(dev))
+    common = (fn_struct, dtype_code(dt), N, max_iterations, float(eps_rel), float(eps_abs), int(bool(use_grid_improve)),
+              int(bool(use_warmup)), vmap.N_intervals, strat.N_strat, strat.N_cubes, float(strat.V_cubes), float(vmap.alpha),
+              float(strat.beta), seed & 0xFFFFFFFFFFFFFFFF, first_call & 0xFFFFFFFF, state)
+    if shard is None:
+        with on_device(dev):
+            call("tq_vegas_run_fused", *common, result, stream_ptr(dev))
+    else:
+        rank, world, lb, all_reduce = shard
+        vmap.hist_pairs()
+        comm = vmap._hist_flat
+        comm.zero_()
+        failure = []
+
+        def _cb(_user, offset, count):
+            try:
+                all_reduce(comm[offset:offset + count])
+                return 0
+            except BaseException as exc:  # noqa: BLE001 - re-raised below
+                failure.append(exc)
+                return 1
+
+        callback = _lib.tq_allreduce_callback(_cb)
+        desc = _lib.tq_vegas_shard(rank, world, lb, 0, strat.N_cubes_local, ptr(comm), callback, None)
+        try:
+            with on_device(dev):
+                call("tq_vegas_run_fused_sharded", *common, desc, result, stream_ptr(dev))
+        except RuntimeError:
+            if failure:
+                raise failure[0]
+            raise
     _vegas_finish(vmap, strat, use_records, nh, offsets)
     del keep
     return result
