@@ -40,7 +40,7 @@ for dt in (torch.float32, torch.float64):
     for cols in (3, 300):
         print(dt, "Simpson vec", cols, float(tq.Simpson().integrate(lambda x: fn(x)[:, None].expand(-1, cols) * 1.0, 3, N=9**3,
                                                                      integration_domain=dom).sum()))
-    c = tq.Simpson().get_jit_compiled_integrate(dim=3, N=9**3, integration_domain=dom)
+    c = tq.Simpson().get_jit_compiled_integrate(dim=3, N=9**3, integration_domain=dom, capture_integrand=True)
     print(dt, "compiled", float(c(fn, dom)), float(c(fn, dom)))
     d1 = torch.tensor([[0.0, 1.0]], dtype=dt, device=dev, requires_grad=True)
     r = tq.VEGAS().integrate(lambda x: x[:, 0] ** 2, 1, N=5000, integration_domain=d1, seed=1); r.backward()

@@ -32,12 +32,12 @@ def bench(label, call, n=300):
 for dim, N in ((3, 10_000), (5, 100_000), (10, 1_000_000)):
     dom = torch.tensor([[0.0, 1.0]] * dim, device=dev)
     mc = tq.MonteCarlo()
-    comp = mc.get_jit_compiled_integrate(dim=dim, N=N, integration_domain=dom, seed=1)
+    comp = mc.get_jit_compiled_integrate(dim=dim, N=N, integration_domain=dom, seed=1, capture_integrand=True)
     bench(f"MC dim={dim} N={N} eager   ", lambda: mc.integrate(fn, dim, N=N, integration_domain=dom, seed=1))
     bench(f"MC dim={dim} N={N} compiled", lambda: comp(fn, dom))
 for dim, n in ((3, 21), (4, 17), (6, 9)):
     dom = torch.tensor([[0.0, 1.0]] * dim, device=dev)
     sp = tq.Simpson()
-    comp = sp.get_jit_compiled_integrate(dim=dim, N=n**dim, integration_domain=dom)
+    comp = sp.get_jit_compiled_integrate(dim=dim, N=n**dim, integration_domain=dom, capture_integrand=True)
     bench(f"Simpson dim={dim} n={n} eager   ", lambda: sp.integrate(fn, dim, N=n**dim, integration_domain=dom))
     bench(f"Simpson dim={dim} n={n} compiled", lambda: comp(fn, dom))

@@ -455,7 +455,7 @@ def test_compiled_integrate_replays_a_cuda_graph(cuda):
         return g + lin
 
     mc = tq.MonteCarlo()
-    compiled = mc.get_jit_compiled_integrate(dim=3, N=200_000, integration_domain=dom, seed=5)
+    compiled = mc.get_jit_compiled_integrate(dim=3, N=200_000, integration_domain=dom, seed=5, capture_integrand=True)
     r = [compiled(fn, dom) for _ in range(3)]
     assert compiled.replays == 3
     assert r[0].dtype == torch.float64 and r[0].is_cuda and r[0].dim() == 0
@@ -463,16 +463,16 @@ def test_compiled_integrate_replays_a_cuda_graph(cuda):
     assert len(set(vals)) == 3  # fresh samples per replay
     for v in vals:
         assert abs(v - exact(dom)) < 0.02 * exact(dom)
-    # replay k runs Philox call 2 (baked at capture) + offset: the first one equals an eager run on call index 4
+    # every step of a compiled function uses Philox call = its device counter: warm-up 0, dry run 1, first replay 2
     rng = RNG(seed=5)
-    rng._call = 4  # warm-up and dry run took calls 0 and 1 (+ offsets 0, 1); the capture baked call 2, offset is 2
+    rng._call = 2
     assert float(tq.MonteCarlo().integrate(fn, 3, N=200_000, integration_domain=dom, rng=rng)) == vals[0]
     dom2 = torch.tensor([[0.0, 0.5], [1.0, 2.0], [0.0, 1.0]], dtype=torch.float64, device=cuda)
     assert abs(float(compiled(fn, dom2)) - exact(dom2)) < 0.02 * exact(dom2)
     assert abs(float(compiled(fn, dom2.tolist())) - exact(dom2)) < 0.02 * exact(dom2)  # list domains work too
 
     for rule, N in ((tq.Simpson(), 41**3), (tq.Boole(), 41**3), (tq.Trapezoid(), 101**3)):
-        c = rule.get_jit_compiled_integrate(dim=3, N=N, integration_domain=dom)
+        c = rule.get_jit_compiled_integrate(dim=3, N=N, integration_domain=dom, capture_integrand=True)
         for d in (dom, dom2, dom):
             got, want = float(c(fn, d)), float(rule.integrate(fn, 3, N=N, integration_domain=d))
             assert abs(got - want) <= 1e-12 * abs(want)
@@ -482,7 +482,7 @@ def test_compiled_integrate_replays_a_cuda_graph(cuda):
     def syncing(x):
         return torch.exp(-(x * x).sum(dim=1)) * float(x[0, 0] * 0 + 1)
 
-    c = tq.Simpson().get_jit_compiled_integrate(dim=3, N=21**3, integration_domain=dom)
+    c = tq.Simpson().get_jit_compiled_integrate(dim=3, N=21**3, integration_domain=dom, capture_integrand=True)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         a = float(c(syncing, dom))
@@ -492,8 +492,63 @@ def test_compiled_integrate_replays_a_cuda_graph(cuda):
     assert abs(a - float(tq.Simpson().integrate(lambda x: torch.exp(-(x * x).sum(dim=1)), 3, N=21**3, integration_domain=dom))) < 1e-12
     # a built-in (fused) integrand is a single launch already and runs eagerly
     unit = torch.tensor([[0.0, 1.0]] * 3, dtype=torch.float64, device=cuda)
-    c = tq.MonteCarlo().get_jit_compiled_integrate(dim=3, N=100_000, integration_domain=unit, seed=1)
+    c = tq.MonteCarlo().get_jit_compiled_integrate(dim=3, N=100_000, integration_domain=unit, seed=1, capture_integrand=True)
     assert abs(float(c(F.SumOfSines(3), unit)) - F.SumOfSines(3).exact()) < 0.02 and c.replays == 0
+
+
+def test_compiled_integrate_default_is_eager_and_differentiable(cuda):
+    """The reference evaluates the integrand eagerly inside compiled_integrate (monte_carlo.py:197-212): current Python
+    state is seen on every call and gradients flow to the domain and to integrand parameters; with capture_integrand=True
+    integrands whose values require grad are kept eager, bound methods share one graph, the graph cache is bounded."""
+    torch.set_default_dtype(torch.float64)
+    dom = torch.tensor([[0.0, 1.0], [0.0, 2.0]], dtype=torch.float64, device=cuda)
+    scale = {"a": 1.0}
+
+    def fn(x):
+        return scale["a"] * (x[:, 0] + x[:, 1])
+
+    for integ, kw in ((tq.MonteCarlo(), dict(N=100_000, seed=3)), (tq.Simpson(), dict(N=21**2))):
+        c = integ.get_jit_compiled_integrate(dim=2, integration_domain=dom, **kw)
+        scale["a"] = 1.0
+        one = float(c(fn, dom))
+        scale["a"] = 3.0
+        three = float(c(fn, dom))
+        assert c.replays == 0 and abs(three / one - 3.0) < 0.05  # the closure value is read on every call
+        # gradient wrt the domain (gradient_test.py:162-259) through the compiled callable
+        d = dom.clone().requires_grad_(True)
+        scale["a"] = 1.0
+        c(fn, d).backward()
+        assert d.grad is not None and torch.isfinite(d.grad).all() and float(d.grad.abs().sum()) > 0
+    # gradient wrt integrand parameters, default mode and capture mode (must stay eager)
+    for capture in (False, True):
+        p = torch.tensor(2.0, dtype=torch.float64, device=cuda, requires_grad=True)
+        c = tq.Simpson().get_jit_compiled_integrate(dim=2, N=21**2, integration_domain=dom, capture_integrand=capture)
+        r = c(lambda x: p * x[:, 0] * x[:, 1], dom)
+        assert r.requires_grad and c.replays == 0
+        r.backward()
+        assert abs(float(p.grad) - 1.0) < 1e-9  # int x y over [0,1]x[0,2] = 1
+    # Monte Carlo with a grad domain after plain calls: the device-side call counter is read back for the backward
+    c = tq.MonteCarlo().get_jit_compiled_integrate(dim=2, N=50_000, integration_domain=dom, seed=1, capture_integrand=True)
+    plain = lambda x: x[:, 0] + x[:, 1]  # noqa: E731
+    assert abs(float(c(plain, dom)) - 3.0) < 0.1 and c.replays == 1
+    d = dom.clone().requires_grad_(True)
+    c(plain, d).backward()
+    assert torch.isfinite(d.grad).all()
+
+    class Model:
+        def __init__(self, k):
+            self.k = k
+
+        def f(self, x):
+            return self.k * x[:, 0]
+
+    m = Model(2.0)
+    c = tq.Trapezoid().get_jit_compiled_integrate(dim=2, N=11**2, integration_domain=dom, capture_integrand=True)
+    vals = [float(c(m.f, dom)) for _ in range(3)]  # m.f is a new bound-method object each time: one graph
+    assert c.replays == 3 and len(c._entries) == 1 and abs(vals[0] - 2.0) < 1e-9
+    for k in range(20):  # a fresh lambda per call: capturing stops after a few misses, memory stays bounded
+        c(lambda x, k=k: x[:, 0] * (k + 1), dom)
+    assert len(c._entries) <= c.max_graphs and c._misses >= c.max_consecutive_misses
 
 
 @pytest.mark.parametrize("native", [True, False])

@@ -163,8 +163,8 @@ def test_deployment_self_check(cuda):
 # ------------------------------------------------------------------------------------------------------------------
 # The reference's OWN test files, unmodified, against this package.
 REF_TESTS = os.path.join(ROOT, "baseline", "_ref", "tests")
-# torch cases of every test file on the hot path (`-k` expression over the reference's test names): the `*_torch*`
-# instantiations of the per-backend tests plus the backend-free ones.  Not selected, with the reason:
+# The torch cases of every test file on the hot path, by node id (no `-k` expression: pytest matches those against
+# directory names too).  Not selected, with the reason:
 #   *_numpy* / *_jax* / *_tensorflow*            other numerical backends: out of scope (north_star pins backend="torch");
 #   utils_integration_test.py::test_linspace_with_grads / test_add_at_indices / test_setup_integration_domain
 #                                                each loops over every INSTALLED backend inside one test and numpy is
@@ -173,11 +173,24 @@ REF_TESTS = os.path.join(ROOT, "baseline", "_ref", "tests")
 #                                                never touches;
 #   rng_test.py::test_consistency_*              compares the torch stream with the numpy backend's stream;
 #   test_deployment.py                           torchquad._deployment_test integrates with backend="numpy" as well.
-REF_SELECT = ("(torch and not save_state and not consistency) or calculate_result_kwargs or calculate_result_error_handling "
-              "or is_compiling")
-REF_FILES = ["vegas_map_test.py", "vegas_stratification_test.py", "vegas_test.py", "monte_carlo_test.py", "boole_test.py",
-             "simpson_test.py", "trapezoid_test.py", "gradient_test.py", "integrator_types_test.py", "rng_test.py",
-             "utils_integration_test.py", "integration_grid_test.py", "gauss_test.py"]
+REF_NODES = [
+    "vegas_map_test.py::test_vegas_map_torch_f32", "vegas_map_test.py::test_vegas_map_torch_f64",
+    "vegas_stratification_test.py::test_vegas_stratification_torch_f32",
+    "vegas_stratification_test.py::test_vegas_stratification_torch_f64",
+    "vegas_test.py::test_integrate_torch",
+    "monte_carlo_test.py::test_monte_carlo_calculate_result_kwargs",
+    "monte_carlo_test.py::test_monte_carlo_calculate_result_error_handling", "monte_carlo_test.py::test_integrate_torch",
+    "boole_test.py::test_boole_calculate_result_kwargs", "boole_test.py::test_boole_calculate_result_error_handling",
+    "boole_test.py::test_integrate_torch",
+    "simpson_test.py::test_simpson_calculate_result_kwargs", "simpson_test.py::test_simpson_calculate_result_error_handling",
+    "simpson_test.py::test_integrate_torch",
+    "trapezoid_test.py::test_trapezoid_calculate_result_kwargs",
+    "trapezoid_test.py::test_trapezoid_calculate_result_error_handling", "trapezoid_test.py::test_integrate_torch",
+    "gradient_test.py::test_gradients_torch", "integrator_types_test.py::test_integrate_torch",
+    "rng_test.py::test_rng_torch_f32", "rng_test.py::test_rng_torch_f64", "rng_test.py::test_edge_cases_torch_f32",
+    "rng_test.py::test_edge_cases_torch_f64", "utils_integration_test.py::test_is_compiling",
+    "integration_grid_test.py::test_integration_grid_torch", "gauss_test.py::test_integrate_torch",
+]
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="baseline/_ref/tests not staged (run baseline/stage_ref.sh)")
@@ -186,11 +199,11 @@ def test_reference_own_suite():
     unmodified from baseline/_ref/tests (tests/_ref_suite_plugin.py).  Everything selected must pass."""
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1",
                PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests"), ROOT, os.environ.get("PYTHONPATH", "")]))
-    cmd = [sys.executable, "-m", "pytest", "-p", "_ref_suite_plugin", "-p", "no:cacheprovider", "-q", "-x", "--no-header",
-           "-k", REF_SELECT, "--rootdir", REF_TESTS, "-c", os.devnull] + [os.path.join(REF_TESTS, f) for f in REF_FILES]
+    cmd = [sys.executable, "-m", "pytest", "-p", "_ref_suite_plugin", "-p", "no:cacheprovider", "-q", "--no-header",
+           "--rootdir", REF_TESTS, "-c", os.devnull] + [os.path.join(REF_TESTS, n) for n in REF_NODES]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, env=env, cwd=REF_TESTS)
     tail = out.stdout[-6000:] + out.stderr[-3000:]
     print(tail)
     assert out.returncode == 0, tail
     m = re.search(r"(\d+) passed", out.stdout)
-    assert m and int(m.group(1)) >= 20, tail
+    assert m and int(m.group(1)) == len(REF_NODES), tail

@@ -13,7 +13,7 @@ from .base_integrator import BaseIntegrator
 from .compiled import GraphedIntegrate
 from .integration_grid import IntegrationGrid, grid_nodes
 from .utils import (_check_integration_domain, _is_compiling, _linspace_with_grads, _setup_integration_domain,
-                    expand_func_values_and_squeeze_integral)
+                    _split_function_values, expand_func_values_and_squeeze_integral)
 
 
 class GridIntegrator(BaseIntegrator):
@@ -110,17 +110,22 @@ class GridIntegrator(BaseIntegrator):
             unit = fn.to_struct([0.0] * dim, [1.0] * dim, 1.0)  # nodes are already in domain coordinates
             total = ops.fused_nc(unit, nodes.detach().contiguous(), table, begin, end)[0]
         else:
-            total = None
+            total, one_d = None, None
             for p0 in range(begin, end, chunk_rows):
                 p1 = min(end, p0 + chunk_rows)
                 pts = ops.nc_grid_points(nodes, p0, p1)
                 vals, _ = self.evaluate_integrand(fn, pts)
+                if one_d is None:  # the reference's 1-D rule (utils.py:235-277): [N] and [N, 1] values give a 0-dim result
+                    _, one_d = _split_function_values(vals)
                 part = ops.nc_contract_f64(vals, table, p0, p1)
                 total = part if total is None else total + part
                 del pts, vals
-            if total is None:
+            if total is None:  # a rank without points still takes part in the all-reduce
                 probe = fn(nodes[:, 0].detach().reshape(1, -1).clone())
+                _, one_d = _split_function_values(probe)
                 total = torch.zeros(probe.shape[1:], dtype=torch.float64, device=domain.device)
+            if one_d:
+                total = total.reshape(())
         if world > 1:
             total = ops.all_reduce_sum_autograd(total)
         self._nr_of_fevals = total_points
@@ -147,11 +152,11 @@ class GridIntegrator(BaseIntegrator):
         grid = IntegrationGrid(N, integration_domain, self._grid_func, disable_integration_domain_check)
         return grid.points, grid.h, grid._N
 
-    def get_jit_compiled_integrate(self, dim, N=None, integration_domain=None, backend=None):
+    def get_jit_compiled_integrate(self, dim, N=None, integration_domain=None, backend=None, capture_integrand=False):
         """`compiled_integrate(fn, integration_domain)` with everything but the two arguments fixed
-        (grid_integrator.py:134-255).  The reference traces grid creation and the contraction with torch.jit; here
-        the whole call -- node/point kernels, the integrand's torch ops, the contraction -- is captured once per
-        integrand as a CUDA graph and replayed (integration/compiled.py)."""
+        (grid_integrator.py:134-255).  As in the reference the integrand is evaluated eagerly on every call;
+        `capture_integrand=True` (extension) captures the whole call -- node/point kernels, the integrand's torch ops,
+        the contraction -- once per integrand as a CUDA graph and replays it (frozen-state rule: integration/compiled.py)."""
         if N is None:
             N = self._get_minimal_N(dim)
         domain0 = _setup_integration_domain(dim, integration_domain, backend)
@@ -160,4 +165,4 @@ class GridIntegrator(BaseIntegrator):
         def run(fn, domain, _rng):
             return self.integrate(fn, dim, N, domain)
 
-        return GraphedIntegrate(run, domain0, None)
+        return GraphedIntegrate(run, domain0, None, capture_integrand)

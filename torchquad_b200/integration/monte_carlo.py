@@ -10,7 +10,7 @@ from ..utils.set_log_level import logger
 from .base_integrator import BaseIntegrator
 from .compiled import GraphedIntegrate
 from .rng import RNG
-from .utils import _setup_integration_domain, expand_func_values_and_squeeze_integral
+from .utils import _setup_integration_domain, _split_function_values, expand_func_values_and_squeeze_integral
 
 
 class MonteCarlo(BaseIntegrator):
@@ -50,31 +50,30 @@ class MonteCarlo(BaseIntegrator):
             # Rows [begin, end) of ONE stream call: any chunking / rank split draws the same samples.
             begin, end = tqdist.shard_range(N, rank, world)
             call = rng.next_call()
-            total, fevals = None, 0
+            total, one_d = None, None
             for r0 in range(begin, end, chunk_rows):
                 rows = min(chunk_rows, end - r0)
                 pts = ops.mc_sample(domain, rows, rng.seed, call, r0, call_offset=rng._call_offset)
-                vals, n = self.evaluate_integrand(fn, pts)
-                fevals += n
+                vals, _ = self.evaluate_integrand(fn, pts)
+                if one_d is None:  # the reference's 1-D rule (utils.py:235-277): [N] and [N, 1] values give a 0-dim result
+                    _, one_d = _split_function_values(vals)
                 part = ops.reduce_sum_f64(vals)
                 total = part if total is None else total + part
                 del pts, vals
             if total is None:  # a rank without rows still takes part in the all-reduce
-                shape = self._probe_shape(fn, domain)
-                total = torch.zeros(shape, dtype=torch.float64, device=domain.device)
+                probe = fn(domain[:, 0].detach().reshape(1, -1).clone())
+                _, one_d = _split_function_values(probe)
+                total = torch.zeros(tuple(probe.shape[1:]), dtype=torch.float64, device=domain.device)
+            if one_d:
+                total = total.reshape(())
             if world > 1:
                 total = ops.all_reduce_sum_autograd(total)
-            self._nr_of_fevals = fevals
+            self._nr_of_fevals = N  # evaluations of the whole job, like the grid rules and VEGAS report them
             volume = torch.prod(domain[:, 1] - domain[:, 0])
             return volume * total.to(domain.dtype) / N
         sample_points = self.calculate_sample_points(N, domain, rng=rng)
         function_values, self._nr_of_fevals = self.evaluate_integrand(fn, sample_points)
         return self.calculate_result(function_values, domain)
-
-    @staticmethod
-    def _probe_shape(fn, domain):
-        pts = domain[:, 0].detach().reshape(1, -1).clone()
-        return tuple(fn(pts).shape[1:])
 
     def _integrate_fused(self, fn, N, domain, rng):
         bounds = domain.detach().tolist()
@@ -82,8 +81,10 @@ class MonteCarlo(BaseIntegrator):
         sizes_t = (domain[:, 1] - domain[:, 0]).detach()
         sizes = sizes_t.tolist()  # differences rounded in the working dtype, like the reference
         begin, end = tqdist.shard_range(N)
-        sums = ops.fused_mc(fn.to_struct(starts, sizes, 1.0), domain.dtype, domain.device, begin, end, rng.seed,
-                            rng.next_call())
+        call = rng.next_call()
+        if rng._call_offset is not None:  # private generator of a compiled integrate: the call counter lives on the device
+            call += int(rng._call_offset.item())
+        sums = ops.fused_mc(fn.to_struct(starts, sizes, 1.0), domain.dtype, domain.device, begin, end, rng.seed, call)
         tqdist.all_reduce_sum_(sums)
         self._nr_of_fevals = N
         volume = torch.prod(sizes_t)
@@ -123,12 +124,14 @@ class MonteCarlo(BaseIntegrator):
         u = rng.uniform(size=[N, dim], dtype=sizes.dtype)
         return u.to(sizes.device) * sizes + starts
 
-    def get_jit_compiled_integrate(self, dim, N=1000, integration_domain=None, seed=None, backend=None):
+    def get_jit_compiled_integrate(self, dim, N=1000, integration_domain=None, seed=None, backend=None,
+                                   capture_integrand=False):
         """`compiled_integrate(fn, integration_domain)` with everything but the two arguments fixed
-        (monte_carlo.py:108-225).  The reference traces its steps with torch.jit; here the whole call -- sampling
-        kernel, the integrand's torch ops, the fp64 reduction -- is captured once per integrand as a CUDA graph
-        and replayed (integration/compiled.py), which removes the per-call launch and Python overhead of small-N
-        repeated quadrature.  Every replay advances the Philox call index on the device: fresh samples per call."""
+        (monte_carlo.py:108-225).  As in the reference the integrand is evaluated eagerly on every call (it sees
+        current Python state, gradients flow); our own steps are single launches.  `capture_integrand=True` (extension)
+        captures the whole call -- sampling kernel, the integrand's torch ops, the fp64 reduction -- once per integrand
+        as a CUDA graph and replays it, under the frozen-state rule documented in integration/compiled.py.  Every call
+        or replay advances the Philox call index on the device: fresh samples per call."""
         self._check_inputs(dim=dim, N=N, integration_domain=integration_domain)
         domain0 = _setup_integration_domain(dim, integration_domain, backend)
         rng = RNG(backend="torch", seed=seed)
@@ -136,4 +139,4 @@ class MonteCarlo(BaseIntegrator):
         def run(fn, domain, graph_rng):
             return self.integrate(fn, dim, N, domain, rng=graph_rng)
 
-        return GraphedIntegrate(run, domain0, rng)
+        return GraphedIntegrate(run, domain0, rng, capture_integrand)

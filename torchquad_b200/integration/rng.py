@@ -36,7 +36,8 @@ class RNG:
     def next_call(self):
         """Reserve the next call index (used by the fused kernels, which draw inside the kernel)."""
         c = self._call
-        self._call += 1
+        if self._call_offset is None:  # device-counted generators (compiled integrate) advance the device word instead
+            self._call += 1
         return c
 
     def uniform(self, size, dtype, device=None, row_begin=0):

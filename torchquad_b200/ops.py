@@ -63,11 +63,13 @@ def mc_sample(domain, rows, seed, call_idx, row_begin=0, call_offset=None):
 
     `call_offset` (uint32/int32 device tensor, 1 element) is added to `call_idx` ON THE DEVICE: launches replayed
     from a CUDA graph draw fresh samples after the word is incremented (no autograd on that path)."""
+    if call_offset is not None and torch.is_grad_enabled() and domain.requires_grad:
+        # the differentiable path regenerates its uniforms in backward from a HOST call index: read the device word
+        # (one sync; this is the eager, gradient-carrying path of a compiled integrate)
+        call_idx, call_offset = call_idx + int(call_offset.item()), None
     if call_offset is None:
         return _MCSample.apply(domain, rows, seed, call_idx, row_begin)
     require_cuda(domain, call_offset)
-    if torch.is_grad_enabled() and domain.requires_grad:
-        raise RuntimeError("mc_sample: a device-side call offset is not differentiable; run without it")
     dom = domain.detach().contiguous()
     dim = dom.shape[0]
     out = torch.empty((rows, dim), dtype=dom.dtype, device=dom.device)
