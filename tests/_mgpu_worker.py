@@ -32,6 +32,11 @@ def both(make, fn, dim, kw, dt):
 
 checks = []
 g = F.GenzGaussian(4, a=4.0, u=0.45)
+# small fused VEGAS runs are replicated by default (a pass of 1e4 samples is launch latency, not work): identical results
+a, b, integ = both(tq.VEGAS, g, 4, dict(N=400_000, seed=3), torch.float64)
+assert integ._replicated and integ._shard is None
+checks.append(("VEGAS fused replicated (small N) float64", a, b, 0.0))
+tq.VEGAS.min_rows_per_rank = 0  # ... but the sharded path must also be right at this size
 for dt, tol in [(torch.float64, 1e-9), (torch.float32, 2e-4)]:
     for label, fn in [("fused", g), ("unfused", lambda x: g(x))]:
         a, b, integ = both(tq.MonteCarlo, fn, 4, dict(N=1_000_003, seed=3), dt)
@@ -54,6 +59,7 @@ checks.append(("VEGAS fused 8-D fevals", float(ref._nr_of_fevals), float(integ._
 checks.append(("VEGAS fused 8-D iterations", float(ref.it), float(integ.it), 0.0))
 g6 = F.GenzProductPeak(6, a=2.0, u=0.5)
 a, b, integ = both(tq.VEGAS, g6, 6, dict(N=3_000_000, seed=2, max_iterations=10), torch.float32)
+assert integ._shard is not None
 checks.append(("VEGAS fused 6-D float32", a, b, 5e-3))
 # large-map record layout ({x, dx, weight, count} per bin), forced on this small problem: the histogram is
 # unpacked into weights/counts before the all-reduce, so sharded == single still holds

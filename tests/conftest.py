@@ -46,3 +46,27 @@ def cuda():
     import torch
 
     return torch.device("cuda", 0)
+
+
+_DELTAS = os.path.join(ROOT, "gpurun_out", "parity_deltas.txt")
+
+
+@pytest.fixture(scope="session")
+def record_delta():
+    """record_delta(name, achieved, bound): print the ACHIEVED parity delta next to the bound the test asserts and append it
+    to gpurun_out/parity_deltas.txt (copied to profiles/ per round), so tolerances are reported as measured values."""
+    lines = []
+
+    def rec(name, achieved, bound):
+        line = f"{name:78s} achieved {achieved:.3e}   bound {bound:.1e}"
+        print("PARITY " + line)
+        lines.append(line)
+        return achieved
+
+    yield rec
+    try:
+        os.makedirs(os.path.dirname(_DELTAS), exist_ok=True)
+        with open(_DELTAS, "a") as f:
+            f.write("\n".join(lines) + ("\n" if lines else ""))
+    except OSError:
+        pass

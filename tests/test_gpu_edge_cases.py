@@ -129,3 +129,24 @@ def test_vector_valued_reductions_every_column_count(cuda, cols):
                               atol=rtol * 50 * float(want.abs().max()))
         # deterministic: the same launch twice gives the same bits
         assert torch.equal(ops.nc_contract(fv.to(cuda), w.to(cuda)), got)
+
+
+def test_complex_integrand_values(cuda):
+    """The reference's tests integrate complex-valued integrands (tests/helper_functions.py:98-110); sums and weighted
+    contractions are linear, so complex values run through the real kernels as [..., 2] views."""
+    import torchquad_b200 as tq
+
+    torch.set_default_dtype(torch.float64)
+    dom = torch.tensor([[0.0, 2.0], [-1.0, 1.0]], dtype=torch.float64, device=cuda)
+    fn = lambda x: (x[:, 0] + 1j * x[:, 1] ** 2) * (2.0 - 0.5j)  # noqa: E731
+    exact = (4.0 + 1j * (2.0 * 2.0 / 3.0)) * (2.0 - 0.5j)  # int x0 = 2*2 = 4; int x1^2 = 2 * 2/3
+    for integ, kw, tol in ((tq.Simpson(), dict(N=41**2), 1e-12), (tq.Boole(), dict(N=41**2), 1e-12), (tq.Trapezoid(), dict(N=201**2), 1e-3),
+                           (tq.MonteCarlo(), dict(N=400_000, seed=1), 2e-2), (tq.GaussLegendre(), dict(N=8**2), 1e-12)):
+        r = integ.integrate(fn, 2, integration_domain=dom, **kw)
+        assert r.is_complex() and r.dtype == torch.complex128 and r.dim() == 0
+        assert abs(complex(r) - exact) <= tol * abs(exact), (type(integ).__name__, complex(r), exact)
+    vec = lambda x: torch.stack([fn(x), 2.0 * fn(x)], dim=1)  # noqa: E731
+    r = tq.Simpson().integrate(vec, 2, N=41**2, integration_domain=dom)
+    assert r.shape == (2,) and abs(complex(r[1]) - 2 * exact) <= 1e-12 * abs(exact)
+    f32 = tq.Simpson().integrate(fn, 2, N=41**2, integration_domain=dom.float())
+    assert f32.dtype == torch.complex64 and abs(complex(f32) - exact) <= 1e-5 * abs(exact)

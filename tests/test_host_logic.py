@@ -192,3 +192,55 @@ def test_record_layout_selection_is_by_table_size():
     p = Probe(8, 10_000_000, torch.float64)
     p.records_min_bytes = None
     assert not p.wants_records()
+
+
+def test_reciprocal_division_is_correctly_rounded(tmp_path):
+    """csrc/common.cuh `div_by_const`: q0 = RN(a * RN(1/b)); q = fma(fma(-q0, b, a), RN(1/b), q0) must equal the IEEE quotient
+    a / b bit for bit for the operands of the stratified sampling (a = digit + u, u a multiple of 2^-24 / 2^-53 in [0, 1),
+    b = N_strat <= 1000).  The same three operations compiled for the host (gcc, hardware FMA, contraction off): every fp32
+    uniform for a few N_strat, 2e5 random operands per N_strat in both precisions."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "div.c"
+    src.write_text(r"""
+#include <math.h>
+#include <stdio.h>
+#include <stdint.h>
+static uint64_t s = 88172645463325252ull;
+static inline uint64_t rnd(void) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
+int main(void) {
+    long bad = 0, n = 0;
+    int exhaustive[] = {3, 7, 10, 1000};
+    for (int bi = 0; bi < 4; ++bi) {
+        const int b = exhaustive[bi];
+        const float bf = (float)b, y = 1.0f / bf;
+        const int p = b - 1;
+        for (uint32_t k = 0; k < (1u << 24); ++k) {
+            const float a = (float)p + (float)k * 5.9604644775390625e-08f, q0 = a * y;
+            bad += fmaf(fmaf(-q0, bf, a), y, q0) != a / bf;
+            ++n;
+        }
+    }
+    for (int b = 1; b <= 1000; ++b) {
+        const double bd = (double)b, y = 1.0 / bd;
+        const float bf = (float)b, yf = 1.0f / bf;
+        for (int i = 0; i < 200000; ++i) {
+            const int p = (int)(rnd() % (uint64_t)b);
+            const double a = (double)p + (double)(rnd() >> 11) * 1.1102230246251565e-16, q0 = a * y;
+            bad += fma(fma(-q0, bd, a), y, q0) != a / bd;
+            const float af = (float)p + (float)(rnd() >> 40) * 5.9604644775390625e-08f, q0f = af * yf;
+            bad += fmaf(fmaf(-q0f, bf, af), yf, q0f) != af / bf;
+            n += 2;
+        }
+    }
+    printf("%ld %ld\n", bad, n);
+    return 0;
+}
+""")
+    exe = tmp_path / "div"
+    subprocess.run(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-o", str(exe), str(src), "-lm"], check=True)
+    bad, n = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    assert bad == 0 and n > 4 * 10**8

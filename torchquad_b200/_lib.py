@@ -138,6 +138,7 @@ _cdll = None
 _fns = {}
 _lock = threading.Lock()
 _workspaces = {}
+_MAX_WORKSPACES = 8
 launch_count = 0  # kernels-launching C-ABI calls issued by this process (bench.py reports it)
 
 
@@ -220,13 +221,20 @@ class on_device:
 
 
 def workspace(device):
-    """Per-device zero-initialised scratch buffer handed to every call that needs temporaries."""
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    ws = _workspaces.get(key)
+    """Zero-initialised scratch buffer handed to every call that needs temporaries: one per (device, stream).
+
+    The buffer holds the per-CTA partials and the ticket of the grid reductions, so two integrations that overlap on
+    different streams (or a CUDA-graph replay overlapping eager work) must not share it; work on ONE stream is ordered
+    and reuses its buffer.  Streams come and go: only the most recently used few buffers are kept."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch._C._cuda_getCurrentRawStream(idx))
+    ws = _workspaces.pop(key, None)
     if ws is None:
         nbytes = load().tq_workspace_bytes()
-        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=torch.device("cuda", idx))
+        while len(_workspaces) >= _MAX_WORKSPACES:
+            _workspaces.pop(next(iter(_workspaces)))  # least recently used (dicts keep insertion order)
+    _workspaces[key] = ws
     return ws
 
 

@@ -128,10 +128,23 @@ fused_mc_kernel(const tq_integrand P, int64_t row_begin, int64_t nrows, uint64_t
 }
 
 // ------------------------------------------------------------------ fused Newton-Cotes
+// Point p of the flattened grid has the multi-index (i_0 .. i_{dim-1}), dimension 0 slowest (integration_grid.py:98-99).
+// A thread keeps its point as (hi, lo) = (p / B, p % B) with B = n^k <= 2^31 and advances both parts by the constant
+// grid stride (an add and a conditional carry), so the loop never divides 64-bit numbers -- grids beyond 2^32 points
+// (6-D Boole at n >= 41) cost the same per point as small ones; the digits come from `lo` (the k fastest dimensions) and
+// `hi` by multiply-shift divisions by n (FastDiv).
+struct NcWalk {
+    FastDiv fd;          // division by n
+    uint32_t B;          // n^k
+    int k;               // digits taken from lo
+    uint64_t step_hi;    // grid stride / B
+    uint32_t step_lo;    // grid stride % B
+};
+
 template <int FAM, typename T>
 __global__ void __launch_bounds__(256)
 fused_nc_kernel(const tq_integrand P, const T* __restrict__ nodes, const T* __restrict__ w, uint32_t n,
-                int64_t p_begin, int64_t p_end, double* partials, unsigned int* ticket, double* out, bool use_smem) {
+                int64_t p_begin, int64_t p_end, NcWalk wk, double* partials, unsigned int* ticket, double* out, bool use_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ FnShared<T> S;
     __shared__ double sh[32];
@@ -148,31 +161,47 @@ fused_nc_kernel(const tq_integrand P, const T* __restrict__ nodes, const T* __re
         sw = b;
     }
     double acc[1] = {0.0};
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < p_end - p_begin;
-         r += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t p = (uint64_t)(p_begin + r);
+    const int64_t r0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = p_end - p_begin;
+    const uint64_t pfirst = (uint64_t)(p_begin + r0);
+    uint64_t hi = pfirst / wk.B;                       // once per thread
+    uint32_t lo = (uint32_t)(pfirst - hi * wk.B);
+    const int d_split = dim - wk.k;                    // dimensions [d_split, dim) come from lo
+    for (int64_t r = r0; r < total; r += (int64_t)gridDim.x * blockDim.x) {
         Integrand<FAM, T> fn;
         fn.init();
         T wt = (T)1;
-        if (p <= 0xffffffffull) {
-            uint32_t q = (uint32_t)p;
-            for (int d = dim - 1; d >= 0; --d) {
-                const uint32_t t = q / n;
+        uint32_t q = lo;
+        for (int d = dim - 1; d >= d_split; --d) {
+            const uint32_t t = wk.fd.div(q);
+            const uint32_t i = q - t * n;
+            q = t;
+            wt *= sw[d * n + i];
+            fn.step(sn[d * n + i], d, S);
+        }
+        if (hi <= 0xffffffffull) {
+            q = (uint32_t)hi;
+            for (int d = d_split - 1; d >= 0; --d) {
+                const uint32_t t = wk.fd.div(q);
                 const uint32_t i = q - t * n;
                 q = t;
                 wt *= sw[d * n + i];
                 fn.step(sn[d * n + i], d, S);
             }
-        } else {
-            for (int d = dim - 1; d >= 0; --d) {
-                const uint64_t t = p / n;
-                const uint32_t i = (uint32_t)(p - t * n);
-                p = t;
+        } else {  // more than 2^63 / n points: never in practice, kept exact
+            uint64_t h = hi;
+            for (int d = d_split - 1; d >= 0; --d) {
+                const uint64_t t = h / n;
+                const uint32_t i = (uint32_t)(h - t * n);
+                h = t;
                 wt *= sw[d * n + i];
                 fn.step(sn[d * n + i], d, S);
             }
         }
         acc[0] += (double)(fn.finish(S) * S.scale) * (double)wt;
+        lo += wk.step_lo;
+        hi += wk.step_hi;
+        if (lo >= wk.B) { lo -= wk.B; ++hi; }
     }
     grid_sum_finish<1>(acc, sh, partials, ticket, out);
 }
@@ -576,13 +605,22 @@ int tq_fused_nc(const tq_integrand* fn_host, const void* nodes, const void* w, i
     if (!ticket || !partials) { set_error("tq_fused_nc: workspace too small"); return TQ_ERR_WORKSPACE; }
     cudaStream_t st = as_stream(stream);
     const int dim = fn_host->dim;
+    NcWalk walk;
+    walk.fd.set((uint32_t)n);
+    walk.B = 1;
+    walk.k = 0;
+    while (walk.k < dim && (uint64_t)walk.B * (uint64_t)n <= (1ull << 31)) { walk.B *= (uint32_t)n; ++walk.k; }
+    if (walk.k == 0) { walk.B = (uint32_t)n; walk.k = 1; }  // n > 2^31 is refused by the int32 argument; n = 1 lands here
+    const uint64_t stride = (uint64_t)grid * 256;
+    walk.step_hi = stride / walk.B;
+    walk.step_lo = (uint32_t)(stride % walk.B);
     TQ_DISPATCH_DTYPE(dtype, {
         const size_t table = (size_t)2 * dim * n * sizeof(T);
         const bool use_smem = table <= 96 * 1024;
         TQ_DISPATCH_FAMILY(fn_host->family, {
             cudaFuncSetAttribute(fused_nc_kernel<FAM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             fused_nc_kernel<FAM, T><<<TQ_GRID(grid), 256, use_smem ? table : 0, st>>>(*fn_host, (const T*)nodes, (const T*)w, (uint32_t)n,
-                                                                           p_begin, p_end, partials, ticket, out_f64, use_smem);
+                                                                           p_begin, p_end, walk, partials, ticket, out_f64, use_smem);
         });
     });
     return check_launch("fused_nc_kernel");

@@ -3,6 +3,8 @@
 // GridIntegrator.calculate_result (grid_integrator.py:70-82) and the per-axis stencil passes of
 // trapezoid.py:28-37 / simpson.py:30-46 / boole.py:30-48, which are one weighted sum
 //   sum_p f(p) * prod_d w[d, i_d(p)],   i_d(p) = (p / n^(dim-1-d)) % n   (dim 0 slowest).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tq {
@@ -201,115 +203,128 @@ __device__ __noinline__ T row_prefix(const T* sw, uint32_t n, int dim, FastDiv f
 }
 
 // cols == 1 contraction: fp64 accumulation of f[p]*W[p], deterministic two-stage reduction.
-// Each thread handles vectors of V consecutive points (32 bytes: two 128-bit loads of f) advancing by a constant step.
-// The point index is carried as (hi, last) = (p / n, p % n) without division; the weight of the leading
-// dim-1 digits (the digits of hi, extracted with multiply-shift divisions) is formed once per vector and the
-// last digit steps through the vector, with a carry when the vector crosses a row of the last dimension.
-template <typename T, int V, bool SMEM>
+// The grid is viewed as (dim - m) leading dimensions of n nodes and ONE trailing super-dimension of R = n^m <= C1_MAXR
+// nodes whose weights (products of the last m dimensions' weights) are tabulated once per CTA in shared memory.  The weight
+// of point p is then prefix(p / R) * wR[p % R]: a CTA owns a contiguous range of points, tabulates the prefixes of the
+// (few) super-rows it covers -- one digit walk each -- and streams its range with 128-bit loads, one multiply-shift
+// division, two shared-memory reads and an fp64 FMA per point; no barrier inside the stream.
+// (Was: one digit walk per 32-byte vector, 207 thread instructions per vector, 3.7 TB/s; profiles/r2 for this version.)
+constexpr int C1_MAXR = 2048;      // entries of the super-dimension table
+constexpr int C1_MAXROWS = 1024;   // super-rows tabulated per pass over a CTA's range
+
+struct C1Plan {
+    FastDiv fdn;     // division by n
+    FastDiv fdR;     // division by R
+    uint32_t R;      // n^m
+    int m;           // trailing dimensions folded into the super-dimension
+    int64_t chunk;   // points per CTA (multiple of the vector width)
+};
+
+template <typename T, int V>
 __global__ void __launch_bounds__(256, 4)
 contract1_kernel(const T* __restrict__ f, const T* __restrict__ w, uint32_t n, int dim, int64_t p_begin,
-                 int64_t p_end, FastDiv fd, double* partials, unsigned int* ticket, double* out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+                 int64_t p_end, C1Plan plan, double* partials, unsigned int* ticket, double* out) {
     __shared__ double sh[32];
-    // SMEM is a template parameter so that the table reads compile to shared-memory loads, not generic ones
-    const T* sw = w;
-    if (SMEM) {
-        T* st = reinterpret_cast<T*>(smem_raw);
-        for (int i = threadIdx.x; i < dim * (int)n; i += blockDim.x) st[i] = w[i];
-        __syncthreads();
-        sw = st;
-    }
-    const T* wl = sw + (dim - 1) * n;
-    const int64_t npts = p_end - p_begin;
-    const int64_t nvec = (npts + V - 1) / V;
-    const int64_t step = (int64_t)gridDim.x * blockDim.x;  // in vectors
-    int64_t vi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double acc[1] = {0.0};
-    if (vi < nvec) {
-        const uint64_t p0 = (uint64_t)(p_begin + vi * V);
-        uint64_t hi = p0 / n;
-        uint32_t last = (uint32_t)(p0 - hi * n);
-        const uint64_t sp = (uint64_t)step * V;
-        const uint64_t step_hi = sp / n;
-        const uint32_t step_last = (uint32_t)(sp - step_hi * n);
-        auto prefix_of = [&](uint64_t h) { return row_prefix<T>(sw, n, dim, fd, h); };
-        // prefixes of rows h and h + 1 (same multiplication order as prefix_of: fastest leading digit first)
-        auto prefix_pair = [&](uint64_t h, T& p0, T& p1) {
-            if (dim < 2) { p0 = p1 = (T)1; return; }
-            if (h >= 0xffffffffull) { p0 = prefix_of(h); p1 = prefix_of(h + 1); return; }
-            uint32_t q = (uint32_t)h;
-            const uint32_t t0 = fd.div_ge2(q);
-            const uint32_t d0 = q - t0 * n;  // fastest leading digit
-            const T* w0 = sw + (dim - 2) * n;
-            p0 = w0[d0];
-            const bool carry = d0 + 1 >= n;
-            p1 = carry ? (T)0 : w0[d0 + 1];
-            q = t0;
-            for (int d = dim - 3; d >= 0; --d) {
-                const uint32_t t = fd.div_ge2(q);
-                const T wd = sw[d * n + (q - t * n)];
-                p0 *= wd;
-                p1 *= wd;
-                q = t;
-            }
-            if (carry) p1 = prefix_of(h + 1);  // one row in n: the carry ripples into slower digits
-        };
-        // The loads of the NEXT vector are issued before the (long, dependent) index arithmetic of the current
-        // one: without that a thread has less than one 32-byte request in flight and the kernel sits at a
-        // quarter of the HBM rate.
-        constexpr int NQ = V > 1 ? (int)(V * sizeof(T) / 16) : 1;  // 128-bit registers per vector
-        auto load_vec = [&](int64_t v, uint4 (&q)[NQ]) {
-            const int64_t r = v * V;
-            if (V > 1 && r + V <= npts) {
-#pragma unroll
-                for (int k = 0; k < NQ; ++k) q[k] = __ldcs(reinterpret_cast<const uint4*>(f + r) + k);
-            } else {
-                T tmp[V];
-#pragma unroll
-                for (int j = 0; j < V; ++j) tmp[j] = r + j < npts ? f[r + j] : (T)0;
-#pragma unroll
-                for (int k = 0; k < NQ; ++k) q[k] = pack_vec<T>(tmp + k * (16 / sizeof(T)), V);
-            }
-        };
-        uint4 nxt[NQ];
-        load_vec(vi, nxt);
-        for (; vi < nvec; vi += step) {
-            T fv[V];
-#pragma unroll
-            for (int j = 0; j < V; ++j) fv[j] = vec_elem<T>(nxt[j / (16 / (int)sizeof(T))], j % (16 / (int)sizeof(T)));
-            if (vi + step < nvec) load_vec(vi + step, nxt);
-            if (n >= (uint32_t)V && n >= 2) {
-                // A vector crosses at most one row of the last dimension.  Both rows' prefixes come from ONE digit
-                // walk (they differ in the fastest leading digit only) and each element selects: a branch on the
-                // crossing would diverge in every warp (32 x V consecutive points span several rows) and execute
-                // the whole digit walk once per element.
-                T p0, p1;
-                prefix_pair(hi, p0, p1);
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const uint32_t lj = last + j;
-                    const bool next_row = lj >= n;
-                    acc[0] += (double)fv[j] * (double)((next_row ? p1 : p0) * wl[next_row ? lj - n : lj]);
-                }
-            } else {  // rows shorter than a vector (tiny grids): generic walk
-                T prefix = prefix_of(hi);
-                uint32_t l = last;
-                uint64_t h = hi;
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    if (l >= n) {
-                        l = 0;
-                        ++h;
-                        prefix = prefix_of(h);
-                    }
-                    acc[0] += (double)fv[j] * (double)(prefix * wl[l]);
-                    ++l;
-                }
-            }
-            hi += step_hi;
-            last += step_last;
-            if (last >= n) { last -= n; ++hi; }
+    // V copies of the table, copy c shifted by c entries: the V weights of a 128-bit vector of f starting at ANY offset
+    // are one aligned 128-bit shared-memory read (consecutive lanes -> consecutive 16-byte words, no bank conflicts; the
+    // scalar reads of a stride-V pattern were 4-way conflicted and capped the kernel at 3.9 TB/s)
+    constexpr int RP = C1_MAXR + 4;  // padded copy length (a multiple of every V)
+    __shared__ __align__(16) T s_wR[V * RP];
+    __shared__ T s_prefix[C1_MAXROWS];
+    const uint32_t R = plan.R;
+    const int lead = dim - plan.m;  // leading dimensions (digits of the super-row index)
+    // super-dimension table: wR[j] = prod over the last m dimensions, slowest of them first
+    const bool table = R <= (uint32_t)C1_MAXR;
+    const T* wR = table ? s_wR : w + (size_t)(dim - 1) * n;  // n > C1_MAXR: m == 1, the weights themselves (global memory)
+    for (uint32_t j = threadIdx.x; j < R && table; j += blockDim.x) {
+        uint32_t q = j;
+        T pr = (T)1;
+        for (int d = dim - 1; d >= lead; --d) {
+            const uint32_t t = plan.fdn.div(q);
+            pr *= w[d * n + (q - t * n)];
+            q = t;
         }
+#pragma unroll
+        for (int c = 0; c < V; ++c)
+            if (j >= (uint32_t)c) s_wR[c * RP + (j - c)] = pr;  // copy c holds wR[i + c] at position i
+    }
+    const int64_t npts = p_end - p_begin;
+    double acc[1] = {0.0};
+    // chunks are dealt round-robin: at any time the CTAs of the grid stream one contiguous window of f
+    for (int64_t c0 = (int64_t)blockIdx.x * plan.chunk; c0 < npts; c0 += (int64_t)gridDim.x * plan.chunk) {
+    const int64_t c1 = c0 + plan.chunk < npts ? c0 + plan.chunk : npts;
+    int64_t r0 = c0;  // start of the current pass, relative to p_begin (f is indexed from there)
+    while (r0 < c1) {
+        const uint64_t p0 = (uint64_t)(p_begin + r0);
+        const uint64_t h0 = p0 / R;                          // first super-row of the pass
+        const uint32_t l0 = (uint32_t)(p0 - h0 * R);         // offset of the pass's first point inside it
+        // as many points as C1_MAXROWS super-rows hold (and 32-bit local offsets allow)
+        int64_t span = (int64_t)C1_MAXROWS * R - l0;
+        if (span > (int64_t)0x7fffffff - R) span = (int64_t)0x7fffffff - R;
+        span -= span % V;                                    // keeps the next pass vector-aligned
+        const int64_t r1 = r0 + span < c1 ? r0 + span : c1;
+        const uint32_t here = (uint32_t)(r1 - r0);
+        const int nrows = (int)plan.fdR.div(l0 + here - 1) + 1;
+        __syncthreads();                                     // table written / previous pass's prefixes no longer read
+        for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+            // prefix of super-row h: product over the leading digits, fastest of them first (same order as row_prefix)
+            uint64_t h = h0 + r;
+            T pr = (T)1;
+            for (int d = lead - 1; d >= 0; --d) {
+                uint32_t digit;
+                if (h <= 0xffffffffull) {
+                    const uint32_t t = plan.fdn.div((uint32_t)h);
+                    digit = (uint32_t)h - t * n;
+                    h = t;
+                } else {
+                    const uint64_t t = h / n;
+                    digit = (uint32_t)(h - t * n);
+                    h = t;
+                }
+                pr *= w[d * n + digit];
+            }
+            s_prefix[r] = pr;
+        }
+        __syncthreads();
+        constexpr int UNROLL = 4;
+        for (uint32_t e0 = threadIdx.x * V; e0 < here; e0 += 256 * V * UNROLL) {
+            T fv[UNROLL][V];
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) {
+                const uint32_t e = e0 + k * 256 * V;
+                if (V > 1 && e + V <= here) {
+                    const uint4 q = __ldcs(reinterpret_cast<const uint4*>(f + r0 + e));
+#pragma unroll
+                    for (int j = 0; j < V; ++j) fv[k][j] = vec_elem<T>(q, j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) fv[k][j] = e + j < here ? f[r0 + e + j] : (T)0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) {
+                const uint32_t e = e0 + k * 256 * V;
+                if (e < here) {
+                    uint32_t row = plan.fdR.div(l0 + e);
+                    uint32_t last = l0 + e - row * R;
+                    if (V > 1 && table && last + V <= R && e + V <= here) {  // the whole vector inside one super-row
+                        const uint32_t c = last % V;
+                        const uint4 q = *reinterpret_cast<const uint4*>(s_wR + c * RP + (last - c));
+                        const T pr = s_prefix[row];
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[0] += (double)fv[k][j] * (double)(pr * vec_elem<T>(q, j));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < V; ++j) {
+                            if (e + j < here) acc[0] += (double)fv[k][j] * (double)(s_prefix[row] * wR[last]);
+                            if (++last >= R) { last = 0; ++row; }
+                        }
+                    }
+                }
+            }
+        }
+        r0 = r1;
+    }
     }
     grid_sum_finish<1>(acc, sh, partials, ticket, out);
 }
@@ -484,27 +499,41 @@ int tq_nc_contract(const void* f, const void* w, int32_t n, int32_t dim, int64_t
     cudaStream_t st = as_stream(stream);
     const int64_t rows = p_end - p_begin;
     if (cols == 1) {
-        const int grid = grid_for((rows + 7) / 8, 256, 4);
-        double* partials = wk.take<double>((size_t)grid);
-        if (!ticket || !partials) { set_error("tq_nc_contract: workspace too small"); return TQ_ERR_WORKSPACE; }
         const bool aligned = (reinterpret_cast<uintptr_t>(f) & 15) == 0;
         TQ_DISPATCH_DTYPE(dtype, {
-            constexpr int V = 32 / sizeof(T);
-            const bool use_smem = (size_t)dim * n * sizeof(T) <= NC_TABLE_SMEM;
-            const size_t smem = use_smem ? (size_t)dim * n * sizeof(T) : 0;
-            FastDiv fd;
-            fd.set((uint32_t)n);
-            auto launch = [&](auto kernel) {
-                if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NC_TABLE_SMEM);
-                kernel<<<TQ_GRID(grid), 256, smem, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end, fd, partials,
-                                                       ticket, out_f64);
-            };
-            if (aligned && use_smem) launch(contract1_kernel<T, V, true>);
-            else if (aligned) launch(contract1_kernel<T, V, false>);
-            else if (use_smem) launch(contract1_kernel<T, 1, true>);
-            else launch(contract1_kernel<T, 1, false>);
+            constexpr int V = 16 / sizeof(T);
+            C1Plan plan;
+            plan.fdn.set((uint32_t)n);
+            plan.R = 1;
+            plan.m = 0;
+            while (plan.m < dim && (uint64_t)plan.R * (uint64_t)n <= (uint64_t)C1_MAXR) { plan.R *= (uint32_t)n; ++plan.m; }
+            if (plan.m == 0) {  // n > C1_MAXR (few, very long dimensions): the last dimension's weights are read from global memory
+                plan.R = (uint32_t)n;
+                plan.m = 1;
+            }
+            {
+                plan.fdR.set(plan.R);
+                // chunks of C1_CHUNK points (a multiple of the vector width), dealt round-robin to a persistent grid
+                static const int64_t chunk_env = getenv("TQ_C1_CHUNK") ? atoll(getenv("TQ_C1_CHUNK")) : 0;
+                int64_t ctas = (int64_t)num_sms() * 4;
+                int64_t chunk = (rows + ctas - 1) / ctas;  // one contiguous range per CTA (measured faster than dealing
+                if (chunk < 8192) chunk = 8192;            // 16K..256K-point chunks round-robin: 3.9 vs 3.6 TB/s)
+                if (chunk_env > 0) chunk = chunk_env;
+                chunk = (chunk + 255) / 256 * 256;
+                ctas = (rows + chunk - 1) / chunk;
+                if (ctas > (int64_t)num_sms() * 4) ctas = (int64_t)num_sms() * 4;
+                plan.chunk = chunk;
+                double* partials = wk.take<double>((size_t)ctas);
+                if (!ticket || !partials) { set_error("tq_nc_contract: workspace too small"); return TQ_ERR_WORKSPACE; }
+                if (aligned)
+                    contract1_kernel<T, V><<<TQ_GRID((unsigned)ctas), 256, 0, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end,
+                                                                                   plan, partials, ticket, out_f64);
+                else
+                    contract1_kernel<T, 1><<<TQ_GRID((unsigned)ctas), 256, 0, st>>>((const T*)f, (const T*)w, (uint32_t)n, dim, p_begin, p_end,
+                                                                                   plan, partials, ticket, out_f64);
+                return check_launch("contract1_kernel");
+            }
         });
-        return check_launch("contract1_kernel");
     }
     const int64_t ntiles = (rows + CK_ROWS - 1) / CK_ROWS;
     int64_t grid = ntiles < (int64_t)num_sms() * 4 ? ntiles : (int64_t)num_sms() * 4;

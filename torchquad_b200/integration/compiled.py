@@ -25,6 +25,7 @@ import collections
 
 import torch
 
+from .. import _lib
 from ..integrands import BuiltinIntegrand
 from ..utils.set_log_level import logger
 from . import utils
@@ -32,7 +33,7 @@ from .utils import _setup_integration_domain
 
 
 class _Entry:
-    __slots__ = ("graph", "domain", "out", "fn")
+    __slots__ = ("graph", "domain", "out", "fn", "workspace")
 
 
 def _fn_key(fn):
@@ -96,10 +97,13 @@ class GraphedIntegrate:
             finally:
                 torch.cuda.set_sync_debug_mode(previous)
                 utils._capture_probe = False
+            # the library's scratch buffer is per stream: capture on the stream the warm-up ran on, and keep the buffer
+            # alive with the graph (its address is baked into the captured launches)
+            entry.workspace = _lib.workspace(dev)
         torch.cuda.current_stream(dev).wait_stream(side)
         entry.graph = torch.cuda.CUDAGraph()
         try:
-            with torch.no_grad(), torch.cuda.graph(entry.graph):
+            with torch.no_grad(), torch.cuda.graph(entry.graph, stream=side):
                 entry.out = self._step(fn, entry.domain)
         except Exception:
             self._repair_after_failed_capture(dev)

@@ -81,7 +81,7 @@ class Gaussian(GridIntegrator):
 
     def integrate_values(self, function_values, dim, n_per_dim, integration_domain):
         """Integral from raw (unweighted) values on the full grid."""
-        table = self._weight_table(n_per_dim, dim, function_values.dtype, function_values.device)
+        table = self._weight_table(n_per_dim, dim, integration_domain.dtype, function_values.device)  # real, also for complex values
         return ops.nc_contract(function_values, table) * self._scale(None, integration_domain)
 
     @expand_func_values_and_squeeze_integral

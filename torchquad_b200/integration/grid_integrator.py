@@ -13,7 +13,7 @@ from .base_integrator import BaseIntegrator
 from .compiled import GraphedIntegrate
 from .integration_grid import IntegrationGrid, grid_nodes
 from .utils import (_check_integration_domain, _is_compiling, _linspace_with_grads, _setup_integration_domain,
-                    _split_function_values, expand_func_values_and_squeeze_integral)
+                    _split_function_values, _to_working_dtype, expand_func_values_and_squeeze_integral)
 
 
 class GridIntegrator(BaseIntegrator):
@@ -129,7 +129,7 @@ class GridIntegrator(BaseIntegrator):
         if world > 1:
             total = ops.all_reduce_sum_autograd(total)
         self._nr_of_fevals = total_points
-        return total.to(domain.dtype) * self._scale(hs, domain)
+        return _to_working_dtype(total, domain.dtype) * self._scale(hs, domain)
 
     @staticmethod
     def _squeeze_1d(function_values, fn, *args):
@@ -143,7 +143,7 @@ class GridIntegrator(BaseIntegrator):
     @expand_func_values_and_squeeze_integral
     def calculate_result(self, function_values, dim, n_per_dim, hs, integration_domain):
         """Apply the composite rule to values on the full grid (grid_integrator.py:57-91)."""
-        table = self._weight_table(n_per_dim, dim, function_values.dtype, function_values.device)
+        table = self._weight_table(n_per_dim, dim, integration_domain.dtype, function_values.device)  # real, also for complex values
         return ops.nc_contract(function_values, table) * self._scale(hs, integration_domain)
 
     def calculate_grid(self, N, integration_domain, disable_integration_domain_check=False):

@@ -10,7 +10,8 @@ from ..utils.set_log_level import logger
 from .base_integrator import BaseIntegrator
 from .compiled import GraphedIntegrate
 from .rng import RNG
-from .utils import _setup_integration_domain, _split_function_values, expand_func_values_and_squeeze_integral
+from .utils import (_setup_integration_domain, _split_function_values, _to_working_dtype,
+                    expand_func_values_and_squeeze_integral)
 
 
 class MonteCarlo(BaseIntegrator):
@@ -70,7 +71,7 @@ class MonteCarlo(BaseIntegrator):
                 total = ops.all_reduce_sum_autograd(total)
             self._nr_of_fevals = N  # evaluations of the whole job, like the grid rules and VEGAS report them
             volume = torch.prod(domain[:, 1] - domain[:, 0])
-            return volume * total.to(domain.dtype) / N
+            return volume * _to_working_dtype(total, domain.dtype) / N
         sample_points = self.calculate_sample_points(N, domain, rng=rng)
         function_values, self._nr_of_fevals = self.evaluate_integrand(fn, sample_points)
         return self.calculate_result(function_values, domain)

@@ -127,5 +127,5 @@ def _contract_shaped(rule_cls, shaped, dim, hs):
     flat = shaped.reshape(*lead, n**dim) if lead else shaped.reshape(n**dim)
     values = flat.movedim(-1, 0).contiguous()
     integ = rule_cls()
-    table = integ._weight_table(n, dim, shaped.dtype, shaped.device)
+    table = integ._weight_table(n, dim, shaped.real.dtype if shaped.is_complex() else shaped.dtype, shaped.device)
     return ops.nc_contract(values, table) * integ._scale(hs)

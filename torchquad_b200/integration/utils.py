@@ -152,3 +152,10 @@ def _is_compiling(x):
     if torch.jit.is_tracing() or _capture_probe:
         return True
     return x.is_cuda and torch.cuda.is_current_stream_capturing()
+
+
+def _to_working_dtype(total, dtype):
+    """fp64-accumulated sums -> the domain's precision (complex sums keep their imaginary part)."""
+    if total.is_complex():
+        return total.to(torch.complex64 if dtype == torch.float32 else torch.complex128)
+    return total.to(dtype)

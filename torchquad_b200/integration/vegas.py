@@ -55,6 +55,7 @@ class VEGAS(BaseIntegrator):
     native_unfused_max_bytes = 1 << 30  # sample buffers (y, x) the callback-integrand loop may allocate up front
     _large_map_bytes = 64 << 20
     _pairs_min_rows = 1 << 20  # fused passes at least this long accumulate the histogram as fp64 pairs
+    min_rows_per_rank = 1 << 17  # multi-GPU fused runs with fewer samples per pass and rank are replicated, not sharded
 
     def __init__(self):
         super().__init__()
@@ -120,8 +121,14 @@ class VEGAS(BaseIntegrator):
         # Multi-GPU, built-in integrand: the hypercubes are dealt to the ranks (block-cyclic), each rank keeps only its
         # share of the stratification state and a pass needs ONE all-reduce (tq_vegas_run_fused_sharded).
         self._shard = None
+        self._replicated = False
         if (tqdist.is_enabled() and self._fused and self.native_loop and self.initial_adaptation is None
                 and max_iterations + 5 <= _lib.TQ_VEGAS_MAX_PASSES):
+            # Passes of a few 1e4 samples are pure launch latency: sharding them only adds a collective per
+            # pass.  Every rank then runs the whole problem (identical samples => identical results, no collective).
+            self._replicated = self._N_increment < self.min_rows_per_rank * tqdist.rank_and_world()[1]
+        if (tqdist.is_enabled() and self._fused and self.native_loop and self.initial_adaptation is None
+                and max_iterations + 5 <= _lib.TQ_VEGAS_MAX_PASSES and not self._replicated):
             n_strat = min(1000, int((self._N_increment / 4.0) ** (1.0 / dim)))
             self._shard = tqdist.cube_shard(n_strat**dim)
         self.strat = VEGASStratification(self._N_increment, dim=dim, rng=self.rng, backend="torch", dtype=self.dtype,
@@ -129,7 +136,7 @@ class VEGAS(BaseIntegrator):
         # Multi-GPU, arbitrary integrand: the float statistics of a pass live in ONE buffer [weights | JF | JF2] so that
         # a pass needs one all-reduce for them plus one for the int64 counts.
         self._stats = None
-        if tqdist.is_enabled() and self._shard is None:
+        if tqdist.is_enabled() and self._shard is None and not self._replicated:
             n_w = dim * N_intervals
             self._stats = torch.zeros(n_w + 2 * self.strat.N_cubes, dtype=self.dtype, device=self.device)
             self.map.weights = self._stats[:n_w].view(dim, N_intervals)
@@ -150,7 +157,7 @@ class VEGAS(BaseIntegrator):
                 and dim * N_intervals * (2 * domain.element_size() + 8) > self._large_map_bytes):
             restore_l2 = _lib.l2_fetch_granularity(self.device, int(self.l2_fetch_bytes))
         try:
-            if self._shard is not None:
+            if self._shard is not None or self._replicated:
                 return self._integrate_native_loop(N, use_warmup)
             native = self.native_loop and not tqdist.is_enabled() and max_iterations + 5 <= _lib.TQ_VEGAS_MAX_PASSES
             if native and self._fused:

@@ -109,8 +109,17 @@ class _ReduceSum(torch.autograd.Function):
         return g.unsqueeze(0).expand(ctx.shape)
 
 
+def _complex_through_real(op, f, *args):
+    """Complex integrand values (the reference's tests integrate a few, tests/integration_test_functions.py) go through
+    the real kernels as [..., 2] real views: sums and weighted contractions are linear, so re / im parts are columns."""
+    out = op(torch.view_as_real(f.contiguous() if not f.is_contiguous() else f), *args)
+    return torch.view_as_complex(out.contiguous())
+
+
 def reduce_sum(f):
     """sum(f, axis=0) accumulated in fp64 and rounded once to f.dtype (monte_carlo.py:77); differentiable."""
+    if f.is_complex():
+        return _complex_through_real(_ReduceSum.apply, f)
     return _ReduceSum.apply(f)
 
 
@@ -128,6 +137,8 @@ class _ReduceSumF64(torch.autograd.Function):
 
 def reduce_sum_f64(f):
     """Like reduce_sum but returns the unrounded fp64 sums (for accumulation over chunks and ranks)."""
+    if f.is_complex():
+        return _complex_through_real(_ReduceSumF64.apply, f)
     return _ReduceSumF64.apply(f)
 
 
@@ -428,11 +439,15 @@ def nc_contract(f, w, p_begin=0, p_end=None):
     """sum_p f[p, ...] * prod_d w[d, i_d(p)] in fp64, rounded once; differentiable wrt f."""
     dim, n = w.shape
     p_end = n**dim if p_end is None else p_end
+    if f.is_complex():
+        return _complex_through_real(_Contract.apply, f, w, p_begin, p_end, False)
     return _Contract.apply(f, w, p_begin, p_end, False)
 
 
 def nc_contract_f64(f, w, p_begin, p_end):
     """Same contraction, unrounded fp64 partial sums (for accumulation over chunks and ranks)."""
+    if f.is_complex():
+        return _complex_through_real(_Contract.apply, f, w, p_begin, p_end, True)
     return _Contract.apply(f, w, p_begin, p_end, True)
 
 
