@@ -255,6 +255,22 @@ TQ_API int tq_fused_vegas_sharded(const tq_integrand* fn_host, int32_t dtype, co
                            int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* hist_pairs,
                            void* JF, void* JF2, uint64_t seed, uint32_t call_idx, int32_t cube_block_log2, int32_t rank,
                            int32_t world, double* out_f64, void* ws, size_t ws_bytes, void* stream);
+/* Maps BEYOND L2 (the reference's Ni = N_increment / 10 of vegas.py:117: 8 x 1e7 bins at N = 2.5e9): a stratified pass in two
+ * steps.  tq_fused_vegas_deferred runs the pass without the histogram (edges gathered from the pair table) and stores
+ * jf^2 of every row in jf2_rows[row - row_begin] (working dtype).  tq_vegas_hist_sweep then accumulates
+ * weights[d,k] += jf^2, counts[d,k] += 1 (vegas_map.py:99-111) into hist_pairs band by band: a sample of cube c can only
+ * fall into the Ni / N_strat bins selected by digit d of c (vegas_stratification.py:140-165), so walking the cubes in the
+ * order of those digits keeps the touched part of the table (dims_per_group * Ni / N_strat * 16 bytes) resident in L2 and
+ * every table line is written to HBM once per band, instead of one random HBM read-modify-write per sample and dimension.
+ * dims_per_group <= 2 (fp64) / 4 (fp32) dimensions share one launch (they share a Philox block).  Same seed / call_idx /
+ * offsets as the pass: the uniforms are regenerated, the bins are identical, counts are exact. */
+TQ_API int tq_fused_vegas_deferred(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
+                            int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_pairs, int64_t n_intervals,
+                            void* jf2_rows, void* JF, void* JF2, uint64_t seed, uint32_t call_idx, void* ws, size_t ws_bytes,
+                            void* stream);
+TQ_API int tq_vegas_hist_sweep(const int64_t* offsets, int64_t n_cubes, int32_t n_strat, int32_t dim, int32_t dtype,
+                        const void* jf2_rows, int64_t n_intervals, void* hist_pairs, int32_t dims_per_group, uint64_t seed,
+                        uint32_t call_idx, void* ws, size_t ws_bytes, void* stream);
 /* weights += hist.sum (rounded once to the working dtype), counts += hist.count, hist = 0 (vegas_map.py:99-111). */
 TQ_API int tq_vegas_map_unpack_hist(void* hist_pairs, void* weights, int64_t* counts, int32_t dim, int64_t n_intervals,
                              int32_t dtype, void* stream);
@@ -285,6 +301,11 @@ typedef struct tq_vegas_state {
     void* weights;      /* [dim, Ni], zero */
     int64_t* counts;    /* [dim, Ni], zero */
     void* hist_pairs;   /* fp64 [dim, Ni, 2], zero, or NULL: see tq_fused_vegas (used for passes of >= 2^20 rows) */
+    void* jf2_rows;     /* working dtype [jf2_rows_cap] or NULL.  Non-NULL (with hist_pairs, TQ_EDGES_PAIRS): stratified passes run
+                           deferred + tq_vegas_hist_sweep (maps beyond L2); cap >= 4 * (N / (max_iterations + 5)) + 2 * n_cubes */
+    int64_t jf2_rows_cap;
+    int32_t sweep_dims_per_group; /* dims_per_group of tq_vegas_hist_sweep */
+    int32_t _pad0;
     void* dh;           /* [n_cubes], initial 1/n_cubes */
     int64_t* nh;        /* [n_cubes] */
     int64_t* offsets;   /* [n_cubes + 1] */

@@ -26,7 +26,13 @@ def vegas_final_pass(fn, dim, N, dt, cap):
     offsets = strat._offsets
     rows = int(offsets[-1].item())
     JF = torch.zeros((2, strat.N_cubes), dtype=dt, device=dev)
-    if vmap.wants_records():
+    g = vmap.sweep_group(strat.N_strat)
+    if vmap.wants_records() and g >= 1:  # deferred pass + band sweeps: the LAST fused_vegas / hist_sweep launches are captured
+        jf2 = torch.empty(rows, dtype=dt, device=dev)
+        h = vmap.hist_pairs()
+        ops.fused_vegas_deferred(v._fn_struct, vmap.packed_edges(), 0, rows, 1, 7, offsets, strat.N_strat, JF[0], JF[1], jf2)
+        ops.hist_sweep(offsets, strat.N_strat, dim, jf2, vmap.N_intervals, h, g, 1, 7)
+    elif vmap.wants_records():
         ops.fused_vegas(v._fn_struct, None, None, None, 0, rows, 1, 7, offsets=offsets, n_strat=strat.N_strat, JF=JF[0], JF2=JF[1],
                         records=vmap.records(), dtype=dt, n_intervals=vmap.N_intervals)
     else:

@@ -655,6 +655,70 @@ def test_compiled_integrate_default_is_eager_and_differentiable(cuda):
     assert len(c._entries) <= c.max_graphs and c._misses >= c.max_consecutive_misses
 
 
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+@pytest.mark.parametrize("dim,ns,ni,g", [(3, 6, 512, 1), (4, 2, 100, 2), (5, 3, 257, 1), (7, 4, 64, 2), (2, 9, 1000, 1), (6, 3, 50, 4)])
+def test_deferred_pass_and_band_sweep_match_direct_histogram(cuda, tag, dim, ns, ni, g):
+    """Maps beyond L2 (tq_fused_vegas_deferred + tq_vegas_hist_sweep): the pass stores jf^2 per row, the sweep regenerates the
+    uniforms and bins the rows band by band.  Must reproduce the direct histogram of the same pass: counts exactly, weights
+    to rounding, per-cube sums bit for bit."""
+    from torchquad_b200.integration.vegas_map import VEGASMap
+
+    dt = DT[tag]
+    if g > (2 if tag == "f64" else 4):
+        pytest.skip("dims_per_group beyond one Philox block")
+    torch.manual_seed(dim * 100 + ns)
+    vm = VEGASMap(ni, dim, "torch", dt, device=cuda)
+    vm.x_edges[:, 1:-1] += (torch.rand(dim, ni - 1, device=cuda, dtype=dt) - 0.5) * (0.5 / ni)
+    vm.dx_edges = (vm.x_edges[:, 1:] - vm.x_edges[:, :-1]).contiguous()
+    fn = F.GenzOscillatory(dim, a=0.7, u=0.2)
+    s = fn.to_struct([0.0] * dim, [1.0] * dim, 1.0)
+    C = ns**dim
+    nh = torch.randint(2, 9, (C,), device=cuda, dtype=torch.int64)
+    nh[C // 3] = 700  # one heavy cube (spans several warps of the pass, many steps of the sweep)
+    offsets = ops.strat_offsets(nh)
+    M = int(offsets[-1])
+    edges = ops.pack_edges(vm.x_edges, vm.dx_edges)
+    w1, c1 = torch.zeros_like(vm.weights), torch.zeros_like(vm.counts)
+    JF1 = torch.zeros((2, C), dtype=dt, device=cuda)
+    ops.fused_vegas(s, edges, w1, c1, 0, M, 1, 7, offsets=offsets, n_strat=ns, JF=JF1[0], JF2=JF1[1])
+    JF2 = torch.zeros((2, C), dtype=dt, device=cuda)
+    jf2_rows = torch.full((M,), float("nan"), dtype=dt, device=cuda)
+    ops.fused_vegas_deferred(s, edges, 0, M, 1, 7, offsets, ns, JF2[0], JF2[1], jf2_rows)
+    hist = torch.zeros((dim, ni, 2), dtype=torch.float64, device=cuda)
+    ops.hist_sweep(offsets, ns, dim, jf2_rows, ni, hist, g, 1, 7)
+    assert torch.isfinite(jf2_rows).all()
+    assert torch.equal(hist[..., 1].to(torch.int64), c1) and int(c1.sum()) == dim * M
+    assert rel_err_t(hist[..., 0].to(dt), w1) <= (1e-12 if tag == "f64" else 2e-5)
+    assert torch.allclose(JF1, JF2, rtol=1e-12 if tag == "f64" else 1e-5)
+
+
+def rel_err_t(a, b):
+    a, b = a.double(), b.double()
+    return float(((a - b).abs() / b.abs().clamp_min(1e-300)).max())
+
+
+def test_vegas_band_sweep_run_matches_default_run(cuda, monkeypatch):
+    """A whole fused run with the large-map path forced (pair tables + deferred passes + band sweeps, csrc/vegas_driver.cu)
+    must reproduce the default run: same schedule, same evaluation count, same map counts, same result."""
+    from torchquad_b200.integration.vegas_map import VEGASMap
+
+    fn = F.GenzGaussian(4, a=5.0, u=0.5)
+    dom = torch.tensor([[0.0, 1.0]] * 4, dtype=torch.float64, device=cuda)
+
+    def run():
+        v = tq.VEGAS()
+        return v, v.integrate(fn, 4, N=30_000_000, integration_domain=dom, seed=3)
+
+    a, ra = run()
+    monkeypatch.setattr(VEGASMap, "records_min_bytes", 0)
+    b, rb = run()
+    assert b.map.sweep_group(b.strat.N_strat) == 1 and b.map._records is None and b.map._hist is not None
+    assert a.it == b.it and a._nr_of_fevals == b._nr_of_fevals
+    assert abs(float(ra) - float(rb)) <= 1e-9 * abs(float(ra))
+    assert float((a.map.x_edges - b.map.x_edges).abs().max()) <= 1e-9
+    assert torch.equal(a.map.counts, b.map.counts)
+
+
 @pytest.mark.parametrize("native", [True, False])
 def test_vegas_record_layout_matches_pair_layout(cuda, monkeypatch, native):
     """Large maps keep {x, dx, weight, count} records (TQ_EDGES_RECORDS); forcing that layout on a small problem

@@ -11,7 +11,7 @@ import threading
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libtqb200.so")
+LIB_PATH = os.environ.get("TQB200_LIB") or os.path.join(_PKG, "libtqb200.so")  # TQB200_LIB: kernel-variant experiments
 
 TQ_F32, TQ_F64 = 0, 1
 TQ_MAX_DIM = 32
@@ -40,6 +40,7 @@ class tq_vegas_state(ctypes.Structure):
 
     _fields_ = [
         ("x_edges", c_p), ("dx_edges", c_p), ("edges_packed", c_p), ("weights", c_p), ("counts", c_p), ("hist_pairs", c_p),
+        ("jf2_rows", c_p), ("jf2_rows_cap", c_i64), ("sweep_dims_per_group", c_i32), ("_pad0", c_i32),
         ("dh", c_p), ("nh", c_p), ("offsets", c_p), ("JF", c_p), ("JF2", c_p), ("records", c_p), ("status", c_p),
         ("map_ws", c_p), ("map_ws_bytes", c_sz), ("ws", c_p), ("ws_bytes", c_sz), ("edges_layout", c_i32),
     ]
@@ -116,6 +117,9 @@ PROTOTYPES = {
     "tq_fused_vegas_sharded": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_p, c_i64, c_i32, c_i64, c_i64, c_p, c_i32, c_i64, c_p, c_p,
                                               c_p, c_p, c_p, c_u64, c_u32, c_i32, c_i32, c_i32, c_p, c_p, c_sz, c_p]),
     "tq_vegas_map_unpack_hist": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_i32, c_p]),
+    "tq_fused_vegas_deferred": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_p, c_i64, c_i32, c_i64, c_i64, c_p, c_i64, c_p, c_p, c_p, c_u64,
+                                               c_u32, c_p, c_sz, c_p]),
+    "tq_vegas_hist_sweep": (ctypes.c_int, [c_p, c_i64, c_i32, c_i32, c_i32, c_p, c_i64, c_p, c_i32, c_u64, c_u32, c_p, c_sz, c_p]),
     "tq_vegas_run_fused_sharded": (ctypes.c_int, [_P_INTEGRAND, c_i32, c_i64, c_i32, c_f64, c_f64, c_i32, c_i32, c_i64, c_i32, c_i64,
                                                   c_f64, c_f64, c_f64, c_u64, c_u32, ctypes.POINTER(tq_vegas_state),
                                                   ctypes.POINTER(tq_vegas_shard), ctypes.POINTER(tq_vegas_result), c_p]),

@@ -2,6 +2,8 @@
 // reaches HBM.  The integrands are the Genz families (not in the reference) and the
 // reference's test integrands (tests/integration_test_functions.py:146-325), all of which factor as
 // finish(combine_d step(x_d)), so a thread streams over the dimensions without holding the point.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "vegas_dev.cuh"
 #include "internal.cuh"
@@ -230,6 +232,10 @@ struct CubeShard {
 #define FV_MIN_CTAS 6
 #endif
 constexpr int FV_SLICE = FV_BLOCK / 2 + 4;
+#ifndef TQ_FV_DIM_UNROLL
+#define TQ_FV_DIM_UNROLL 1  // measured (profiles/r2/exp_variants.txt): 1 / 2 / 4 x {3..8 CTAs per SM} all within 5 %
+#endif
+constexpr int FV_DIM_UNROLL = TQ_FV_DIM_UNROLL;  // Philox blocks of a sample processed per unrolled step of the dimension loop
 
 template <typename T> struct Pair2;
 template <> struct Pair2<float> { using type = float2; };
@@ -254,6 +260,7 @@ enum HistMode {
     HIST_SMEM = 2,     // whole map privatised in shared memory (tiny maps), flushed to weights / counts
     HIST_PAIRS = 3,    // {sum jf^2, count} as an fp64 pair per bin: ONE reduction sector per (sample, dim), see below
     HIST_RECORDS = 4,  // the {weight, count} words of the bin's record (large maps)
+    HIST_DEFER = 5,    // jf^2 of every row is written out; hist_sweep_kernel bins the rows band by band afterwards
 };
 
 // Sector-paired reductions.  L2 executes a reduction per 32-byte SECTOR, not per lane (measured on B200,
@@ -266,9 +273,9 @@ __global__ void __launch_bounds__(FV_BLOCK, FV_MIN_CTAS)
 fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, int64_t n_cubes, CubeShard shard, FastDiv ns_div, T inv_ns,
                    int64_t row_begin, int64_t row_end, bool rows_from_offsets, int64_t rows_per_cta,
                    const void* __restrict__ edges_raw, bool records, long long ni, T* __restrict__ weights,
-                   unsigned long long* __restrict__ counts, double* __restrict__ hist_pairs, T* __restrict__ JF,
-                   T* __restrict__ JF2, uint64_t seed, uint32_t call, int hist_mode, double* partials, unsigned int* ticket,
-                   double* out) {
+                   unsigned long long* __restrict__ counts, double* __restrict__ hist_pairs, T* __restrict__ jf2_rows,
+                   T* __restrict__ JF, T* __restrict__ JF2, uint64_t seed, uint32_t call, int hist_mode, double* partials,
+                   unsigned int* ticket, double* out) {
     constexpr int LANES = U01<T>::LANES;
     using P2 = typename Pair2<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -285,7 +292,7 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
     unsigned int* s_c = reinterpret_cast<unsigned int*>(s_w + (hist_smem ? dim * ni : 0));
     const P2* __restrict__ edges = reinterpret_cast<const P2*>(edges_raw);
     MapRecord<T>* recs = reinterpret_cast<MapRecord<T>*>(const_cast<void*>(edges_raw));
-    const bool do_hist = hist_mode != HIST_NONE;
+    const bool do_hist = hist_mode != HIST_NONE && hist_mode != HIST_DEFER;
     // fp64 records keep their count as an fp64 next to the weight: the same sector-paired reduction applies
     const bool paired = hist_mode == HIST_PAIRS || (hist_mode == HIST_RECORDS && sizeof(T) == 8);
     double* pair_base = hist_mode == HIST_PAIRS ? hist_pairs : reinterpret_cast<double*>(recs) + 2;
@@ -348,7 +355,8 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
                 Integrand<FAM, T> fn;
                 fn.init();
                 T jac = (T)1;
-                for (int d0 = 0; d0 < dim; d0 += LANES) {
+#pragma unroll FV_DIM_UNROLL
+                for (int d0 = 0; d0 < dim; d0 += LANES) {  // unrolled: the edge gathers of several Philox blocks are in flight together
                     T u[LANES];
                     philox_block<T>(seed, call, i0, i1, (uint32_t)(d0 / LANES), u);
     #pragma unroll
@@ -382,6 +390,7 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
                 const T f = mul_rn(fn.finish(S), S.scale);
                 jf = mul_rn(f, jac);
                 jf2 = mul_rn(jf, jf);
+                if (hist_mode == HIST_DEFER) jf2_rows[row - row_begin] = jf2;
                 if (do_hist && !paired) {
                     if (hist_smem) {
                         for (int d = 0; d < dim; ++d) {
@@ -509,6 +518,121 @@ unpack_hist_kernel(double2* __restrict__ hist, T* __restrict__ weights, long lon
             counts[i] += (long long)h.y;
             hist[i] = make_double2(0.0, 0.0);
         }
+    }
+}
+
+// ---- maps beyond L2: the histogram of a stratified pass, band by band -------------------------------------------------
+// A sample of cube c falls, in dimension d, into the band of Ni / N_strat bins selected by digit d of c
+// (y_d = (digit + u) / N_strat, vegas_stratification.py:140-165).  With the reference's map size (Ni = 1e7 per dimension)
+// the histogram table is far beyond L2 and every reduction of the fused pass is a random read-modify-write in HBM.  Instead
+// the pass only stores jf^2 per row (HIST_DEFER) and this kernel re-bins the rows afterwards, one GROUP of g <= LANES
+// consecutive dimensions (= one Philox block) per launch, walking the cubes in the order of the group's digits: all cubes
+// that are in flight at a time share the group's g bands (g * Ni / N_strat * 16 bytes, 40 MB for configs[3]), so the
+// reductions hit L2 and every table line goes to HBM once per band.  The uniforms are regenerated from the cube-keyed
+// Philox stream (same block, same lanes, same arithmetic as the pass: identical bins), jf^2 is read back (8 bytes / row).
+// One warp handles 32 cubes; per step every lane has at most one sample, binned with the sector-paired reductions.
+constexpr uint32_t SWEEP_CHUNK = 1024;  // cubes per scheduling unit
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+hist_sweep_kernel(const long long* __restrict__ offsets, uint32_t n_cubes, const T* __restrict__ jf2_rows,
+                  double* __restrict__ hist, long long ni, int d0, int g, FastDiv ns_div, FastDiv low_div, uint32_t pow_g,
+                  FastDiv cpc_div, T inv_ns, uint64_t seed, uint32_t call, int lane0, unsigned int* next_chunk) {
+    constexpr int LANES = U01<T>::LANES;
+    __shared__ unsigned int s_chunk;
+    const int lane = threadIdx.x & 31, word = lane & 1;
+    const T nif = (T)ni, nsf = (T)ns_div.d;
+    const uint32_t cubes_per_combo = cpc_div.d, pow_low = low_div.d;
+    // Chunks of SWEEP_CHUNK cubes are handed out IN ORDER by a global counter: the cubes in flight then always form one
+    // compact window of the band-major order, whatever the spread of the per-cube work.  (A static grid-stride assignment
+    // lets the CTAs drift apart once nh is adapted -- measured: 16 HBM round trips per table line instead of one.)
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = atomicAdd(next_chunk, 1u);
+        __syncthreads();
+        const uint64_t chunk0 = (uint64_t)s_chunk * SWEEP_CHUNK;
+        if (chunk0 >= n_cubes) break;
+    for (uint32_t base = (uint32_t)chunk0 + (threadIdx.x - lane); base < n_cubes && base < chunk0 + SWEEP_CHUNK; base += blockDim.x) {
+        const uint32_t j = base + lane;  // position in the band-major order
+        uint32_t c = 0, combo = 0;
+        long long row0 = 0;
+        int nh = 0;
+        if (j < n_cubes) {
+            combo = cpc_div.div(j);                       // the group's digits (dimension d0 fastest)
+            const uint32_t r = j - combo * cubes_per_combo;
+            const uint32_t high = low_div.div(r), low = r - high * pow_low;
+            c = (high * pow_g + combo) * pow_low + low;   // the cube with those digits at positions d0 .. d0+g-1
+            row0 = __ldcs(&offsets[c]);
+            nh = (int)(__ldcs(&offsets[c + 1]) - row0);
+        }
+        // The warp's 32 cubes hold `total` samples; they are flattened so that every step gives each lane one sample
+        // whatever the spread of nh (after adaptation nh varies by an order of magnitude between neighbouring cubes).
+        int incl = nh;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - nh;
+        for (int s0 = 0; s0 < total; s0 += 32) {
+            const int sidx = s0 + lane;
+            const bool act = sidx < total;
+            // owner = first lane whose inclusive count exceeds sidx (5-step search over the lanes' counts)
+            int lo = 0, hi = 31;
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const int mid = (lo + hi) >> 1;
+                const int vmid = __shfl_sync(0xffffffffu, incl, mid);
+                if (vmid <= sidx) lo = mid + 1; else hi = mid;
+            }
+            const int owner = lo;
+            const uint32_t oc = __shfl_sync(0xffffffffu, c, owner);
+            const uint32_t ocombo = __shfl_sync(0xffffffffu, combo, owner);
+            const long long orow0 = __shfl_sync(0xffffffffu, row0, owner);
+            const int oi = sidx - __shfl_sync(0xffffffffu, excl, owner);
+            double v = 0.0;
+            int k[LANES];
+#pragma unroll
+            for (int t = 0; t < LANES; ++t) k[t] = 0;
+            if (act) {
+                T u[LANES];
+                philox_block<T>(seed, call, oc, (uint32_t)oi, (uint32_t)(d0 / LANES), u);
+                v = (double)__ldcs(&jf2_rows[orow0 + oi]);
+                uint32_t q = ocombo;
+#pragma unroll
+                for (int t = 0; t < LANES; ++t) {
+                    if (t < g) {
+                        const uint32_t qq = ns_div.div(q);
+                        const uint32_t p = q - qq * ns_div.d;
+                        q = qq;
+                        T ut = u[0];  // lane lane0 + t of the block (dimension d0 + t), selected without dynamic indexing
+#pragma unroll
+                        for (int l = 1; l < LANES; ++l)
+                            if (lane0 + t == l) ut = u[l];
+                        T y = div_by_const(add_rn((T)p, ut), nsf, inv_ns);
+                        if (y >= (T)1) y = (T)0.999999;
+                        const T fl = floor(mul_rn(y, nif));
+                        long long kk = (long long)fl;
+                        kk = kk < 0 ? 0 : (kk >= ni ? ni - 1 : kk);
+                        k[t] = (int)kk;
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // lanes 2i / 2i+1 serve sample i of a 16-sample half: {sum jf^2, count} of one bin
+                const int src = (lane >> 1) + 16 * h;
+                const bool a = __shfl_sync(0xffffffffu, (int)act, src) != 0;
+                const double sv = __shfl_sync(0xffffffffu, v, src);  // every lane takes part in the shuffle
+                const double val = word ? 1.0 : sv;
+#pragma unroll
+                for (int t = 0; t < LANES; ++t) {
+                    const int kk = __shfl_sync(0xffffffffu, k[t], src);
+                    if (t < g && a) atomicAdd(hist + ((int64_t)(d0 + t) * ni + kk) * 2 + word, val);
+                }
+            }
+        }
+    }
     }
 }
 
@@ -689,6 +813,76 @@ int tq_fused_vegas_sharded(const tq_integrand* fn_host, int32_t dtype, const int
                            int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* hist_pairs,
                            void* JF, void* JF2, uint64_t seed, uint32_t call_idx, int32_t cube_block_log2, int32_t rank,
                            int32_t world, double* out_f64, void* ws, size_t ws_bytes, void* stream) {
+    return fused_vegas_launch(fn_host, dtype, offsets, n_cubes, n_strat, row_begin, row_end, edges_packed, edges_layout, n_intervals,
+                              weights, counts, hist_pairs, nullptr, JF, JF2, seed, call_idx, cube_block_log2, rank, world, out_f64,
+                              ws, ws_bytes, stream);
+}
+
+int tq_fused_vegas_deferred(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
+                            int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_pairs, int64_t n_intervals,
+                            void* jf2_rows, void* JF, void* JF2, uint64_t seed, uint32_t call_idx, void* ws, size_t ws_bytes,
+                            void* stream) {
+    TQ_REQUIRE(offsets && jf2_rows, "tq_fused_vegas_deferred: a stratified pass (offsets) and jf2_rows are required");
+    return fused_vegas_launch(fn_host, dtype, offsets, n_cubes, n_strat, row_begin, row_end, edges_pairs, TQ_EDGES_PAIRS, n_intervals,
+                              nullptr, nullptr, nullptr, jf2_rows, JF, JF2, seed, call_idx, 0, 0, 1, nullptr, ws, ws_bytes, stream);
+}
+
+int tq_vegas_hist_sweep(const int64_t* offsets, int64_t n_cubes, int32_t n_strat, int32_t dim, int32_t dtype,
+                        const void* jf2_rows, int64_t n_intervals, void* hist_pairs, int32_t dims_per_group, uint64_t seed,
+                        uint32_t call_idx, void* ws, size_t ws_bytes, void* stream) {
+    TQ_REQUIRE(offsets && jf2_rows && hist_pairs, "tq_vegas_hist_sweep: NULL argument");
+    Workspace wsp(ws, ws_bytes);
+    wsp.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
+    unsigned int* counters = wsp.take<unsigned int>(TQ_MAX_DIM);  // one chunk counter per launch of this call
+    if (!counters) { set_error("tq_vegas_hist_sweep: workspace too small"); return TQ_ERR_WORKSPACE; }
+    TQ_REQUIRE(n_cubes >= 1 && n_cubes < (1LL << 31) && n_strat >= 1 && dim >= 1 && dim <= TQ_MAX_DIM && n_intervals >= 1 &&
+                   n_intervals < (1LL << 31), "tq_vegas_hist_sweep: bad sizes");
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(counters, 0, TQ_MAX_DIM * sizeof(unsigned int), st);
+    int launch = 0;
+    FastDiv ns_div;
+    ns_div.set((uint32_t)n_strat);
+    TQ_DISPATCH_DTYPE(dtype, {
+        constexpr int LANES = U01<T>::LANES;
+        TQ_REQUIRE(dims_per_group >= 1 && dims_per_group <= LANES, "tq_vegas_hist_sweep: dims_per_group must be 1..%d for this dtype", LANES);
+        const T inv_ns = (T)1 / (T)n_strat;
+        static const int ctas_env = getenv("TQ_SWEEP_CTAS_PER_SM") ? atoi(getenv("TQ_SWEEP_CTAS_PER_SM")) : 0;
+        // few CTAs: the cubes in flight then stay inside ONE band (measured, 8-D Ni=1e7: 1 / 2 / 4 / 8 / 16 CTAs per SM ->
+        // 1.40 / 0.81 / 0.80 / 1.54 / 1.78 ms per dimension, profiles/r2/exp_sweep_grid.txt)
+        const int grid = grid_for(n_cubes, 256, ctas_env > 0 ? ctas_env : 4);
+        // groups never straddle a Philox block: dimensions [b * LANES, (b + 1) * LANES) in pieces of dims_per_group
+        for (int b0 = 0; b0 < dim; b0 += LANES) {
+            for (int d0 = b0; d0 < dim && d0 < b0 + LANES; d0 += dims_per_group) {
+                // dimensions d0 .. d0+g-1 are lanes d0-b0 .. of Philox block b0 / LANES (a piece inside a block re-runs it)
+                int g = dims_per_group;
+                if (d0 + g > dim) g = dim - d0;
+                if (d0 + g > b0 + LANES) g = b0 + LANES - d0;
+                uint64_t pow_low = 1;
+                for (int i = 0; i < d0; ++i) pow_low *= (uint64_t)n_strat;
+                uint64_t pow_g = 1;
+                for (int i = 0; i < g; ++i) pow_g *= (uint64_t)n_strat;
+                FastDiv low_div, cpc_div;
+                low_div.set((uint32_t)pow_low);
+                cpc_div.set((uint32_t)((uint64_t)n_cubes / pow_g));
+                hist_sweep_kernel<T><<<TQ_GRID(grid), 256, 0, st>>>((const long long*)offsets, (uint32_t)n_cubes, (const T*)jf2_rows,
+                                                                   (double*)hist_pairs, n_intervals, d0, g, ns_div, low_div,
+                                                                   (uint32_t)pow_g, cpc_div, inv_ns, seed, call_idx, d0 - b0,
+                                                                   counters + launch++);
+            }
+        }
+    });
+    return check_launch("hist_sweep_kernel");
+}
+
+}  // extern "C"
+
+namespace tq {
+
+int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
+                       int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_packed,
+                       int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* hist_pairs,
+                       void* jf2_rows, void* JF, void* JF2, uint64_t seed, uint32_t call_idx, int32_t cube_block_log2,
+                       int32_t rank, int32_t world, double* out_f64, void* ws, size_t ws_bytes, void* stream) {
     int rc = check_integrand("tq_fused_vegas", fn_host);
     if (rc) return rc;
     TQ_REQUIRE(world >= 1 && rank >= 0 && rank < world && cube_block_log2 >= 0 && cube_block_log2 < 31,
@@ -726,21 +920,29 @@ int tq_fused_vegas_sharded(const tq_integrand* fn_host, int32_t dtype, const int
     // Shared-memory privatised histogram only for SMALL maps (<= 4096 bins, where same-address contention on
     // L2 atomics would serialise) and only when every CTA sees enough rows to amortise zero + flush.
     const int64_t bins = (int64_t)dim * n_intervals;
-    int hist_mode = records ? HIST_RECORDS : hist_pairs ? HIST_PAIRS : weights ? HIST_ARRAYS : HIST_NONE;
+    int hist_mode = jf2_rows ? HIST_DEFER : records ? HIST_RECORDS : hist_pairs ? HIST_PAIRS : weights ? HIST_ARRAYS : HIST_NONE;
     if (hist_mode == HIST_ARRAYS && bins <= 4096 && nrows >= 64 * bins) hist_mode = HIST_SMEM;
     // Record layout = tables beyond L2: a sample's histogram reductions find its record still in L2 only if few
     // samples are in flight between the gather and the reduction.  Measured (8-D fp64, Ni=1e7): 6 CTAs/SM refetch
     // every record from HBM for the reductions (5 DRAM sectors read per gather, 1.7e9 evals/s); 2 CTAs/SM: 2.07e9.
-    const int per_sm = records ? 2 : 6;
+    const int per_sm = records ? 2 : FV_MIN_CTAS;
     int64_t ctas = tiles < (int64_t)sms * per_sm ? tiles : (int64_t)sms * per_sm;
     if (hist_mode == HIST_SMEM) {
         const int64_t cap = nrows / (16 * bins) > 0 ? nrows / (16 * bins) : 1;
         if (ctas > cap) ctas = cap;
     }
     int64_t rows_per_cta = (nrows + ctas - 1) / ctas;
+    static const int64_t rpc_env = getenv("TQ_FV_ROWS_PER_CTA") ? atoll(getenv("TQ_FV_ROWS_PER_CTA")) : 0;
+    // maps beyond L2: deal the rows in small chunks, so that the rows in flight share the bands of the slow dimensions
+    // (1024 rows per chunk: 13.4 ms vs 14.0 ms with one contiguous range per CTA, profiles/r2/exp_defer_interleave.txt)
+    if (hist_mode == HIST_DEFER) {
+        const int64_t rpc = rpc_env > 0 ? rpc_env : 1024;
+        if (rpc < rows_per_cta) rows_per_cta = rpc;
+    }
     rows_per_cta = ((rows_per_cta + FV_BLOCK - 1) / FV_BLOCK) * FV_BLOCK;
     if (rows_per_cta < FV_BLOCK) rows_per_cta = FV_BLOCK;
     ctas = nrows > 0 ? (nrows + rows_per_cta - 1) / rows_per_cta : 1;
+    if (ctas > (int64_t)sms * per_sm) ctas = (int64_t)sms * per_sm;  // small chunks are dealt round-robin (the kernel's stride loop)
     double* partials = w.take<double>((size_t)ctas * 2);
     if (!ticket || !partials) { set_error("tq_fused_vegas: workspace too small"); return TQ_ERR_WORKSPACE; }
     const size_t smem = ids_bytes + (hist_mode == HIST_SMEM ? hist_bytes : 0);
@@ -755,17 +957,17 @@ int tq_fused_vegas_sharded(const tq_integrand* fn_host, int32_t dtype, const int
                 fused_vegas_kernel<FAM, T, true><<<TQ_GRID((unsigned)ctas), FV_BLOCK, smem, st>>>(
                     *fn_host, (const long long*)offsets, n_cubes, shard, ns_div, inv_ns, row_begin, row_end, rows_from_offsets, rows_per_cta,
                     edges_packed, records, n_intervals, (T*)weights, (unsigned long long*)counts, (double*)hist_pairs,
-                    (T*)JF, (T*)JF2, seed, call_idx, hist_mode, partials, ticket, out_f64);
+                    (T*)jf2_rows, (T*)JF, (T*)JF2, seed, call_idx, hist_mode, partials, ticket, out_f64);
             } else {
                 if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, false><<<TQ_GRID((unsigned)ctas), FV_BLOCK, smem, st>>>(
                     *fn_host, nullptr, 0, shard, ns_div, inv_ns, row_begin, row_end, false, rows_per_cta, edges_packed, records,
-                    n_intervals, (T*)weights, (unsigned long long*)counts, (double*)hist_pairs, nullptr, nullptr, seed, call_idx,
-                    hist_mode, partials, ticket, out_f64);
+                    n_intervals, (T*)weights, (unsigned long long*)counts, (double*)hist_pairs, nullptr, nullptr, nullptr, seed,
+                    call_idx, hist_mode, partials, ticket, out_f64);
             }
         });
     });
     return check_launch("fused_vegas_kernel");
 }
 
-}  // extern "C"
+}  // namespace tq

@@ -14,6 +14,12 @@ int strat_nh_launch(const void* dh, int64_t n_cubes, double nevals_exp, int32_t 
 int strat_update_partial_launch(const void* JF, const void* JF2, const int64_t* nh, int64_t n_cubes, double v_cubes, double beta,
                                 int32_t dtype, void* dh, double* scalars, void* ws, size_t ws_bytes, void* stream);
 int strat_normalise_launch(void* dh, int64_t n_cubes, const double* scalars, int32_t dtype, void* stream);
+// fused.cu: the one launcher behind tq_fused_vegas / _sharded / _deferred (jf2_rows != NULL: HIST_DEFER)
+int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
+                       int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_packed,
+                       int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* hist_pairs,
+                       void* jf2_rows, void* JF, void* JF2, uint64_t seed, uint32_t call_idx, int32_t cube_block_log2,
+                       int32_t rank, int32_t world, double* out_f64, void* ws, size_t ws_bytes, void* stream);
 // fused.cu: pairs += {record.w, record.c}, record fields back to zero (records -> the all-reduce buffer)
 int records_to_pairs_launch(void* records, double* pairs, int32_t dim, int64_t ni, int32_t dtype, void* stream);
 

@@ -111,6 +111,9 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
     // dimension instead of two, tq_fused_vegas); it is folded into weights / counts right before the map update.
     const bool pairs_ok = !recs && !small && s->hist_pairs != nullptr;
     bool pairs_dirty = false;
+    // Maps beyond L2 (pair layout + jf2_rows): a stratified pass stores jf^2 per row and tq_vegas_hist_sweep bins the rows band
+    // by band afterwards, so the reductions hit L2 instead of being random HBM read-modify-writes.
+    const bool sweep_ok = pairs_ok && grid_improve && s->jf2_rows != nullptr && s->sweep_dims_per_group >= 1 && n_strat >= 2;
     auto hist_args = [&](int64_t rows, void*& w, int64_t*& c, void*& h) {
         const bool use_pairs = pairs_ok && rows >= (1 << 20);
         w = use_pairs ? nullptr : hist_w;
@@ -165,11 +168,21 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
         // sum nh <= starting * sum(dh) + 2 * n_cubes; the estimate only sizes the grid
         const int64_t m_est = starting + 2 * n_cubes + 1024;
         // without grid improvement nothing is accumulated: the pass only needs the {x, dx} gather
-        void *hw = nullptr, *hp = nullptr;
-        int64_t* hc = nullptr;
-        if (grid_improve) hist_args(starting, hw, hc, hp);
-        rc = tq_fused_vegas(fn, dtype, s->offsets, n_cubes, n_strat, 0, -m_est, s->edges_packed, layout, ni, hw, hc, hp, s->JF,
-                            s->JF2, seed, call++, nullptr, s->ws, s->ws_bytes, stream);
+        if (sweep_ok && starting >= (1 << 20) && starting + 2 * n_cubes <= s->jf2_rows_cap) {
+            rc = tq_fused_vegas_deferred(fn, dtype, s->offsets, n_cubes, n_strat, 0, -m_est, s->edges_packed, ni, s->jf2_rows, s->JF,
+                                         s->JF2, seed, call, s->ws, s->ws_bytes, stream);
+            if (!rc)
+                rc = tq_vegas_hist_sweep(s->offsets, n_cubes, n_strat, dim, dtype, s->jf2_rows, ni, s->hist_pairs,
+                                         s->sweep_dims_per_group, seed, call, s->ws, s->ws_bytes, stream);
+            ++call;
+            pairs_dirty = true;
+        } else {
+            void *hw = nullptr, *hp = nullptr;
+            int64_t* hc = nullptr;
+            if (grid_improve) hist_args(starting, hw, hc, hp);
+            rc = tq_fused_vegas(fn, dtype, s->offsets, n_cubes, n_strat, 0, -m_est, s->edges_packed, layout, ni, hw, hc, hp, s->JF,
+                                s->JF2, seed, call++, nullptr, s->ws, s->ws_bytes, stream);
+        }
         if (rc) return rc;
         if (it > TQ_VEGAS_MAX_PASSES) { set_error("tq_vegas_run_fused: too many iterations"); return TQ_ERR_UNSUPPORTED; }
         double* record = s->records + 4 * (it - 1);

@@ -144,6 +144,19 @@ class VEGASMap:
         elt = 4 if self.dtype == torch.float32 else 8
         return self.dim * self.N_intervals * 4 * elt >= self.records_min_bytes  # = tq_vegas_map_records_bytes
 
+    sweep_l2_budget = 64 << 20  # bytes of one histogram band tq_vegas_hist_sweep keeps in flight (L2 is 126 MB)
+
+    def sweep_group(self, n_strat):
+        """Dimensions per launch of `tq_vegas_hist_sweep` for this map (0: not applicable).  Large maps only; the bands of a
+        group ((Ni / N_strat) bins x 16 bytes per dimension) must stay resident in L2 while the group's cubes are binned."""
+        if not self.wants_records() or n_strat < 2:
+            return 0
+        # ONE dimension per launch: every bin of the band in flight is then hit ~(rows / Ni) times while it is resident.
+        # With g dimensions per launch the cubes are ordered by the g digits together and only the slowest digit's band
+        # stays resident across the whole group (measured, 8-D Ni=1e7: g=2 19.8 ms per pass, g=1 see profiles/r2).
+        band_bytes = (self.N_intervals // n_strat + 2) * 16
+        return 1 if band_bytes <= self.sweep_l2_budget else 0
+
     def records(self):
         """The record table of the current edges with zeroed histogram fields (opaque uint8 tensor), cached."""
         if self._records is None or self._records_stale:

@@ -544,8 +544,28 @@ def fused_vegas(fn_struct, edges_packed, weights, counts, row_begin, row_end, se
     return out
 
 
-def _vegas_state(vmap, strat, use_records):
-    """(tq_vegas_state, keep-alive tensors) over the map / stratification tensors of a native-loop run."""
+def fused_vegas_deferred(fn_struct, edges_packed, row_begin, row_end, seed, call_idx, offsets, n_strat, JF, JF2, jf2_rows):
+    """A stratified fused pass WITHOUT the histogram: jf^2 of row r goes to jf2_rows[r - row_begin] (tq_fused_vegas_deferred)."""
+    require_cuda(edges_packed, offsets, JF, JF2, jf2_rows)
+    with on_device(edges_packed.device):
+        wsp, wsn = _ws(edges_packed.device)
+        call("tq_fused_vegas_deferred", fn_struct, dtype_code(edges_packed.dtype), ptr(offsets), offsets.shape[0] - 1, n_strat,
+             row_begin, row_end, ptr(edges_packed), edges_packed.shape[1], ptr(jf2_rows), ptr(JF), ptr(JF2),
+             seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, wsp, wsn, stream_ptr(edges_packed.device))
+
+
+def hist_sweep(offsets, n_strat, dim, jf2_rows, n_intervals, hist_pairs, dims_per_group, seed, call_idx):
+    """Bin the rows of a deferred pass band by band into the fp64 pair table (tq_vegas_hist_sweep)."""
+    require_cuda(offsets, jf2_rows, hist_pairs)
+    with on_device(offsets.device):
+        call("tq_vegas_hist_sweep", ptr(offsets), offsets.shape[0] - 1, n_strat, dim, dtype_code(jf2_rows.dtype), ptr(jf2_rows),
+             n_intervals, ptr(hist_pairs), dims_per_group, seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, *_ws(offsets.device),
+             stream_ptr(offsets.device))
+
+
+def _vegas_state(vmap, strat, use_records, sweep=None):
+    """(tq_vegas_state, keep-alive tensors) over the map / stratification tensors of a native-loop run.
+    `sweep` = (dims_per_group, rows capacity) enables the deferred + band-sweep histogram of maps beyond L2."""
     dev, dt = vmap.device, vmap.dtype
     n_cubes = strat.N_cubes_local
     # JF and JF2 must be adjacent ([2, n_cubes]); the constructor's layout is, a user-replaced pair may not be
@@ -561,11 +581,13 @@ def _vegas_state(vmap, strat, use_records):
     ws = workspace(dev)
     packed = vmap.records() if use_records else vmap.packed_edges()
     hist = None if use_records else vmap.hist_pairs()
+    jf2 = torch.empty(sweep[1], dtype=dt, device=dev) if sweep else None
     state = _lib.tq_vegas_state(
-        ptr(vmap.x_edges), ptr(vmap.dx_edges), ptr(packed), ptr(vmap.weights), ptr(vmap.counts), ptr(hist), ptr(strat.dh), ptr(nh),
+        ptr(vmap.x_edges), ptr(vmap.dx_edges), ptr(packed), ptr(vmap.weights), ptr(vmap.counts), ptr(hist), ptr(jf2),
+        sweep[1] if sweep else 0, sweep[0] if sweep else 0, 0, ptr(strat.dh), ptr(nh),
         ptr(offsets), ptr(strat.JF), ptr(strat.JF2), ptr(records), ptr(status), ptr(scratch), scratch.numel(), ws.data_ptr(),
         ws.numel(), _lib.TQ_EDGES_RECORDS if use_records else _lib.TQ_EDGES_PAIRS)
-    return state, (ints, records, status, scratch, packed, hist), nh, offsets
+    return state, (ints, records, status, scratch, packed, hist, jf2), nh, offsets
 
 
 def _vegas_finish(vmap, strat, use_records, nh, offsets):
@@ -588,7 +610,12 @@ def vegas_run_fused(fn_struct, vmap, strat, N, max_iterations, eps_rel, eps_abs,
     device tensor over the ranks in place on the current stream (torch.distributed.all_reduce)."""
     dev, dt = vmap.device, vmap.dtype
     use_records = bool(use_grid_improve) and vmap.wants_records()
-    state, keep, nh, offsets = _vegas_state(vmap, strat, use_records)
+    sweep = None
+    if use_records and shard is None and vmap.sweep_group(strat.N_strat) >= 1 and N // (max_iterations + 5) >= (1 << 20):
+        # maps beyond L2 on one GPU: pair tables + deferred histogram, binned band by band (tq_vegas_hist_sweep)
+        use_records = False
+        sweep = (vmap.sweep_group(strat.N_strat), 4 * (N // (max_iterations + 5)) + 2 * strat.N_cubes + 1024)
+    state, keep, nh, offsets = _vegas_state(vmap, strat, use_records, sweep)
     result = _lib.tq_vegas_result()
     common = (fn_struct, dtype_code(dt), N, max_iterations, float(eps_rel), float(eps_abs), int(bool(use_grid_improve)),
               int(bool(use_warmup)), vmap.N_intervals, strat.N_strat, strat.N_cubes, float(strat.V_cubes), float(vmap.alpha),
