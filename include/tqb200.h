@@ -245,10 +245,12 @@ TQ_API int tq_fused_vegas(const tq_integrand* fn_host, int32_t dtype, const int6
                    int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* hist_pairs,
                    void* JF, void* JF2, uint64_t seed, uint32_t call_idx, double* out_f64, void* ws,
                    size_t ws_bytes, void* stream);
-/* The same pass on one rank of a multi-GPU run.  Cubes are dealt to the ranks block-cyclically in blocks of
- * 2^cube_block_log2 cubes; offsets/JF/JF2 index this rank's cubes only (n_cubes = how many it owns), local cube l being
- * global cube l + (((l >> cube_block_log2) * (world - 1) + rank) << cube_block_log2), which keys its Philox stream and
- * gives its position in the unit cube -- so every world size draws exactly the samples of the single-GPU run.
+/* The same pass on one rank of a multi-GPU run.  Cubes are dealt to the ranks in blocks of B = 2^cube_block_log2 cubes:
+ * round b (world consecutive blocks) gives every rank one block, rank r the one at position (r + skew(b)) % world with
+ * skew(b) = b + (b>>3) + (b>>6) + ... + (b>>18) (a rotation, so that no rank owns a fixed digit of the cube index).
+ * offsets/JF/JF2 index this rank's cubes only (n_cubes = how many it owns); local cube l = global cube
+ * ((l / B * world + (rank + skew(l / B)) % world) * B + l % B, which keys its Philox stream and gives its position in the
+ * unit cube -- so every world size draws exactly the samples of the single-GPU run.
  * Warm-up passes (offsets == NULL) are sharded by the caller through [row_begin, row_end). */
 TQ_API int tq_fused_vegas_sharded(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
                            int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_packed,

@@ -54,6 +54,11 @@ def case(label, fn, dim, dt, ns, ni, nh_mean, modes=("arrays", "pairs")):
             h.zero_()
             run = lambda: ops.fused_vegas(s, vm.packed_edges(), None, None, 0, M, 1, 7, offsets=offsets, n_strat=ns, JF=JF[0],
                                           JF2=JF[1], hist_pairs=h)
+        elif mode == "tile":  # whole pass (row_end < 0: count read on the device) -> band-privatised tile kernel when it applies
+            h = vm.hist_pairs()
+            h.zero_()
+            run = lambda: ops.fused_vegas(s, vm.packed_edges(), None, None, 0, -M, 1, 7, offsets=offsets, n_strat=ns, JF=JF[0],
+                                          JF2=JF[1], hist_pairs=h)
         elif mode == "records":
             rec = vm.records()
             run = lambda: ops.fused_vegas(s, None, None, None, 0, M, 1, 7, offsets=offsets, n_strat=ns, JF=JF[0], JF2=JF[1],
@@ -75,7 +80,7 @@ def case(label, fn, dim, dt, ns, ni, nh_mean, modes=("arrays", "pairs")):
                                           JF2=JF[1])
         run()
         torch.cuda.synchronize()
-        if mode in ("pairs", "sweep"):
+        if mode in ("pairs", "sweep", "tile"):
             vm.unpack_hist()
         if mode == "records":
             vm.unpack_records()
@@ -95,10 +100,10 @@ def case(label, fn, dim, dt, ns, ni, nh_mean, modes=("arrays", "pairs")):
 
 which = sys.argv[1:] or ["v8", "v16", "v8ref", "v4"]
 if "v8" in which:
-    case("8D f64 osc Ns=8 Ni=4096 nh=5", F.GenzOscillatory(8, a=0.5, u=0.3), 8, torch.float64, 8, 4096, 5, ("arrays", "pairs", "nohist"))
-    case("8D f32 osc Ns=8 Ni=4096 nh=5", F.GenzOscillatory(8, a=0.5, u=0.3), 8, torch.float32, 8, 4096, 5, ("arrays", "pairs", "nohist"))
+    case("8D f64 osc Ns=8 Ni=4096 nh=5", F.GenzOscillatory(8, a=0.5, u=0.3), 8, torch.float64, 8, 4096, 5, ("arrays", "pairs", "tile", "nohist"))
+    case("8D f32 osc Ns=8 Ni=4096 nh=5", F.GenzOscillatory(8, a=0.5, u=0.3), 8, torch.float32, 8, 4096, 5, ("arrays", "pairs", "tile", "nohist"))
 if "v16" in which:
-    case("16D f32 prodpeak Ns=3 Ni=4096 nh=9", F.GenzProductPeak(16, a=2.0, u=0.5), 16, torch.float32, 3, 4096, 9, ("arrays", "pairs", "nohist"))
+    case("16D f32 prodpeak Ns=3 Ni=4096 nh=9", F.GenzProductPeak(16, a=2.0, u=0.5), 16, torch.float32, 3, 4096, 9, ("arrays", "pairs", "tile", "nohist"))
 if "v8ref" in which:
     case("8D f64 osc Ns=8 Ni=1e7 nh=5", F.GenzOscillatory(8, a=0.5, u=0.3), 8, torch.float64, 8, 10_000_000, 5, ("arrays", "pairs", "records", "sweep", "deferred"))
     case("7D f64 osc Ns=5 Ni=3e6 nh=7", F.GenzOscillatory(7, a=0.5, u=0.3), 7, torch.float64, 5, 3_000_000, 7, ("arrays", "records", "sweep"))
@@ -117,3 +122,6 @@ if "l2gran" in which:
         prev = _lib.l2_fetch_granularity(dev, gran)
         print(f"-- cudaLimitMaxL2FetchGranularity {gran} (was {prev})", flush=True)
         case("8D f64 osc Ns=8 Ni=1e7 nh=5", F.GenzOscillatory(8, a=0.5, u=0.3), 8, torch.float64, 8, 10_000_000, 5, ("sweep", "deferred"))
+if "tile_small" in which:
+    case("6D f64 gauss Ns=6 Ni=1000 nh=6 (tile)", F.GenzGaussian(6, a=3.0, u=0.5), 6, torch.float64, 6, 1000, 6, ("arrays", "pairs", "tile"))
+    case("7D f32 osc Ns=5 Ni=777 nh=4 (tile)", F.GenzOscillatory(7, a=0.5, u=0.3), 7, torch.float32, 5, 777, 4, ("arrays", "pairs", "tile"))

@@ -221,12 +221,23 @@ fused_nc_kernel(const tq_integrand P, const T* __restrict__ nodes, const T* __re
 // Map edges arrive packed as {x_edge[k], dx_edge[k]} pairs: one 8/16-byte gather per dimension.
 constexpr int FV_BLOCK = 256;
 
-// Multi-GPU: cubes are dealt to the ranks block-cyclically (blocks of 2^lb cubes), so that the hot regions VEGAS
-// concentrates its samples on are spread over all ranks.  A rank's state arrays (dh, nh, offsets, JF, JF2) hold only
-// its own cubes, numbered locally 0..n_local; local cube l is global cube l + (((l >> lb) * (world-1) + rank) << lb).
+// Multi-GPU: cubes are dealt to the ranks in blocks of 2^lb cubes, so that the hot regions VEGAS concentrates its samples
+// on are spread over all ranks.  Round b (= `world` consecutive blocks) gives every rank one block; WHICH one rotates with
+// the round: rank r takes position (r + skew(b)) % world.  A plain r-th-block rule would hand each rank a fixed digit of
+// the cube index whenever world and the block size are powers of N_strat (8 GPUs, N_strat = 8: rank = digit 4 = a slab of
+// dimension 4), and the samples VEGAS allocates per slab differ (measured: 47 % strong-scaling efficiency at 8 GPUs).
+// A rank's state arrays (dh, nh, offsets, JF, JF2) hold only its own cubes, numbered locally 0..n_local.
 struct CubeShard {
-    uint32_t lb, mul, add;  // log2(block), world - 1, rank
-    __device__ __forceinline__ uint32_t global_cube(uint32_t l) const { return l + ((((l >> lb) * mul) + add) << lb); }
+    uint32_t lb, rank;
+    FastDiv world;
+    __host__ __device__ static uint32_t skew(uint32_t b) { return b + (b >> 3) + (b >> 6) + (b >> 9) + (b >> 12) + (b >> 15) + (b >> 18); }
+    __device__ __forceinline__ uint32_t global_cube(uint32_t l) const {
+        if (world.d <= 1) return l;
+        const uint32_t b = l >> lb;
+        const uint32_t t = rank + skew(b);
+        const uint32_t pos = t - world.div(t) * world.d;  // (rank + skew(b)) % world
+        return ((b * world.d + pos) << lb) + (l & ((1u << lb) - 1u));
+    }
 };
 #ifndef FV_MIN_CTAS
 #define FV_MIN_CTAS 6
@@ -457,6 +468,208 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
         }
     }
     if (!STRAT) grid_sum_finish<2>(acc, sh, partials, ticket, out);
+}
+
+// ------------------------------------------------------------------ fused VEGAS pass, band-privatised (tile) version
+// Shared-memory privatised histograms for maps that stay in L2 (north_star).  Cube c = sum_d p_d N_strat^d
+// has its samples of dimension d inside the band of ~Ni / N_strat bins selected by digit p_d.  A TILE is an aligned
+// block of N_strat^g consecutive cubes: the g low digits run over everything, the digits of the dim - g HIGH dimensions are
+// fixed, so for those dimensions one CTA stages the band's {x, dx} edges in shared memory (the gather becomes a 16-byte
+// shared-memory read: 0.3 instead of ~1 L1TEX cycles per lane) and keeps a private {sum jf^2, count} band that takes
+// shared-memory atomics (0.65 cycles per sample and dimension instead of 1.8 for an L2 reduction sector) and is flushed
+// once per tile with sector-paired reductions.  The low dimensions go through L2 exactly like in fused_vegas_kernel.
+// Tiles are handed out in order by a global counter; one 1024-thread CTA per SM (the bands need up to ~200 KB).
+constexpr int FT_BLOCK = 1024;
+constexpr int FT_SLICE = FT_BLOCK / 2 + 4;
+
+template <int FAM, typename T>
+__global__ void __launch_bounds__(FT_BLOCK, 1)
+fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offsets, uint32_t n_cubes, CubeShard shard, FastDiv ns_div,
+                        T inv_ns, const typename Pair2<T>::type* __restrict__ edges, long long ni, double* __restrict__ hist,
+                        T* __restrict__ JF, T* __restrict__ JF2, uint64_t seed, uint32_t call, int g, uint32_t tile_cubes,
+                        FastDiv tile_div, int band_w, unsigned int* next_tile) {
+    constexpr int LANES = U01<T>::LANES;
+    using P2 = typename Pair2<T>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ FnShared<T> S;
+    __shared__ long long s_off[2][FT_SLICE];
+    __shared__ unsigned short s_cube[2][FT_BLOCK];
+    __shared__ int s_blo[TQ_MAX_DIM];
+    __shared__ unsigned int s_tile;
+    stage_integrand<T>(P, S);
+    const int dim = S.dim;
+    const int ns = dim - g;  // band (high) dimensions
+    // dynamic shared memory: edges bands | weight bands | jf^2 of the rows in flight | count bands | low-dim bin ids | band ids
+    P2* s_edge = reinterpret_cast<P2*>(smem_raw);                                  // [ns][band_w]
+    T* s_hw = reinterpret_cast<T*>(s_edge + (size_t)ns * band_w);                 // [ns][band_w]
+    double* s_jf2 = reinterpret_cast<double*>(s_hw + (((size_t)ns * band_w + 1) & ~(size_t)1));  // [FT_BLOCK]
+    unsigned int* s_hc = reinterpret_cast<unsigned int*>(s_jf2 + FT_BLOCK);       // [ns][band_w]
+    int* s_ids = reinterpret_cast<int*>(s_hc + (size_t)ns * band_w);              // [g][FT_BLOCK]
+    unsigned short* s_bid = reinterpret_cast<unsigned short*>(s_ids + (size_t)g * FT_BLOCK);  // [ns][FT_BLOCK]
+    const T nif = (T)ni;
+    const T nsf = (T)ns_div.d;
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31, word = lane & 1;
+    int buf = 0;
+    for (;;) {
+        __syncthreads();  // previous tile flushed
+        if (threadIdx.x == 0) s_tile = atomicAdd(next_tile, 1u);
+        __syncthreads();
+        const uint64_t c_first64 = (uint64_t)s_tile * tile_cubes;
+        if (c_first64 >= n_cubes) break;
+        const uint32_t c_first = (uint32_t)c_first64;
+        const uint32_t c_end = c_first + tile_cubes < n_cubes ? c_first + tile_cubes : n_cubes;
+        const int64_t r_lo = __ldg(&offsets[c_first]), r_hi = __ldg(&offsets[c_end]);
+        if (threadIdx.x < ns) {  // the band of every high dimension: digit (g + sd) of the tile's GLOBAL cube ids
+            uint32_t q = tile_div.div(shard.global_cube(c_first));
+            uint32_t p = 0;
+            for (int sd = 0; sd <= (int)threadIdx.x; ++sd) {
+                const uint32_t qq = ns_div.div(q);
+                p = q - qq * ns_div.d;
+                q = qq;
+            }
+            long long lo = ((long long)p * ni) / (long long)ns_div.d - 1;  // one bin of slack on either side (rounding of y * Ni)
+            s_blo[threadIdx.x] = (int)(lo < 0 ? 0 : lo);
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < ns * band_w; idx += FT_BLOCK) {
+            const int sd = idx / band_w, wdx = idx - sd * band_w;
+            const long long k = (long long)s_blo[sd] + wdx;
+            P2 e;
+            e.x = (T)0;
+            e.y = (T)0;
+            if (k < ni) e = __ldg(&edges[(int64_t)(g + sd) * ni + k]);
+            s_edge[idx] = e;
+            s_hw[idx] = (T)0;
+            s_hc[idx] = 0u;
+        }
+        __syncthreads();
+        long long c_lo = c_first;
+        for (int64_t rb = r_lo; rb < r_hi; rb += FT_BLOCK, buf ^= 1) {
+            const int64_t re = rb + FT_BLOCK < r_hi ? rb + FT_BLOCK : r_hi;
+            const int64_t row = rb + threadIdx.x;
+            const bool active = row < re;
+            if (threadIdx.x < FT_SLICE) {
+                const long long c = c_lo + threadIdx.x;
+                const long long lo = __ldg(&offsets[c < n_cubes ? c : n_cubes]);
+                const long long hi = __ldg(&offsets[c + 1 < n_cubes ? c + 1 : n_cubes]);
+                s_off[buf][threadIdx.x] = lo;
+                const long long a = lo > rb ? lo : rb, b = hi < re ? hi : re;
+                for (long long r = a; r < b; ++r) s_cube[buf][r - rb] = (unsigned short)threadIdx.x;
+            }
+            __syncthreads();
+            T jf = (T)0, jf2 = (T)0;
+            unsigned key = 0xffffu;
+            if (active) {
+                key = s_cube[buf][threadIdx.x];
+                const uint32_t i0 = shard.global_cube((uint32_t)(c_lo + key));
+                const uint32_t i1 = (uint32_t)(row - s_off[buf][key]);
+                uint32_t c = i0;
+                Integrand<FAM, T> fn;
+                fn.init();
+                T jac = (T)1;
+                for (int d0 = 0; d0 < dim; d0 += LANES) {
+                    T u[LANES];
+                    philox_block<T>(seed, call, i0, i1, (uint32_t)(d0 / LANES), u);
+#pragma unroll
+                    for (int j = 0; j < LANES; ++j) {
+                        const int d = d0 + j;
+                        if (d < dim) {
+                            const uint32_t q = ns_div.div(c);
+                            const uint32_t p = c - q * ns_div.d;
+                            c = q;
+                            T y = div_by_const(add_rn((T)p, u[j]), nsf, inv_ns);
+                            if (y >= (T)1) y = (T)0.999999;
+                            const T t = mul_rn(y, nif);
+                            const T fl = floor(t);
+                            long long k = (long long)fl;
+                            k = k < 0 ? 0 : (k >= ni ? ni - 1 : k);
+                            const T o = sub_rn(t, fl);
+                            P2 e;
+                            if (d < g) {
+                                e = __ldg(&edges[(int64_t)d * ni + k]);
+                                s_ids[d * FT_BLOCK + threadIdx.x] = (int)k;
+                            } else {
+                                const int sd = d - g;
+                                const long long loc = k - s_blo[sd];
+                                if (loc >= 0 && loc < band_w) {
+                                    e = s_edge[sd * band_w + (int)loc];
+                                    s_bid[sd * FT_BLOCK + threadIdx.x] = (unsigned short)loc;
+                                } else {  // outside the staged band: cannot happen with the slack for Ni <= 2^20; kept exact anyway
+                                    e = __ldg(&edges[(int64_t)d * ni + k]);
+                                    s_bid[sd * FT_BLOCK + threadIdx.x] = 0xffffu;
+                                }
+                            }
+                            const T x = add_rn(e.x, mul_rn(e.y, o));
+                            jac = mul_rn(jac, mul_rn(nif, e.y));
+                            fn.step(add_rn(mul_rn(x, S.size[d]), S.start[d]), d, S);
+                        }
+                    }
+                }
+                const T f = mul_rn(fn.finish(S), S.scale);
+                jf = mul_rn(f, jac);
+                jf2 = mul_rn(jf, jf);
+                for (int sd = 0; sd < ns; ++sd) {  // band dimensions: private shared-memory histogram
+                    const unsigned loc = s_bid[sd * FT_BLOCK + threadIdx.x];
+                    if (loc != 0xffffu) {
+                        atomicAdd(&s_hw[sd * band_w + loc], jf2);
+                        atomicAdd(&s_hc[sd * band_w + loc], 1u);
+                    } else {  // recompute the bin of dimension g + sd and update the global table directly
+                        const int d = g + sd;
+                        T u[LANES];
+                        philox_block<T>(seed, call, i0, i1, (uint32_t)(d / LANES), u);
+                        T ud = u[0];
+#pragma unroll
+                        for (int l = 1; l < LANES; ++l)
+                            if (d % LANES == l) ud = u[l];
+                        uint32_t q = i0, p = 0;
+                        for (int dd = 0; dd <= d; ++dd) {
+                            const uint32_t qq = ns_div.div(q);
+                            p = q - qq * ns_div.d;
+                            q = qq;
+                        }
+                        T y = div_by_const(add_rn((T)p, ud), nsf, inv_ns);
+                        if (y >= (T)1) y = (T)0.999999;
+                        long long k = (long long)floor(mul_rn(y, nif));
+                        k = k < 0 ? 0 : (k >= ni ? ni - 1 : k);
+                        atomicAdd(hist + ((int64_t)d * ni + k) * 2, (double)jf2);
+                        atomicAdd(hist + ((int64_t)d * ni + k) * 2 + 1, 1.0);
+                    }
+                }
+            }
+            // low dimensions: sector-paired L2 reductions (lanes 2i / 2i+1 serve sample i of a 16-sample half)
+            s_jf2[threadIdx.x] = active ? (double)jf2 : -1.0;
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int src = wbase + (lane >> 1) + 16 * h;
+                const double sv = s_jf2[src];
+                if (sv >= 0.0 || sv != sv) {  // active source row (NaN weights are kept, like the direct path keeps them)
+                    const double v = word ? 1.0 : sv;
+                    for (int d = 0; d < g; ++d) atomicAdd(hist + ((int64_t)d * ni + s_ids[d * FT_BLOCK + src]) * 2 + word, v);
+                }
+            }
+            __syncwarp();
+            {
+                const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+                T a = jf, b = jf2;
+                segmented_warp_sum2<T>(key, a, b);
+                if (active && (lane == 0 || prev != key)) {
+                    atomicAdd(&JF[c_lo + key], a);
+                    atomicAdd(&JF2[c_lo + key], b);
+                }
+                c_lo += s_cube[buf][(int)(re - rb) - 1];
+            }
+        }
+        __syncthreads();  // every row of the tile is binned
+        for (int idx = threadIdx.x; idx < ns * band_w * 2; idx += FT_BLOCK) {  // flush: lanes 2i / 2i+1 -> {sum, count} of bin i
+            const int b = idx >> 1, wd = idx & 1;
+            const unsigned int cnt = s_hc[b];
+            if (cnt) {
+                const int sd = b / band_w, wdx = b - sd * band_w;
+                atomicAdd(hist + ((int64_t)(g + sd) * ni + s_blo[sd] + wdx) * 2 + wd, wd ? (double)cnt : (double)s_hw[b]);
+            }
+        }
+    }
 }
 
 // {x_edges[d,k], dx_edges[d,k]} -> packed pairs [dim, Ni]
@@ -887,7 +1100,10 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
     if (rc) return rc;
     TQ_REQUIRE(world >= 1 && rank >= 0 && rank < world && cube_block_log2 >= 0 && cube_block_log2 < 31,
                "tq_fused_vegas: bad cube shard (block 2^%d, rank %d of %d)", cube_block_log2, rank, world);
-    const CubeShard shard = {(uint32_t)cube_block_log2, (uint32_t)(world - 1), (uint32_t)rank};
+    CubeShard shard;
+    shard.lb = (uint32_t)cube_block_log2;
+    shard.rank = (uint32_t)rank;
+    shard.world.set((uint32_t)world);
     const bool strat = offsets != nullptr;
     const bool rows_from_offsets = row_end < 0;  // count stays on the device; -row_end is the sizing estimate
     if (rows_from_offsets) {
@@ -949,6 +1165,57 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
     cudaStream_t st = as_stream(stream);
     FastDiv ns_div;
     ns_div.set((uint32_t)(strat ? n_strat : 1));
+    // Band-privatised tile version (fused_vegas_tile_kernel): whole stratified passes into the pair table, when some high
+    // dimensions' bands fit shared memory and there are enough tiles to balance one CTA per SM.
+    // Measured on B200 (profiles/r2/exp_tile.txt): fp32 +8 .. +10 % over the all-L2 version (16-D N_strat=3: 8.07e9 -> 8.75e9
+    // samples/s; 8-D N_strat=8: 1.65e10 -> 1.81e10), fp64 -5 % (8-D: 1.476e10 -> 1.405e10: a shared-memory fp64 atomicAdd is a
+    // 64-bit compare-and-swap loop that retries when two lanes of a warp meet in a 512-bin band).  Default: fp32 only.
+    static const int tile_env = getenv("TQ_FV_TILE") ? atoi(getenv("TQ_FV_TILE")) : -1;  // 0: never, 1: always, default: fp32
+    const bool tile_ok = tile_env == 1 || (tile_env != 0 && dtype == TQ_F32);
+    if (tile_ok && hist_mode == HIST_PAIRS && strat && rows_from_offsets && n_strat >= 2 && dim >= 2 &&
+        n_intervals <= (1 << 20)) {
+        const int64_t band_w = (n_intervals + n_strat - 1) / n_strat + 3;
+        const size_t per_band = (size_t)band_w * (2 * elt + elt + 4);
+        int best_g = -1;
+        size_t best_smem = 0;
+        uint64_t best_tile = 0;
+        for (int sb = dim - 1; sb >= 1 && band_w < 65535; --sb) {
+            const int g = dim - sb;
+            uint64_t tile_cubes = 1;
+            for (int i = 0; i < g; ++i) tile_cubes *= (uint64_t)n_strat;
+            if (tile_cubes > (uint64_t)n_cubes || (uint64_t)n_cubes % tile_cubes) continue;
+            const uint64_t n_tiles = (uint64_t)n_cubes / tile_cubes;
+            if (n_tiles < (uint64_t)sms * 4) break;                               // larger tiles only get fewer
+            if (world > 1 && ((1ull << cube_block_log2) % tile_cubes)) continue;  // a tile must not straddle a rank's cube block
+            const size_t need = (size_t)sb * per_band + 16 + (size_t)FT_BLOCK * 8 + (size_t)g * FT_BLOCK * 4 + (size_t)sb * FT_BLOCK * 2;
+            if (need > 200 * 1024) continue;
+            if ((uint64_t)nrows / n_tiles < 4ull * sb * band_w) continue;         // the flush must stay small next to the tile's rows
+            best_g = g;
+            best_smem = need;
+            best_tile = tile_cubes;
+            break;
+        }
+        if (best_g > 0) {
+            unsigned int* next_tile = w.take<unsigned int>(64);
+            if (!next_tile) { set_error("tq_fused_vegas: workspace too small"); return TQ_ERR_WORKSPACE; }
+            cudaMemsetAsync(next_tile, 0, sizeof(unsigned int), st);
+            FastDiv tile_div;
+            tile_div.set((uint32_t)best_tile);
+            const uint64_t n_tiles = (uint64_t)n_cubes / best_tile;
+            const unsigned grid = (unsigned)(n_tiles < (uint64_t)sms ? n_tiles : (uint64_t)sms);
+            TQ_DISPATCH_DTYPE(dtype, {
+                using P2 = typename Pair2<T>::type;
+                const T inv_ns = (T)1 / (T)n_strat;
+                TQ_DISPATCH_FAMILY(fn_host->family, {
+                    cudaFuncSetAttribute(fused_vegas_tile_kernel<FAM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                    fused_vegas_tile_kernel<FAM, T><<<TQ_GRID(grid), FT_BLOCK, best_smem, st>>>(
+                        *fn_host, (const long long*)offsets, (uint32_t)n_cubes, shard, ns_div, inv_ns, (const P2*)edges_packed, n_intervals,
+                        (double*)hist_pairs, (T*)JF, (T*)JF2, seed, call_idx, best_g, (uint32_t)best_tile, tile_div, (int)band_w, next_tile);
+                });
+            });
+            return check_launch("fused_vegas_tile_kernel");
+        }
+    }
     TQ_DISPATCH_DTYPE(dtype, {
         const T inv_ns = (T)1 / (T)(strat ? n_strat : 1);  // RN(1 / N_strat) in the working precision (div_by_const)
         TQ_DISPATCH_FAMILY(fn_host->family, {

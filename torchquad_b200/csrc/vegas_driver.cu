@@ -11,6 +11,7 @@
 //                         evaluates them, one 8-byte read-back per pass sizes its view.
 //   tq_vegas_schedule     the checkpoint decision alone (host only; tested against the oracle on CPU).
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "common.cuh"
@@ -237,6 +238,38 @@ static int run_fused(const tq_integrand* fn, int32_t dtype, int64_t N, int32_t m
     return TQ_OK;
 }
 
+// Optional phase timing of the sharded loop (TQ_VEGAS_TIMING=1): CUDA events around every phase of every pass, summed and
+// printed per rank when the run ends.  The all-reduce phase includes the wait for the slowest rank, i.e. the load imbalance.
+struct PhaseTimer {
+    bool on;
+    cudaStream_t st;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> phase;
+    explicit PhaseTimer(cudaStream_t s) : on(getenv("TQ_VEGAS_TIMING") != nullptr), st(s) {}
+    void mark(int ph) {  // start of phase `ph` (= end of the previous one)
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        phase.push_back(ph);
+    }
+    void report(int rank, const char* const* names, int nph) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        std::vector<double> tot(nph, 0.0);
+        for (size_t i = 0; i + 1 < ev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            if (phase[i] >= 0 && phase[i] < nph) tot[phase[i]] += ms;
+        }
+        fprintf(stderr, "[tq timing rank %d]", rank);
+        for (int k = 0; k < nph; ++k) fprintf(stderr, " %s %.3f ms;", names[k], tot[k]);
+        fprintf(stderr, "\n");
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+};
+
 // Multi-GPU fused run: every rank owns a block-cyclic share of the hypercubes -- its slice of dh / nh /
 // offsets / JF / JF2 never leaves the GPU -- and the map is replicated.  Per pass ONE collective: the fp64 buffer
 // [{sum jf^2, count} pairs of the map histogram | I, sigma^2, sum d^beta, sum nh] is summed over the ranks through the
@@ -284,16 +317,21 @@ static int run_fused_sharded(const tq_integrand* fn, int32_t dtype, int64_t N, i
     };
     cudaMemsetAsync(s->status, 0, 4 * (size_t)max_passes * sizeof(int32_t), st);
     cudaMemsetAsync(tail, 0, 8 * sizeof(double), st);
+    PhaseTimer tm(st);
+    static const char* const PH[] = {"get_NH", "pass", "strat_update", "all_reduce", "normalise+map_update", "warmup_pass"};
     if (warmup) {  // vegas.py:211-266, rows split evenly over the ranks
         const int64_t ns = starting / 5;
         const int64_t r0 = ns * rank / world, r1 = ns * (rank + 1) / world;
         for (int w = 0; w < 5; ++w) {
+            tm.mark(5);
             int rc = tq_fused_vegas(fn, dtype, nullptr, 0, 1, r0, r1, s->edges_packed, layout, ni, nullptr, nullptr,
                                     recs ? nullptr : comm, nullptr, nullptr, seed, call++, s->records, s->ws, s->ws_bytes, stream);
             if (rc) return rc;
             if (recs && (rc = records_to_pairs_launch(s->edges_packed, comm, dim, ni, dtype, stream))) return rc;
             fevals += ns;
+            tm.mark(3);
             if ((rc = allreduce(0, hist_len))) return rc;
+            tm.mark(4);
             if ((rc = update_map())) return rc;
         }
     }
@@ -303,8 +341,10 @@ static int run_fused_sharded(const tq_integrand* fn, int32_t dtype, int64_t N, i
     int first_rec = 0;
     while (true) {
         ++it;
+        tm.mark(0);
         int rc = strat_nh_launch(s->dh, n_local, (double)starting, dtype, s->nh, s->offsets, s->JF, jf_bytes, s->ws, s->ws_bytes, stream);
         if (rc) return rc;
+        tm.mark(1);
         const int64_t m_est = starting / world + 2 * n_local + 1024;
         rc = tq_fused_vegas_sharded(fn, dtype, s->offsets, n_local, n_strat, 0, -m_est, s->edges_packed, layout, ni, nullptr, nullptr,
                                     grid_improve && !recs ? comm : nullptr, s->JF, s->JF2, seed, call++, lb, rank, world, nullptr,
@@ -313,12 +353,16 @@ static int run_fused_sharded(const tq_integrand* fn, int32_t dtype, int64_t N, i
         if (grid_improve && recs && (rc = records_to_pairs_launch(s->edges_packed, comm, dim, ni, dtype, stream))) return rc;
         if (it > TQ_VEGAS_MAX_PASSES) { set_error("tq_vegas_run_fused_sharded: too many iterations"); return TQ_ERR_UNSUPPORTED; }
         // local estimator sums + unnormalised d^beta, then the pass's one collective, then the normalisation
+        tm.mark(2);
         if ((rc = strat_update_partial_launch(s->JF, s->JF2, s->nh, n_local, v_cubes, beta, dtype, s->dh, tail, s->ws, s->ws_bytes, stream))) return rc;
+        tm.mark(3);
         if ((rc = grid_improve ? allreduce(0, hist_len + 4) : allreduce(hist_len, 4))) return rc;
+        tm.mark(4);
         double* record = s->records + 4 * (it - 1);
         cudaMemcpyAsync(record, tail, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st);
         if ((rc = strat_normalise_launch(s->dh, n_local, record, dtype, stream))) return rc;
         if (grid_improve && (rc = update_map())) return rc;
+        tm.mark(-1);
         if (it % 5 > 0) continue;
         const int nrec = it - first_rec;
         std::vector<double> rec(4 * nrec);
@@ -337,6 +381,7 @@ static int run_fused_sharded(const tq_integrand* fn, int32_t dtype, int64_t N, i
         if (schedule_checkpoint<T>(blk, eps_rel, eps_abs, N, fevals, it, max_it, increment, starting)) break;
         first_rec = it;
     }
+    tm.report(rank, PH, 6);
     out->it = it;
     out->n_block = (int32_t)blk.res.size();
     out->fevals = fevals;

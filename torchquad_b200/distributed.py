@@ -47,27 +47,36 @@ def shard_range(total, rank=None, world=None):
     return (total * rank) // world, (total * (rank + 1)) // world
 
 
+def _skew(b):
+    """Rotation of a round's blocks among the ranks (include/tqb200.h, tq_fused_vegas_sharded); ints or int64 tensors."""
+    return b + (b >> 3) + (b >> 6) + (b >> 9) + (b >> 12) + (b >> 15) + (b >> 18)
+
+
 def cube_shard(n_cubes, rank=None, world=None):
-    """Block-cyclic deal of the VEGAS hypercubes: (log2 block, cubes owned by this rank), or None when there are too few
+    """Deal of the VEGAS hypercubes to the ranks: (log2 block, cubes owned by this rank), or None when there are too few
     cubes to share (every rank then runs the whole problem redundantly, no collective).  Blocks of up to 4096 cubes
-    spread the regions VEGAS concentrates its samples on over all ranks; local cube l of rank r is global cube
-    l + (((l >> lb) * (world - 1) + r) << lb) (include/tqb200.h, tq_fused_vegas_sharded)."""
+    spread the regions VEGAS concentrates its samples on over all ranks; round b of `world` consecutive blocks gives rank r
+    the block at position (r + skew(b)) % world -- the rotation keeps a rank from owning a fixed digit of the cube index
+    (a slab of one dimension) when world and the block size are powers of N_strat."""
     if rank is None or world is None:
         rank, world = rank_and_world()
     if world == 1 or n_cubes < 16 * world:
         return None
     lb = min(12, (n_cubes // (8 * world)).bit_length() - 1)
     block = 1 << lb
-    full, rem = divmod(n_cubes, block)
-    owned = full // world + (1 if rank < full % world else 0)
-    n_local = owned * block + (rem if full % world == rank else 0)
+    full, rem = divmod(n_cubes, block)       # full blocks, cubes of the trailing partial block
+    rounds, last = divmod(full, world)       # full rounds, full blocks of the last (incomplete) round
+    pos = (rank + _skew(rounds)) % world     # this rank's position in the last round
+    owned = rounds + (1 if pos < last else 0)
+    n_local = owned * block + (rem if pos == last else 0)
     return lb, n_local
 
 
 def global_cube_ids(n_local, lb, rank, world, device=None):
     """Global ids of this rank's cubes in local order (int64 tensor), the mapping of `cube_shard`."""
     l = torch.arange(n_local, dtype=torch.int64, device=device)
-    return l + ((((l >> lb) * (world - 1)) + rank) << lb)
+    b = l >> lb
+    return ((b * world + (rank + _skew(b)) % world) << lb) + (l & ((1 << lb) - 1))
 
 
 def all_reduce_sum_(*tensors):
