@@ -573,9 +573,12 @@ def vegas_kernel_roofline(name, wl, info, device):
                 "note": "random 32-byte sector accesses: HBM delivers 64-byte bursts, so 0.5 is the ceiling of this fraction"}
     h = vmap.hist_pairs()
     h.zero_()
-    run = lambda: ops.fused_vegas(s, vmap.packed_edges(), None, None, 0, rows, 1, 7, offsets=offsets, n_strat=strat.N_strat,  # noqa: E731
+    # row_end < 0: the pass reads its row count on the device, exactly like the passes of the run (which selects the
+    # band-privatised tile kernel for fp32)
+    run = lambda: ops.fused_vegas(s, vmap.packed_edges(), None, None, 0, -rows, 1, 7, offsets=offsets, n_strat=strat.N_strat,  # noqa: E731
                                   JF=JF[0], JF2=JF[1], hist_pairs=h)
     t = time_call(run)
+    tile = dt == torch.float32
     h.zero_()
     bins = dim * vmap.N_intervals
     table = torch.zeros((bins, 2), dtype=torch.float64, device=device)
@@ -584,12 +587,13 @@ def vegas_kernel_roofline(name, wl, info, device):
                                         _lib.stream_ptr(device)))
     peak = ops_out.value / t_red
     ach = rows * dim / t
-    e = ncu_entry(name + ":fused_vegas_kernel")
-    return {"kernel": "fused_vegas_kernel<STRAT> (pair layout, one pass)", "bound": "l2 reduction sectors (map resident in L2)",
+    e = ncu_entry(name + (":fused_vegas_tile_kernel" if tile else ":fused_vegas_kernel"))
+    return {"kernel": ("fused_vegas_tile_kernel (slow dimensions' bands in shared memory, one pass)" if tile
+                       else "fused_vegas_kernel<STRAT> (pair layout, one pass)"), "bound": "l2 reduction sectors (map resident in L2)",
             "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G reduction sectors/s", "frac": ach / peak,
             "traffic": e.get("dram_bytes"), "launch_ms": t * 1e3, "rows_per_launch": rows, "samples_per_s": rows / t,
             "algorithmic_sectors_per_sample": dim, "ncu_issue_active_pct": e.get("issue_active_pct"),
-            "ncu_lts_throughput_pct": e.get("lts_throughput_pct"),
+            "ncu_lts_throughput_pct": e.get("lts_throughput_pct"), "ncu_l1tex_throughput_pct": e.get("l1tex_throughput_pct"),
             "peak_source": f"tq_red_microbench: paired RED.F64 alone on a {bins}-bin fp64 pair table, measured in this run"}
 
 

@@ -150,6 +150,25 @@ TQ_API int tq_vegas_map_accumulate(const void* y, const void* jf2, void* weights
 TQ_API int tq_vegas_accumulate_fused(const void* y, const void* f, const void* jac, double volume, void* jf_out, void* weights,
                               int64_t* counts, void* records, int64_t rows, int32_t dim, int64_t n_intervals,
                               int32_t dtype, void* stream);
+/* An unfused VEGAS pass as TWO kernels around the user's integrand (round 2; replaces tq_vegas_strat_sample ->
+ * tq_vegas_map_forward_packed -> ... -> tq_vegas_accumulate_fused whenever the uniforms come from the Philox stream):
+ *  tq_vegas_sample_map: get_Y (vegas_stratification.py:140-165) + get_X / get_Jac (vegas_map.py:44-74) + the
+ *   x*size + start transform of vegas.py:109-110 for rows [row_begin,row_end): x[row - row_begin, :] and
+ *   jac[row - row_begin]; the stratified y is never written.  offsets == NULL: a warm-up pass, y = u * 0.999999 from the
+ *   row-keyed stream (vegas.py:230-233).  x, jac are bit-identical to the three-kernel pipeline.
+ *  tq_vegas_accumulate_regen: jf = (f*volume)*jac -> jf_out (nullable), and VEGASMap.accumulate_weight
+ *   (vegas_map.py:99-111) with the bin ids REGENERATED from the same Philox blocks (same arithmetic: identical bins)
+ *   into `hist_pairs` (fp64 {sum jf^2, count} per bin, tq_vegas_map_unpack_hist), into the large-map `records`, or
+ *   into `weights` / `counts` directly (two reductions per bin: small passes); at most one target, none: jf only (no grid improvement).  jf2_out (nullable) receives jf^2 per row: maps beyond L2 bin those rows
+ *   afterwards, band by band, with tq_vegas_hist_sweep. */
+TQ_API int tq_vegas_sample_map(const int64_t* offsets, int64_t n_cubes, int32_t n_strat, int32_t dim, int32_t dtype,
+                        int64_t row_begin, int64_t row_end, const void* edges_packed, int32_t edges_layout,
+                        int64_t n_intervals, const void* domain, uint64_t seed, uint32_t call_idx, void* x, void* jac,
+                        void* stream);
+TQ_API int tq_vegas_accumulate_regen(const int64_t* offsets, int64_t n_cubes, int32_t n_strat, int32_t dim, int32_t dtype,
+                              int64_t row_begin, int64_t row_end, int64_t n_intervals, const void* f, const void* jac,
+                              double volume, void* jf_out, void* jf2_out, void* hist_pairs, void* records,
+                              void* weights, int64_t* counts, uint64_t seed, uint32_t call_idx, void* stream);
 /* Scratch bytes tq_vegas_map_smooth / tq_vegas_map_update need for a [dim, Ni] map (pass as ws). */
 TQ_API size_t tq_vegas_map_workspace_bytes(int32_t dim, int64_t n_intervals, int32_t dtype);
 /* _smooth_map (:113-172) written to `smoothed[dim, Ni]`; status[0] = 1 when a dimension sums to zero
@@ -362,16 +381,16 @@ TQ_API int tq_vegas_run_fused_sharded(const tq_integrand* fn_host, int32_t dtype
                                const tq_vegas_shard* shard, tq_vegas_result* result_host, void* stream);
 
 /* ---- whole VEGAS run with a CALLBACK integrand (the drop-in path for arbitrary Python callables) -------
- * Same loop and schedule as tq_vegas_run_fused, but every pass materialises its samples: stratified y
- * (tq_vegas_strat_sample) -> x, jac (tq_vegas_map_forward_packed, with the unit-cube -> domain transform) ->
- * `eval(user, rows, &f)` -> jf, histogram (tq_vegas_accumulate_fused) -> per-cube sums
+ * Same loop and schedule as tq_vegas_run_fused, but every pass materialises x: tq_vegas_sample_map (stratified y ->
+ * x, jac with the unit-cube -> domain transform, y itself stays in registers) ->
+ * `eval(user, rows, &f)` -> jf, histogram with regenerated bins (tq_vegas_accumulate_regen) -> per-cube sums
  * (tq_vegas_strat_accumulate) -> updates.  The callback evaluates the integrand on the first `rows` rows of
  * buffers->x on the SAME stream and stores the device pointer of its `rows` values (working dtype) in *f;
  * non-zero return aborts the run with TQ_ERR_CALLBACK.  One 8-byte read-back per pass (rows sizes the
  * callback's view).  Buffers hold `cap_rows` rows; a pass that needs more fails with TQ_ERR_WORKSPACE. */
 typedef int (*tq_eval_callback)(void* user, int64_t rows, const void** f);
 typedef struct tq_vegas_unfused_buffers {
-    void* y;            /* [cap_rows, dim] */
+    void* y;            /* unused since round 2 (the samples y are never materialised); may be NULL */
     void* x;            /* [cap_rows, dim] */
     void* jac;          /* [cap_rows] */
     void* jf;           /* [cap_rows] */

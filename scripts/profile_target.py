@@ -38,8 +38,8 @@ def vegas_final_pass(fn, dim, N, dt, cap):
     else:
         h = vmap.hist_pairs()
         h.zero_()
-        ops.fused_vegas(v._fn_struct, vmap.packed_edges(), None, None, 0, rows, 1, 7, offsets=offsets, n_strat=strat.N_strat,
-                        JF=JF[0], JF2=JF[1], hist_pairs=h)
+        ops.fused_vegas(v._fn_struct, vmap.packed_edges(), None, None, 0, -rows, 1, 7, offsets=offsets, n_strat=strat.N_strat,
+                        JF=JF[0], JF2=JF[1], hist_pairs=h)  # device-side row count, like the passes of the run
     torch.cuda.synchronize()
     print("RESULT", float(r), "fevals", v._nr_of_fevals, "Ni", vmap.N_intervals)
     print("UNITS", rows)

@@ -95,6 +95,9 @@ PROTOTYPES = {
     "tq_vegas_map_forward": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
     "tq_vegas_map_forward_packed": (ctypes.c_int, [c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
     "tq_vegas_accumulate_fused": (ctypes.c_int, [c_p, c_p, c_p, c_f64, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
+    "tq_vegas_sample_map": (ctypes.c_int, [c_p, c_i64, c_i32, c_i32, c_i32, c_i64, c_i64, c_p, c_i32, c_i64, c_p, c_u64, c_u32, c_p, c_p, c_p]),
+    "tq_vegas_accumulate_regen": (ctypes.c_int, [c_p, c_i64, c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_p, c_p, c_f64, c_p, c_p, c_p, c_p,
+                                                 c_p, c_p, c_u64, c_u32, c_p]),
     "tq_vegas_map_accumulate": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i32, c_i64, c_i32, c_p]),
     "tq_vegas_map_workspace_bytes": (c_sz, [c_i32, c_i64, c_i32]),
     "tq_vegas_map_smooth": (ctypes.c_int, [c_p, c_p, c_p, c_i32, c_i64, c_f64, c_i32, c_p, c_p, c_sz, c_p]),

@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "libtqb200.so")
-SOURCES = ["runtime.cu", "rng_mc.cu", "vegas_map.cu", "vegas_strat.cu", "newton_cotes.cu", "fused.cu", "vegas_small.cu",
+SOURCES = ["runtime.cu", "rng_mc.cu", "vegas_map.cu", "vegas_strat.cu", "newton_cotes.cu", "fused.cu", "vegas_unfused.cu", "vegas_small.cu",
            "vegas_driver.cu"]
 NVCC_FLAGS = [
     *os.environ.get("TQ_NVCC_EXTRA", "").split(),

@@ -417,23 +417,29 @@ static int run_unfused(tq_eval_callback eval, void* user, int dim, int32_t dtype
         set_error("tq_vegas_run_unfused: map workspace too small");
         return TQ_ERR_WORKSPACE;
     }
+    const bool to_pairs = !recs && !small && s->hist_pairs != nullptr;
     auto update_map = [&]() -> int {
         if (passes >= max_passes) { set_error("tq_vegas_run_unfused: more than %d passes", max_passes); return TQ_ERR_UNSUPPORTED; }
         int rc = TQ_OK;
         if (recs && (rc = tq_vegas_map_unpack_records(s->edges_packed, s->weights, s->counts, dim, ni, dtype, stream))) return rc;
+        if (to_pairs && (rc = tq_vegas_map_unpack_hist(s->hist_pairs, s->weights, s->counts, dim, ni, dtype, stream))) return rc;
         rc = map_update_launch(s->x_edges, s->dx_edges, s->weights, s->counts, recs ? nullptr : s->edges_packed, dim, ni, alpha,
                                dtype, s->status + 4 * passes, false, s->map_ws, s->map_ws_bytes, stream);
         ++passes;
         if (!rc && recs) rc = tq_vegas_map_pack_records(s->x_edges, s->dx_edges, s->edges_packed, dim, ni, dtype, stream);
         return rc;
     };
-    // y -> x, jac -> f = eval(x) -> jf (+ histogram): everything between sampling and the per-cube sums
-    auto evaluate = [&](int64_t rows, bool hist, void* jf_out) -> int {
+    // One pass around the integrand in two kernels (vegas_unfused.cu): x, jac straight from the Philox stream -> f = eval(x) ->
+    // jf + histogram with regenerated bins.  The samples y never exist in HBM.  `offs` NULL: a warm-up pass.
+    // Histogram target: the records (large maps), the weights / counts arrays (small problems: what the one-launch
+    // cluster update reads), else the fp64 pair table (one reduction sector per sample and dimension).
+    auto evaluate = [&](const int64_t* offs, int64_t rows, uint32_t call_idx, bool hist, void* jf_out) -> int {
         if (rows > b->cap_rows) {
             set_error("tq_vegas_run_unfused: a pass of %lld rows exceeds the buffers (%lld)", (long long)rows, (long long)b->cap_rows);
             return TQ_ERR_WORKSPACE;
         }
-        int rc = tq_vegas_map_forward_packed(b->y, s->edges_packed, layout, b->domain, b->x, b->jac, nullptr, rows, dim, ni, dtype, stream);
+        int rc = tq_vegas_sample_map(offs, n_cubes, n_strat, dim, dtype, 0, rows, s->edges_packed, layout, ni, b->domain, seed, call_idx,
+                                     b->x, b->jac, stream);
         if (rc) return rc;
         const void* f = nullptr;
         if (eval(user, rows, &f) != 0 || f == nullptr) {
@@ -441,18 +447,18 @@ static int run_unfused(tq_eval_callback eval, void* user, int dim, int32_t dtype
             return TQ_ERR_CALLBACK;
         }
         fevals += rows;
-        const bool to_arrays = hist && !recs;
-        return tq_vegas_accumulate_fused(b->y, f, b->jac, b->volume, jf_out, to_arrays ? s->weights : nullptr,
-                                         to_arrays ? s->counts : nullptr, hist && recs ? s->edges_packed : nullptr, rows, dim, ni,
-                                         dtype, stream);
+        if (!hist && !jf_out) return TQ_OK;
+        const bool arrays = hist && !recs && !to_pairs;
+        return tq_vegas_accumulate_regen(offs, n_cubes, n_strat, dim, dtype, 0, rows, ni, f, b->jac, b->volume, jf_out, nullptr,
+                                         hist && to_pairs ? s->hist_pairs : nullptr, hist && recs ? s->edges_packed : nullptr,
+                                         arrays ? s->weights : nullptr, arrays ? s->counts : nullptr, seed, call_idx, stream);
     };
     cudaMemsetAsync(s->status, 0, 4 * (size_t)max_passes * sizeof(int32_t), st);
     if (warmup) {  // vegas.py:211-266
         const int64_t ns = starting / 5;
         for (int w = 0; w < 5; ++w) {
-            int rc = tq_mc_sample(b->y, b->warm_domain, 0, ns, dim, dtype, seed, call++, stream);
+            int rc = evaluate(nullptr, ns, call++, true, nullptr);
             if (rc) return rc;
-            if ((rc = evaluate(ns, true, nullptr))) return rc;
             if ((rc = update_map())) return rc;
         }
     }
@@ -475,9 +481,7 @@ static int run_unfused(tq_eval_callback eval, void* user, int dim, int32_t dtype
             set_error("tq_vegas_run_unfused: a pass of %lld rows exceeds the buffers (%lld)", M, (long long)b->cap_rows);
             return TQ_ERR_WORKSPACE;
         }
-        rc = tq_vegas_strat_sample(s->offsets, n_cubes, n_strat, dim, dtype, nullptr, seed, call++, 0, M, b->y, stream);
-        if (rc) return rc;
-        if ((rc = evaluate(M, grid_improve, b->jf))) return rc;
+        if ((rc = evaluate(s->offsets, M, call++, grid_improve, b->jf))) return rc;
         rc = tq_vegas_strat_accumulate(b->jf, 0, s->offsets, 0, n_cubes, s->JF, s->JF2, dtype, stream);
         if (rc) return rc;
         if (it > TQ_VEGAS_MAX_PASSES) { set_error("tq_vegas_run_unfused: too many iterations"); return TQ_ERR_UNSUPPORTED; }

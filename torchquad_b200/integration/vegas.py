@@ -51,8 +51,9 @@ class VEGAS(BaseIntegrator):
     max_map_intervals = None
     l2_fetch_bytes = None
     initial_adaptation = None  # adaptation_state() of an earlier run: start from its map and stratification
+    regenerate_samples = True  # callback integrands: never materialise y (False: the round-1 pipeline with y in HBM)
     native_loop = True  # single-GPU runs: drive all passes from C++ (tq_vegas_run_fused / tq_vegas_run_unfused)
-    native_unfused_max_bytes = 1 << 30  # sample buffers (y, x) the callback-integrand loop may allocate up front
+    native_unfused_max_bytes = 1 << 30  # sample buffer (x) the callback-integrand loop may allocate up front
     _large_map_bytes = 64 << 20
     _pairs_min_rows = 1 << 20  # fused passes at least this long accumulate the histogram as fp64 pairs
     min_rows_per_rank = 1 << 17  # multi-GPU fused runs with fewer samples per pass and rank are replicated, not sharded
@@ -110,6 +111,11 @@ class VEGAS(BaseIntegrator):
 
         self._fused = (isinstance(fn, BuiltinIntegrand) and type(rng) is RNG and fn.dim == dim
                        and not domain.requires_grad)
+        # Callback integrands with the library's own generator: every pass is two kernels around the integrand and the
+        # samples y are never materialised (ops.sample_map / ops.accumulate_regen); injected generators and gradients
+        # through the domain keep the materialised pipeline.  dim <= 128: wider rows use another Philox keying (RNG.uniform).
+        self._regen = (type(rng) is RNG and self._fuse_tail and not self._fused and dim <= 128 and self.regenerate_samples
+                       and getattr(rng, "_call_offset", None) is None)
         if self._fused:
             sizes = [float(self._np(hi) - self._np(lo)) for lo, hi in bounds]  # the working-dtype difference
             self._fn_struct = fn.to_struct([lo for lo, _ in bounds], sizes, host[-1])
@@ -133,6 +139,8 @@ class VEGAS(BaseIntegrator):
             self._shard = tqdist.cube_shard(n_strat**dim)
         self.strat = VEGASStratification(self._N_increment, dim=dim, rng=self.rng, backend="torch", dtype=self.dtype,
                                          device=self.device, shard=self._shard)
+        # maps beyond L2, callback integrand, one GPU: the histogram of a stratified pass is binned band by band
+        self._regen_sweep = 0 if tqdist.is_enabled() else self.map.sweep_group(self.strat.N_strat)
         # Multi-GPU, arbitrary integrand: the float statistics of a pass live in ONE buffer [weights | JF | JF2] so that
         # a pass needs one all-reduce for them plus one for the int64 counts.
         self._stats = None
@@ -162,10 +170,10 @@ class VEGAS(BaseIntegrator):
             native = self.native_loop and not tqdist.is_enabled() and max_iterations + 5 <= _lib.TQ_VEGAS_MAX_PASSES
             if native and self._fused:
                 return self._integrate_native_loop(N, use_warmup)
-            if native and self._fuse_tail and type(rng) is RNG:
+            if native and self._regen:  # callback integrand, library generator: the C++ loop (two kernels per pass)
                 # a pass has at most starting_N * sum(dh) + 2 * N_cubes rows and the schedule keeps 5 * starting_N <= N
                 cap_rows = N // 5 + N // 500 + 2 * self.strat.N_cubes + 4096
-                if 2 * cap_rows * dim * domain.element_size() <= self.native_unfused_max_bytes:
+                if cap_rows * dim * domain.element_size() <= self.native_unfused_max_bytes:
                     try:
                         return self._integrate_native_unfused(N, use_warmup, cap_rows)
                     except _NeedsAutograd:
@@ -315,18 +323,34 @@ class VEGAS(BaseIntegrator):
                 self._fused_pass(begin, end, hist=True)
                 self._nr_of_fevals += N_samples
             else:
-                if type(self.rng) is RNG:
+                regen = self._regen
+                if regen:
+                    # two kernels around the integrand: x, jac straight from the Philox stream; the bins are regenerated
+                    # for the histogram, so the warm-up samples y never exist in HBM (ops.sample_map / accumulate_regen)
+                    call_idx = self.rng.next_call()
+                    yrnd = None
+                    x, jac = self._sample_map(None, begin, end, call_idx)
+                    f_raw = self._eval_raw(x)
+                    del x
+                elif type(self.rng) is RNG:
                     yrnd = self.rng.uniform([end - begin, self._dim], self.dtype, device=self.device, row_begin=begin)
                     yrnd = yrnd * 0.999999
+                    f_raw, jac = self._map_and_eval(yrnd)
                 else:
                     yrnd = self.rng.uniform(size=[N_samples, self._dim], dtype=self.dtype).to(self.device) * 0.999999
                     yrnd = yrnd[begin:end]
-                f_raw, jac = self._map_and_eval(yrnd)
+                    f_raw, jac = self._map_and_eval(yrnd)
                 if tqdist.is_enabled():
                     self._nr_of_fevals += N_samples - (end - begin)
                 if f_raw is not None and not (torch.is_grad_enabled() and f_raw.requires_grad):
-                    self._accumulate_tail(yrnd, f_raw, jac, want_jf=False)
+                    if regen:
+                        self._accumulate_regen(None, begin, end, call_idx, f_raw, jac, hist=True, want_jf=False)
+                    else:
+                        self._accumulate_tail(yrnd, f_raw, jac, want_jf=False)
                 else:
+                    if regen:  # the integrand's values carry a graph: the reference expressions need the samples
+                        yrnd = ops.philox_uniform(end - begin, self._dim, self.dtype, self.device, self.rng.seed, call_idx, begin) * 0.999999
+                        self._last_f_eval = f_raw * self._volume
                     f_eval = self._last_f_eval
                     jf_vec2 = ((f_eval * jac) ** 2).detach()
                     self.map.accumulate_weight(yrnd, jf_vec2)
@@ -356,22 +380,37 @@ class VEGAS(BaseIntegrator):
             self._reduce_stats(with_cubes=True)
             strat.JF, strat.JF2 = JFs[0], JFs[1]
         else:
-            if type(self.rng) is RNG:
+            regen = self._regen
+            if regen:
+                call_idx = self.rng.next_call()
+                y = None
+                x, jac = self._sample_map(offsets, begin, end, call_idx)
+                f_raw = self._eval_raw(x)
+                del x
+            elif type(self.rng) is RNG:
                 y = ops.strat_sample(offsets, strat.N_strat, self._dim, self.dtype, begin, end, seed=self.rng.seed,
                                      call_idx=self.rng.next_call())
+                f_raw, jac = self._map_and_eval(y)
             else:
                 u = self.rng.uniform(size=[M, self._dim], dtype=self.dtype).to(self.device)
                 y = ops.strat_sample(offsets, strat.N_strat, self._dim, self.dtype, begin, end,
                                      u_in=u[begin:end].contiguous())
-            f_raw, jac = self._map_and_eval(y)
+                f_raw, jac = self._map_and_eval(y)
             if tqdist.is_enabled():
                 self._nr_of_fevals += M - (end - begin)
             if f_raw is not None and not (torch.is_grad_enabled() and f_raw.requires_grad):
-                if self.use_grid_improve:
+                if regen:
+                    jf_vec = self._accumulate_regen(offsets, begin, end, call_idx, f_raw, jac, hist=self.use_grid_improve,
+                                                    want_jf=True, whole_pass=(begin == 0 and end == M))
+                elif self.use_grid_improve:
                     jf_vec = self._accumulate_tail(y, f_raw, jac, want_jf=True)
                 else:
                     jf_vec = (f_raw * self._volume.detach()) * jac
             else:
+                if regen:  # the integrand's values carry a graph: the reference expressions need the samples
+                    y = ops.strat_sample(offsets, strat.N_strat, self._dim, self.dtype, begin, end, seed=self.rng.seed,
+                                         call_idx=call_idx)
+                    self._last_f_eval = f_raw * self._volume
                 f_eval = self._last_f_eval
                 jf_vec = f_eval * jac
                 if self.use_grid_improve:
@@ -412,6 +451,47 @@ class VEGAS(BaseIntegrator):
             return jf
         return ops.accumulate_fused(y, f_raw, jac, self._volume_host, vmap.weights, vmap.counts, want_jf=want_jf)
 
+    def _sample_map(self, offsets, begin, end, call_idx):
+        """(x in domain coordinates, jac) of rows [begin, end) of a pass without materialising y (ops.sample_map)."""
+        vmap = self.map
+        n_strat = self.strat.N_strat if offsets is not None else 1
+        if vmap.wants_records() and self._regen_sweep == 0:
+            return ops.sample_map(offsets, n_strat, self._dim, self.dtype, begin, end, self.rng.seed, call_idx,
+                                  self._domain.detach(), records=vmap.records(), n_intervals=vmap.N_intervals)
+        return ops.sample_map(offsets, n_strat, self._dim, self.dtype, begin, end, self.rng.seed, call_idx,
+                              self._domain.detach(), edges_packed=vmap.packed_edges())
+
+    def _accumulate_regen(self, offsets, begin, end, call_idx, f_raw, jac, hist, want_jf, whole_pass=False):
+        """jf and the map histogram of the rows of `_sample_map`, bins regenerated from the Philox stream.  Maps beyond L2,
+        whole stratified passes: jf^2 rows + band-ordered sweeps; otherwise their record table; ordinary
+        maps: the fp64 pair table.  The histogram is folded into weights / counts (what update_map and the all-reduce read)."""
+        vmap = self.map
+        n_strat = self.strat.N_strat if offsets is not None else 1
+        args = (offsets, n_strat, self._dim, begin, end, vmap.N_intervals, f_raw, jac, self._volume_host, self.rng.seed, call_idx)
+        if not hist:
+            return ops.accumulate_regen(*args, want_jf=want_jf)[0]
+        if vmap.wants_records() and self._regen_sweep == 0:
+            jf, _ = ops.accumulate_regen(*args, records=vmap.records(), want_jf=want_jf)
+            vmap.unpack_records()
+            return jf
+        if vmap.wants_records() and whole_pass and offsets is not None:
+            jf, jf2 = ops.accumulate_regen(*args, want_jf=want_jf, want_jf2=True)
+            ops.hist_sweep(offsets, n_strat, self._dim, jf2, vmap.N_intervals, vmap.hist_pairs(), self._regen_sweep, self.rng.seed,
+                           call_idx)
+        else:
+            jf, _ = ops.accumulate_regen(*args, hist_pairs=vmap.hist_pairs(), want_jf=want_jf)
+        vmap.unpack_hist()
+        return jf
+
+    def _eval_raw(self, x):
+        """The user's integrand on x (already in domain coordinates) as a flat vector of the working dtype."""
+        f_raw, n = self.evaluate_integrand(self._user_fn, x)
+        self._nr_of_fevals += n
+        f_raw = f_raw.reshape(-1) if f_raw.numel() == n else f_raw.squeeze()
+        if f_raw.dtype != self.dtype:
+            f_raw = f_raw.to(self.dtype)
+        return f_raw
+
     def _map_and_eval(self, y):
         """y -> (raw integrand values, jac).  Fused tail: x comes out of the map kernel already in domain
         coordinates and the raw values are returned for `accumulate_fused`; otherwise (gradient through the
@@ -423,11 +503,7 @@ class VEGAS(BaseIntegrator):
                                                    n_intervals=self.map.N_intervals)
             else:
                 x, jac, _ = ops.map_forward_packed(y, self.map.packed_edges(), self._domain.detach())
-            f_raw, n = self.evaluate_integrand(self._user_fn, x)
-            self._nr_of_fevals += n
-            f_raw = f_raw.reshape(-1) if f_raw.numel() == n else f_raw.squeeze()
-            if f_raw.dtype != self.dtype:
-                f_raw = f_raw.to(self.dtype)
+            f_raw = self._eval_raw(x)
             if torch.is_grad_enabled() and f_raw.requires_grad:
                 self._last_f_eval = f_raw * self._volume
                 return f_raw, jac

@@ -220,6 +220,46 @@ def accumulate_fused(y, f, jac, volume, weights, counts, want_jf=True, records=N
     return jf
 
 
+def sample_map(offsets, n_strat, dim, dtype, row_begin, row_end, seed, call_idx, domain, edges_packed=None, records=None,
+               n_intervals=None):
+    """Rows [row_begin, row_end) of a VEGAS pass straight to (x [rows, dim] in domain coordinates, jac [rows]): get_Y + get_X +
+    get_Jac + the x*size + start transform in one kernel, y never materialised (tq_vegas_sample_map).  `offsets` None: a
+    warm-up pass (y = u * 0.999999 from the row-keyed stream)."""
+    table = records if records is not None else edges_packed
+    require_cuda(offsets, table, domain)
+    rows = row_end - row_begin
+    x = torch.empty((rows, dim), dtype=dtype, device=table.device)
+    jac = torch.empty(rows, dtype=dtype, device=table.device)
+    if rows > 0:
+        ni = n_intervals if records is not None else edges_packed.shape[1]
+        dom = domain.detach().contiguous()
+        with on_device(table.device):
+            call("tq_vegas_sample_map", ptr(offsets), 0 if offsets is None else offsets.shape[0] - 1, n_strat, dim, dtype_code(dtype),
+                 row_begin, row_end, ptr(table), _lib.TQ_EDGES_RECORDS if records is not None else _lib.TQ_EDGES_PAIRS, ni, ptr(dom),
+                 seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF, ptr(x), ptr(jac), stream_ptr(table.device))
+    return x, jac
+
+
+def accumulate_regen(offsets, n_strat, dim, row_begin, row_end, n_intervals, f, jac, volume, seed, call_idx, hist_pairs=None,
+                     records=None, weights=None, counts=None, want_jf=True, want_jf2=False):
+    """jf = (f*volume)*jac for the rows of `sample_map` and, with a target, the map histogram of those rows with the bin
+    ids regenerated from the Philox stream (tq_vegas_accumulate_regen).  Returns (jf or None, jf^2 rows or None)."""
+    require_cuda(offsets, f, jac, hist_pairs, records, weights, counts)
+    rows = row_end - row_begin
+    f = f.detach().contiguous()
+    if f.shape != (rows,) or f.dtype != jac.dtype:
+        raise ValueError(f"integrand values must have shape ({rows},) and dtype {jac.dtype}, got {tuple(f.shape)} / {f.dtype}")
+    jf = torch.empty(rows, dtype=f.dtype, device=f.device) if want_jf else None
+    jf2 = torch.empty(rows, dtype=f.dtype, device=f.device) if want_jf2 else None
+    if rows > 0 and (want_jf or want_jf2 or hist_pairs is not None or records is not None or weights is not None):
+        with on_device(f.device):
+            call("tq_vegas_accumulate_regen", ptr(offsets), 0 if offsets is None else offsets.shape[0] - 1, n_strat, dim,
+                 dtype_code(f.dtype), row_begin, row_end, n_intervals, ptr(f), ptr(jac), float(volume), ptr(jf), ptr(jf2),
+                 ptr(hist_pairs), ptr(records), ptr(weights), ptr(counts), seed & 0xFFFFFFFFFFFFFFFF, call_idx & 0xFFFFFFFF,
+                 stream_ptr(f.device))
+    return jf, jf2
+
+
 def map_accumulate(y, jf2, weights, counts):
     """weights[d,k] += jf2, counts[d,k] += 1 in place (vegas_map.py:99-111)."""
     require_cuda(y, jf2, weights, counts)
@@ -662,13 +702,12 @@ def vegas_run_unfused(evaluate, vmap, strat, domain, volume, cap_rows, N, max_it
     dim = vmap.dim
     use_records = bool(use_grid_improve) and vmap.wants_records()
     state, keep, nh, offsets = _vegas_state(vmap, strat, use_records)
-    y = torch.empty((cap_rows, dim), dtype=dt, device=dev)
-    x = torch.empty((cap_rows, dim), dtype=dt, device=dev)
+    x = torch.empty((cap_rows, dim), dtype=dt, device=dev)  # the only [rows, dim] buffer: y is never materialised
     jac = torch.empty(cap_rows, dtype=dt, device=dev)
     jf = torch.empty(cap_rows, dtype=dt, device=dev)
     warm = torch.tensor([[0.0, 0.999999]] * dim, dtype=dt, device=dev)
     dom = domain.detach().contiguous()
-    buffers = _lib.tq_vegas_unfused_buffers(ptr(y), ptr(x), ptr(jac), ptr(jf), ptr(dom), ptr(warm), cap_rows, float(volume))
+    buffers = _lib.tq_vegas_unfused_buffers(None, ptr(x), ptr(jac), ptr(jf), ptr(dom), ptr(warm), cap_rows, float(volume))
     failure = []
     last = [None]  # keeps the latest value tensor alive until the kernels that read it are queued behind it
 
