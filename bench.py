@@ -623,7 +623,7 @@ def measure(name, wl, args, ctx, headline):
                 "last_integral": float(info["fused_fast"]()),
                 "note": "same fused kernel with sin() evaluated by the SFU (__sinf, abs error ~5e-7): opt-in "
                         "SumOfSines(dim, fast_math=True); not used for `value`"}
-    if not args.no_unfused and world == 1 and (headline or name in ("boole6", "vegas4")):
+    if not args.no_unfused and world == 1 and (headline or name in ("boole6", "vegas4", "vegas8_cap4096")):
         u_steps = 2
         t_unf = sum(timed_steps(unfused, u_steps, 1, flush, barrier, min_warm_s=0.0))
         unf = {"value": evals() * u_steps / t_unf, "unit": "evals/s", "ms_per_step": t_unf / u_steps * 1e3,
