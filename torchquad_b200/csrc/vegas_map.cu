@@ -330,25 +330,17 @@ map_prefix_kernel(const T* __restrict__ smoothed, const double* __restrict__ til
 //   idx = #{j <= Ni-2 : trunc(S_j/delta) <= m}   (the reference builds it as histogram + cumsum)
 //   acc = (m+1)*delta - S_{idx-1}                (reference: cumsum of delta - val_per_multiple)
 //   x_new[m+1] = xe[idx] + acc/sm[idx]*dxe[idx]
-template <typename T>
-__global__ void __launch_bounds__(256)
-map_edges_kernel(const T* __restrict__ smoothed, const double* __restrict__ S, const double* __restrict__ row_totals,
-                 const T* __restrict__ xe, const T* __restrict__ dxe, T* __restrict__ x_new, long long ni,
-                 const int32_t* status) {
-    if (status[0]) return;
-    const int d = blockIdx.y;
-    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const T* x_old = xe + (int64_t)d * (ni + 1);
-    T* xn = x_new + (int64_t)d * (ni + 1);
-    if (m == 0) { xn[0] = x_old[0]; xn[ni] = x_old[ni]; }
-    if (m > ni - 2) return;
-    const double* Sd = S + (int64_t)d * ni;
-    const T delta_t = div_rn((T)row_totals[d], (T)ni);
-    const double delta = (double)delta_t;
-    // smallest j in [0, Ni-2] with trunc(S_j/delta) > m; Ni-1 when there is none: bisection on S_j >= t
-    // (division_threshold, vegas_dev.cuh)
-    const double thr = division_threshold((double)(m + 1), delta);
-    long long lo = 0, hi = ni - 1;
+// idx is monotone in m, so the search is windowed: map_edge_bounds_kernel finds idx of the FIRST edge of every block of
+// ME_BLOCK edges with a full bisection (one thread per block), and map_edges_kernel searches each edge only inside its
+// block's window [bounds[b], bounds[b+1]], staged in shared memory with coalesced loads.  (One full bisection per edge --
+// 23 dependent probes at Ni = 1e7 -- made this kernel 8.7 % of a VEGAS run at the reference's map size.)
+constexpr int ME_BLOCK = 1024;   // edges per CTA of map_edges_kernel (4 per thread)
+constexpr int ME_WINDOW = 3072;  // prefix sums staged per CTA (24 KB); wider windows are searched in global memory
+
+// smallest j in [lo, hi] with trunc(S_j/delta) > m, hi when there is none: bisection on S_j >= thr
+// (division_threshold, vegas_dev.cuh; thr < 0: the division itself)
+__device__ __forceinline__ long long edge_search(const double* __restrict__ Sd, long long lo, long long hi, double thr, double delta,
+                                                 long long m) {
     if (thr >= 0.0) {
         while (lo < hi) {
             const long long mid = (lo + hi) >> 1;
@@ -360,11 +352,63 @@ map_edges_kernel(const T* __restrict__ smoothed, const double* __restrict__ S, c
             if ((long long)(__ddiv_rn(Sd[mid], delta)) > m) hi = mid; else lo = mid + 1;
         }
     }
-    const long long idx = lo;
-    const double below = idx > 0 ? Sd[idx - 1] : 0.0;
-    const T acc = (T)((double)(m + 1) * delta - below);
-    const T sm = smoothed[(int64_t)d * ni + idx];
-    xn[m + 1] = add_rn(x_old[idx], mul_rn(div_rn(acc, sm), dxe[(int64_t)d * ni + idx]));
+    return lo;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+map_edge_bounds_kernel(const double* __restrict__ S, const double* __restrict__ row_totals, long long* __restrict__ bounds,
+                       long long ni, int nblk, const int32_t* status) {
+    if (status[0]) return;
+    const int d = blockIdx.y;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const long long m = (long long)b * ME_BLOCK;  // <= Ni - 2 by the choice of nblk
+    const double delta = (double)div_rn((T)row_totals[d], (T)ni);
+    const double thr = division_threshold((double)(m + 1), delta);
+    bounds[(int64_t)d * nblk + b] = edge_search(S + (int64_t)d * ni, 0, ni - 1, thr, delta, m);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+map_edges_kernel(const T* __restrict__ smoothed, const double* __restrict__ S, const double* __restrict__ row_totals,
+                 const long long* __restrict__ bounds, int nblk, const T* __restrict__ xe, const T* __restrict__ dxe,
+                 T* __restrict__ x_new, long long ni, const int32_t* status) {
+    __shared__ double s_S[ME_WINDOW];
+    if (status[0]) return;
+    const int d = blockIdx.y;
+    const int b = blockIdx.x;
+    const T* x_old = xe + (int64_t)d * (ni + 1);
+    T* xn = x_new + (int64_t)d * (ni + 1);
+    if (b == 0 && threadIdx.x == 0) { xn[0] = x_old[0]; xn[ni] = x_old[ni]; }
+    const double* Sd = S + (int64_t)d * ni;
+    const double delta = (double)div_rn((T)row_totals[d], (T)ni);
+    const long long w_lo = bounds[(int64_t)d * nblk + b];
+    const long long w_hi = b + 1 < nblk ? bounds[(int64_t)d * nblk + b + 1] : ni - 1;  // idx of the next block's first edge
+    const bool staged = w_hi - w_lo < ME_WINDOW;
+    if (staged) {
+        for (long long j = w_lo + threadIdx.x; j <= w_hi; j += 256) s_S[j - w_lo] = Sd[j];
+        __syncthreads();
+    }
+    const long long m0 = (long long)b * ME_BLOCK;
+#pragma unroll
+    for (int i = 0; i < ME_BLOCK / 256; ++i) {
+        const long long m = m0 + threadIdx.x + 256 * i;
+        if (m > ni - 2) break;
+        const double thr = division_threshold((double)(m + 1), delta);
+        long long idx;
+        double below;
+        if (staged) {
+            idx = w_lo + edge_search(s_S, 0, w_hi - w_lo, thr, delta, m);
+            below = idx > w_lo ? s_S[idx - 1 - w_lo] : (idx > 0 ? Sd[idx - 1] : 0.0);
+        } else {
+            idx = edge_search(Sd, w_lo, w_hi, thr, delta, m);
+            below = idx > 0 ? Sd[idx - 1] : 0.0;
+        }
+        const T acc = (T)((double)(m + 1) * delta - below);
+        const T sm = smoothed[(int64_t)d * ni + idx];
+        xn[m + 1] = add_rn(x_old[idx], mul_rn(div_rn(acc, sm), dxe[(int64_t)d * ni + idx]));
+    }
 }
 
 // K5: non-finite repair (vegas_map.py:240-257, repaired_edge in vegas_dev.cuh), dx = diff(x) (:259) and the
@@ -526,8 +570,15 @@ int map_update_launch(void* x_edges, void* dx_edges, void* weights, int64_t* cou
         if (rc) return rc;
         dim3 grid(s.ntiles, dim);
         map_prefix_kernel<T><<<TQ_GRID(grid), 256, 0, st>>>((const T*)s.smoothed, s.tile_sums, s.S, ni, s.ntiles, status);
-        dim3 grid_e((unsigned)((ni + 255) / 256), dim);
-        map_edges_kernel<T><<<TQ_GRID(grid_e), 256, 0, st>>>((const T*)s.smoothed, s.S, s.totals2, (const T*)x_edges,
+        // blocks of ME_BLOCK new edges m = 0 .. Ni-2; their search windows live in tile_sums, free again after the prefix
+        // kernel (nblk <= ntiles because ME_BLOCK == MAP_TILE)
+        static_assert(ME_BLOCK == MAP_TILE, "the window bounds reuse the tile-sum scratch");
+        const int nblk = (int)((ni - 1 + ME_BLOCK - 1) / ME_BLOCK);
+        long long* bounds = reinterpret_cast<long long*>(s.tile_sums);
+        dim3 grid_b((unsigned)((nblk + 255) / 256), dim);
+        map_edge_bounds_kernel<T><<<TQ_GRID(grid_b), 256, 0, st>>>(s.S, s.totals2, bounds, ni, nblk, status);
+        dim3 grid_e((unsigned)nblk, dim);
+        map_edges_kernel<T><<<TQ_GRID(grid_e), 256, 0, st>>>((const T*)s.smoothed, s.S, s.totals2, bounds, nblk, (const T*)x_edges,
                                                    (const T*)dx_edges, (T*)s.x_new, ni, status);
         dim3 grid_f((unsigned)((ni + 1 + 255) / 256), dim);
         map_finalize_kernel<T><<<TQ_GRID(grid_f), 256, 0, st>>>((const T*)s.x_new, (T*)x_edges, (T*)dx_edges, (T*)weights,
