@@ -252,15 +252,20 @@ template <typename T> struct Pair2;
 template <> struct Pair2<float> { using type = float2; };
 template <> struct Pair2<double> { using type = double2; };
 
+// Sum of (a, b) over the lanes that follow this one inside its segment (a run of equal keys; rows of a cube are consecutive
+// lanes).  The segment's last lane comes from ONE ballot of the head flags, so the five rounds shuffle only the two values.
 template <typename T>
 __device__ __forceinline__ void segmented_warp_sum2(unsigned key, T& a, T& b) {
     const int lane = threadIdx.x & 31;
+    const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != key);
+    const unsigned later = lane == 31 ? 0u : heads & (0xfffffffeu << lane);  // heads of the segments after this lane
+    const int last = later ? __ffs(later) - 2 : 31;                         // last lane of this lane's segment
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-        const unsigned k2 = __shfl_down_sync(0xffffffffu, key, off);
         const T a2 = __shfl_down_sync(0xffffffffu, a, off);
         const T b2 = __shfl_down_sync(0xffffffffu, b, off);
-        if (lane + off < 32 && k2 == key) { a += a2; b += b2; }
+        if (lane + off <= last) { a += a2; b += b2; }
     }
 }
 
@@ -282,6 +287,7 @@ enum HistMode {
 template <int FAM, typename T, bool STRAT>
 __global__ void __launch_bounds__(FV_BLOCK, FV_MIN_CTAS)
 fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, int64_t n_cubes, CubeShard shard, FastDiv ns_div, T inv_ns,
+                   T nsf, T nif,
                    int64_t row_begin, int64_t row_end, bool rows_from_offsets, int64_t rows_per_cta,
                    const void* __restrict__ edges_raw, bool records, long long ni, T* __restrict__ weights,
                    unsigned long long* __restrict__ counts, double* __restrict__ hist_pairs, T* __restrict__ jf2_rows,
@@ -301,7 +307,6 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
     T* s_w = reinterpret_cast<T*>(s_ids + dim * FV_BLOCK);                 // [dim*ni] when hist_smem
     const bool hist_smem = hist_mode == HIST_SMEM;
     unsigned int* s_c = reinterpret_cast<unsigned int*>(s_w + (hist_smem ? dim * ni : 0));
-    const P2* __restrict__ edges = reinterpret_cast<const P2*>(edges_raw);
     MapRecord<T>* recs = reinterpret_cast<MapRecord<T>*>(const_cast<void*>(edges_raw));
     const bool do_hist = hist_mode != HIST_NONE && hist_mode != HIST_DEFER;
     // fp64 records keep their count as an fp64 next to the weight: the same sector-paired reduction applies
@@ -313,8 +318,11 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
     }
     __syncthreads();
     if (STRAT && rows_from_offsets) row_end = __ldg(&offsets[n_cubes]);  // sample count of the pass, never read back
-    const T nif = (T)ni;
-    const T nsf = (T)ns_div.d;
+    // nif = (T)ni and nsf = (T)N_strat arrive as kernel parameters: operands straight from the constant bank (computed here
+    // they were re-converted from integers for every dimension to save registers)
+    const int ni32 = (int)ni;                       // n_intervals < 2^31 (checked by the launcher)
+    const int estride = records ? 2 : 1, eshift = records ? 1 : 0;  // a record's first half is its {x, dx} pair
+    const P2* __restrict__ etab = reinterpret_cast<const P2*>(edges_raw);
     double acc[2] = {0.0, 0.0};
     int buf = 0;
     // The host sizes the grid so that one chunk per CTA covers its row estimate; the stride loop keeps the pass
@@ -386,14 +394,13 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
                             }
                             const T t = mul_rn(y, nif);
                             const T fl = floor(t);
-                            long long k = (long long)fl;
-                            k = k < 0 ? 0 : (k >= ni ? ni - 1 : k);
+                            int k = (int)fl;  // 0 <= t < 2^31
+                            k = max(0, min(k, ni32 - 1));
                             const T o = sub_rn(t, fl);
-                            const int64_t bin = (int64_t)d * ni + k;
-                            const P2 e = records ? __ldg(reinterpret_cast<const P2*>(&recs[bin])) : __ldg(&edges[bin]);
+                            const P2 e = __ldg(etab + (int64_t)d * ni * estride + (k << eshift));  // uniform table base + a 32-bit offset
                             const T x = add_rn(e.x, mul_rn(e.y, o));
                             jac = mul_rn(jac, mul_rn(nif, e.y));
-                            s_ids[d * FV_BLOCK + threadIdx.x] = (int)k;
+                            s_ids[d * FV_BLOCK + threadIdx.x] = k;
                             fn.step(add_rn(mul_rn(x, S.size[d]), S.start[d]), d, S);
                         }
                     }
@@ -485,7 +492,7 @@ constexpr int FT_SLICE = FT_BLOCK / 2 + 4;
 template <int FAM, typename T>
 __global__ void __launch_bounds__(FT_BLOCK, 1)
 fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offsets, uint32_t n_cubes, CubeShard shard, FastDiv ns_div,
-                        T inv_ns, const typename Pair2<T>::type* __restrict__ edges, long long ni, double* __restrict__ hist,
+                        T inv_ns, T nsf, T nif, const typename Pair2<T>::type* __restrict__ edges, long long ni, double* __restrict__ hist,
                         T* __restrict__ JF, T* __restrict__ JF2, uint64_t seed, uint32_t call, int g, uint32_t tile_cubes,
                         FastDiv tile_div, int band_w, unsigned int* next_tile) {
     constexpr int LANES = U01<T>::LANES;
@@ -506,8 +513,7 @@ fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offs
     unsigned int* s_hc = reinterpret_cast<unsigned int*>(s_jf2 + FT_BLOCK);       // [ns][band_w]
     int* s_ids = reinterpret_cast<int*>(s_hc + (size_t)ns * band_w);              // [g][FT_BLOCK]
     unsigned short* s_bid = reinterpret_cast<unsigned short*>(s_ids + (size_t)g * FT_BLOCK);  // [ns][FT_BLOCK]
-    const T nif = (T)ni;
-    const T nsf = (T)ns_div.d;
+    const int ni32 = (int)ni;  // n_intervals <= 2^20 on this path; nif = (T)ni, nsf = (T)N_strat are kernel parameters
     const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31, word = lane & 1;
     int buf = 0;
     for (;;) {
@@ -581,17 +587,17 @@ fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offs
                             if (y >= (T)1) y = (T)0.999999;
                             const T t = mul_rn(y, nif);
                             const T fl = floor(t);
-                            long long k = (long long)fl;
-                            k = k < 0 ? 0 : (k >= ni ? ni - 1 : k);
+                            int k = (int)fl;
+                            k = max(0, min(k, ni32 - 1));
                             const T o = sub_rn(t, fl);
                             P2 e;
-                            if (d < g) {
+                            if (d < g) {  // uniform over the CTA
                                 e = __ldg(&edges[(int64_t)d * ni + k]);
-                                s_ids[d * FT_BLOCK + threadIdx.x] = (int)k;
+                                s_ids[d * FT_BLOCK + threadIdx.x] = k;
                             } else {
                                 const int sd = d - g;
-                                const long long loc = k - s_blo[sd];
-                                if (loc >= 0 && loc < band_w) {
+                                const unsigned loc = (unsigned)(k - s_blo[sd]);
+                                if (loc < (unsigned)band_w) {
                                     e = s_edge[sd * band_w + (int)loc];
                                     s_bid[sd * FT_BLOCK + threadIdx.x] = (unsigned short)loc;
                                 } else {  // outside the staged band: cannot happen with the slack for Ni <= 2^20; kept exact anyway
@@ -1209,7 +1215,8 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
                 TQ_DISPATCH_FAMILY(fn_host->family, {
                     cudaFuncSetAttribute(fused_vegas_tile_kernel<FAM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
                     fused_vegas_tile_kernel<FAM, T><<<TQ_GRID(grid), FT_BLOCK, best_smem, st>>>(
-                        *fn_host, (const long long*)offsets, (uint32_t)n_cubes, shard, ns_div, inv_ns, (const P2*)edges_packed, n_intervals,
+                        *fn_host, (const long long*)offsets, (uint32_t)n_cubes, shard, ns_div, inv_ns, (T)n_strat, (T)n_intervals,
+                        (const P2*)edges_packed, n_intervals,
                         (double*)hist_pairs, (T*)JF, (T*)JF2, seed, call_idx, best_g, (uint32_t)best_tile, tile_div, (int)band_w, next_tile);
                 });
             });
@@ -1222,14 +1229,14 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
             if (strat) {
                 if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, true><<<TQ_GRID((unsigned)ctas), FV_BLOCK, smem, st>>>(
-                    *fn_host, (const long long*)offsets, n_cubes, shard, ns_div, inv_ns, row_begin, row_end, rows_from_offsets, rows_per_cta,
-                    edges_packed, records, n_intervals, (T*)weights, (unsigned long long*)counts, (double*)hist_pairs,
+                    *fn_host, (const long long*)offsets, n_cubes, shard, ns_div, inv_ns, (T)n_strat, (T)n_intervals, row_begin, row_end,
+                    rows_from_offsets, rows_per_cta, edges_packed, records, n_intervals, (T*)weights, (unsigned long long*)counts, (double*)hist_pairs,
                     (T*)jf2_rows, (T*)JF, (T*)JF2, seed, call_idx, hist_mode, partials, ticket, out_f64);
             } else {
                 if (smem > 48 * 1024) cudaFuncSetAttribute(fused_vegas_kernel<FAM, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
                 fused_vegas_kernel<FAM, T, false><<<TQ_GRID((unsigned)ctas), FV_BLOCK, smem, st>>>(
-                    *fn_host, nullptr, 0, shard, ns_div, inv_ns, row_begin, row_end, false, rows_per_cta, edges_packed, records,
-                    n_intervals, (T*)weights, (unsigned long long*)counts, (double*)hist_pairs, nullptr, nullptr, nullptr, seed,
+                    *fn_host, nullptr, 0, shard, ns_div, inv_ns, (T)1, (T)n_intervals, row_begin, row_end, false, rows_per_cta, edges_packed,
+                    records, n_intervals, (T*)weights, (unsigned long long*)counts, (double*)hist_pairs, nullptr, nullptr, nullptr, seed,
                     call_idx, hist_mode, partials, ticket, out_f64);
             }
         });
