@@ -70,6 +70,13 @@ VEGASMap.records_min_bytes = 0
 a, b, integ = both(tq.VEGAS, g, 4, dict(N=400_000, seed=3), torch.float64)
 checks.append(("VEGAS fused records float64", a, b, 1e-9))
 assert integ.map._records is not None
+# maps beyond L2 with >= 2^20 rows per pass: deferred histogram + band sweeps, every rank sweeping its own cubes
+# (hist_sweep_launch with a CubeShard); the single-GPU run takes the same path with all cubes
+a, b, integ = both(tq.VEGAS, g, 4, dict(N=30_000_000, seed=4), torch.float64)
+checks.append(("VEGAS fused band sweeps float64", a, b, 1e-9))
+assert integ._shard is not None and integ.map.sweep_group(integ.strat.N_strat) >= 1
+a, b, integ = both(tq.VEGAS, g6, 6, dict(N=40_000_000, seed=2, max_iterations=10), torch.float32)
+checks.append(("VEGAS fused band sweeps 6-D float32", a, b, 5e-3))
 VEGASMap.records_min_bytes = default_threshold
 ok = True
 for name, a, b, tol in checks:

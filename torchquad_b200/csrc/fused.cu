@@ -238,6 +238,16 @@ struct CubeShard {
         const uint32_t pos = t - world.div(t) * world.d;  // (rank + skew(b)) % world
         return ((b * world.d + pos) << lb) + (l & ((1u << lb) - 1u));
     }
+    // inverse: does this rank own global cube c, and under which local id?  (local block index = round)
+    __device__ __forceinline__ bool local_cube(uint32_t c, uint32_t& l) const {
+        if (world.d <= 1) { l = c; return true; }
+        const uint32_t blk = c >> lb;
+        const uint32_t round = world.div(blk);
+        const uint32_t pos = blk - round * world.d;
+        const uint32_t t = rank + skew(round);
+        l = (round << lb) + (c & ((1u << lb) - 1u));
+        return t - world.div(t) * world.d == pos;
+    }
 };
 #ifndef FV_MIN_CTAS
 #define FV_MIN_CTAS 6
@@ -754,7 +764,7 @@ constexpr uint32_t SWEEP_CHUNK = 1024;  // cubes per scheduling unit
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-hist_sweep_kernel(const long long* __restrict__ offsets, uint32_t n_cubes, const T* __restrict__ jf2_rows,
+hist_sweep_kernel(const long long* __restrict__ offsets, uint32_t n_cubes, CubeShard shard, const T* __restrict__ jf2_rows,
                   double* __restrict__ hist, long long ni, int d0, int g, FastDiv ns_div, FastDiv low_div, uint32_t pow_g,
                   FastDiv cpc_div, T inv_ns, uint64_t seed, uint32_t call, int lane0, unsigned int* next_chunk) {
     constexpr int LANES = U01<T>::LANES;
@@ -780,9 +790,15 @@ hist_sweep_kernel(const long long* __restrict__ offsets, uint32_t n_cubes, const
             combo = cpc_div.div(j);                       // the group's digits (dimension d0 fastest)
             const uint32_t r = j - combo * cubes_per_combo;
             const uint32_t high = low_div.div(r), low = r - high * pow_low;
-            c = (high * pow_g + combo) * pow_low + low;   // the cube with those digits at positions d0 .. d0+g-1
-            row0 = __ldcs(&offsets[c]);
-            nh = (int)(__ldcs(&offsets[c + 1]) - row0);
+            c = (high * pow_g + combo) * pow_low + low;   // the (GLOBAL) cube with those digits at positions d0 .. d0+g-1
+            // multi-GPU: the sweep walks the global band-major order and bins only the cubes this rank owns; `offsets`,
+            // `jf2_rows` are the rank's local arrays (a skipped cube costs the index arithmetic above and nothing else)
+            uint32_t l = c;
+            const bool mine = shard.local_cube(c, l);
+            if (mine) {
+                row0 = __ldcs(&offsets[l]);
+                nh = (int)(__ldcs(&offsets[l + 1]) - row0);
+            }
         }
         // The warp's 32 cubes hold `total` samples; they are flattened so that every step gives each lane one sample
         // whatever the spread of nh (after adaptation nh varies by an order of magnitude between neighbouring cubes).
@@ -1049,7 +1065,25 @@ int tq_fused_vegas_deferred(const tq_integrand* fn_host, int32_t dtype, const in
 int tq_vegas_hist_sweep(const int64_t* offsets, int64_t n_cubes, int32_t n_strat, int32_t dim, int32_t dtype,
                         const void* jf2_rows, int64_t n_intervals, void* hist_pairs, int32_t dims_per_group, uint64_t seed,
                         uint32_t call_idx, void* ws, size_t ws_bytes, void* stream) {
+    return hist_sweep_launch(offsets, n_cubes, n_strat, dim, dtype, jf2_rows, n_intervals, hist_pairs, dims_per_group, seed, call_idx,
+                             0, 0, 1, ws, ws_bytes, stream);
+}
+
+}  // extern "C"
+
+namespace tq {
+
+// `n_cubes` is the GLOBAL cube count; with world > 1 `offsets` / `jf2_rows` are the rank's local arrays (CubeShard deal).
+int hist_sweep_launch(const int64_t* offsets, int64_t n_cubes, int32_t n_strat, int32_t dim, int32_t dtype, const void* jf2_rows,
+                      int64_t n_intervals, void* hist_pairs, int32_t dims_per_group, uint64_t seed, uint32_t call_idx,
+                      int32_t cube_block_log2, int32_t rank, int32_t world, void* ws, size_t ws_bytes, void* stream) {
     TQ_REQUIRE(offsets && jf2_rows && hist_pairs, "tq_vegas_hist_sweep: NULL argument");
+    TQ_REQUIRE(world >= 1 && rank >= 0 && rank < world && cube_block_log2 >= 0 && cube_block_log2 < 31,
+               "tq_vegas_hist_sweep: bad cube shard (block 2^%d, rank %d of %d)", cube_block_log2, rank, world);
+    CubeShard shard;
+    shard.lb = (uint32_t)cube_block_log2;
+    shard.rank = (uint32_t)rank;
+    shard.world.set((uint32_t)world);
     Workspace wsp(ws, ws_bytes);
     wsp.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
     unsigned int* counters = wsp.take<unsigned int>(TQ_MAX_DIM);  // one chunk counter per launch of this call
@@ -1083,7 +1117,7 @@ int tq_vegas_hist_sweep(const int64_t* offsets, int64_t n_cubes, int32_t n_strat
                 FastDiv low_div, cpc_div;
                 low_div.set((uint32_t)pow_low);
                 cpc_div.set((uint32_t)((uint64_t)n_cubes / pow_g));
-                hist_sweep_kernel<T><<<TQ_GRID(grid), 256, 0, st>>>((const long long*)offsets, (uint32_t)n_cubes, (const T*)jf2_rows,
+                hist_sweep_kernel<T><<<TQ_GRID(grid), 256, 0, st>>>((const long long*)offsets, (uint32_t)n_cubes, shard, (const T*)jf2_rows,
                                                                    (double*)hist_pairs, n_intervals, d0, g, ns_div, low_div,
                                                                    (uint32_t)pow_g, cpc_div, inv_ns, seed, call_idx, d0 - b0,
                                                                    counters + launch++);
@@ -1092,10 +1126,6 @@ int tq_vegas_hist_sweep(const int64_t* offsets, int64_t n_cubes, int32_t n_strat
     });
     return check_launch("hist_sweep_kernel");
 }
-
-}  // extern "C"
-
-namespace tq {
 
 int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t* offsets, int64_t n_cubes,
                        int32_t n_strat, int64_t row_begin, int64_t row_end, const void* edges_packed,

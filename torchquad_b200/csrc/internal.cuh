@@ -20,6 +20,10 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
                        int32_t edges_layout, int64_t n_intervals, void* weights, int64_t* counts, void* hist_pairs,
                        void* jf2_rows, void* JF, void* JF2, uint64_t seed, uint32_t call_idx, int32_t cube_block_log2,
                        int32_t rank, int32_t world, double* out_f64, void* ws, size_t ws_bytes, void* stream);
+// fused.cu: tq_vegas_hist_sweep for one rank's share of the cubes (n_cubes = GLOBAL count, offsets / jf2_rows local)
+int hist_sweep_launch(const int64_t* offsets, int64_t n_cubes, int32_t n_strat, int32_t dim, int32_t dtype, const void* jf2_rows,
+                      int64_t n_intervals, void* hist_pairs, int32_t dims_per_group, uint64_t seed, uint32_t call_idx,
+                      int32_t cube_block_log2, int32_t rank, int32_t world, void* ws, size_t ws_bytes, void* stream);
 // fused.cu: pairs += {record.w, record.c}, record fields back to zero (records -> the all-reduce buffer)
 int records_to_pairs_launch(void* records, double* pairs, int32_t dim, int64_t ni, int32_t dtype, void* stream);
 

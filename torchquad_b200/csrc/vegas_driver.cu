@@ -315,6 +315,7 @@ static int run_fused_sharded(const tq_integrand* fn, int32_t dtype, int64_t N, i
         if (!rc && recs) rc = tq_vegas_map_pack_records(s->x_edges, s->dx_edges, s->edges_packed, dim, ni, dtype, stream);
         return rc;
     };
+    const bool sweep_ok = !recs && grid_improve && s->jf2_rows != nullptr && s->sweep_dims_per_group >= 1 && n_strat >= 2;
     cudaMemsetAsync(s->status, 0, 4 * (size_t)max_passes * sizeof(int32_t), st);
     cudaMemsetAsync(tail, 0, 8 * sizeof(double), st);
     PhaseTimer tm(st);
@@ -346,9 +347,21 @@ static int run_fused_sharded(const tq_integrand* fn, int32_t dtype, int64_t N, i
         if (rc) return rc;
         tm.mark(1);
         const int64_t m_est = starting / world + 2 * n_local + 1024;
-        rc = tq_fused_vegas_sharded(fn, dtype, s->offsets, n_local, n_strat, 0, -m_est, s->edges_packed, layout, ni, nullptr, nullptr,
-                                    grid_improve && !recs ? comm : nullptr, s->JF, s->JF2, seed, call++, lb, rank, world, nullptr,
-                                    s->ws, s->ws_bytes, stream);
+        if (sweep_ok && starting >= (1 << 20) && starting + 2 * n_local <= s->jf2_rows_cap) {
+            // maps beyond L2: the pass stores jf^2 per local row, the band sweeps bin this rank's cubes into `comm`
+            // (a rank's rows never exceed starting * sum(dh) + 2 * n_local <= the capacity checked above)
+            rc = fused_vegas_launch(fn, dtype, s->offsets, n_local, n_strat, 0, -m_est, s->edges_packed, TQ_EDGES_PAIRS, ni, nullptr,
+                                    nullptr, nullptr, s->jf2_rows, s->JF, s->JF2, seed, call, lb, rank, world, nullptr, s->ws,
+                                    s->ws_bytes, stream);
+            if (!rc)
+                rc = hist_sweep_launch(s->offsets, n_cubes, n_strat, dim, dtype, s->jf2_rows, ni, comm, s->sweep_dims_per_group, seed,
+                                       call, lb, rank, world, s->ws, s->ws_bytes, stream);
+            ++call;
+        } else {
+            rc = tq_fused_vegas_sharded(fn, dtype, s->offsets, n_local, n_strat, 0, -m_est, s->edges_packed, layout, ni, nullptr, nullptr,
+                                        grid_improve && !recs ? comm : nullptr, s->JF, s->JF2, seed, call++, lb, rank, world, nullptr,
+                                        s->ws, s->ws_bytes, stream);
+        }
         if (rc) return rc;
         if (grid_improve && recs && (rc = records_to_pairs_launch(s->edges_packed, comm, dim, ni, dtype, stream))) return rc;
         if (it > TQ_VEGAS_MAX_PASSES) { set_error("tq_vegas_run_fused_sharded: too many iterations"); return TQ_ERR_UNSUPPORTED; }

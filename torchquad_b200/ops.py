@@ -651,10 +651,11 @@ def vegas_run_fused(fn_struct, vmap, strat, N, max_iterations, eps_rel, eps_abs,
     dev, dt = vmap.device, vmap.dtype
     use_records = bool(use_grid_improve) and vmap.wants_records()
     sweep = None
-    if use_records and shard is None and vmap.sweep_group(strat.N_strat) >= 1 and N // (max_iterations + 5) >= (1 << 20):
-        # maps beyond L2 on one GPU: pair tables + deferred histogram, binned band by band (tq_vegas_hist_sweep)
+    if use_records and vmap.sweep_group(strat.N_strat) >= 1 and N // (max_iterations + 5) >= (1 << 20):
+        # maps beyond L2: pair tables + deferred histogram, binned band by band (tq_vegas_hist_sweep); on several GPUs every rank
+        # sweeps its own cubes.  A pass has at most budget * sum(dh) + 2 * cubes rows and the budget stays below 4 increments.
         use_records = False
-        sweep = (vmap.sweep_group(strat.N_strat), 4 * (N // (max_iterations + 5)) + 2 * strat.N_cubes + 1024)
+        sweep = (vmap.sweep_group(strat.N_strat), 4 * (N // (max_iterations + 5)) + 2 * strat.N_cubes_local + 1024)
     state, keep, nh, offsets = _vegas_state(vmap, strat, use_records, sweep)
     result = _lib.tq_vegas_result()
     common = (fn_struct, dtype_code(dt), N, max_iterations, float(eps_rel), float(eps_abs), int(bool(use_grid_improve)),
