@@ -28,6 +28,12 @@ for dt in (torch.float32, torch.float64):
         v = tq.VEGAS(); v.native_loop = native
         print(dt, "VEGAS records", native, float(v.integrate(g, 3, N=30000, integration_domain=dom, seed=4)),
               float(v.integrate(fn, 3, N=30000, integration_domain=dom, seed=4)))
+    # maps "beyond L2" with >= 2^20 rows per pass: deferred histogram + band sweeps (fused), jf^2 rows + sweeps (callback)
+    if "--no-sweeps" not in sys.argv:
+        v = tq.VEGAS(); v.native_loop = False
+        print(dt, "VEGAS band sweeps", float(tq.VEGAS().integrate(F.GenzGaussian(2, a=3.0, u=0.5), 2, N=27_000_000, integration_domain=dom[:2], seed=4)),
+              float(v.integrate(lambda x: torch.exp(-torch.sum((x - 0.4) ** 2, dim=1)), 2, N=27_000_000, integration_domain=dom[:2], seed=4)),
+              v._regen_sweep)
     VEGASMap.records_min_bytes = keep
     v = tq.VEGAS(); v.native_loop = False
     print(dt, "VEGAS python loop", float(v.integrate(g, 3, N=30000, integration_domain=dom, seed=5)),

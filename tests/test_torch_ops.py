@@ -21,6 +21,11 @@ def test_operators_are_registered_with_schemas_and_fake_impls():
         assert x.shape == (1000, 3) and jac.shape == (1000,)
         off = torch.empty(28, dtype=torch.int64, device="cuda")
         assert torch.ops.tqb200.vegas_strat_sample(off, 3, 3, torch.float32, 77, 1, 0).shape == (77, 3)
+        edges = dom.new_empty((3, 10, 2))
+        x2, jac2 = torch.ops.tqb200.vegas_sample_map(off, 3, 3, 77, edges, dom, 1, 0)
+        assert x2.shape == (77, 3) and jac2.shape == (77,) and x2.dtype == torch.float64
+        hist = dom.new_empty((3, 10, 2))
+        assert torch.ops.tqb200.vegas_accumulate_regen_(off, 3, 3, 77, jac2, jac2, 1.0, hist, 1, 0).shape == (77,)
         JF, JF2 = torch.ops.tqb200.vegas_strat_accumulate(dom.new_empty(77), off)
         assert JF.shape == JF2.shape == (27,)
         assert torch.ops.tqb200.nc_grid_points(dom.new_empty((3, 5))).shape == (125, 3)

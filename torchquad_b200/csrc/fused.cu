@@ -100,31 +100,57 @@ struct Integrand {
 };
 
 // ------------------------------------------------------------------ fused Monte Carlo
+#ifndef TQ_MC_MIN_CTAS
+#define TQ_MC_MIN_CTAS 1
+#endif
+#ifndef TQ_MC_ROWS
+#define TQ_MC_ROWS 2  // rows a thread evaluates side by side (independent Philox chains and integrand evaluations): the kernel is
+                      // issue-bound and gains from ILP, not occupancy -- measured on configs[1] (profiles/r2/exp_mc_variants.txt):
+                      // 1 row 4.96e10 evals/s, 2 rows 5.50e10, 3 / 4 / 6 rows 5.29 / 5.39 / 5.15e10; capping registers for 6 / 8
+                      // CTAs per SM instead: 4.60 / 4.34e10
+#endif
 template <int FAM, typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, TQ_MC_MIN_CTAS)
 fused_mc_kernel(const tq_integrand P, int64_t row_begin, int64_t nrows, uint64_t seed, uint32_t call,
                 double* partials, unsigned int* ticket, double* out) {
     constexpr int LANES = U01<T>::LANES;
+    constexpr int R = TQ_MC_ROWS;
     __shared__ FnShared<T> S;
     __shared__ double sh[32 * 2];
     stage_integrand<T>(P, S);
     const int dim = S.dim;
     double acc[2] = {0.0, 0.0};
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows;
-         r += (int64_t)gridDim.x * blockDim.x) {
-        const uint64_t grow = (uint64_t)(row_begin + r);
-        Integrand<FAM, T> fn;
-        fn.init();
-        for (int d0 = 0; d0 < dim; d0 += LANES) {
-            T u[LANES];
-            philox_block<T>(seed, call, (uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)(d0 / LANES), u);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += R * stride) {
+        Integrand<FAM, T> fn[R];
+        uint64_t grow[R];
 #pragma unroll
-            for (int j = 0; j < LANES; ++j)
-                if (d0 + j < dim) fn.step(add_rn(mul_rn(u[j], S.size[d0 + j]), S.start[d0 + j]), d0 + j, S);
+        for (int k = 0; k < R; ++k) {
+            fn[k].init();
+            grow[k] = (uint64_t)(row_begin + r + k * stride);
         }
-        const double f = (double)(fn.finish(S) * S.scale);
-        acc[0] += f;
-        acc[1] += f * f;
+        for (int d0 = 0; d0 < dim; d0 += LANES) {
+            T u[R][LANES];
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+                philox_block<T>(seed, call, (uint32_t)grow[k], (uint32_t)(grow[k] >> 32), (uint32_t)(d0 / LANES), u[k]);
+#pragma unroll
+            for (int j = 0; j < LANES; ++j) {
+                if (d0 + j < dim) {
+                    const T sz = S.size[d0 + j], st = S.start[d0 + j];
+#pragma unroll
+                    for (int k = 0; k < R; ++k) fn[k].step(add_rn(mul_rn(u[k][j], sz), st), d0 + j, S);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            if (k == 0 || r + k * stride < nrows) {  // the extra rows of the last step are evaluated but not counted
+                const double f = (double)(fn[k].finish(S) * S.scale);
+                acc[0] += f;
+                acc[1] += f * f;
+            }
+        }
     }
     grid_sum_finish<2>(acc, sh, partials, ticket, out);
 }
@@ -143,6 +169,9 @@ struct NcWalk {
     uint32_t step_lo;    // grid stride % B
 };
 
+#ifndef TQ_NC_ROWS
+#define TQ_NC_ROWS 2  // grid points a thread evaluates side by side (see TQ_MC_ROWS)
+#endif
 template <int FAM, typename T>
 __global__ void __launch_bounds__(256)
 fused_nc_kernel(const tq_integrand P, const T* __restrict__ nodes, const T* __restrict__ w, uint32_t n,
@@ -163,47 +192,77 @@ fused_nc_kernel(const tq_integrand P, const T* __restrict__ nodes, const T* __re
         sw = b;
     }
     double acc[1] = {0.0};
+    // R points per thread side by side (p, p + stride, ...): independent digit walks and integrand evaluations give the
+    // issue-bound kernel instruction-level parallelism; every copy keeps its own (hi, lo) and advances by R grid strides.
+    constexpr int R = TQ_NC_ROWS;
     const int64_t r0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = p_end - p_begin;
-    const uint64_t pfirst = (uint64_t)(p_begin + r0);
-    uint64_t hi = pfirst / wk.B;                       // once per thread
-    uint32_t lo = (uint32_t)(pfirst - hi * wk.B);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint64_t hi[R];
+    uint32_t lo[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const uint64_t pfirst = (uint64_t)(p_begin + r0 + k * stride);
+        hi[k] = pfirst / wk.B;                       // once per thread
+        lo[k] = (uint32_t)(pfirst - hi[k] * wk.B);
+    }
     const int d_split = dim - wk.k;                    // dimensions [d_split, dim) come from lo
-    for (int64_t r = r0; r < total; r += (int64_t)gridDim.x * blockDim.x) {
-        Integrand<FAM, T> fn;
-        fn.init();
-        T wt = (T)1;
-        uint32_t q = lo;
-        for (int d = dim - 1; d >= d_split; --d) {
-            const uint32_t t = wk.fd.div(q);
-            const uint32_t i = q - t * n;
-            q = t;
-            wt *= sw[d * n + i];
-            fn.step(sn[d * n + i], d, S);
+    for (int64_t r = r0; r < total; r += R * stride) {
+        Integrand<FAM, T> fn[R];
+        T wt[R];
+        uint32_t q[R];
+        bool wide = false;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            fn[k].init();
+            wt[k] = (T)1;
+            q[k] = lo[k];
+            wide |= hi[k] > 0xffffffffull;
         }
-        if (hi <= 0xffffffffull) {
-            q = (uint32_t)hi;
+        for (int d = dim - 1; d >= d_split; --d) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const uint32_t t = wk.fd.div(q[k]);
+                const uint32_t i = q[k] - t * n;
+                q[k] = t;
+                wt[k] *= sw[d * n + i];
+                fn[k].step(sn[d * n + i], d, S);
+            }
+        }
+        if (!wide) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) q[k] = (uint32_t)hi[k];
             for (int d = d_split - 1; d >= 0; --d) {
-                const uint32_t t = wk.fd.div(q);
-                const uint32_t i = q - t * n;
-                q = t;
-                wt *= sw[d * n + i];
-                fn.step(sn[d * n + i], d, S);
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const uint32_t t = wk.fd.div(q[k]);
+                    const uint32_t i = q[k] - t * n;
+                    q[k] = t;
+                    wt[k] *= sw[d * n + i];
+                    fn[k].step(sn[d * n + i], d, S);
+                }
             }
         } else {  // more than 2^63 / n points: never in practice, kept exact
-            uint64_t h = hi;
-            for (int d = d_split - 1; d >= 0; --d) {
-                const uint64_t t = h / n;
-                const uint32_t i = (uint32_t)(h - t * n);
-                h = t;
-                wt *= sw[d * n + i];
-                fn.step(sn[d * n + i], d, S);
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                uint64_t h = hi[k];
+                for (int d = d_split - 1; d >= 0; --d) {
+                    const uint64_t t = h / n;
+                    const uint32_t i = (uint32_t)(h - t * n);
+                    h = t;
+                    wt[k] *= sw[d * n + i];
+                    fn[k].step(sn[d * n + i], d, S);
+                }
             }
         }
-        acc[0] += (double)(fn.finish(S) * S.scale) * (double)wt;
-        lo += wk.step_lo;
-        hi += wk.step_hi;
-        if (lo >= wk.B) { lo -= wk.B; ++hi; }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            if (k == 0 || r + k * stride < total)  // copies beyond the grid's end are evaluated (on valid table entries) but not added
+                acc[0] += (double)(fn[k].finish(S) * S.scale) * (double)wt[k];
+            lo[k] += wk.step_lo;
+            hi[k] += wk.step_hi;
+            if (lo[k] >= wk.B) { lo[k] -= wk.B; ++hi[k]; }
+        }
     }
     grid_sum_finish<1>(acc, sh, partials, ticket, out);
 }
@@ -940,7 +999,7 @@ int tq_fused_mc(const tq_integrand* fn_host, int32_t dtype, int64_t row_begin, i
     Workspace w(ws, ws_bytes);
     unsigned int* ticket = w.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
     const int64_t nrows = row_end - row_begin;
-    const int grid = grid_for(nrows, 256, 8);
+    const int grid = grid_for((nrows + TQ_MC_ROWS - 1) / TQ_MC_ROWS, 256, 8);  // a thread evaluates TQ_MC_ROWS rows per step
     double* partials = w.take<double>((size_t)grid * 2);
     if (!ticket || !partials) { set_error("tq_fused_mc: workspace too small"); return TQ_ERR_WORKSPACE; }
     cudaStream_t st = as_stream(stream);
@@ -959,7 +1018,7 @@ int tq_fused_nc(const tq_integrand* fn_host, const void* nodes, const void* w, i
     TQ_REQUIRE(n >= 1 && p_begin >= 0 && p_end >= p_begin, "tq_fused_nc: bad grid arguments");
     Workspace wk(ws, ws_bytes);
     unsigned int* ticket = wk.take<unsigned int>(WS_HEADER / sizeof(unsigned int));
-    const int grid = grid_for(p_end - p_begin, 256, 8);
+    const int grid = grid_for((p_end - p_begin + TQ_NC_ROWS - 1) / TQ_NC_ROWS, 256, 8);  // TQ_NC_ROWS points per thread and step
     double* partials = wk.take<double>((size_t)grid);
     if (!ticket || !partials) { set_error("tq_fused_nc: workspace too small"); return TQ_ERR_WORKSPACE; }
     cudaStream_t st = as_stream(stream);
@@ -970,7 +1029,7 @@ int tq_fused_nc(const tq_integrand* fn_host, const void* nodes, const void* w, i
     walk.k = 0;
     while (walk.k < dim && (uint64_t)walk.B * (uint64_t)n <= (1ull << 31)) { walk.B *= (uint32_t)n; ++walk.k; }
     if (walk.k == 0) { walk.B = (uint32_t)n; walk.k = 1; }  // n > 2^31 is refused by the int32 argument; n = 1 lands here
-    const uint64_t stride = (uint64_t)grid * 256;
+    const uint64_t stride = (uint64_t)grid * 256 * TQ_NC_ROWS;  // a thread's copies advance by TQ_NC_ROWS grid strides per step
     walk.step_hi = stride / walk.B;
     walk.step_lo = (uint32_t)(stride % walk.B);
     TQ_DISPATCH_DTYPE(dtype, {

@@ -287,7 +287,7 @@ int tq_vegas_sample_map(const int64_t* offsets, int64_t n_cubes, int32_t n_strat
                         int64_t row_end, const void* edges_packed, int32_t edges_layout, int64_t n_intervals, const void* domain,
                         uint64_t seed, uint32_t call_idx, void* x, void* jac, void* stream) {
     TQ_REQUIRE(row_end >= row_begin && row_begin >= 0, "tq_vegas_sample_map: bad row range");
-    TQ_REQUIRE(dim >= 1 && dim <= 4096 && n_intervals >= 1 && n_intervals < (1LL << 31), "tq_vegas_sample_map: bad map shape");
+    TQ_REQUIRE(dim >= 1 && dim <= 1024 && n_intervals >= 1 && n_intervals < (1LL << 31), "tq_vegas_sample_map: bad map shape (dim <= 1024)");
     TQ_REQUIRE(edges_packed && domain && x && jac, "tq_vegas_sample_map: NULL argument");
     TQ_REQUIRE(edges_layout == TQ_EDGES_PAIRS || edges_layout == TQ_EDGES_RECORDS, "tq_vegas_sample_map: unknown edges layout %d", edges_layout);
     const bool strat = offsets != nullptr;

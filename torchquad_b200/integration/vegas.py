@@ -36,6 +36,9 @@ class VEGAS(BaseIntegrator):
     """VEGAS Enhanced, arXiv:2009.05112.  Same surface as the reference class.
 
     Extension attributes (defaults reproduce the reference):
+      regenerate_samples callback integrands with the library's generator: every pass is two kernels around the integrand
+                         (ops.sample_map, ops.accumulate_regen) and the stratified samples y are never written to HBM.
+                         False: the round-1 pipeline (y materialised, read back for the map and the histogram).
       max_map_intervals  cap on the map size per dimension.  The reference uses Ni = (N // (max_it + 5)) // 10
                          (vegas.py:117), i.e. 1e7 .. 4e7 bins per dimension for N = 2.5e9 .. 1e10: tables far
                          larger than L2 that turn every bin lookup and histogram update into a random HBM

@@ -145,6 +145,34 @@ def _(jf, offsets):
     return jf.new_empty((n,)), jf.new_empty((n,))
 
 
+@_define("vegas_sample_map")
+def vegas_sample_map(offsets: torch.Tensor, n_strat: int, dim: int, rows: int, edges_packed: torch.Tensor, domain: torch.Tensor,
+                     seed: int, call_idx: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """(x [rows, dim] in domain coordinates, jac [rows]) of a stratified pass straight from the Philox stream: get_Y + get_X +
+    get_Jac + x*size+start in one kernel, y never materialised (vegas_stratification.py:140-165, vegas_map.py:44-74)."""
+    return ops.sample_map(offsets, n_strat, dim, edges_packed.dtype, 0, rows, seed, call_idx, domain, edges_packed=edges_packed)
+
+
+@vegas_sample_map.register_fake
+def _(offsets, n_strat, dim, rows, edges_packed, domain, seed, call_idx):
+    return edges_packed.new_empty((rows, dim)), edges_packed.new_empty((rows,))
+
+
+@_define("vegas_accumulate_regen_", mutates=("hist_pairs",))
+def vegas_accumulate_regen_(offsets: torch.Tensor, n_strat: int, dim: int, rows: int, f: torch.Tensor, jac: torch.Tensor,
+                            volume: float, hist_pairs: torch.Tensor, seed: int, call_idx: int) -> torch.Tensor:
+    """jf = (f*volume)*jac for the rows of `vegas_sample_map`, and hist_pairs[d, k] += {jf^2, 1} with the bin ids regenerated
+    from the same Philox blocks (vegas.py:104-112,284-287, vegas_map.py:99-111).  Returns jf."""
+    jf, _ = ops.accumulate_regen(offsets, n_strat, dim, 0, rows, hist_pairs.shape[1], f, jac, volume, seed, call_idx,
+                                 hist_pairs=hist_pairs)
+    return jf
+
+
+@vegas_accumulate_regen_.register_fake
+def _(offsets, n_strat, dim, rows, f, jac, volume, hist_pairs, seed, call_idx):
+    return f.new_empty((rows,))
+
+
 # ------------------------------------------------------------------------------------------- Newton-Cotes
 @_define("nc_grid_points")
 def nc_grid_points(nodes: torch.Tensor) -> torch.Tensor:
@@ -186,4 +214,5 @@ def _nc_contract_backward(ctx, g):
 nc_contract.register_autograd(_nc_contract_backward, setup_context=_nc_contract_setup)
 
 OPERATORS = ["philox_uniform", "mc_sample", "mc_sample_backward", "sum_columns", "vegas_map_forward", "vegas_map_accumulate_",
-             "vegas_strat_sample", "vegas_strat_accumulate", "nc_grid_points", "nc_contract"]
+             "vegas_strat_sample", "vegas_strat_accumulate", "vegas_sample_map", "vegas_accumulate_regen_", "nc_grid_points",
+             "nc_contract"]
