@@ -22,6 +22,8 @@ CAPTURES = {
     "vegas8:fused_vegas_kernel": ("vegas8", "fused_vegas_kernel", 15),
     "vegas8:hist_sweep_kernel": ("vegas8", "hist_sweep_kernel", 87),   # 10 passes x 8 dims + the 8 of the final pass: the last one
     "vegas16_cap4096:fused_vegas_tile_kernel": ("vegas16_cap4096", "fused_vegas_tile_kernel", 10),  # fp32: 10 passes + the final one
+    "vegas8_unfused:sample_map_kernel": ("unfused8_cap", "sample_map_kernel", 14),
+    "vegas8_unfused:accumulate_regen_kernel": ("unfused8_cap", "accumulate_regen_kernel", 14),
     "uniform_kernel_f32_d10": ("uniform_f32_d10", "uniform_kernel", 1),
     "sum1_kernel_f32": ("sum1_f32", "sum1_kernel", 1),
     "contract1_kernel_f64": ("contract1_f64", "contract1_kernel", 1),

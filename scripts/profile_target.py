@@ -92,6 +92,14 @@ elif what == "contract1_f64":
         ops.nc_contract(f, nodes, 0, P)
     torch.cuda.synchronize()
     print("UNITS", P)
+elif what == "unfused8_cap":  # callback integrand, capped map: the two-kernel pass (5 warm-up + 10 stratified passes)
+    dom = torch.tensor([[0.0, 1.0]] * 8, dtype=torch.float64, device=dev)
+    v = tq.VEGAS()
+    v.max_map_intervals = 4096
+    r = v.integrate(lambda x: torch.cos(2.0 * 3.141592653589793 * 0.3 + torch.sum(0.5 * x, dim=1)), 8, N=250_000_000,
+                    integration_domain=dom, seed=1)
+    print("RESULT", float(r))
+    print("UNITS", int(v.strat._offsets[-1].item()))
 elif what == "unfused8":
     dom = torch.tensor([[0.0, 1.0]] * 8, dtype=torch.float64, device=dev)
     fn = F.GenzOscillatory(8, a=0.5, u=0.3)

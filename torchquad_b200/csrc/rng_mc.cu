@@ -30,6 +30,9 @@ template <> struct RawBits<double> {
     static constexpr double SCALE = 1.1102230246251565e-16;  // 2^-53
 };
 
+#ifndef TQ_UNIFORM_ROWS
+#define TQ_UNIFORM_ROWS 1
+#endif
 template <typename T, bool AFFINE>
 __global__ void __launch_bounds__(256)
 uniform_kernel(T* __restrict__ out, const T* __restrict__ domain, int64_t row_begin, int64_t nrows,
@@ -63,25 +66,38 @@ uniform_kernel(T* __restrict__ out, const T* __restrict__ domain, int64_t row_be
     const bool base16 = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const int mode = (nvalid == LANES && base16 && (dim % LANES) == 0) ? 2
                    : (sizeof(T) == 4 && base16 && (dim % 2) == 0 && (nvalid % 2) == 0) ? 1 : 0;
-    for (; row < nrows; row += stride, p += pstride) {
-        const uint64_t grow = (uint64_t)(row_begin + row);
-        const uint4 r = Philox::run((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)blk, call, k0, k1);
-        T v[LANES];
-        RawBits<T>::get(r, v);
+    // TQ_UNIFORM_ROWS rows per step side by side (independent Philox chains).  Unlike the fused Monte Carlo kernel this one does
+    // NOT gain from the extra instruction-level parallelism: it is bound by the quarter-rate IMAD.WIDE pipe (math-pipe throttle),
+    // not by issue latency -- measured dim 10 fp32: 1 / 2 / 4 rows = 3784 / 3330 / 3347 GB/s (profiles/r2/exp_uniform_rows.txt).
+    constexpr int R = TQ_UNIFORM_ROWS;
+    for (; row < nrows; row += R * stride, p += R * pstride) {
+        uint4 r[R];
 #pragma unroll
-        for (int j = 0; j < LANES; ++j) v[j] = AFFINE ? add_rn(mul_rn(v[j], sz[j]), st[j]) : mul_rn(v[j], sz[j]);
-        if (mode == 2) {
-            if constexpr (LANES == 4) __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
-            else __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1]));
-        } else if (mode == 1) {
-            if constexpr (LANES == 4) {
-                __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
-                if (nvalid == 4) __stcs(reinterpret_cast<float2*>(p) + 1, make_float2(v[2], v[3]));
+        for (int k = 0; k < R; ++k) {
+            const uint64_t grow = (uint64_t)(row_begin + row + k * stride);
+            r[k] = Philox::run((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)blk, call, k0, k1);
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            if (k > 0 && row + k * stride >= nrows) break;
+            T* pk = p + k * pstride;
+            T v[LANES];
+            RawBits<T>::get(r[k], v);
+#pragma unroll
+            for (int j = 0; j < LANES; ++j) v[j] = AFFINE ? add_rn(mul_rn(v[j], sz[j]), st[j]) : mul_rn(v[j], sz[j]);
+            if (mode == 2) {
+                if constexpr (LANES == 4) __stcs(reinterpret_cast<float4*>(pk), make_float4(v[0], v[1], v[2], v[3]));
+                else __stcs(reinterpret_cast<double2*>(pk), make_double2(v[0], v[1]));
+            } else if (mode == 1) {
+                if constexpr (LANES == 4) {
+                    __stcs(reinterpret_cast<float2*>(pk), make_float2(v[0], v[1]));
+                    if (nvalid == 4) __stcs(reinterpret_cast<float2*>(pk) + 1, make_float2(v[2], v[3]));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < LANES; ++j)
+                    if (j < nvalid) pk[j] = v[j];
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < LANES; ++j)
-                if (j < nvalid) p[j] = v[j];
         }
     }
 }
