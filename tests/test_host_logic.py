@@ -244,3 +244,32 @@ int main(void) {
     subprocess.run(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-o", str(exe), str(src), "-lm"], check=True)
     bad, n = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
     assert bad == 0 and n > 4 * 10**8
+
+
+def test_cube_shard_inverse_matches_the_deal():
+    """The band sweeps of a sharded run walk GLOBAL cube ids and keep the cubes this rank owns (CubeShard::local_cube,
+    csrc/fused.cu): owner and local id must invert distributed.global_cube_ids for every rank, including the incomplete
+    last round and the trailing partial block."""
+    from torchquad_b200 import distributed as tqdist
+
+    def local_cube(c, lb, rank, world):  # the device formula, restated
+        blk = c >> lb
+        rnd, pos = divmod(blk, world)
+        return (rank + tqdist._skew(rnd)) % world == pos, (rnd << lb) + (c & ((1 << lb) - 1))
+
+    for n_cubes, world in [(8**8, 8), (3**16 // 9, 4), (10007, 2), (65536 + 17, 8), (6561, 3), (8**5, 5)]:
+        seen = 0
+        for rank in range(world):
+            shard = tqdist.cube_shard(n_cubes, rank, world)
+            assert shard is not None
+            lb, n_local = shard
+            ids = tqdist.global_cube_ids(n_local, lb, rank, world).tolist()
+            step = max(1, n_local // 5000)
+            for l in list(range(0, n_local, step)) + [n_local - 1]:
+                mine, l2 = local_cube(ids[l], lb, rank, world)
+                assert mine and l2 == l, (n_cubes, world, rank, l)
+            other = (rank + 1) % world
+            for l in range(0, n_local, max(1, n_local // 200)):
+                assert not local_cube(ids[l], lb, other, world)[0]
+            seen += n_local
+        assert seen == n_cubes
