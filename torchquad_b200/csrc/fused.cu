@@ -1249,6 +1249,11 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
     if (hist_mode == HIST_DEFER) {
         const int64_t rpc = rpc_env > 0 ? rpc_env : 1024;
         if (rpc < rows_per_cta) rows_per_cta = rpc;
+    } else if (rpc_env > 0 && strat && rpc_env < rows_per_cta) {
+        // experiment only: interleaved chunks for L2-resident maps make every CTA in flight hit the SAME bands, and the
+        // reductions then contend for the same L2 sectors: 8-D fp64 pairs 1.48e10 -> 1.24e10 samples/s at 1024-row chunks
+        // (profiles/r2/exp_interleave_l2_resident.txt).  One contiguous range per CTA stays the default.
+        rows_per_cta = rpc_env;
     }
     rows_per_cta = ((rows_per_cta + FV_BLOCK - 1) / FV_BLOCK) * FV_BLOCK;
     if (rows_per_cta < FV_BLOCK) rows_per_cta = FV_BLOCK;
