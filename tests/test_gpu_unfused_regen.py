@@ -166,3 +166,65 @@ def test_gradient_through_integrand_still_uses_the_samples(cuda):
     r = v.integrate(lambda x: p * torch.sum(x * x, dim=1), 2, N=50_000, integration_domain=dom, seed=1)
     (g,) = torch.autograd.grad(r, p)
     assert abs(float(r) - 2.0 * 2.0 / 3.0) < 2e-2 and abs(float(g) - 2.0 / 3.0) < 1e-2
+
+
+def _cube_keyed_uniforms(seed, call, nh, dim, dt):
+    """The cube-keyed Philox stream restated with the oracle's generator: counter = (cube, index in cube, block, call)."""
+    import numpy as np
+
+    from oracle import ref_oracle as O
+
+    lanes = 4 if dt == torch.float32 else 2
+    nblk = (dim + lanes - 1) // lanes
+    cube = np.repeat(np.arange(nh.shape[0], dtype=np.uint32), nh.numpy())
+    idx = np.concatenate([np.arange(int(n), dtype=np.uint32) for n in nh.tolist()])
+    ctr = np.empty((cube.shape[0], nblk, 4), dtype=np.uint32)
+    ctr[..., 0], ctr[..., 1] = cube[:, None], idx[:, None]
+    ctr[..., 2], ctr[..., 3] = np.arange(nblk, dtype=np.uint32)[None, :], np.uint32(call)
+    out = O.philox4x32_10(ctr, np.array([seed & 0xFFFFFFFF, seed >> 32], dtype=np.uint32))
+    if dt == torch.float32:
+        u = ((out >> np.uint32(8)).astype(np.float32) * np.float32(2.0**-24)).reshape(cube.shape[0], nblk * 4)[:, :dim]
+    else:
+        lo, hi = out[..., 0::2].astype(np.uint64), out[..., 1::2].astype(np.uint64)
+        u = ((((hi << np.uint64(32)) | lo) >> np.uint64(11)).astype(np.float64) * 2.0**-53).reshape(cube.shape[0], nblk * 2)[:, :dim]
+    return torch.from_numpy(np.ascontiguousarray(u))
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_two_kernel_pass_against_the_oracle_directly(cuda, tag):
+    """tq_vegas_sample_map / tq_vegas_accumulate_regen against oracle/ref_oracle.py (the reference's ATen expressions on the
+    CPU) on the same Philox uniforms: x, jac, jf bit-identical, counts exact, weights to the order of the atomics."""
+    from oracle import ref_oracle as O
+
+    dt = DT[tag]
+    dim, n_strat, ni, seed, call, volume = 5, 4, 300, 424242, 9, 2.5
+    vm = _adapted_map(ni, dim, dt, cuda, seed=3)
+    xe, dxe = vm.x_edges.cpu(), vm.dx_edges.cpu()
+    dom = torch.tensor([[-1.0, 1.0], [0.0, 2.0], [0.5, 0.75], [-3.0, -1.0], [0.0, 1.0]], dtype=dt)
+    starts, sizes = dom[:, 0], dom[:, 1] - dom[:, 0]
+    offsets = _offsets(n_strat, dim, 3.7, dt, cuda, seed=5)
+    nh = (offsets[1:] - offsets[:-1]).cpu()
+    M = int(offsets[-1])
+    # stratified pass
+    y = O.strat_get_y(nh, n_strat, dim, _cube_keyed_uniforms(seed, call, nh, dim, dt))
+    x_ref = O.map_get_x(y, xe, dxe) * sizes + starts
+    jac_ref = O.map_get_jac(y, dxe)
+    x, jac = ops.sample_map(offsets, n_strat, dim, dt, 0, M, seed, call, dom.to(cuda), edges_packed=vm.packed_edges())
+    assert torch.equal(x.cpu(), x_ref) and torch.equal(jac.cpu(), jac_ref)
+    f = torch.sin(x_ref.sum(dim=1)) + 1.25
+    jf_ref = (f * volume) * jac_ref
+    w_ref, c_ref = O.map_reset(ni, dim, dt)
+    O.map_accumulate(w_ref, c_ref, y, jf_ref * jf_ref)
+    h = vm.hist_pairs()
+    h.zero_()
+    jf, _ = ops.accumulate_regen(offsets, n_strat, dim, 0, M, ni, f.to(cuda), jac, volume, seed, call, hist_pairs=h)
+    assert torch.equal(jf.cpu(), jf_ref)
+    assert torch.equal(h[..., 1].cpu().to(torch.int64), c_ref)
+    tol = 1e-12 if dt == torch.float64 else 2e-5
+    assert float(((h[..., 0].cpu() - w_ref.double()).abs() / w_ref.double().abs().clamp_min(1e-300)).max()) <= tol
+    h.zero_()
+    # warm-up pass: y = u * 0.999999 from the row-keyed stream (vegas.py:230-233)
+    rows, row0 = 3001, 11
+    yw = O.philox_uniform(seed, call + 1, row0, rows, dim, dt) * 0.999999
+    xw, jw = ops.sample_map(None, 1, dim, dt, row0, row0 + rows, seed, call + 1, dom.to(cuda), edges_packed=vm.packed_edges())
+    assert torch.equal(xw.cpu(), O.map_get_x(yw, xe, dxe) * sizes + starts) and torch.equal(jw.cpu(), O.map_get_jac(yw, dxe))
