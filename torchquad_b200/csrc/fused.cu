@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1)
 fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offsets, uint32_t n_cubes, CubeShard shard, FastDiv ns_div,
                         T inv_ns, T nsf, T nif, const typename Pair2<T>::type* __restrict__ edges, long long ni, double* __restrict__ hist,
                         T* __restrict__ JF, T* __restrict__ JF2, uint64_t seed, uint32_t call, int g, uint32_t tile_cubes,
-                        FastDiv tile_div, int band_w, unsigned int* next_tile) {
+                        FastDiv tile_div, int band_w, int ne, unsigned int* next_tile) {
     constexpr int LANES = U01<T>::LANES;
     using P2 = typename Pair2<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -576,8 +576,10 @@ fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offs
     const int dim = S.dim;
     const int ns = dim - g;  // band (high) dimensions
     // dynamic shared memory: edges bands | weight bands | jf^2 of the rows in flight | count bands | low-dim bin ids | band ids
-    P2* s_edge = reinterpret_cast<P2*>(smem_raw);                                  // [ns][band_w]
-    T* s_hw = reinterpret_cast<T*>(s_edge + (size_t)ns * band_w);                 // [ns][band_w]
+    // Every band dimension has a private {weight, count} band (a shared-memory atomic replaces an L2 reduction sector: the
+    // larger saving); the first `ne` of them also have their {x, dx} edges staged (a shared-memory read replaces a gather).
+    P2* s_edge = reinterpret_cast<P2*>(smem_raw);                                  // [ne][band_w]
+    T* s_hw = reinterpret_cast<T*>(s_edge + (size_t)ne * band_w);                 // [ns][band_w]
     double* s_jf2 = reinterpret_cast<double*>(s_hw + (((size_t)ns * band_w + 1) & ~(size_t)1));  // [FT_BLOCK]
     unsigned int* s_hc = reinterpret_cast<unsigned int*>(s_jf2 + FT_BLOCK);       // [ns][band_w]
     int* s_ids = reinterpret_cast<int*>(s_hc + (size_t)ns * band_w);              // [g][FT_BLOCK]
@@ -609,11 +611,13 @@ fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offs
         for (int idx = threadIdx.x; idx < ns * band_w; idx += FT_BLOCK) {
             const int sd = idx / band_w, wdx = idx - sd * band_w;
             const long long k = (long long)s_blo[sd] + wdx;
-            P2 e;
-            e.x = (T)0;
-            e.y = (T)0;
-            if (k < ni) e = __ldg(&edges[(int64_t)(g + sd) * ni + k]);
-            s_edge[idx] = e;
+            if (sd < ne) {
+                P2 e;
+                e.x = (T)0;
+                e.y = (T)0;
+                if (k < ni) e = __ldg(&edges[(int64_t)(g + sd) * ni + k]);
+                s_edge[idx] = e;
+            }
             s_hw[idx] = (T)0;
             s_hc[idx] = 0u;
         }
@@ -667,7 +671,7 @@ fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offs
                                 const int sd = d - g;
                                 const unsigned loc = (unsigned)(k - s_blo[sd]);
                                 if (loc < (unsigned)band_w) {
-                                    e = s_edge[sd * band_w + (int)loc];
+                                    e = sd < ne ? s_edge[sd * band_w + (int)loc] : __ldg(&edges[(int64_t)d * ni + k]);
                                     s_bid[sd * FT_BLOCK + threadIdx.x] = (unsigned short)loc;
                                 } else {  // outside the staged band: cannot happen with the slack for Ni <= 2^20; kept exact anyway
                                     e = __ldg(&edges[(int64_t)d * ni + k]);
@@ -1275,11 +1279,12 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
     if (tile_ok && hist_mode == HIST_PAIRS && strat && rows_from_offsets && n_strat >= 2 && dim >= 2 &&
         n_intervals <= (1 << 20)) {
         const int64_t band_w = (n_intervals + n_strat - 1) / n_strat + 3;
-        const size_t per_band = (size_t)band_w * (2 * elt + elt + 4);
-        int best_g = -1;
+        const size_t hist_band = (size_t)band_w * (elt + 4), edge_band = (size_t)band_w * 2 * elt;
+        static const int sb_env = getenv("TQ_FV_TILE_SB") ? atoi(getenv("TQ_FV_TILE_SB")) : 0;  // experiments: cap on band dimensions
+        int best_g = -1, best_ne = 0;
         size_t best_smem = 0;
         uint64_t best_tile = 0;
-        for (int sb = dim - 1; sb >= 1 && band_w < 65535; --sb) {
+        for (int sb = sb_env > 0 && sb_env < dim ? sb_env : dim - 1; sb >= 1 && band_w < 65535; --sb) {
             const int g = dim - sb;
             uint64_t tile_cubes = 1;
             for (int i = 0; i < g; ++i) tile_cubes *= (uint64_t)n_strat;
@@ -1287,11 +1292,15 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
             const uint64_t n_tiles = (uint64_t)n_cubes / tile_cubes;
             if (n_tiles < (uint64_t)sms * 4) break;                               // larger tiles only get fewer
             if (world > 1 && ((1ull << cube_block_log2) % tile_cubes)) continue;  // a tile must not straddle a rank's cube block
-            const size_t need = (size_t)sb * per_band + 16 + (size_t)FT_BLOCK * 8 + (size_t)g * FT_BLOCK * 4 + (size_t)sb * FT_BLOCK * 2;
-            if (need > 200 * 1024) continue;
+            // as many band dimensions as possible get a private histogram band; the shared memory left over stages edges
+            const size_t fixed = (size_t)sb * hist_band + 16 + (size_t)FT_BLOCK * 8 + (size_t)g * FT_BLOCK * 4 + (size_t)sb * FT_BLOCK * 2;
+            if (fixed > 200 * 1024) continue;
             if ((uint64_t)nrows / n_tiles < 4ull * sb * band_w) continue;         // the flush must stay small next to the tile's rows
+            int ne = (int)((200 * 1024 - fixed) / edge_band);
+            if (ne > sb) ne = sb;
             best_g = g;
-            best_smem = need;
+            best_ne = ne;
+            best_smem = fixed + (size_t)ne * edge_band;
             best_tile = tile_cubes;
             break;
         }
@@ -1311,7 +1320,7 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
                     fused_vegas_tile_kernel<FAM, T><<<TQ_GRID(grid), FT_BLOCK, best_smem, st>>>(
                         *fn_host, (const long long*)offsets, (uint32_t)n_cubes, shard, ns_div, inv_ns, (T)n_strat, (T)n_intervals,
                         (const P2*)edges_packed, n_intervals,
-                        (double*)hist_pairs, (T*)JF, (T*)JF2, seed, call_idx, best_g, (uint32_t)best_tile, tile_div, (int)band_w, next_tile);
+                        (double*)hist_pairs, (T*)JF, (T*)JF2, seed, call_idx, best_g, (uint32_t)best_tile, tile_div, (int)band_w, best_ne, next_tile);
                 });
             });
             return check_launch("fused_vegas_tile_kernel");
