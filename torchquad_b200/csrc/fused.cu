@@ -556,6 +556,7 @@ fused_vegas_kernel(const tq_integrand P, const long long* __restrict__ offsets, 
 // once per tile with sector-paired reductions.  The low dimensions go through L2 exactly like in fused_vegas_kernel.
 // Tiles are handed out in order by a global counter; one 1024-thread CTA per SM (the bands need up to ~200 KB).
 constexpr int FT_BLOCK = 1024;
+constexpr size_t FT_SMEM_CAP = 210 * 1024;  // dynamic shared memory of the tile kernel (227 KB per CTA minus ~14 KB of static arrays)
 constexpr int FT_SLICE = FT_BLOCK / 2 + 4;
 
 template <int FAM, typename T>
@@ -1280,6 +1281,7 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
         n_intervals <= (1 << 20)) {
         const int64_t band_w = (n_intervals + n_strat - 1) / n_strat + 3;
         const size_t hist_band = (size_t)band_w * (elt + 4), edge_band = (size_t)band_w * 2 * elt;
+        static const int flush_factor = getenv("TQ_FV_TILE_FLUSH") ? atoi(getenv("TQ_FV_TILE_FLUSH")) : 4;  // rows per flushed bin
         static const int sb_env = getenv("TQ_FV_TILE_SB") ? atoi(getenv("TQ_FV_TILE_SB")) : 0;  // experiments: cap on band dimensions
         int best_g = -1, best_ne = 0;
         size_t best_smem = 0;
@@ -1294,9 +1296,9 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
             if (world > 1 && ((1ull << cube_block_log2) % tile_cubes)) continue;  // a tile must not straddle a rank's cube block
             // as many band dimensions as possible get a private histogram band; the shared memory left over stages edges
             const size_t fixed = (size_t)sb * hist_band + 16 + (size_t)FT_BLOCK * 8 + (size_t)g * FT_BLOCK * 4 + (size_t)sb * FT_BLOCK * 2;
-            if (fixed > 200 * 1024) continue;
-            if ((uint64_t)nrows / n_tiles < 4ull * sb * band_w) continue;         // the flush must stay small next to the tile's rows
-            int ne = (int)((200 * 1024 - fixed) / edge_band);
+            if (fixed > FT_SMEM_CAP) continue;
+            if ((uint64_t)nrows / n_tiles < (uint64_t)flush_factor * sb * band_w) continue;  // the flush must stay small next to the tile's rows
+            int ne = (int)((FT_SMEM_CAP - fixed) / edge_band);
             if (ne > sb) ne = sb;
             best_g = g;
             best_ne = ne;
@@ -1316,7 +1318,7 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
                 using P2 = typename Pair2<T>::type;
                 const T inv_ns = (T)1 / (T)n_strat;
                 TQ_DISPATCH_FAMILY(fn_host->family, {
-                    cudaFuncSetAttribute(fused_vegas_tile_kernel<FAM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                    cudaFuncSetAttribute(fused_vegas_tile_kernel<FAM, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM_CAP);
                     fused_vegas_tile_kernel<FAM, T><<<TQ_GRID(grid), FT_BLOCK, best_smem, st>>>(
                         *fn_host, (const long long*)offsets, (uint32_t)n_cubes, shard, ns_div, inv_ns, (T)n_strat, (T)n_intervals,
                         (const P2*)edges_packed, n_intervals,
