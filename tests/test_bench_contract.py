@@ -34,3 +34,19 @@ def test_workloads_cover_the_baseline_configs():
     assert {"mc", "vegas", "boole"} <= kinds
     mc = bench.WORKLOADS["mc10"]
     assert mc["dim"] == 10 and mc["N"] == 10**9 and mc["dtype"] == "float32"  # configs[1], the default workload
+
+
+def test_rooflines_have_their_ncu_captures():
+    """bench.py takes warp instructions per eval and DRAM bytes from profiles/r2/ncu_metrics.json (scripts/capture_ncu.py);
+    a missing key would silently turn a workload's `roofline.frac` / `traffic` into null."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    m = bench.ncu_metrics()
+    for key in ("mc10:fused_mc_kernel", "boole6:fused_nc_kernel"):
+        assert m[key]["warp_inst_per_unit"] > 0 and m[key]["units_per_launch"] > 0, key
+    for key in ("vegas8_cap4096:fused_vegas_kernel", "vegas16_cap4096:fused_vegas_tile_kernel", "vegas8:fused_vegas_kernel",
+                "vegas8:hist_sweep_kernel", "uniform_kernel_f32_d10", "sum1_kernel_f32"):
+        assert m[key]["dram_bytes"] > 0 and m[key]["time_ns"] > 0, key
+    # every sub-workload of the default run is a known workload, the headline is configs[1]
+    assert bench.HEADLINE == "mc10" and set(bench.SUB_WORKLOADS) <= set(bench.WORKLOADS)
