@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(FT_BLOCK, 1)
 fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offsets, uint32_t n_cubes, CubeShard shard, FastDiv ns_div,
                         T inv_ns, T nsf, T nif, const typename Pair2<T>::type* __restrict__ edges, long long ni, double* __restrict__ hist,
                         T* __restrict__ JF, T* __restrict__ JF2, uint64_t seed, uint32_t call, int g, uint32_t tile_cubes,
-                        FastDiv tile_div, int band_w, int ne, unsigned int* next_tile) {
+                        FastDiv tile_div, int band_w, int ne, bool hist_smem, unsigned int* next_tile) {
     constexpr int LANES = U01<T>::LANES;
     using P2 = typename Pair2<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -579,12 +579,16 @@ fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offs
     // dynamic shared memory: edges bands | weight bands | jf^2 of the rows in flight | count bands | low-dim bin ids | band ids
     // Every band dimension has a private {weight, count} band (a shared-memory atomic replaces an L2 reduction sector: the
     // larger saving); the first `ne` of them also have their {x, dx} edges staged (a shared-memory read replaces a gather).
+    // hist_smem == false (fp64: a shared-memory fp64 atomicAdd is a compare-and-swap loop): only the edges are staged, every
+    // dimension's histogram goes through the sector-paired L2 reductions and s_ids holds the bin ids of ALL dimensions.
+    const size_t nband = hist_smem ? (size_t)ns * band_w : 0;
+    const int nid = hist_smem ? g : dim;  // dimensions binned through L2
     P2* s_edge = reinterpret_cast<P2*>(smem_raw);                                  // [ne][band_w]
     T* s_hw = reinterpret_cast<T*>(s_edge + (size_t)ne * band_w);                 // [ns][band_w]
-    double* s_jf2 = reinterpret_cast<double*>(s_hw + (((size_t)ns * band_w + 1) & ~(size_t)1));  // [FT_BLOCK]
+    double* s_jf2 = reinterpret_cast<double*>(s_hw + ((nband + 1) & ~(size_t)1)); // [FT_BLOCK]
     unsigned int* s_hc = reinterpret_cast<unsigned int*>(s_jf2 + FT_BLOCK);       // [ns][band_w]
-    int* s_ids = reinterpret_cast<int*>(s_hc + (size_t)ns * band_w);              // [g][FT_BLOCK]
-    unsigned short* s_bid = reinterpret_cast<unsigned short*>(s_ids + (size_t)g * FT_BLOCK);  // [ns][FT_BLOCK]
+    int* s_ids = reinterpret_cast<int*>(s_hc + nband);                            // [nid][FT_BLOCK]
+    unsigned short* s_bid = reinterpret_cast<unsigned short*>(s_ids + (size_t)nid * FT_BLOCK);  // [ns][FT_BLOCK] (hist_smem)
     const int ni32 = (int)ni;  // n_intervals <= 2^20 on this path; nif = (T)ni, nsf = (T)N_strat are kernel parameters
     const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31, word = lane & 1;
     int buf = 0;
@@ -619,8 +623,10 @@ fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offs
                 if (k < ni) e = __ldg(&edges[(int64_t)(g + sd) * ni + k]);
                 s_edge[idx] = e;
             }
-            s_hw[idx] = (T)0;
-            s_hc[idx] = 0u;
+            if (hist_smem) {
+                s_hw[idx] = (T)0;
+                s_hc[idx] = 0u;
+            }
         }
         __syncthreads();
         long long c_lo = c_first;
@@ -671,13 +677,11 @@ fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offs
                             } else {
                                 const int sd = d - g;
                                 const unsigned loc = (unsigned)(k - s_blo[sd]);
-                                if (loc < (unsigned)band_w) {
-                                    e = sd < ne ? s_edge[sd * band_w + (int)loc] : __ldg(&edges[(int64_t)d * ni + k]);
-                                    s_bid[sd * FT_BLOCK + threadIdx.x] = (unsigned short)loc;
-                                } else {  // outside the staged band: cannot happen with the slack for Ni <= 2^20; kept exact anyway
-                                    e = __ldg(&edges[(int64_t)d * ni + k]);
-                                    s_bid[sd * FT_BLOCK + threadIdx.x] = 0xffffu;
-                                }
+                                const bool in_band = loc < (unsigned)band_w;
+                                // outside the staged band: cannot happen with the slack for Ni <= 2^20; kept exact anyway
+                                e = (in_band && sd < ne) ? s_edge[sd * band_w + (int)loc] : __ldg(&edges[(int64_t)d * ni + k]);
+                                if (hist_smem) s_bid[sd * FT_BLOCK + threadIdx.x] = in_band ? (unsigned short)loc : (unsigned short)0xffffu;
+                                else s_ids[d * FT_BLOCK + threadIdx.x] = k;
                             }
                             const T x = add_rn(e.x, mul_rn(e.y, o));
                             jac = mul_rn(jac, mul_rn(nif, e.y));
@@ -688,7 +692,7 @@ fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offs
                 const T f = mul_rn(fn.finish(S), S.scale);
                 jf = mul_rn(f, jac);
                 jf2 = mul_rn(jf, jf);
-                for (int sd = 0; sd < ns; ++sd) {  // band dimensions: private shared-memory histogram
+                for (int sd = 0; sd < ns && hist_smem; ++sd) {  // band dimensions: private shared-memory histogram
                     const unsigned loc = s_bid[sd * FT_BLOCK + threadIdx.x];
                     if (loc != 0xffffu) {
                         atomicAdd(&s_hw[sd * band_w + loc], jf2);
@@ -725,7 +729,7 @@ fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offs
                 const double sv = s_jf2[src];
                 if (sv >= 0.0 || sv != sv) {  // active source row (NaN weights are kept, like the direct path keeps them)
                     const double v = word ? 1.0 : sv;
-                    for (int d = 0; d < g; ++d) atomicAdd(hist + ((int64_t)d * ni + s_ids[d * FT_BLOCK + src]) * 2 + word, v);
+                    for (int d = 0; d < nid; ++d) atomicAdd(hist + ((int64_t)d * ni + s_ids[d * FT_BLOCK + src]) * 2 + word, v);
                 }
             }
             __syncwarp();
@@ -741,7 +745,7 @@ fused_vegas_tile_kernel(const tq_integrand P, const long long* __restrict__ offs
             }
         }
         __syncthreads();  // every row of the tile is binned
-        for (int idx = threadIdx.x; idx < ns * band_w * 2; idx += FT_BLOCK) {  // flush: lanes 2i / 2i+1 -> {sum, count} of bin i
+        for (int idx = threadIdx.x; idx < ns * band_w * 2 && hist_smem; idx += FT_BLOCK) {  // flush: lanes 2i / 2i+1 -> {sum, count} of bin i
             const int b = idx >> 1, wd = idx & 1;
             const unsigned int cnt = s_hc[b];
             if (cnt) {
@@ -1276,7 +1280,12 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
     // samples/s; 8-D N_strat=8: 1.65e10 -> 1.81e10), fp64 -5 % (8-D: 1.476e10 -> 1.405e10: a shared-memory fp64 atomicAdd is a
     // 64-bit compare-and-swap loop that retries when two lanes of a warp meet in a 512-bin band).  Default: fp32 only.
     static const int tile_env = getenv("TQ_FV_TILE") ? atoi(getenv("TQ_FV_TILE")) : -1;  // 0: never, 1: always, default: fp32
-    const bool tile_ok = tile_env == 1 || (tile_env != 0 && dtype == TQ_F32);
+    // fp64: edges-only variant (hist_smem = false: staged edges, every histogram update through L2), behind TQ_FV_TILE64=1.
+    // Measured slower than the plain kernel (8-D Ni=4096: 1.23e10 vs 1.50e10 samples/s): tiles are handed out in order, so all
+    // CTAs reduce into the same slow-dimension bands at once (same-sector contention) at half the occupancy.  Off by default.
+    static const int tile64_env = getenv("TQ_FV_TILE64") ? atoi(getenv("TQ_FV_TILE64")) : 0;
+    const bool edges_only = dtype == TQ_F64 && tile_env != 1;
+    const bool tile_ok = tile_env == 1 || (tile_env != 0 && (dtype == TQ_F32 || tile64_env == 1));
     if (tile_ok && hist_mode == HIST_PAIRS && strat && rows_from_offsets && n_strat >= 2 && dim >= 2 &&
         n_intervals <= (1 << 20)) {
         const int64_t band_w = (n_intervals + n_strat - 1) / n_strat + 3;
@@ -1295,11 +1304,15 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
             if (n_tiles < (uint64_t)sms * 4) break;                               // larger tiles only get fewer
             if (world > 1 && ((1ull << cube_block_log2) % tile_cubes)) continue;  // a tile must not straddle a rank's cube block
             // as many band dimensions as possible get a private histogram band; the shared memory left over stages edges
-            const size_t fixed = (size_t)sb * hist_band + 16 + (size_t)FT_BLOCK * 8 + (size_t)g * FT_BLOCK * 4 + (size_t)sb * FT_BLOCK * 2;
+            const size_t fixed = edges_only ? 16 + (size_t)FT_BLOCK * 8 + (size_t)dim * FT_BLOCK * 4
+                                            : (size_t)sb * hist_band + 16 + (size_t)FT_BLOCK * 8 + (size_t)g * FT_BLOCK * 4 + (size_t)sb * FT_BLOCK * 2;
             if (fixed > FT_SMEM_CAP) continue;
-            if ((uint64_t)nrows / n_tiles < (uint64_t)flush_factor * sb * band_w) continue;  // the flush must stay small next to the tile's rows
+            if (edges_only) {  // nothing to flush: a tile only has to amortise its staging and barriers (>= 4 row steps)
+                if ((uint64_t)nrows / n_tiles < 4ull * FT_BLOCK) continue;
+            } else if ((uint64_t)nrows / n_tiles < (uint64_t)flush_factor * sb * band_w) continue;  // the flush must stay small next to the tile's rows
             int ne = (int)((FT_SMEM_CAP - fixed) / edge_band);
             if (ne > sb) ne = sb;
+            if (edges_only && ne < 1) continue;
             best_g = g;
             best_ne = ne;
             best_smem = fixed + (size_t)ne * edge_band;
@@ -1322,7 +1335,7 @@ int fused_vegas_launch(const tq_integrand* fn_host, int32_t dtype, const int64_t
                     fused_vegas_tile_kernel<FAM, T><<<TQ_GRID(grid), FT_BLOCK, best_smem, st>>>(
                         *fn_host, (const long long*)offsets, (uint32_t)n_cubes, shard, ns_div, inv_ns, (T)n_strat, (T)n_intervals,
                         (const P2*)edges_packed, n_intervals,
-                        (double*)hist_pairs, (T*)JF, (T*)JF2, seed, call_idx, best_g, (uint32_t)best_tile, tile_div, (int)band_w, best_ne, next_tile);
+                        (double*)hist_pairs, (T*)JF, (T*)JF2, seed, call_idx, best_g, (uint32_t)best_tile, tile_div, (int)band_w, best_ne, !edges_only, next_tile);
                 });
             });
             return check_launch("fused_vegas_tile_kernel");
