@@ -273,3 +273,25 @@ def test_cube_shard_inverse_matches_the_deal():
                 assert not local_cube(ids[l], lb, other, world)[0]
             seen += n_local
         assert seen == n_cubes
+
+
+def test_tile_kernel_band_contains_every_reachable_bin():
+    """fused_vegas_tile_kernel stages, per slow dimension, the bins [blo, blo + band_w) with blo = max(0, p*Ni//Ns - 1) and
+    band_w = ceil(Ni/Ns) + 3 (csrc/fused.cu).  Every bin a sample of digit p can reach -- k = floor(fl(fl((p + u)/Ns) * Ni)),
+    the arithmetic of vegas_stratification.py:140-165 + vegas_map.py:76-85 in the working precision -- must lie inside, so
+    the kernel's out-of-band fallback is never taken.  Checked in fp32 for the extremes of u and random u."""
+    import numpy as np
+
+    rng = np.random.default_rng(0)
+    u_ext = np.array([0.0, 2.0**-24, 0.5, 1.0 - 2.0**-24], dtype=np.float32)
+    for ns in (2, 3, 5, 7, 8, 13, 56, 1000):
+        for ni in (2, 97, 777, 1000, 4096, 65536, 1 << 20):
+            band_w = (ni + ns - 1) // ns + 3
+            p = np.arange(ns, dtype=np.int64)
+            u = np.concatenate([u_ext, rng.integers(0, 1 << 24, 64).astype(np.float32) * np.float32(2.0**-24)])
+            y = ((p[:, None].astype(np.float32) + u[None, :]) / np.float32(ns)).astype(np.float32)
+            y[y >= 1.0] = np.float32(0.999999)
+            k = np.floor(y * np.float32(ni)).astype(np.int64)
+            k = np.clip(k, 0, ni - 1)
+            blo = np.maximum(0, (p * ni) // ns - 1)[:, None]
+            assert np.all(k >= blo) and np.all(k < blo + band_w), (ns, ni)
