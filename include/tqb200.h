@@ -159,8 +159,9 @@ TQ_API int tq_vegas_accumulate_fused(const void* y, const void* f, const void* j
  *  tq_vegas_accumulate_regen: jf = (f*volume)*jac -> jf_out (nullable), and VEGASMap.accumulate_weight
  *   (vegas_map.py:99-111) with the bin ids REGENERATED from the same Philox blocks (same arithmetic: identical bins)
  *   into `hist_pairs` (fp64 {sum jf^2, count} per bin, tq_vegas_map_unpack_hist), into the large-map `records`, or
- *   into `weights` / `counts` directly (two reductions per bin: small passes); at most one target, none: jf only (no grid improvement).  jf2_out (nullable) receives jf^2 per row: maps beyond L2 bin those rows
- *   afterwards, band by band, with tq_vegas_hist_sweep. */
+ *   into `weights` / `counts` directly (two reductions per bin: small passes); at most one target, none: jf only
+ *   (no grid improvement).  jf2_out (nullable) receives jf^2 per row: maps beyond L2 bin those rows afterwards, band by
+ *   band, with tq_vegas_hist_sweep.  f and jac point at row `row_begin` (the rows of the matching tq_vegas_sample_map). */
 TQ_API int tq_vegas_sample_map(const int64_t* offsets, int64_t n_cubes, int32_t n_strat, int32_t dim, int32_t dtype,
                         int64_t row_begin, int64_t row_end, const void* edges_packed, int32_t edges_layout,
                         int64_t n_intervals, const void* domain, uint64_t seed, uint32_t call_idx, void* x, void* jac,
