@@ -227,6 +227,10 @@ def sample_map(offsets, n_strat, dim, dtype, row_begin, row_end, seed, call_idx,
     warm-up pass (y = u * 0.999999 from the row-keyed stream)."""
     table = records if records is not None else edges_packed
     require_cuda(offsets, table, domain)
+    if domain.dtype != dtype or tuple(domain.shape) != (dim, 2):
+        raise ValueError(f"domain must be a [{dim}, 2] tensor of dtype {dtype}, got {tuple(domain.shape)} / {domain.dtype}")
+    if edges_packed is not None and (edges_packed.dtype != dtype or edges_packed.shape[0] != dim):
+        raise ValueError(f"edges_packed must be [{dim}, Ni, 2] of dtype {dtype}, got {tuple(edges_packed.shape)} / {edges_packed.dtype}")
     rows = row_end - row_begin
     x = torch.empty((rows, dim), dtype=dtype, device=table.device)
     jac = torch.empty(rows, dtype=dtype, device=table.device)
